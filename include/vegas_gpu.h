@@ -1,0 +1,176 @@
+/*
+ * vegas_gpu.h -- C ABI of the B200-native Metropolis sweep for vegas-rs 0.9.0.
+ *
+ * This is the boundary a Rust `GpuMetropolis` shim (extern "C" + build.rs/cc, see
+ * INTEGRATION.md) binds.  The reference has no FFI layer; its extension points are the
+ * generic traits Integrator (src/integrator.rs:40-49), Hamiltonian (src/energy.rs:45-60),
+ * Instrument (src/instrument.rs:19-58) and Program (src/program.rs:55-63).  Each entry
+ * point below names the reference item it replaces.  All citations are relative to
+ * /root/reference.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every call returns 0 on
+ * success or a negative vegas_status_t and never throws or aborts (the reference bubbles
+ * Result<> up to main, src/error.rs:13-88); vegas_gpu_last_error() gives the message.
+ * A handle is bound to ONE CUDA device and is not thread-safe (the reference Machine is
+ * single-threaded, src/machine.rs:44-55).  There is no CPU fallback: without a CUDA
+ * device every create call fails with VEGAS_ERR_CUDA.
+ */
+#ifndef VEGAS_GPU_H
+#define VEGAS_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vegas_gpu* vegas_gpu_t;
+
+typedef enum {
+    VEGAS_OK = 0,
+    VEGAS_ERR_INVALID = -1,     /* bad argument / unsupported combination */
+    VEGAS_ERR_CUDA = -2,        /* CUDA runtime error (message in last_error) */
+    VEGAS_ERR_ALLOC = -3,
+    VEGAS_ERR_STATE = -4,       /* call not valid in the handle's current state */
+    VEGAS_ERR_NO_STEPS = -10,   /* ProgramError::NoSteps             src/error.rs:31-46 */
+    VEGAS_ERR_ZERO_TEMPERATURE = -11,
+    VEGAS_ERR_TMAX_LT_TMIN = -12,
+    VEGAS_ERR_ZERO_COOL_RATE = -13,
+    VEGAS_ERR_ZERO_FIELD = -14,
+    VEGAS_ERR_ZERO_FIELD_STEP = -15
+} vegas_status_t;
+
+typedef enum { VEGAS_ISING = 0, VEGAS_HEISENBERG = 1 } vegas_model_t;              /* src/input.rs:19-26 */
+typedef enum { VEGAS_PROPOSE_FLIP = 0, VEGAS_PROPOSE_RANDOM = 1 } vegas_proposal_t; /* src/integrator.rs:125 vs :79 */
+typedef enum { VEGAS_F32 = 0, VEGAS_F64 = 1 } vegas_precision_t;                   /* Heisenberg device storage */
+typedef enum { VEGAS_SC = 0, VEGAS_BCC = 1, VEGAS_FCC = 2 } vegas_unitcell_t;      /* src/input.rs:38-48 */
+
+/* Which total_energy the reference would report for this Hamiltonian:
+ *  PHYSICAL            every bond once, -|H| sum s.o, k sum (s.n)^2, g N
+ *  REFERENCE_COMPOUND  trait default sum_i energy(i) of hamiltonian!(...) (src/energy.rs:55-59,254-256):
+ *                      exchange double counted, Zeeman with '+', anisotropy with k
+ *  REFERENCE_EXCHANGE  Exchange::total_energy alone (src/energy.rs:208-213), as `vegas bench` uses */
+typedef enum { VEGAS_E_PHYSICAL = 0, VEGAS_E_REFERENCE_COMPOUND = 1, VEGAS_E_REFERENCE_EXCHANGE = 2 } vegas_energy_conv_t;
+
+/* Structured lattice = unit cell x expansion, src/input.rs:296-322.  Site index is
+ * ((iz*ny+iy)*nx+ix)*n_basis+b.  The z range may be a slab of a larger lattice (multi-GPU):
+ * this handle then owns planes/cells [z_offset, z_offset+nz) of nz_global. */
+typedef struct {
+    int unitcell;                 /* vegas_unitcell_t */
+    uint64_t nx, ny, nz;          /* local extent in unit cells */
+    int pbc_x, pbc_y, pbc_z;      /* src/input.rs:79-96 */
+    int literal_from_lattice_filter; /* 1: apply `source <= target` (src/energy.rs:180) to the generated edge list */
+    uint64_t nz_global;           /* 0 or ==nz: not decomposed */
+    uint64_t z_offset;
+} vegas_lattice_desc;
+
+/* General adjacency = Exchange::new(CsMat<f64>), src/energy.rs:171-173.  Columns sorted
+ * ascending per row (sprs CSR); values==NULL means the uniform `exchange` of the model. */
+typedef struct {
+    uint64_t n;
+    const uint64_t* row_ptr;      /* n+1 */
+    const uint32_t* col_idx;
+    const double* values;
+} vegas_csr_desc;
+
+typedef struct {
+    int model;                    /* vegas_model_t */
+    int proposal;                 /* vegas_proposal_t */
+    int precision;                /* vegas_precision_t (Heisenberg only) */
+    double exchange;              /* uniform J, src/input.rs:163 (default 1.0, :352) */
+    int has_exchange;             /* Exchange term present */
+    int has_zeeman;               /* Zeeman term present, src/input.rs:271 */
+    int has_anisotropy; double anisotropy_k; double anisotropy_axis[3]; /* src/energy.rs:96-101 */
+    int has_gauge; double gauge;  /* src/energy.rs:70-72 */
+    uint64_t seed;                /* Philox key; replaces --seed, src/main.rs:27-30 */
+    int device;                   /* CUDA device ordinal */
+    int force_general;            /* 1: never use the structured-stencil kernels (testing) */
+} vegas_model_desc;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+int vegas_gpu_create_lattice(const vegas_model_desc*, const vegas_lattice_desc*, vegas_gpu_t* out);
+int vegas_gpu_create_csr(const vegas_model_desc*, const vegas_csr_desc*, vegas_gpu_t* out);
+void vegas_gpu_destroy(vegas_gpu_t);
+const char* vegas_gpu_last_error(vegas_gpu_t);      /* NULL handle: error of the last failed create */
+const char* vegas_gpu_version(void);
+
+/* ---- introspection -------------------------------------------------------------------- */
+uint64_t vegas_gpu_n_sites(vegas_gpu_t);            /* State::len, src/state.rs:279-281 (local sites) */
+int vegas_gpu_n_colours(vegas_gpu_t);
+/* kernel family in use: "ising_msc", "heis_stencil", "ising_csr", "heis_csr" */
+const char* vegas_gpu_kernel_family(vegas_gpu_t);
+/* the host-side adjacency this handle was built with, in the reference's CSR form (tests/oracle parity).
+ * Pass NULL arrays to query sizes. Not available (VEGAS_ERR_STATE) for stencil handles above 2^27 sites. */
+int vegas_gpu_adjacency(vegas_gpu_t, uint64_t* n, uint64_t* nnz, uint64_t* row_ptr, uint32_t* col_idx, double* values);
+int vegas_gpu_colours(vegas_gpu_t, uint8_t* colour_of_site);
+
+/* pure host-side helpers (no CUDA device needed): the adjacency Exchange::from_lattice would build for a
+ * lattice descriptor (src/energy.rs:176-187) and the colouring the general-adjacency sweep uses for it.
+ * Pass NULL arrays to query sizes. */
+int vegas_gpu_lattice_adjacency(const vegas_lattice_desc*, double exchange, uint64_t* n, uint64_t* nnz,
+                                uint64_t* row_ptr, uint32_t* col_idx, double* values);
+int vegas_gpu_lattice_colours(const vegas_lattice_desc*, int* n_colours, uint8_t* colour_of_site);
+
+/* ---- state I/O in the REFERENCE's host layouts (src/state.rs:60-63,133-134,245-246) ---- */
+int vegas_gpu_upload_ising(vegas_gpu_t, const int8_t* s, uint64_t n);          /* +1 Up / -1 Down per site */
+int vegas_gpu_upload_heisenberg(vegas_gpu_t, const double* sxyz, uint64_t n);  /* AoS [f64;3] per site */
+int vegas_gpu_download_ising(vegas_gpu_t, int8_t* s, uint64_t n);
+int vegas_gpu_download_heisenberg(vegas_gpu_t, double* sxyz, uint64_t n);
+int vegas_gpu_randomize(vegas_gpu_t);               /* State::rand_with_size on device, src/state.rs:260-262 */
+int vegas_gpu_fill(vegas_gpu_t, int up);            /* State::{up,down}_with_size, src/state.rs:250-258 */
+
+/* ---- thermostat, src/thermostat.rs:19-79: T clamped to >= DBL_EPSILON; the field is an
+ * orientation spin (Ising: sign of dir[2]) and a magnitude of which |.| is used (src/state.rs:219-221) */
+int vegas_gpu_set_thermostat(vegas_gpu_t, double temperature, const double field_dir[3], double field_mag);
+int vegas_gpu_set_energy_convention(vegas_gpu_t, int conv /* vegas_energy_conv_t */);
+
+/* ---- the hot path: Integrator::step x n_steps (src/integrator.rs:66-92,109-138) with the
+ * per-step observers of src/instrument.rs:133-141 fused in.  1 step = N attempts.  When
+ * energy / mag_xyz are non-NULL they receive, per step, Hamiltonian::total_energy in the
+ * selected convention and the raw magnetisation projections (sum sx, sum sy, sum sz;
+ * |M| = Field magnitude is their norm, src/state.rs:235-242).  Host pointers. */
+int vegas_gpu_step(vegas_gpu_t, uint64_t n_steps, double* energy, double* mag_xyz);
+/* Same, asynchronous: nothing is copied back; observables of the last `n` steps stay on the device
+ * until vegas_gpu_read_observables.  Used by the multi-GPU driver and the benchmark. */
+int vegas_gpu_step_async(vegas_gpu_t, uint64_t n_steps, int record_observables);
+int vegas_gpu_read_observables(vegas_gpu_t, uint64_t n_steps, double* energy, double* mag_xyz);
+int vegas_gpu_synchronize(vegas_gpu_t);
+/* Literal drop-in of Integrator::step's signature: host State in, host State out (one step),
+ * host<->device copies included.  Ising: int8 per site; Heisenberg: double[3] per site. */
+int vegas_gpu_step_host_ising(vegas_gpu_t, int8_t* state_inout, uint64_t n, double* energy, double* mag_xyz);
+int vegas_gpu_step_host_heisenberg(vegas_gpu_t, double* sxyz_inout, uint64_t n, double* energy, double* mag_xyz);
+
+/* ---- deterministic parity entry points ----------------------------------------------- */
+int vegas_gpu_total_energy(vegas_gpu_t, double* out);                    /* Hamiltonian::total_energy, selected convention */
+int vegas_gpu_magnetization(vegas_gpu_t, double out_xyz[3]);             /* State::magnetization projections */
+int vegas_gpu_site_energies(vegas_gpu_t, double* out_n);                 /* Hamiltonian::energy(i) for all i (compound) */
+/* e_new - e_old of src/integrator.rs:77-81/:123-127 for every site: flip proposal when
+ * proposal==NULL, else the given spins (Ising int8[n], Heisenberg double[3n]). */
+int vegas_gpu_delta_energies(vegas_gpu_t, const void* proposal, double* out_n);
+int vegas_gpu_attempt_count(vegas_gpu_t, uint64_t* attempts, uint64_t* accepted);
+int vegas_gpu_sweep_count(vegas_gpu_t, uint64_t* sweeps);                /* Philox sweep counter */
+int vegas_gpu_set_sweep_count(vegas_gpu_t, uint64_t sweeps);
+/* integer acceptance thresholds in use (Ising, uniform J): thr[2][n_classes], always[2][n_classes] */
+int vegas_gpu_ising_thresholds(vegas_gpu_t, int* n_classes, uint64_t* thr, uint8_t* always);
+
+/* ---- z-slab decomposition over one process per GPU (no reference counterpart) ---------
+ * Each rank exports CUDA IPC handles of its halo buffers and flags; the launcher (torch.distributed,
+ * any transport) delivers them to the z-neighbours, which connect.  After connect the sweep kernels
+ * store boundary planes straight into the neighbour's halo over NVLink and signal with flags. */
+#define VEGAS_IPC_BYTES 256
+int vegas_gpu_slab_export(vegas_gpu_t, void* blob /* VEGAS_IPC_BYTES */);
+int vegas_gpu_slab_connect(vegas_gpu_t, const void* blob_lower_neighbour, const void* blob_upper_neighbour);
+/* single-process variant: both handles live in this process (tests, or one process driving several GPUs) */
+int vegas_gpu_slab_connect_local(vegas_gpu_t self, vegas_gpu_t lower, vegas_gpu_t upper);
+
+/* ---- timing hooks for bench.py (CUDA events on the handle's own stream) --------------- */
+int vegas_gpu_timer_start(vegas_gpu_t);
+int vegas_gpu_timer_stop(vegas_gpu_t, float* elapsed_ms);
+uint64_t vegas_gpu_launch_count(vegas_gpu_t);       /* kernels launched by this handle so far */
+void* vegas_gpu_stream(vegas_gpu_t);                /* cudaStream_t */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VEGAS_GPU_H */

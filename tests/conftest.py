@@ -1,0 +1,22 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def built():
+    """Build the CUDA extension and the oracle once per session (nvcc/gcc only, no GPU needed)."""
+    from vegas_rs_b200 import build as vb
+    from oracle import binding as ob
+    vb.build()
+    ob.build()
+    return True

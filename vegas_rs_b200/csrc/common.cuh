@@ -1,0 +1,81 @@
+// common.cuh -- device helpers shared by every vegas_gpu kernel (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vg {
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 (Random123), counter-based, all state in registers.  The key is the run
+// seed; the counter is (site-or-word index, sweep, call) so that any decomposition of the
+// lattice over GPUs reproduces the same random numbers per site.
+// Round keys are thread-invariant, so the compiler keeps them on the uniform datapath.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Counter layout used everywhere: c0,c1 = 64-bit index (bit 62 of the index carries the
+// colour for word-keyed streams), c2 = sweep low, c3 = sweep bits 32..55 | call << 24.
+__device__ __forceinline__ void philox_at(uint64_t index, uint64_t sweep, uint32_t call, uint32_t k0, uint32_t k1,
+                                          uint32_t (&out)[4]) {
+    philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), (uint32_t)sweep,
+                  ((uint32_t)(sweep >> 32) & 0x00FFFFFFu) | (call << 24), k0, k1, out);
+}
+
+// ---------------------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sums NV values per thread over the block and lets thread 0 add them to out[0..NV) with
+// one atomic each.  `red` is shared scratch of NV * 32 elements.
+template <typename T, int NV>
+__device__ __forceinline__ void block_atomic_add(T (&v)[NV], T* red, T* out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        T s = warp_sum(v[i]);
+        if (lane == 0) red[i * 32 + warp] = s;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            T s = lane < nwarp ? red[i * 32 + lane] : T(0);
+            s = warp_sum(s);
+            if (lane == 0) atomicAdd(out + i, s);
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned long long* as_ull(long long* p) { return reinterpret_cast<unsigned long long*>(p); }
+
+// ---------------------------------------------------------------------------------------
+// uniform variates
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
+    return (double)((((uint64_t)hi << 32) | lo) >> 11) * 0x1.0p-53;
+}
+__device__ __forceinline__ float u24(uint32_t w) { return (float)(w >> 8) * 0x1.0p-24f; }
+
+}  // namespace vg

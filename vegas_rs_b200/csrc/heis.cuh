@@ -1,0 +1,271 @@
+// heis.cuh -- K3: Heisenberg checkerboard half-sweep for sc lattices (pbc), SoA colour-split storage,
+// plus the single-site update shared with the general-adjacency kernels.
+//
+// Replaces MetropolisIntegrator::step (src/integrator.rs:66-92; MetropolisFlipIntegrator :109-138
+// when FLIP) for HeisenbergSpin with the compound Gauge+Exchange+Anisotropy+Zeeman energy
+// (src/energy.rs:63-214) in the closed form of SURVEY App. B:
+//   dE = -(s'-s).n + (s'-s).h + k[(s'.a)^2 - (s.a)^2],   n = sum_j J_ij s_j,  h = |H| * orientation
+// (reference sign: Zeeman::energy = +|H| s.o, src/energy.rs:147-151).
+#pragma once
+#include "common.cuh"
+
+namespace vg {
+
+template <typename real>
+struct HeisParams {
+    real J;        // uniform exchange (multiplies the neighbour sum)
+    real h[3];     // |H| * field orientation
+    real k;        // anisotropy strength (0 when absent)
+    real a[3];     // anisotropy reference spin
+    real invT;
+};
+
+// Uniform point on the sphere from two uniforms (Archimedes); same distribution as
+// util.rs:21-34 (Marsaglia) without a rejection loop.
+__device__ __forceinline__ void sphere_point(float u0, float u1, float& x, float& y, float& z) {
+    z = 1.0f - 2.0f * u0;
+    const float rxy = sqrtf(fmaxf(0.0f, (1.0f - z) * (1.0f + z)));
+    float sn, cs;
+    sincospif(2.0f * u1, &sn, &cs);
+    x = rxy * cs; y = rxy * sn;
+}
+__device__ __forceinline__ void sphere_point(double u0, double u1, double& x, double& y, double& z) {
+    z = 1.0 - 2.0 * u0;
+    const double rxy = sqrt(fmax(0.0, (1.0 - z) * (1.0 + z)));
+    double sn, cs;
+    sincospi(2.0 * u1, &sn, &cs);
+    x = rxy * cs; y = rxy * sn;
+}
+
+__device__ __forceinline__ float fast_exp(float x) { return __expf(x); }
+__device__ __forceinline__ double fast_exp(double x) { return exp(x); }
+
+// One Metropolis attempt on a site whose local field (nx,ny,nz) is known.  `site` is the
+// global natural site index; randoms are Philox(site, sweep).  Returns true when accepted.
+template <typename real, bool FLIP>
+__device__ __forceinline__ bool heis_attempt(real& sx, real& sy, real& sz, real nx, real ny, real nz,
+                                             const HeisParams<real>& p, uint64_t site, uint64_t sweep, uint32_t k0,
+                                             uint32_t k1) {
+    uint32_t r[4];
+    philox_at(site, sweep, 0u, k0, k1, r);
+    real px, py, pz, u;
+    if (sizeof(real) == 4) {
+        if (FLIP) { px = -sx; py = -sy; pz = -sz; }
+        else {
+            float fx, fy, fz;
+            sphere_point(((float)(r[0] >> 8) + 0.5f) * 0x1.0p-24f, u24(r[1]), fx, fy, fz);
+            px = fx; py = fy; pz = fz;
+        }
+        u = u24(r[2]);
+    } else {
+        if (FLIP) { px = -sx; py = -sy; pz = -sz; }
+        else {
+            double dx, dy, dz;
+            sphere_point(u53(r[0], r[1]), u53(r[2], r[3]), dx, dy, dz);
+            px = dx; py = dy; pz = dz;
+        }
+        uint32_t q[4];
+        philox_at(site, sweep, 1u, k0, k1, q);
+        u = (real)u53(q[0], q[1]);
+    }
+    const real dx = px - sx, dy = py - sy, dz = pz - sz;
+    real dE = -(dx * nx + dy * ny + dz * nz) + (dx * p.h[0] + dy * p.h[1] + dz * p.h[2]);
+    const real da_new = px * p.a[0] + py * p.a[1] + pz * p.a[2];
+    const real da_old = sx * p.a[0] + sy * p.a[1] + sz * p.a[2];
+    dE += p.k * (da_new * da_new - da_old * da_old);
+    // src/integrator.rs:82-88: accept if dE < 0, else if u < exp(-dE/T)
+    const bool acc = (dE < real(0)) || (u < fast_exp(-dE * p.invT));
+    if (acc) { sx = px; sy = py; sz = pz; }
+    return acc;
+}
+
+struct HeisGeom {
+    uint32_t Gx;        // vector groups per row per colour
+    uint32_t Hx;        // elements per row per colour = Lx / 2
+    uint32_t Ly, Lz;
+    uint32_t z_offset;
+    uint32_t Lx;
+};
+
+template <typename real> struct VecOf;
+template <> struct VecOf<float> { typedef float4 type; static constexpr int N = 4; };
+template <> struct VecOf<double> { typedef double2 type; static constexpr int N = 2; };
+
+__device__ __forceinline__ void vec_load(const float* p, float (&v)[4]) {
+    const float4 q = *reinterpret_cast<const float4*>(p);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+}
+__device__ __forceinline__ void vec_load(const double* p, double (&v)[2]) {
+    const double2 q = *reinterpret_cast<const double2*>(p);
+    v[0] = q.x; v[1] = q.y;
+}
+__device__ __forceinline__ void vec_store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void vec_store(double* p, const double (&v)[2]) {
+    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+}
+
+template <typename real>
+struct HeisPtrs {
+    real* own[3];
+    const real* oth[3];
+    const real* oth_lo[3];  // plane below local z = 0 (halo or periodic wrap)
+    const real* oth_hi[3];  // plane above local z = Lz-1
+    real* peer_lo[3];       // neighbour GPU's halo that receives my plane 0 (or null)
+    real* peer_hi[3];
+};
+
+// MODE 0: update; 1: update + fused reductions; 2: reductions only.
+// obs[0] += -sum_own s.n (exchange energy, each bond once)   obs[1..3] += sum s (both colours)
+// obs[4] += sum (s.a)^2 (both colours)                         obs[5] += accepted (as double)
+template <typename real, int NDIM, bool FLIP, int MODE>
+__global__ void __launch_bounds__(128)
+heis_stencil_kernel(HeisPtrs<real> P, HeisGeom g, int colour, uint32_t z_begin, uint32_t z_count, HeisParams<real> p,
+                    uint64_t sweep, uint32_t k0, uint32_t k1, double* __restrict__ obs) {
+    constexpr int N = VecOf<real>::N;
+    __shared__ double s_red[6 * 32];
+    const uint32_t rows = g.Ly * g.Gx;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = t < z_count * rows;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    if (active) {
+        const uint32_t zl = z_begin + t / rows;
+        const uint32_t rem = t % rows;
+        const uint32_t y = rem / g.Gx, gx = rem % g.Gx;
+        const uint32_t zg = zl + g.z_offset;
+        const uint32_t rp = (y + zg + (uint32_t)colour) & 1u;
+        const size_t row = ((size_t)zl * g.Ly + y) * g.Hx;
+        const size_t e0 = row + (size_t)gx * N;
+        const uint32_t ym = y == 0 ? g.Ly - 1 : y - 1, yp = y + 1 == g.Ly ? 0 : y + 1;
+        const size_t ea = ((size_t)zl * g.Ly + ym) * g.Hx + (size_t)gx * N;
+        const size_t eb = ((size_t)zl * g.Ly + yp) * g.Hx + (size_t)gx * N;
+        const size_t plane = (size_t)g.Ly * g.Hx;
+        // carry element of the x-neighbour that lives in the adjacent group
+        const uint32_t xc_carry = rp ? ((gx + 1 == g.Gx) ? 0u : (gx + 1) * N) : ((gx == 0 ? g.Gx : gx) * N - 1);
+
+        real s[3][N], nsum[3][N], partner[3][N];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            real n0[N], a[N], b[N];
+            vec_load(P.own[c] + e0, s[c]);
+            vec_load(P.oth[c] + e0, n0);
+            vec_load(P.oth[c] + ea, a);
+            vec_load(P.oth[c] + eb, b);
+            const real carry = P.oth[c][row + xc_carry];
+#pragma unroll
+            for (int e = 0; e < N; ++e) {
+                const real sh = rp ? (e + 1 < N ? n0[(e + 1) % N] : carry) : (e > 0 ? n0[(e + N - 1) % N] : carry);
+                nsum[c][e] = (n0[e] + sh) + (a[e] + b[e]);
+                partner[c][e] = n0[e];
+            }
+            if (NDIM == 3) {
+                real lo[N], hi[N];
+                const size_t el = (size_t)y * g.Hx + (size_t)gx * N;
+                vec_load(zl == 0 ? P.oth_lo[c] + el : P.oth[c] + e0 - plane, lo);
+                vec_load(zl + 1 == g.Lz ? P.oth_hi[c] + el : P.oth[c] + e0 + plane, hi);
+#pragma unroll
+                for (int e = 0; e < N; ++e) nsum[c][e] += lo[e] + hi[e];
+            }
+        }
+        real facc[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int e = 0; e < N; ++e) {
+            const real nx = p.J * nsum[0][e], ny = p.J * nsum[1][e], nz = p.J * nsum[2][e];
+            if (MODE != 2) {
+                const uint32_t x = 2u * (gx * N + e) + rp;
+                const uint64_t site = ((uint64_t)zg * g.Ly + y) * g.Lx + x;
+                const bool ok = heis_attempt<real, FLIP>(s[0][e], s[1][e], s[2][e], nx, ny, nz, p, site, sweep, k0, k1);
+                facc[5] += ok ? real(1) : real(0);
+            }
+            if (MODE != 0) {
+                facc[0] -= s[0][e] * nx + s[1][e] * ny + s[2][e] * nz;
+                facc[1] += s[0][e] + partner[0][e];
+                facc[2] += s[1][e] + partner[1][e];
+                facc[3] += s[2][e] + partner[2][e];
+                const real d1 = s[0][e] * p.a[0] + s[1][e] * p.a[1] + s[2][e] * p.a[2];
+                const real d2 = partner[0][e] * p.a[0] + partner[1][e] * p.a[1] + partner[2][e] * p.a[2];
+                facc[4] += d1 * d1 + d2 * d2;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) acc[i] = (double)facc[i];
+        if (MODE != 2) {
+            const size_t el = (size_t)y * g.Hx + (size_t)gx * N;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                vec_store(P.own[c] + e0, s[c]);
+                if (NDIM == 3) {
+                    if (P.peer_lo[c] != nullptr && zl == 0) vec_store(P.peer_lo[c] + el, s[c]);
+                    if (P.peer_hi[c] != nullptr && zl + 1 == g.Lz) vec_store(P.peer_hi[c] + el, s[c]);
+                }
+            }
+        }
+    }
+    block_atomic_add<double, 6>(acc, s_red, obs);
+}
+
+// ---------------------------------------------------------------------------------------
+// K7: reference host layout (AoS double[3] per site, natural order) <-> colour-split SoA.
+// One thread per site; reads/writes of the AoS side are 24 B strided (one-off cost).
+// ---------------------------------------------------------------------------------------
+template <typename real>
+__global__ void __launch_bounds__(256)
+heis_pack_kernel(const double* __restrict__ aos, real* c0x, real* c0y, real* c0z, real* c1x, real* c1y, real* c1z,
+                 uint32_t Lx, uint32_t Ly, uint32_t Lz, uint32_t z_offset) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)Lx * Ly * Lz;
+    if (t >= total) return;
+    const uint32_t x = (uint32_t)(t % Lx), y = (uint32_t)((t / Lx) % Ly), z = (uint32_t)(t / ((size_t)Lx * Ly));
+    const uint32_t col = (x + y + z + z_offset) & 1u;
+    const size_t e = ((size_t)z * Ly + y) * (Lx / 2) + (x >> 1);
+    const double sx = aos[3 * t], sy = aos[3 * t + 1], sz = aos[3 * t + 2];
+    if (col == 0) { c0x[e] = (real)sx; c0y[e] = (real)sy; c0z[e] = (real)sz; }
+    else { c1x[e] = (real)sx; c1y[e] = (real)sy; c1z[e] = (real)sz; }
+}
+
+template <typename real, typename outT>
+__global__ void __launch_bounds__(256)
+heis_unpack_kernel(outT* __restrict__ ox, outT* __restrict__ oy, outT* __restrict__ oz, size_t stride,
+                   const real* c0x, const real* c0y, const real* c0z, const real* c1x, const real* c1y,
+                   const real* c1z, uint32_t Lx, uint32_t Ly, uint32_t Lz, uint32_t z_offset) {
+    // stride 3 with ox=aos, oy=aos+1, oz=aos+2 writes AoS; stride 1 writes natural-order SoA
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)Lx * Ly * Lz;
+    if (t >= total) return;
+    const uint32_t x = (uint32_t)(t % Lx), y = (uint32_t)((t / Lx) % Ly), z = (uint32_t)(t / ((size_t)Lx * Ly));
+    const uint32_t col = (x + y + z + z_offset) & 1u;
+    const size_t e = ((size_t)z * Ly + y) * (Lx / 2) + (x >> 1);
+    ox[t * stride] = (outT)(col ? c1x[e] : c0x[e]);
+    oy[t * stride] = (outT)(col ? c1y[e] : c0y[e]);
+    oz[t * stride] = (outT)(col ? c1z[e] : c0z[e]);
+}
+
+// State::rand_with_size for Heisenberg spins on device, natural site index keyed.
+template <typename real>
+__device__ __forceinline__ void heis_random_spin(uint64_t site, uint32_t k0, uint32_t k1, real& x, real& y, real& z) {
+    uint32_t r[4];
+    philox_at(site | (1ull << 61), ~0ull, 0xFEu, k0, k1, r);
+    double dx, dy, dz;
+    sphere_point(u53(r[0], r[1]), u53(r[2], r[3]), dx, dy, dz);
+    x = (real)dx; y = (real)dy; z = (real)dz;
+}
+
+template <typename real>
+__global__ void __launch_bounds__(256)
+heis_stencil_randomize_kernel(real* c0x, real* c0y, real* c0z, real* c1x, real* c1y, real* c1z, uint32_t Lx, uint32_t Ly,
+                              uint32_t Lz, uint32_t z_offset, uint32_t k0, uint32_t k1) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)Lx * Ly * Lz;
+    if (t >= total) return;
+    const uint32_t x = (uint32_t)(t % Lx), y = (uint32_t)((t / Lx) % Ly), z = (uint32_t)(t / ((size_t)Lx * Ly));
+    const uint32_t col = (x + y + z + z_offset) & 1u;
+    const size_t e = ((size_t)z * Ly + y) * (Lx / 2) + (x >> 1);
+    const uint64_t site = ((uint64_t)(z + z_offset) * Ly + y) * Lx + x;
+    real sx, sy, sz;
+    heis_random_spin<real>(site, k0, k1, sx, sy, sz);
+    if (col == 0) { c0x[e] = sx; c0y[e] = sy; c0z[e] = sz; }
+    else { c1x[e] = sx; c1y[e] = sy; c1z[e] = sz; }
+}
+
+}  // namespace vg

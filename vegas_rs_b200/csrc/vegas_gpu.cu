@@ -1,0 +1,1338 @@
+// vegas_gpu.cu -- C ABI (include/vegas_gpu.h) of the B200-native Metropolis sweep.
+// Host logic only: handle, layout selection, thermostat tables, launch sequencing.
+// Kernels live in ising_msc.cuh (K1), heis.cuh (K3), general.cuh (K2/K4/K5).
+#include "../../include/vegas_gpu.h"
+
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "general.cuh"
+#include "heis.cuh"
+#include "ising_msc.cuh"
+#include "lattice.hpp"
+
+using namespace vg;
+
+namespace {
+
+enum Family { FAM_ISING_MSC = 0, FAM_HEIS_STENCIL = 1, FAM_ISING_GEN = 2, FAM_HEIS_GEN = 3 };
+const char* const FAMILY_NAME[4] = {"ising_msc", "heis_stencil", "ising_general", "heis_general"};
+
+constexpr uint64_t OBS_CAP = 4096;  // steps of observables kept on the device per batch
+constexpr int OBS_W = 8;            // 8 x 8-byte slots per step
+
+std::string g_create_error;
+
+}  // namespace
+
+struct vegas_gpu {
+    vegas_model_desc md{};
+    int family = 0;
+    bool structured = false, csr_input = false;
+    vgl::Desc ld{};                 // local lattice (structured)
+    uint64_t nz_global = 0, z_offset = 0;
+    uint64_t n = 0;                 // local sites
+    int n_colours = 0;
+    int ndim = 3;                   // stencil dimensionality (2 when nz == 1)
+    int n_self = 0;                 // periodic axes of extent 1 (self bond, constant energy)
+    // thermostat (src/thermostat.rs:19-79)
+    double T = 2.8, fdir[3] = {0, 0, 1}, fmag = 0.0;
+    int econv = VEGAS_E_REFERENCE_COMPOUND;
+    // device
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // --- Ising MSC
+    uint4* msc[2] = {nullptr, nullptr};   // colour arrays
+    uint4* msc_bits = nullptr;            // [MSC_MAX_SLOT][16] threshold bit-plane masks
+    MscTable msc_tab{};
+    int msc_nslot = 0;
+    bool msc_field = false;
+    std::vector<uint64_t> ising_thr;      // [2][8]
+    std::vector<uint8_t> ising_always;    // [2][8]
+    // --- Heisenberg stencil: [colour][component]
+    void* hs[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    // --- halos (slab decomposition): per colour lower/upper halo of the *other* ranks' planes
+    void* halo = nullptr;                 // one allocation: [colour][lo/hi][comp] planes
+    size_t halo_plane_bytes = 0;          // bytes of one colour plane (one component)
+    unsigned long long* flags = nullptr;  // [2]: pass counters written by lower / upper neighbour
+    void* peer_halo[2] = {nullptr, nullptr};            // lower / upper neighbour's halo allocation
+    unsigned long long* peer_flags[2] = {nullptr, nullptr};
+    bool slab = false, connected = false, peer_is_ipc = false;
+    uint64_t pass_counter = 0;
+    // --- general family
+    int8_t* g_s8 = nullptr;               // Ising natural order
+    void* g_s[3] = {nullptr, nullptr, nullptr};  // Heisenberg SoA natural order
+    std::vector<uint32_t*> g_sites;       // per colour site lists (device)
+    std::vector<uint32_t> g_counts;
+    unsigned long long* d_row_ptr = nullptr; uint32_t* d_col = nullptr; double* d_val = nullptr;
+    unsigned long long* g_thr = nullptr; uint8_t* g_code = nullptr;
+    std::vector<uint64_t> h_row_ptr; std::vector<uint32_t> h_col; std::vector<double> h_val;  // csr input copy
+    std::vector<uint8_t> h_colour;
+    // --- observables
+    unsigned long long* obs = nullptr;    // [OBS_CAP + 2][OBS_W]; row OBS_CAP = scratch, OBS_CAP+1 = query
+    // --- counters
+    uint64_t sweeps = 0, attempts = 0, accepted = 0, launches = 0;
+    bool tables_dirty = true;
+    std::string err;
+};
+
+namespace {
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            char b__[512];                                                                         \
+            snprintf(b__, sizeof b__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            if (h) h->err = b__; else g_create_error = b__;                                        \
+            return VEGAS_ERR_CUDA;                                                                 \
+        }                                                                                          \
+    } while (0)
+
+int fail(vegas_gpu* h, int code, const std::string& msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+
+inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
+inline size_t real_bytes(const vegas_gpu* h) { return h->md.precision == VEGAS_F64 ? 8 : 4; }
+
+double h_abs(const vegas_gpu* h) { return h->md.has_zeeman ? std::fabs(h->fmag) : 0.0; }
+// Ising: (orientation . up) * |H|   (IsingSpin::dot src/state.rs:95-101; orientation Up when dir[2] >= 0)
+double ising_h_o(const vegas_gpu* h) { return h_abs(h) * (h->fdir[2] >= 0.0 ? 1.0 : -1.0); }
+
+// ---------------------------------------------------------------------------------------
+// Acceptance thresholds: accept iff U < thr, U uniform in [0, 2^64)  (src/integrator.rs:82-88, :128-134)
+// ---------------------------------------------------------------------------------------
+void threshold(double delta, double T, uint64_t& thr, uint8_t& code) {
+    if (delta < 0.0) { code = 2; thr = ~0ull; return; }
+    const double p = std::exp(-delta / T);
+    if (!(p < 1.0)) { code = 2; thr = ~0ull; return; }      // u < 1 always holds
+    const double scaled = std::floor(std::ldexp(p, 64));
+    thr = scaled >= 18446744073709551615.0 ? ~0ull : (uint64_t)scaled;
+    code = thr == 0 ? 0 : 1;
+}
+
+// dE of flipping a spin s whose neighbours sum to m (uniform J), reference arithmetic:
+// e_old = -J*(s*m) + (s.o)|H|,  e_new = -e_old  (gauge and Ising anisotropy cancel).
+double ising_delta(const vegas_gpu* h, int s, int m) {
+    const double ex = h->md.has_exchange ? -h->md.exchange * (double)(s * m) : 0.0;
+    const double ze = h->md.has_zeeman ? (double)s * ising_h_o(h) : 0.0;
+    const double e_old = ex + ze, e_new = (-ex) + (-ze);
+    return e_new - e_old;
+}
+
+int update_tables(vegas_gpu* h) {
+    if (!h->tables_dirty) return VEGAS_OK;
+    if (h->family == FAM_ISING_MSC) {
+        const int Z = 2 * h->ndim;
+        h->ising_thr.assign(16, 0); h->ising_always.assign(16, 0);
+        std::vector<uint64_t> slots;
+        h->msc_field = h->md.has_zeeman && std::fabs(h->fmag) != 0.0;
+        for (int sidx = 0; sidx < 2; ++sidx)
+            for (int c = 0; c <= Z; ++c) {
+                const int s = sidx ? 1 : -1;
+                const int m = s * (Z - 2 * c);  // s*m = Z - 2c
+                uint64_t thr; uint8_t code;
+                threshold(ising_delta(h, s, m), h->T, thr, code);
+                h->ising_thr[sidx * 8 + c] = thr;
+                h->ising_always[sidx * 8 + c] = code == 2;
+                uint8_t slot;
+                if (code == 2) slot = MSC_ALWAYS;
+                else if (code == 0) slot = MSC_NEVER;
+                else {
+                    size_t q = 0;
+                    while (q < slots.size() && slots[q] != thr) ++q;
+                    if (q == slots.size()) slots.push_back(thr);
+                    slot = (uint8_t)q;
+                }
+                h->msc_tab.slot_of[sidx][c] = slot;
+            }
+        h->msc_nslot = h->msc_field ? 14 : 3;
+        if ((int)slots.size() > h->msc_nslot) return fail(h, VEGAS_ERR_INVALID, "internal: too many threshold slots");
+        std::vector<uint32_t> bits((size_t)MSC_MAX_SLOT * 64, 0u);
+        for (size_t q = 0; q < slots.size(); ++q)
+            for (int j = 0; j < 64; ++j) bits[q * 64 + j] = (slots[q] >> (63 - j) & 1ull) ? 0xFFFFFFFFu : 0u;
+        CU(cudaMemcpyAsync(h->msc_bits, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));  // `bits` is pageable host memory
+    } else if (h->family == FAM_ISING_GEN) {
+        const int W = 2 * ISING_ZMAX + 1;
+        std::vector<uint64_t> thr((size_t)2 * W);
+        std::vector<uint8_t> code((size_t)2 * W);
+        for (int sidx = 0; sidx < 2; ++sidx)
+            for (int m = -ISING_ZMAX; m <= ISING_ZMAX; ++m)
+                threshold(ising_delta(h, sidx ? 1 : -1, m), h->T, thr[sidx * W + m + ISING_ZMAX], code[sidx * W + m + ISING_ZMAX]);
+        CU(cudaMemcpyAsync(h->g_thr, thr.data(), thr.size() * 8, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->g_code, code.data(), code.size(), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    h->tables_dirty = false;
+    return VEGAS_OK;
+}
+
+template <typename real>
+HeisParams<real> heis_params(const vegas_gpu* h) {
+    HeisParams<real> p;
+    p.J = (real)(h->md.has_exchange ? h->md.exchange : 0.0);
+    const double ha = h_abs(h);
+    for (int c = 0; c < 3; ++c) {
+        p.h[c] = (real)(ha * h->fdir[c]);
+        p.a[c] = (real)(h->md.has_anisotropy ? h->md.anisotropy_axis[c] : 0.0);
+    }
+    p.k = (real)(h->md.has_anisotropy ? h->md.anisotropy_k : 0.0);
+    p.invT = (real)(1.0 / h->T);
+    return p;
+}
+
+EnergyParams energy_params(const vegas_gpu* h) {
+    EnergyParams ep{};
+    const double ha = h_abs(h);
+    const bool ising = h->md.model == VEGAS_ISING;
+    for (int c = 0; c < 3; ++c) {
+        ep.h[c] = ising ? 0.0 : ha * h->fdir[c];
+        ep.a[c] = ising ? 0.0 : h->md.anisotropy_axis[c];
+    }
+    if (ising) { ep.h[2] = ising_h_o(h); ep.a[2] = h->md.anisotropy_axis[2] >= 0.0 ? 1.0 : -1.0; }
+    ep.k = h->md.anisotropy_k; ep.gauge = h->md.gauge;
+    ep.has_exchange = h->md.has_exchange; ep.has_zeeman = h->md.has_zeeman;
+    ep.has_aniso = h->md.has_anisotropy; ep.has_gauge = h->md.has_gauge;
+    return ep;
+}
+
+StructuredNb structured_nb(const vegas_gpu* h) {
+    StructuredNb nb{};
+    nb.nx = (uint32_t)h->ld.nx; nb.ny = (uint32_t)h->ld.ny; nb.nz = (uint32_t)h->ld.nz;
+    nb.nb = vgl::basis_count(h->ld.unitcell);
+    for (int a = 0; a < 3; ++a) nb.pbc[a] = h->ld.pbc[a];
+    nb.literal = h->ld.literal;
+    nb.J = h->md.has_exchange ? h->md.exchange : 0.0;
+    for (int b = 0; b < 4; ++b) nb.count[b] = 0;
+    for (const vgl::UcEdge& e : vgl::unitcell_edges(h->ld.unitcell)) {
+        NbEntry f{}; f.tb = (int8_t)e.t; f.dx = (int8_t)e.dx; f.dy = (int8_t)e.dy; f.dz = (int8_t)e.dz; f.fwd = 1;
+        nb.e[e.s][nb.count[e.s]++] = f;
+    }
+    for (const vgl::UcEdge& e : vgl::unitcell_edges(h->ld.unitcell)) {
+        NbEntry r{}; r.tb = (int8_t)e.s; r.dx = (int8_t)-e.dx; r.dy = (int8_t)-e.dy; r.dz = (int8_t)-e.dz; r.fwd = 0;
+        nb.e[e.t][nb.count[e.t]++] = r;
+    }
+    return nb;
+}
+
+CsrNb csr_nb(const vegas_gpu* h) {
+    CsrNb nb{};
+    nb.row_ptr = h->d_row_ptr; nb.col = h->d_col; nb.val = h->d_val;
+    nb.J = h->md.has_exchange ? h->md.exchange : 0.0;
+    return nb;
+}
+
+// ---------------------------------------------------------------------------------------
+// stencil geometry helpers
+// ---------------------------------------------------------------------------------------
+MscGeom msc_geom(const vegas_gpu* h) {
+    MscGeom g{};
+    g.Gx = (uint32_t)(h->ld.nx / 256); g.Ly = (uint32_t)h->ld.ny; g.Lz = (uint32_t)h->ld.nz;
+    g.z_offset = (uint32_t)h->z_offset; g.Ly_g = (uint32_t)h->ld.ny;
+    return g;
+}
+size_t msc_groups(const vegas_gpu* h) { return (size_t)(h->ld.nx / 256) * h->ld.ny * h->ld.nz; }
+
+HeisGeom heis_geom(const vegas_gpu* h) {
+    HeisGeom g{};
+    const int N = h->md.precision == VEGAS_F64 ? 2 : 4;
+    g.Hx = (uint32_t)(h->ld.nx / 2); g.Gx = g.Hx / N; g.Ly = (uint32_t)h->ld.ny; g.Lz = (uint32_t)h->ld.nz;
+    g.z_offset = (uint32_t)h->z_offset; g.Lx = (uint32_t)h->ld.nx;
+    return g;
+}
+size_t heis_colour_elems(const vegas_gpu* h) { return (size_t)(h->ld.nx / 2) * h->ld.ny * h->ld.nz; }
+
+// halo layout inside h->halo: [colour 0/1][lo 0 / hi 1][component] planes of halo_plane_bytes
+size_t halo_offset(const vegas_gpu* h, int colour, int hi, int comp) {
+    const int ncomp = h->family == FAM_ISING_MSC ? 1 : 3;
+    return (((size_t)colour * 2 + hi) * ncomp + comp) * h->halo_plane_bytes;
+}
+
+// ---------------------------------------------------------------------------------------
+// kernel dispatch
+// ---------------------------------------------------------------------------------------
+template <int NDIM, bool FIELD, int NSLOT, bool RP>
+void launch_msc_mode(vegas_gpu* h, int mode, dim3 grid, uint4* own, const uint4* oth, const uint4* lo, const uint4* hi,
+                     uint4* plo, uint4* phi, int colour, uint32_t zb, uint32_t zc, unsigned long long* obs) {
+    const MscGeom g = msc_geom(h);
+    const uint32_t k0 = (uint32_t)h->md.seed, k1 = (uint32_t)(h->md.seed >> 32);
+    if (mode == 0)
+        ising_msc_kernel<NDIM, FIELD, NSLOT, RP, 0><<<grid, 256, 0, h->stream>>>(own, oth, lo, hi, plo, phi, g, colour, zb, zc,
+                                                                                h->msc_tab, h->msc_bits, h->sweeps, k0, k1, obs);
+    else
+        ising_msc_kernel<NDIM, FIELD, NSLOT, RP, 1><<<grid, 256, 0, h->stream>>>(own, oth, lo, hi, plo, phi, g, colour, zb, zc,
+                                                                                h->msc_tab, h->msc_bits, h->sweeps, k0, k1, obs);
+}
+
+template <int NDIM>
+void launch_msc(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, const uint4* lo, const uint4* hi, uint4* plo,
+                uint4* phi, unsigned long long* obs) {
+    const MscGeom g = msc_geom(h);
+    const dim3 grid(cdiv((uint64_t)zc * g.Ly * g.Gx, 256));
+    uint4* own = h->msc[colour];
+    const uint4* oth = h->msc[1 - colour];
+    const uint32_t k0 = (uint32_t)h->md.seed, k1 = (uint32_t)(h->md.seed >> 32);
+    const bool rp = h->md.proposal == VEGAS_PROPOSE_RANDOM;
+    h->launches++;
+    if (mode == 2) {
+        ising_msc_kernel<NDIM, false, 3, false, 2><<<grid, 256, 0, h->stream>>>(own, oth, lo, hi, plo, phi, g, colour, zb, zc,
+                                                                              h->msc_tab, h->msc_bits, h->sweeps, k0, k1, obs);
+        return;
+    }
+    if (h->msc_field) {
+        if (rp) launch_msc_mode<NDIM, true, 14, true>(h, mode, grid, own, oth, lo, hi, plo, phi, colour, zb, zc, obs);
+        else launch_msc_mode<NDIM, true, 14, false>(h, mode, grid, own, oth, lo, hi, plo, phi, colour, zb, zc, obs);
+    } else {
+        if (rp) launch_msc_mode<NDIM, false, 3, true>(h, mode, grid, own, oth, lo, hi, plo, phi, colour, zb, zc, obs);
+        else launch_msc_mode<NDIM, false, 3, false>(h, mode, grid, own, oth, lo, hi, plo, phi, colour, zb, zc, obs);
+    }
+}
+
+template <typename real, int NDIM>
+void launch_heis(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, const HeisPtrs<real>& P, double* obs) {
+    const HeisGeom g = heis_geom(h);
+    const dim3 grid(cdiv((uint64_t)zc * g.Ly * g.Gx, 128));
+    const HeisParams<real> p = heis_params<real>(h);
+    const uint32_t k0 = (uint32_t)h->md.seed, k1 = (uint32_t)(h->md.seed >> 32);
+    const bool flip = h->md.proposal == VEGAS_PROPOSE_FLIP;
+    h->launches++;
+#define HL(FLIP, MODE) heis_stencil_kernel<real, NDIM, FLIP, MODE><<<grid, 128, 0, h->stream>>>(P, g, colour, zb, zc, p, h->sweeps, k0, k1, obs)
+    if (mode == 2) HL(false, 2);
+    else if (mode == 1) { if (flip) HL(true, 1); else HL(false, 1); }
+    else { if (flip) HL(true, 0); else HL(false, 0); }
+#undef HL
+}
+
+// One colour pass of a stencil family over local planes [zb, zb+zc).
+template <typename real>
+void heis_pass(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, double* obs) {
+    HeisPtrs<real> P{};
+    const size_t plane = (size_t)(h->ld.nx / 2) * h->ld.ny;
+    for (int c = 0; c < 3; ++c) {
+        P.own[c] = (real*)h->hs[colour][c];
+        P.oth[c] = (const real*)h->hs[1 - colour][c];
+        if (h->slab && h->connected) {
+            P.oth_lo[c] = (const real*)((char*)h->halo + halo_offset(h, 1 - colour, 0, c));
+            P.oth_hi[c] = (const real*)((char*)h->halo + halo_offset(h, 1 - colour, 1, c));
+            // my plane 0 goes to the lower neighbour's *upper* halo of my colour, plane Lz-1 to the upper neighbour's lower halo
+            P.peer_lo[c] = mode == 2 ? nullptr : (real*)((char*)h->peer_halo[0] + halo_offset(h, colour, 1, c));
+            P.peer_hi[c] = mode == 2 ? nullptr : (real*)((char*)h->peer_halo[1] + halo_offset(h, colour, 0, c));
+        } else {
+            P.oth_lo[c] = P.oth[c] + (size_t)(h->ld.nz - 1) * plane;
+            P.oth_hi[c] = P.oth[c];
+            P.peer_lo[c] = nullptr; P.peer_hi[c] = nullptr;
+        }
+    }
+    if (h->ndim == 3) launch_heis<real, 3>(h, mode, colour, zb, zc, P, obs);
+    else launch_heis<real, 2>(h, mode, colour, zb, zc, P, obs);
+}
+
+void msc_pass(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, unsigned long long* obs) {
+    const size_t plane = (size_t)(h->ld.nx / 256) * h->ld.ny;
+    const uint4 *lo, *hi;
+    uint4 *plo = nullptr, *phi = nullptr;
+    if (h->slab && h->connected) {
+        lo = (const uint4*)((char*)h->halo + halo_offset(h, 1 - colour, 0, 0));
+        hi = (const uint4*)((char*)h->halo + halo_offset(h, 1 - colour, 1, 0));
+        if (mode != 2) {
+            plo = (uint4*)((char*)h->peer_halo[0] + halo_offset(h, colour, 1, 0));
+            phi = (uint4*)((char*)h->peer_halo[1] + halo_offset(h, colour, 0, 0));
+        }
+    } else {
+        lo = h->msc[1 - colour] + (size_t)(h->ld.nz - 1) * plane;
+        hi = h->msc[1 - colour];
+    }
+    if (h->ndim == 3) launch_msc<3>(h, mode, colour, zb, zc, lo, hi, plo, phi, obs);
+    else launch_msc<2>(h, mode, colour, zb, zc, lo, hi, plo, phi, obs);
+}
+
+// ---- slab flags: tiny kernels on the sweep stream (no host sync per colour) -------------
+__global__ void signal_kernel(unsigned long long* lower_flag, unsigned long long* upper_flag, unsigned long long value) {
+    __threadfence_system();
+    if (threadIdx.x == 0) {
+        // the lower neighbour reads what its upper neighbour (me) wrote in its flags[1]; vice versa
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(lower_flag + 1), "l"(value) : "memory");
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(upper_flag + 0), "l"(value) : "memory");
+    }
+}
+__global__ void wait_kernel(const unsigned long long* flags, unsigned long long value) {
+    if (threadIdx.x < 2) {
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory");
+        } while (v < value);
+    }
+    __threadfence_system();
+}
+
+void stencil_colour_pass(vegas_gpu* h, int mode, int colour, void* obs_row) {
+    const uint32_t Lz = (uint32_t)h->ld.nz;
+    auto run = [&](uint32_t zb, uint32_t zc) {
+        if (zc == 0) return;
+        if (h->family == FAM_ISING_MSC) msc_pass(h, mode, colour, zb, zc, (unsigned long long*)obs_row);
+        else if (h->md.precision == VEGAS_F64) heis_pass<double>(h, mode, colour, zb, zc, (double*)obs_row);
+        else heis_pass<float>(h, mode, colour, zb, zc, (double*)obs_row);
+    };
+    if (h->slab && h->connected && mode != 2) {
+        // boundary planes first (they feed the neighbours), then signal, then the interior
+        h->pass_counter++;
+        if (h->pass_counter > 1) { wait_kernel<<<1, 32, 0, h->stream>>>(h->flags, h->pass_counter - 1); h->launches++; }
+        if (Lz >= 2) { run(0, 1); run(Lz - 1, 1); } else run(0, 1);
+        signal_kernel<<<1, 32, 0, h->stream>>>(h->peer_flags[0], h->peer_flags[1], h->pass_counter);
+        h->launches++;
+        if (Lz > 2) run(1, Lz - 2);
+    } else {
+        run(0, Lz);
+    }
+}
+
+// ---- general family ---------------------------------------------------------------------
+template <typename NB>
+void general_colour_pass(vegas_gpu* h, const NB& nb, int colour, unsigned long long* obs_row) {
+    const uint32_t count = h->g_counts[colour];
+    if (count == 0) return;
+    const uint32_t k0 = (uint32_t)h->md.seed, k1 = (uint32_t)(h->md.seed >> 32);
+    h->launches++;
+    if (h->family == FAM_ISING_GEN) {
+        IsingGeneralParams p{};
+        p.thr = h->g_thr; p.code = h->g_code;
+        p.uniform = (h->csr_input && h->d_val) ? 0 : 1;
+        p.h_o = ising_h_o(h); p.invT = 1.0 / h->T;
+        const dim3 grid(cdiv(count, 256));
+        if (h->md.proposal == VEGAS_PROPOSE_RANDOM)
+            ising_general_sweep_kernel<NB, true><<<grid, 256, 0, h->stream>>>(h->g_s8, nb, h->g_sites[colour], count, p, 0, h->sweeps, k0, k1, obs_row + 4);
+        else
+            ising_general_sweep_kernel<NB, false><<<grid, 256, 0, h->stream>>>(h->g_s8, nb, h->g_sites[colour], count, p, 0, h->sweeps, k0, k1, obs_row + 4);
+    } else {
+        const dim3 grid(cdiv(count, 128));
+        const bool flip = h->md.proposal == VEGAS_PROPOSE_FLIP;
+        if (h->md.precision == VEGAS_F64) {
+            const HeisParams<double> p = heis_params<double>(h);
+            if (flip) heis_general_sweep_kernel<NB, double, true><<<grid, 128, 0, h->stream>>>((double*)h->g_s[0], (double*)h->g_s[1], (double*)h->g_s[2], nb, h->g_sites[colour], count, p, 0, h->sweeps, k0, k1, (double*)obs_row);
+            else heis_general_sweep_kernel<NB, double, false><<<grid, 128, 0, h->stream>>>((double*)h->g_s[0], (double*)h->g_s[1], (double*)h->g_s[2], nb, h->g_sites[colour], count, p, 0, h->sweeps, k0, k1, (double*)obs_row);
+        } else {
+            const HeisParams<float> p = heis_params<float>(h);
+            if (flip) heis_general_sweep_kernel<NB, float, true><<<grid, 128, 0, h->stream>>>((float*)h->g_s[0], (float*)h->g_s[1], (float*)h->g_s[2], nb, h->g_sites[colour], count, p, 0, h->sweeps, k0, k1, (double*)obs_row);
+            else heis_general_sweep_kernel<NB, float, false><<<grid, 128, 0, h->stream>>>((float*)h->g_s[0], (float*)h->g_s[1], (float*)h->g_s[2], nb, h->g_sites[colour], count, p, 0, h->sweeps, k0, k1, (double*)obs_row);
+        }
+    }
+}
+
+template <typename NB>
+void general_reduce(vegas_gpu* h, const NB& nb, double* obs_row) {
+    const uint32_t n = (uint32_t)h->n;
+    const dim3 grid(std::min<uint32_t>(cdiv(n, 256), 148 * 8));
+    double ax = 0, ay = 0, az = 1;
+    if (h->md.model == VEGAS_HEISENBERG) { ax = h->md.anisotropy_axis[0]; ay = h->md.anisotropy_axis[1]; az = h->md.anisotropy_axis[2]; }
+    h->launches++;
+    if (h->family == FAM_ISING_GEN) {
+        IsingSpins sp{h->g_s8};
+        general_reduce_kernel<NB, IsingSpins><<<grid, 256, 0, h->stream>>>(nb, sp, n, ax, ay, az, obs_row);
+    } else if (h->md.precision == VEGAS_F64) {
+        HeisSpins<double> sp{(const double*)h->g_s[0], (const double*)h->g_s[1], (const double*)h->g_s[2]};
+        general_reduce_kernel<NB, HeisSpins<double>><<<grid, 256, 0, h->stream>>>(nb, sp, n, ax, ay, az, obs_row);
+    } else {
+        HeisSpins<float> sp{(const float*)h->g_s[0], (const float*)h->g_s[1], (const float*)h->g_s[2]};
+        general_reduce_kernel<NB, HeisSpins<float>><<<grid, 256, 0, h->stream>>>(nb, sp, n, ax, ay, az, obs_row);
+    }
+}
+
+// One Monte Carlo step (= N attempts): every colour once.  obs_row != null records observables.
+void do_step(vegas_gpu* h, void* obs_row, void* scratch_row) {
+    const bool rec = obs_row != nullptr;
+    if (h->family == FAM_ISING_MSC || h->family == FAM_HEIS_STENCIL) {
+        for (int c = 0; c < 2; ++c) {
+            const int mode = (rec && c == 1) ? 1 : 0;
+            stencil_colour_pass(h, mode, c, rec ? obs_row : scratch_row);
+        }
+    } else {
+        unsigned long long* row = (unsigned long long*)(rec ? obs_row : scratch_row);
+        for (int c = 0; c < h->n_colours; ++c) {
+            if (h->csr_input) general_colour_pass(h, csr_nb(h), c, row);
+            else general_colour_pass(h, structured_nb(h), c, row);
+        }
+        if (rec) {
+            if (h->csr_input) general_reduce(h, csr_nb(h), (double*)obs_row);
+            else general_reduce(h, structured_nb(h), (double*)obs_row);
+        }
+    }
+    h->sweeps++;
+    h->attempts += h->n;
+}
+
+// ---------------------------------------------------------------------------------------
+// observables: device row -> canonical (E_exchange physical, M, A, accepted) -> convention
+// ---------------------------------------------------------------------------------------
+struct Canon { double eex, m[3], a; uint64_t accepted; };
+
+Canon canon_of(const vegas_gpu* h, const unsigned long long* row) {
+    Canon c{};
+    const double J = h->md.has_exchange ? h->md.exchange : 0.0;
+    const double N = (double)h->n;
+    if (h->family == FAM_ISING_MSC) {
+        const long long bonds = (long long)row[0], M = (long long)row[1];
+        c.eex = -J * (double)bonds; c.m[2] = (double)M; c.a = N; c.accepted = row[2];
+        c.eex += -J * N * h->n_self;
+    } else if (h->family == FAM_HEIS_STENCIL) {
+        const double* d = (const double*)row;
+        c.eex = d[0] + (-J * N * h->n_self); c.m[0] = d[1]; c.m[1] = d[2]; c.m[2] = d[3]; c.a = d[4];
+        c.accepted = (uint64_t)llround(d[5]);
+    } else {
+        const double* d = (const double*)row;
+        c.eex = -d[0] / 2.0; c.m[0] = d[1]; c.m[1] = d[2]; c.m[2] = d[3];
+        c.a = h->md.model == VEGAS_ISING ? N : d[4];
+        c.accepted = h->family == FAM_ISING_GEN ? row[6] : (uint64_t)llround(d[5]);
+    }
+    return c;
+}
+
+double energy_of(const vegas_gpu* h, const Canon& c) {
+    const double N = (double)h->n;
+    const double ha = h_abs(h);
+    double zs;  // sum_i s_i . orientation
+    if (h->md.model == VEGAS_ISING) zs = c.m[2] * (h->fdir[2] >= 0.0 ? 1.0 : -1.0);
+    else zs = c.m[0] * h->fdir[0] + c.m[1] * h->fdir[1] + c.m[2] * h->fdir[2];
+    const double k = h->md.has_anisotropy ? h->md.anisotropy_k : 0.0;
+    const double g = h->md.has_gauge ? h->md.gauge : 0.0;
+    const double eex = h->md.has_exchange ? c.eex : 0.0;
+    switch (h->econv) {
+        case VEGAS_E_PHYSICAL: return eex - ha * zs + k * c.a + g * N;
+        case VEGAS_E_REFERENCE_EXCHANGE: return eex;
+        default: return 2.0 * eex + ha * zs + k * c.a + g * N;  // src/energy.rs:55-59 over the compound
+    }
+}
+
+int measure_now(vegas_gpu* h, Canon& out) {
+    unsigned long long* row = h->obs + (OBS_CAP + 1) * OBS_W;
+    CU(cudaMemsetAsync(row, 0, OBS_W * 8, h->stream));
+    if (h->family == FAM_ISING_MSC || h->family == FAM_HEIS_STENCIL) stencil_colour_pass(h, 2, 1, row);
+    else if (h->csr_input) general_reduce(h, csr_nb(h), (double*)row);
+    else general_reduce(h, structured_nb(h), (double*)row);
+    unsigned long long host[OBS_W];
+    CU(cudaMemcpyAsync(host, row, sizeof host, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    out = canon_of(h, host);
+    return VEGAS_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// creation
+// ---------------------------------------------------------------------------------------
+int common_init(vegas_gpu* h) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(h, VEGAS_ERR_CUDA, "no CUDA device: the vegas_gpu sweep has no CPU fallback");
+    if (h->md.device < 0 || h->md.device >= ndev) return fail(h, VEGAS_ERR_INVALID, "device ordinal out of range");
+    h->device = h->md.device;
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&h->ev0));
+    CU(cudaEventCreate(&h->ev1));
+    CU(cudaMalloc(&h->obs, (OBS_CAP + 2) * OBS_W * 8));
+    CU(cudaMemsetAsync(h->obs, 0, (OBS_CAP + 2) * OBS_W * 8, h->stream));
+    return VEGAS_OK;
+}
+
+int alloc_general(vegas_gpu* h, const std::vector<uint8_t>& colour) {
+    const uint64_t n = h->n;
+    if (n >= (1ull << 32)) return fail(h, VEGAS_ERR_INVALID, "general-adjacency path supports < 2^32 sites");
+    if (h->md.model == VEGAS_ISING) {
+        CU(cudaMalloc(&h->g_s8, n));
+        CU(cudaMalloc(&h->g_thr, (size_t)2 * (2 * ISING_ZMAX + 1) * 8));
+        CU(cudaMalloc(&h->g_code, (size_t)2 * (2 * ISING_ZMAX + 1)));
+    } else {
+        for (int c = 0; c < 3; ++c) CU(cudaMalloc(&h->g_s[c], n * real_bytes(h)));
+    }
+    std::vector<std::vector<uint32_t>> lists(h->n_colours);
+    for (uint64_t i = 0; i < n; ++i) lists[colour[i]].push_back((uint32_t)i);
+    h->g_sites.assign(h->n_colours, nullptr);
+    h->g_counts.assign(h->n_colours, 0);
+    for (int c = 0; c < h->n_colours; ++c) {
+        h->g_counts[c] = (uint32_t)lists[c].size();
+        if (lists[c].empty()) continue;
+        CU(cudaMalloc(&h->g_sites[c], lists[c].size() * 4));
+        CU(cudaMemcpy(h->g_sites[c], lists[c].data(), lists[c].size() * 4, cudaMemcpyHostToDevice));
+    }
+    return VEGAS_OK;
+}
+
+int check_model(vegas_gpu* h, const vegas_model_desc* md) {
+    if (!md) return fail(h, VEGAS_ERR_INVALID, "null model descriptor");
+    if (md->model != VEGAS_ISING && md->model != VEGAS_HEISENBERG) return fail(h, VEGAS_ERR_INVALID, "unknown model");
+    if (md->proposal != VEGAS_PROPOSE_FLIP && md->proposal != VEGAS_PROPOSE_RANDOM) return fail(h, VEGAS_ERR_INVALID, "unknown proposal");
+    if (md->precision != VEGAS_F32 && md->precision != VEGAS_F64) return fail(h, VEGAS_ERR_INVALID, "unknown precision");
+    return VEGAS_OK;
+}
+
+int run_fill(vegas_gpu* h, int up);
+int push_boundaries(vegas_gpu* h);
+
+}  // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+const char* vegas_gpu_version(void) { return "vegas_gpu 0.1 (sm_100a)"; }
+
+const char* vegas_gpu_last_error(vegas_gpu_t h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int vegas_gpu_create_lattice(const vegas_model_desc* md, const vegas_lattice_desc* ldesc, vegas_gpu_t* out) {
+    vegas_gpu* h = nullptr;
+    if (!out) return fail(h, VEGAS_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    int rc = check_model(h, md);
+    if (rc) return rc;
+    if (!ldesc || ldesc->unitcell < 0 || ldesc->unitcell > 2) return fail(h, VEGAS_ERR_INVALID, "unknown unit cell");
+    if (ldesc->nx == 0 || ldesc->ny == 0 || ldesc->nz == 0) return fail(h, VEGAS_ERR_INVALID, "empty lattice");
+    vegas_gpu* hh = new vegas_gpu();
+    hh->md = *md;
+    hh->structured = true;
+    hh->ld.unitcell = ldesc->unitcell;
+    hh->ld.nx = ldesc->nx; hh->ld.ny = ldesc->ny; hh->ld.nz = ldesc->nz;
+    hh->ld.pbc[0] = ldesc->pbc_x != 0; hh->ld.pbc[1] = ldesc->pbc_y != 0; hh->ld.pbc[2] = ldesc->pbc_z != 0;
+    hh->ld.literal = ldesc->literal_from_lattice_filter != 0;
+    hh->nz_global = ldesc->nz_global ? ldesc->nz_global : ldesc->nz;
+    hh->z_offset = ldesc->z_offset;
+    hh->slab = hh->nz_global != ldesc->nz;
+    hh->n = ldesc->nx * ldesc->ny * ldesc->nz * (uint64_t)vgl::basis_count(ldesc->unitcell);
+    h = hh;
+    auto bail = [&](int code) { std::string e = h->err; vegas_gpu_destroy(h); g_create_error = e; return code; };
+    if ((rc = common_init(h))) return bail(rc);
+
+    // ---- family selection: structured stencil needs sc, periodic even extents, no literal filter
+    const uint64_t L[3] = {hh->ld.nx, hh->ld.ny, hh->nz_global};
+    bool stencil = ldesc->unitcell == VEGAS_SC && !hh->ld.literal && !md->force_general;
+    for (int a = 0; a < 2 && stencil; ++a) stencil = hh->ld.pbc[a] && L[a] >= 2 && (L[a] % 2 == 0);
+    if (stencil) stencil = (L[2] == 1) || (hh->ld.pbc[2] && L[2] % 2 == 0);
+    if (stencil && md->model == VEGAS_ISING) stencil = L[0] % 256 == 0;
+    if (stencil && md->model == VEGAS_HEISENBERG) stencil = L[0] % 8 == 0;
+    if (stencil && hh->ld.nx * hh->ld.ny * hh->ld.nz >= (1ull << 32) * 64) stencil = false;
+    if (hh->slab) {
+        if (!stencil || L[2] == 1) return bail(fail(h, VEGAS_ERR_INVALID, "z-slab decomposition needs the sc stencil path (periodic, even extents)"));
+        if (hh->z_offset + hh->ld.nz > hh->nz_global) return bail(fail(h, VEGAS_ERR_INVALID, "slab outside the global lattice"));
+    }
+    if (stencil) {
+        h->family = md->model == VEGAS_ISING ? FAM_ISING_MSC : FAM_HEIS_STENCIL;
+        h->ndim = L[2] == 1 ? 2 : 3;
+        h->n_self = (L[2] == 1 && hh->ld.pbc[2]) ? 1 : 0;
+        h->n_colours = 2;
+        if (h->family == FAM_ISING_MSC) {
+            const size_t bytes = msc_groups(h) * sizeof(uint4);
+            for (int c = 0; c < 2; ++c) { if (cudaMalloc(&h->msc[c], bytes) != cudaSuccess) return bail(fail(h, VEGAS_ERR_ALLOC, "cudaMalloc (spins) failed")); }
+            if (cudaMalloc(&h->msc_bits, (size_t)MSC_MAX_SLOT * 64 * 4) != cudaSuccess) return bail(fail(h, VEGAS_ERR_ALLOC, "cudaMalloc failed"));
+            h->halo_plane_bytes = (size_t)(h->ld.nx / 256) * h->ld.ny * sizeof(uint4);
+        } else {
+            const size_t bytes = heis_colour_elems(h) * real_bytes(h);
+            for (int c = 0; c < 2; ++c)
+                for (int k = 0; k < 3; ++k)
+                    if (cudaMalloc(&h->hs[c][k], bytes) != cudaSuccess) return bail(fail(h, VEGAS_ERR_ALLOC, "cudaMalloc (spins) failed"));
+            h->halo_plane_bytes = (size_t)(h->ld.nx / 2) * h->ld.ny * real_bytes(h);
+        }
+        if (h->slab) {
+            const int ncomp = h->family == FAM_ISING_MSC ? 1 : 3;
+            if (cudaMalloc(&h->halo, h->halo_plane_bytes * 4 * ncomp) != cudaSuccess || cudaMalloc(&h->flags, 2 * 8) != cudaSuccess)
+                return bail(fail(h, VEGAS_ERR_ALLOC, "cudaMalloc (halo) failed"));
+            cudaMemsetAsync(h->halo, 0, h->halo_plane_bytes * 4 * ncomp, h->stream);
+            cudaMemsetAsync(h->flags, 0, 16, h->stream);
+            cudaStreamSynchronize(h->stream);
+        }
+    } else {
+        h->family = md->model == VEGAS_ISING ? FAM_ISING_GEN : FAM_HEIS_GEN;
+        if (h->n >= (1ull << 32)) return bail(fail(h, VEGAS_ERR_INVALID, "general-adjacency path supports < 2^32 sites"));
+        vgl::Colouring col(h->ld);
+        h->n_colours = col.n_colours;
+        std::vector<uint8_t> colour(h->n);
+        for (uint64_t i = 0; i < h->n; ++i) colour[i] = (uint8_t)col.colour(i);
+        h->h_colour = colour;
+        if ((rc = alloc_general(h, colour))) return bail(rc);
+    }
+    if ((rc = run_fill(h, 1))) return bail(rc);
+    *out = h;
+    return VEGAS_OK;
+}
+
+int vegas_gpu_create_csr(const vegas_model_desc* md, const vegas_csr_desc* cd, vegas_gpu_t* out) {
+    vegas_gpu* h = nullptr;
+    if (!out) return fail(h, VEGAS_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    int rc = check_model(h, md);
+    if (rc) return rc;
+    if (!cd || cd->n == 0 || !cd->row_ptr || (!cd->col_idx && cd->row_ptr[cd->n] > 0)) return fail(h, VEGAS_ERR_INVALID, "bad CSR descriptor");
+    if (cd->n >= (1ull << 32)) return fail(h, VEGAS_ERR_INVALID, "CSR path supports < 2^32 sites");
+    const uint64_t nnz = cd->row_ptr[cd->n];
+    for (uint64_t i = 0; i < cd->n; ++i) {
+        if (cd->row_ptr[i + 1] < cd->row_ptr[i]) return fail(h, VEGAS_ERR_INVALID, "row_ptr not monotone");
+        if (!cd->values && cd->row_ptr[i + 1] - cd->row_ptr[i] > (uint64_t)ISING_ZMAX && md->model == VEGAS_ISING)
+            return fail(h, VEGAS_ERR_INVALID, "uniform-J Ising rows longer than 32 are not supported");
+    }
+    for (uint64_t p = 0; p < nnz; ++p)
+        if (cd->col_idx[p] >= cd->n) return fail(h, VEGAS_ERR_INVALID, "column index out of range");
+    vegas_gpu* hh = new vegas_gpu();
+    hh->md = *md;
+    hh->csr_input = true;
+    hh->n = cd->n;
+    hh->family = md->model == VEGAS_ISING ? FAM_ISING_GEN : FAM_HEIS_GEN;
+    hh->h_row_ptr.assign(cd->row_ptr, cd->row_ptr + cd->n + 1);
+    hh->h_col.assign(cd->col_idx, cd->col_idx + nnz);
+    if (cd->values) hh->h_val.assign(cd->values, cd->values + nnz);
+    h = hh;
+    auto bail = [&](int code) { std::string e = h->err; vegas_gpu_destroy(h); g_create_error = e; return code; };
+    if ((rc = common_init(h))) return bail(rc);
+    std::vector<uint8_t> colour;
+    const int nc = vgl::greedy_colour(h->n, h->h_row_ptr.data(), h->h_col.data(), colour);
+    if (nc < 0) return bail(fail(h, VEGAS_ERR_INVALID, "graph needs more than 64 colours"));
+    h->n_colours = nc;
+    h->h_colour = colour;
+    if (cudaMalloc(&h->d_row_ptr, (h->n + 1) * 8) != cudaSuccess || cudaMalloc(&h->d_col, (nnz + 1) * 4) != cudaSuccess)
+        return bail(fail(h, VEGAS_ERR_ALLOC, "cudaMalloc (csr) failed"));
+    cudaMemcpy(h->d_row_ptr, h->h_row_ptr.data(), (h->n + 1) * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(h->d_col, h->h_col.data(), nnz * 4, cudaMemcpyHostToDevice);
+    if (cd->values) {
+        if (cudaMalloc(&h->d_val, (nnz + 1) * 8) != cudaSuccess) return bail(fail(h, VEGAS_ERR_ALLOC, "cudaMalloc (csr) failed"));
+        cudaMemcpy(h->d_val, h->h_val.data(), nnz * 8, cudaMemcpyHostToDevice);
+    }
+    if ((rc = alloc_general(h, colour))) return bail(rc);
+    if ((rc = run_fill(h, 1))) return bail(rc);
+    *out = h;
+    return VEGAS_OK;
+}
+
+void vegas_gpu_destroy(vegas_gpu_t h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int c = 0; c < 2; ++c) {
+        cudaFree(h->msc[c]);
+        for (int k = 0; k < 3; ++k) cudaFree(h->hs[c][k]);
+    }
+    cudaFree(h->msc_bits);
+    if (h->peer_is_ipc) {
+        for (int d = 0; d < 2; ++d) {
+            if (h->peer_halo[d]) cudaIpcCloseMemHandle(h->peer_halo[d]);
+            if (h->peer_flags[d] && !(d == 1 && h->peer_flags[1] == h->peer_flags[0])) cudaIpcCloseMemHandle(h->peer_flags[d]);
+        }
+    }
+    cudaFree(h->halo); cudaFree(h->flags);
+    cudaFree(h->g_s8);
+    for (int k = 0; k < 3; ++k) cudaFree(h->g_s[k]);
+    for (uint32_t* p : h->g_sites) cudaFree(p);
+    cudaFree(h->d_row_ptr); cudaFree(h->d_col); cudaFree(h->d_val);
+    cudaFree(h->g_thr); cudaFree(h->g_code);
+    cudaFree(h->obs);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+uint64_t vegas_gpu_n_sites(vegas_gpu_t h) { return h ? h->n : 0; }
+int vegas_gpu_n_colours(vegas_gpu_t h) { return h ? h->n_colours : 0; }
+const char* vegas_gpu_kernel_family(vegas_gpu_t h) { return h ? FAMILY_NAME[h->family] : ""; }
+void* vegas_gpu_stream(vegas_gpu_t h) { return h ? (void*)h->stream : nullptr; }
+uint64_t vegas_gpu_launch_count(vegas_gpu_t h) { return h ? h->launches : 0; }
+
+int vegas_gpu_adjacency(vegas_gpu_t h, uint64_t* n, uint64_t* nnz, uint64_t* row_ptr, uint32_t* col_idx, double* values) {
+    if (!h) return VEGAS_ERR_INVALID;
+    if (h->csr_input) {
+        if (n) *n = h->n;
+        if (nnz) *nnz = h->h_col.size();
+        if (row_ptr) memcpy(row_ptr, h->h_row_ptr.data(), (h->n + 1) * 8);
+        if (col_idx) memcpy(col_idx, h->h_col.data(), h->h_col.size() * 4);
+        if (values) for (size_t p = 0; p < h->h_col.size(); ++p) values[p] = h->h_val.empty() ? h->md.exchange : h->h_val[p];
+        return VEGAS_OK;
+    }
+    if (h->slab) return fail(h, VEGAS_ERR_STATE, "adjacency export is not available for a slab");
+    if (h->n > (1ull << 27)) return fail(h, VEGAS_ERR_STATE, "adjacency export limited to 2^27 sites");
+    std::vector<uint64_t> rp; std::vector<uint32_t> col; std::vector<double> val;
+    vgl::build_csr(h->ld, h->md.exchange, rp, col, val);
+    if (n) *n = h->n;
+    if (nnz) *nnz = col.size();
+    if (row_ptr) memcpy(row_ptr, rp.data(), rp.size() * 8);
+    if (col_idx) memcpy(col_idx, col.data(), col.size() * 4);
+    if (values) memcpy(values, val.data(), val.size() * 8);
+    return VEGAS_OK;
+}
+
+static int desc_of(const vegas_lattice_desc* ld, vgl::Desc& d) {
+    if (!ld || ld->unitcell < 0 || ld->unitcell > 2 || ld->nx == 0 || ld->ny == 0 || ld->nz == 0) return VEGAS_ERR_INVALID;
+    d.unitcell = ld->unitcell; d.nx = ld->nx; d.ny = ld->ny; d.nz = ld->nz;
+    d.pbc[0] = ld->pbc_x != 0; d.pbc[1] = ld->pbc_y != 0; d.pbc[2] = ld->pbc_z != 0;
+    d.literal = ld->literal_from_lattice_filter != 0;
+    return VEGAS_OK;
+}
+
+int vegas_gpu_lattice_adjacency(const vegas_lattice_desc* ld, double exchange, uint64_t* n, uint64_t* nnz,
+                                uint64_t* row_ptr, uint32_t* col_idx, double* values) {
+    vgl::Desc d{};
+    if (desc_of(ld, d)) return fail(nullptr, VEGAS_ERR_INVALID, "bad lattice descriptor");
+    const uint64_t sites = d.nx * d.ny * d.nz * (uint64_t)vgl::basis_count(d.unitcell);
+    if (sites > (1ull << 27)) return fail(nullptr, VEGAS_ERR_INVALID, "adjacency export limited to 2^27 sites");
+    std::vector<uint64_t> rp; std::vector<uint32_t> col; std::vector<double> val;
+    vgl::build_csr(d, exchange, rp, col, val);
+    if (n) *n = sites;
+    if (nnz) *nnz = col.size();
+    if (row_ptr) memcpy(row_ptr, rp.data(), rp.size() * 8);
+    if (col_idx) memcpy(col_idx, col.data(), col.size() * 4);
+    if (values) memcpy(values, val.data(), val.size() * 8);
+    return VEGAS_OK;
+}
+
+int vegas_gpu_lattice_colours(const vegas_lattice_desc* ld, int* n_colours, uint8_t* colour_of_site) {
+    vgl::Desc d{};
+    if (desc_of(ld, d)) return fail(nullptr, VEGAS_ERR_INVALID, "bad lattice descriptor");
+    vgl::Colouring col(d);
+    if (n_colours) *n_colours = col.n_colours;
+    const uint64_t sites = d.nx * d.ny * d.nz * (uint64_t)vgl::basis_count(d.unitcell);
+    if (colour_of_site) for (uint64_t i = 0; i < sites; ++i) colour_of_site[i] = (uint8_t)col.colour(i);
+    return VEGAS_OK;
+}
+
+int vegas_gpu_colours(vegas_gpu_t h, uint8_t* colour_of_site) {
+    if (!h || !colour_of_site) return VEGAS_ERR_INVALID;
+    if (h->family == FAM_ISING_MSC || h->family == FAM_HEIS_STENCIL) {
+        if (h->n > (1ull << 30)) return fail(h, VEGAS_ERR_STATE, "colour export limited to 2^30 sites");
+        for (uint64_t i = 0; i < h->n; ++i) {
+            const uint64_t x = i % h->ld.nx, y = (i / h->ld.nx) % h->ld.ny, z = i / (h->ld.nx * h->ld.ny) + h->z_offset;
+            colour_of_site[i] = (uint8_t)((x + y + z) & 1);
+        }
+        return VEGAS_OK;
+    }
+    memcpy(colour_of_site, h->h_colour.data(), h->n);
+    return VEGAS_OK;
+}
+
+// ---- state I/O --------------------------------------------------------------------------
+int vegas_gpu_upload_ising(vegas_gpu_t h, const int8_t* s, uint64_t n) {
+    if (!h || !s) return VEGAS_ERR_INVALID;
+    if (h->md.model != VEGAS_ISING || n != h->n) return fail(h, VEGAS_ERR_INVALID, "upload_ising: wrong model or size");
+    CU(cudaSetDevice(h->device));
+    if (h->family == FAM_ISING_GEN) {
+        CU(cudaMemcpyAsync(h->g_s8, s, n, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        int8_t* tmp = nullptr;
+        CU(cudaMallocAsync(&tmp, n, h->stream));
+        CU(cudaMemcpyAsync(tmp, s, n, cudaMemcpyHostToDevice, h->stream));
+        const uint32_t Wx = (uint32_t)(h->ld.nx / 64);
+        const size_t total = (size_t)Wx * h->ld.ny * h->ld.nz;
+        ising_msc_pack_kernel<<<cdiv(total, 256), 256, 0, h->stream>>>(tmp, (uint32_t*)h->msc[0], (uint32_t*)h->msc[1], Wx,
+                                                                      (uint32_t)h->ld.ny, (uint32_t)h->ld.nz, (uint32_t)h->z_offset);
+        h->launches++;
+        CU(cudaFreeAsync(tmp, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return push_boundaries(h);
+}
+
+int vegas_gpu_download_ising(vegas_gpu_t h, int8_t* s, uint64_t n) {
+    if (!h || !s) return VEGAS_ERR_INVALID;
+    if (h->md.model != VEGAS_ISING || n != h->n) return fail(h, VEGAS_ERR_INVALID, "download_ising: wrong model or size");
+    CU(cudaSetDevice(h->device));
+    if (h->family == FAM_ISING_GEN) {
+        CU(cudaMemcpyAsync(s, h->g_s8, n, cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        int8_t* tmp = nullptr;
+        CU(cudaMallocAsync(&tmp, n, h->stream));
+        const uint32_t Wx = (uint32_t)(h->ld.nx / 64);
+        const size_t total = (size_t)Wx * h->ld.ny * h->ld.nz;
+        ising_msc_unpack_kernel<<<cdiv(total, 256), 256, 0, h->stream>>>(tmp, (const uint32_t*)h->msc[0], (const uint32_t*)h->msc[1], Wx,
+                                                                        (uint32_t)h->ld.ny, (uint32_t)h->ld.nz, (uint32_t)h->z_offset);
+        h->launches++;
+        CU(cudaMemcpyAsync(s, tmp, n, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaFreeAsync(tmp, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return VEGAS_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+template <typename real>
+int heis_upload_t(vegas_gpu* h, const double* dev_aos) {
+    const uint32_t n = (uint32_t)h->n;
+    if (h->family == FAM_HEIS_GEN) {
+        aos_to_soa_kernel<real><<<cdiv(n, 256), 256, 0, h->stream>>>(dev_aos, (real*)h->g_s[0], (real*)h->g_s[1], (real*)h->g_s[2], n);
+    } else {
+        heis_pack_kernel<real><<<cdiv(h->n, 256), 256, 0, h->stream>>>(dev_aos, (real*)h->hs[0][0], (real*)h->hs[0][1], (real*)h->hs[0][2],
+                                                                      (real*)h->hs[1][0], (real*)h->hs[1][1], (real*)h->hs[1][2],
+                                                                      (uint32_t)h->ld.nx, (uint32_t)h->ld.ny, (uint32_t)h->ld.nz, (uint32_t)h->z_offset);
+    }
+    h->launches++;
+    return VEGAS_OK;
+}
+
+template <typename real>
+int heis_download_t(vegas_gpu* h, double* dev_aos) {
+    const uint32_t n = (uint32_t)h->n;
+    if (h->family == FAM_HEIS_GEN) {
+        soa_to_aos_kernel<real><<<cdiv(n, 256), 256, 0, h->stream>>>(dev_aos, (const real*)h->g_s[0], (const real*)h->g_s[1], (const real*)h->g_s[2], n);
+    } else {
+        heis_unpack_kernel<real, double><<<cdiv(h->n, 256), 256, 0, h->stream>>>(
+            dev_aos, dev_aos + 1, dev_aos + 2, 3, (const real*)h->hs[0][0], (const real*)h->hs[0][1], (const real*)h->hs[0][2],
+            (const real*)h->hs[1][0], (const real*)h->hs[1][1], (const real*)h->hs[1][2], (uint32_t)h->ld.nx, (uint32_t)h->ld.ny,
+            (uint32_t)h->ld.nz, (uint32_t)h->z_offset);
+    }
+    h->launches++;
+    return VEGAS_OK;
+}
+
+int run_fill(vegas_gpu* h, int up) {
+    CU(cudaSetDevice(h->device));
+    if (h->family == FAM_ISING_MSC) {
+        for (int c = 0; c < 2; ++c) CU(cudaMemsetAsync(h->msc[c], up ? 0xFF : 0x00, msc_groups(h) * sizeof(uint4), h->stream));
+    } else if (h->family == FAM_ISING_GEN) {
+        CU(cudaMemsetAsync(h->g_s8, up ? 0x01 : 0xFF, h->n, h->stream));
+    } else {
+        const bool f64 = h->md.precision == VEGAS_F64;
+        auto fill = [&](void* p, size_t cnt, double v) {
+            if (f64) fill_kernel<double><<<cdiv(cnt, 256), 256, 0, h->stream>>>((double*)p, cnt, v);
+            else fill_kernel<float><<<cdiv(cnt, 256), 256, 0, h->stream>>>((float*)p, cnt, (float)v);
+            h->launches++;
+        };
+        if (h->family == FAM_HEIS_GEN) {
+            fill(h->g_s[0], h->n, 0.0); fill(h->g_s[1], h->n, 0.0); fill(h->g_s[2], h->n, up ? 1.0 : -1.0);
+        } else {
+            for (int c = 0; c < 2; ++c) {
+                fill(h->hs[c][0], heis_colour_elems(h), 0.0); fill(h->hs[c][1], heis_colour_elems(h), 0.0);
+                fill(h->hs[c][2], heis_colour_elems(h), up ? 1.0 : -1.0);
+            }
+        }
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return VEGAS_OK;
+}
+
+// Fill the halos of a connected slab from the neighbours' current boundary planes is done by the
+// neighbours themselves: each rank pushes its own boundary planes (both colours) to its peers.
+__global__ void copy_plane_kernel(uint4* dst, const uint4* src, size_t n16) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n16) dst[i] = src[i];
+}
+
+int push_boundaries(vegas_gpu* h) {
+    if (!(h->slab && h->connected)) return VEGAS_OK;
+    const int ncomp = h->family == FAM_ISING_MSC ? 1 : 3;
+    const size_t n16 = h->halo_plane_bytes / 16;
+    for (int colour = 0; colour < 2; ++colour)
+        for (int c = 0; c < ncomp; ++c) {
+            const char* base = h->family == FAM_ISING_MSC ? (const char*)h->msc[colour] : (const char*)h->hs[colour][c];
+            const char* first = base;
+            const char* last = base + (size_t)(h->ld.nz - 1) * h->halo_plane_bytes;
+            copy_plane_kernel<<<cdiv(n16, 256), 256, 0, h->stream>>>((uint4*)((char*)h->peer_halo[0] + halo_offset(h, colour, 1, c)), (const uint4*)first, n16);
+            copy_plane_kernel<<<cdiv(n16, 256), 256, 0, h->stream>>>((uint4*)((char*)h->peer_halo[1] + halo_offset(h, colour, 0, c)), (const uint4*)last, n16);
+            h->launches += 2;
+        }
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return VEGAS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vegas_gpu_upload_heisenberg(vegas_gpu_t h, const double* sxyz, uint64_t n) {
+    if (!h || !sxyz) return VEGAS_ERR_INVALID;
+    if (h->md.model != VEGAS_HEISENBERG || n != h->n) return fail(h, VEGAS_ERR_INVALID, "upload_heisenberg: wrong model or size");
+    CU(cudaSetDevice(h->device));
+    double* tmp = nullptr;
+    CU(cudaMallocAsync(&tmp, n * 24, h->stream));
+    CU(cudaMemcpyAsync(tmp, sxyz, n * 24, cudaMemcpyHostToDevice, h->stream));
+    if (h->md.precision == VEGAS_F64) heis_upload_t<double>(h, tmp); else heis_upload_t<float>(h, tmp);
+    CU(cudaFreeAsync(tmp, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return push_boundaries(h);
+}
+
+int vegas_gpu_download_heisenberg(vegas_gpu_t h, double* sxyz, uint64_t n) {
+    if (!h || !sxyz) return VEGAS_ERR_INVALID;
+    if (h->md.model != VEGAS_HEISENBERG || n != h->n) return fail(h, VEGAS_ERR_INVALID, "download_heisenberg: wrong model or size");
+    CU(cudaSetDevice(h->device));
+    double* tmp = nullptr;
+    CU(cudaMallocAsync(&tmp, n * 24, h->stream));
+    if (h->md.precision == VEGAS_F64) heis_download_t<double>(h, tmp); else heis_download_t<float>(h, tmp);
+    CU(cudaMemcpyAsync(sxyz, tmp, n * 24, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaFreeAsync(tmp, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return VEGAS_OK;
+}
+
+int vegas_gpu_randomize(vegas_gpu_t h) {
+    if (!h) return VEGAS_ERR_INVALID;
+    CU(cudaSetDevice(h->device));
+    const uint32_t k0 = (uint32_t)h->md.seed, k1 = (uint32_t)(h->md.seed >> 32);
+    h->launches++;
+    if (h->family == FAM_ISING_MSC) {
+        const size_t groups = msc_groups(h);
+        const uint64_t goff = (uint64_t)h->z_offset * h->ld.ny * (h->ld.nx / 256);
+        ising_msc_randomize_kernel<<<cdiv(groups, 256), 256, 0, h->stream>>>(h->msc[0], h->msc[1], groups, goff, k0, k1);
+    } else if (h->family == FAM_ISING_GEN) {
+        ising_general_randomize_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(h->g_s8, (uint32_t)h->n, 0, k0, k1);
+    } else if (h->family == FAM_HEIS_GEN) {
+        if (h->md.precision == VEGAS_F64) heis_general_randomize_kernel<double><<<cdiv(h->n, 256), 256, 0, h->stream>>>((double*)h->g_s[0], (double*)h->g_s[1], (double*)h->g_s[2], (uint32_t)h->n, 0, k0, k1);
+        else heis_general_randomize_kernel<float><<<cdiv(h->n, 256), 256, 0, h->stream>>>((float*)h->g_s[0], (float*)h->g_s[1], (float*)h->g_s[2], (uint32_t)h->n, 0, k0, k1);
+    } else {
+        const uint32_t Lx = (uint32_t)h->ld.nx, Ly = (uint32_t)h->ld.ny, Lz = (uint32_t)h->ld.nz, zo = (uint32_t)h->z_offset;
+        if (h->md.precision == VEGAS_F64)
+            heis_stencil_randomize_kernel<double><<<cdiv(h->n, 256), 256, 0, h->stream>>>((double*)h->hs[0][0], (double*)h->hs[0][1], (double*)h->hs[0][2], (double*)h->hs[1][0], (double*)h->hs[1][1], (double*)h->hs[1][2], Lx, Ly, Lz, zo, k0, k1);
+        else
+            heis_stencil_randomize_kernel<float><<<cdiv(h->n, 256), 256, 0, h->stream>>>((float*)h->hs[0][0], (float*)h->hs[0][1], (float*)h->hs[0][2], (float*)h->hs[1][0], (float*)h->hs[1][1], (float*)h->hs[1][2], Lx, Ly, Lz, zo, k0, k1);
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return push_boundaries(h);
+}
+
+int vegas_gpu_fill(vegas_gpu_t h, int up) {
+    if (!h) return VEGAS_ERR_INVALID;
+    int rc = run_fill(h, up);
+    if (rc) return rc;
+    return push_boundaries(h);
+}
+
+// ---- thermostat -------------------------------------------------------------------------
+int vegas_gpu_set_thermostat(vegas_gpu_t h, double temperature, const double field_dir[3], double field_mag) {
+    if (!h) return VEGAS_ERR_INVALID;
+    if (temperature != temperature) return fail(h, VEGAS_ERR_INVALID, "temperature is NaN");
+    h->T = temperature < DBL_EPSILON ? DBL_EPSILON : temperature;  // src/thermostat.rs:30-34
+    if (field_dir) { h->fdir[0] = field_dir[0]; h->fdir[1] = field_dir[1]; h->fdir[2] = field_dir[2]; }
+    h->fmag = field_mag;
+    h->tables_dirty = true;
+    return VEGAS_OK;
+}
+
+int vegas_gpu_set_energy_convention(vegas_gpu_t h, int conv) {
+    if (!h || conv < 0 || conv > 2) return VEGAS_ERR_INVALID;
+    h->econv = conv;
+    return VEGAS_OK;
+}
+
+// ---- the hot path -----------------------------------------------------------------------
+int vegas_gpu_step_async(vegas_gpu_t h, uint64_t n_steps, int record) {
+    if (!h) return VEGAS_ERR_INVALID;
+    if (record && n_steps > OBS_CAP) return fail(h, VEGAS_ERR_INVALID, "step_async records at most 4096 steps per call");
+    CU(cudaSetDevice(h->device));
+    int rc = update_tables(h);
+    if (rc) return rc;
+    unsigned long long* scratch = h->obs + OBS_CAP * OBS_W;
+    if (record) CU(cudaMemsetAsync(h->obs, 0, n_steps * OBS_W * 8, h->stream));
+    for (uint64_t s = 0; s < n_steps; ++s) do_step(h, record ? (void*)(h->obs + s * OBS_W) : nullptr, scratch);
+    CU(cudaGetLastError());
+    return VEGAS_OK;
+}
+
+int vegas_gpu_read_observables(vegas_gpu_t h, uint64_t n_steps, double* energy, double* mag_xyz) {
+    if (!h || n_steps > OBS_CAP) return VEGAS_ERR_INVALID;
+    CU(cudaSetDevice(h->device));
+    std::vector<unsigned long long> host(n_steps * OBS_W);
+    CU(cudaMemcpyAsync(host.data(), h->obs, host.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    for (uint64_t s = 0; s < n_steps; ++s) {
+        const Canon c = canon_of(h, host.data() + s * OBS_W);
+        h->accepted += c.accepted;
+        if (energy) energy[s] = energy_of(h, c);
+        if (mag_xyz) { mag_xyz[3 * s] = c.m[0]; mag_xyz[3 * s + 1] = c.m[1]; mag_xyz[3 * s + 2] = c.m[2]; }
+    }
+    return VEGAS_OK;
+}
+
+int vegas_gpu_step(vegas_gpu_t h, uint64_t n_steps, double* energy, double* mag_xyz) {
+    if (!h) return VEGAS_ERR_INVALID;
+    const bool rec = energy != nullptr || mag_xyz != nullptr;
+    uint64_t done = 0;
+    while (done < n_steps) {
+        const uint64_t batch = std::min<uint64_t>(n_steps - done, rec ? OBS_CAP : 1024);
+        int rc = vegas_gpu_step_async(h, batch, rec);
+        if (rc) return rc;
+        if (rec) {
+            rc = vegas_gpu_read_observables(h, batch, energy ? energy + done : nullptr, mag_xyz ? mag_xyz + 3 * done : nullptr);
+            if (rc) return rc;
+        }
+        done += batch;
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return VEGAS_OK;
+}
+
+int vegas_gpu_synchronize(vegas_gpu_t h) {
+    if (!h) return VEGAS_ERR_INVALID;
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return VEGAS_OK;
+}
+
+int vegas_gpu_step_host_ising(vegas_gpu_t h, int8_t* state, uint64_t n, double* energy, double* mag_xyz) {
+    int rc = vegas_gpu_upload_ising(h, state, n);
+    if (rc) return rc;
+    double e, m[3];
+    if ((rc = vegas_gpu_step(h, 1, &e, m))) return rc;
+    if (energy) *energy = e;
+    if (mag_xyz) { mag_xyz[0] = m[0]; mag_xyz[1] = m[1]; mag_xyz[2] = m[2]; }
+    return vegas_gpu_download_ising(h, state, n);
+}
+
+int vegas_gpu_step_host_heisenberg(vegas_gpu_t h, double* sxyz, uint64_t n, double* energy, double* mag_xyz) {
+    int rc = vegas_gpu_upload_heisenberg(h, sxyz, n);
+    if (rc) return rc;
+    double e, m[3];
+    if ((rc = vegas_gpu_step(h, 1, &e, m))) return rc;
+    if (energy) *energy = e;
+    if (mag_xyz) { mag_xyz[0] = m[0]; mag_xyz[1] = m[1]; mag_xyz[2] = m[2]; }
+    return vegas_gpu_download_heisenberg(h, sxyz, n);
+}
+
+// ---- deterministic parity entry points ----------------------------------------------------
+int vegas_gpu_total_energy(vegas_gpu_t h, double* out) {
+    if (!h || !out) return VEGAS_ERR_INVALID;
+    CU(cudaSetDevice(h->device));
+    Canon c;
+    int rc = measure_now(h, c);
+    if (rc) return rc;
+    *out = energy_of(h, c);
+    return VEGAS_OK;
+}
+
+int vegas_gpu_magnetization(vegas_gpu_t h, double out_xyz[3]) {
+    if (!h || !out_xyz) return VEGAS_ERR_INVALID;
+    CU(cudaSetDevice(h->device));
+    Canon c;
+    int rc = measure_now(h, c);
+    if (rc) return rc;
+    out_xyz[0] = c.m[0]; out_xyz[1] = c.m[1]; out_xyz[2] = c.m[2];
+    return VEGAS_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+// Per-site energies run on natural-order copies of the state with the implicit / CSR adjacency.
+template <typename NB>
+int site_energy_run(vegas_gpu* h, const NB& nb, const void* proposal, int want_delta, double* out_host) {
+    const uint32_t n = (uint32_t)h->n;
+    double *d_out = nullptr, *d_prop = nullptr;
+    CU(cudaMallocAsync(&d_out, (size_t)n * 8, h->stream));
+    const EnergyParams ep = energy_params(h);
+    const int flip = proposal == nullptr;
+    if (want_delta && proposal) {
+        CU(cudaMallocAsync(&d_prop, (size_t)n * 24, h->stream));
+        if (h->md.model == VEGAS_ISING) {
+            std::vector<double> p3((size_t)n * 3, 0.0);
+            const int8_t* p8 = (const int8_t*)proposal;
+            for (uint32_t i = 0; i < n; ++i) p3[3 * (size_t)i + 2] = p8[i] > 0 ? 1.0 : -1.0;
+            CU(cudaMemcpyAsync(d_prop, p3.data(), (size_t)n * 24, cudaMemcpyHostToDevice, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+        } else {
+            CU(cudaMemcpyAsync(d_prop, proposal, (size_t)n * 24, cudaMemcpyHostToDevice, h->stream));
+        }
+    }
+    double* oe = want_delta ? nullptr : d_out;
+    double* ode = want_delta ? d_out : nullptr;
+    const dim3 grid(cdiv(n, 256));
+    void* tmp[3] = {nullptr, nullptr, nullptr};
+    h->launches++;
+    if (h->md.model == VEGAS_ISING) {
+        const int8_t* s8 = h->g_s8;
+        if (h->family == FAM_ISING_MSC) {
+            CU(cudaMallocAsync(&tmp[0], n, h->stream));
+            const uint32_t Wx = (uint32_t)(h->ld.nx / 64);
+            const size_t total = (size_t)Wx * h->ld.ny * h->ld.nz;
+            ising_msc_unpack_kernel<<<cdiv(total, 256), 256, 0, h->stream>>>((int8_t*)tmp[0], (const uint32_t*)h->msc[0], (const uint32_t*)h->msc[1], Wx, (uint32_t)h->ld.ny, (uint32_t)h->ld.nz, (uint32_t)h->z_offset);
+            s8 = (const int8_t*)tmp[0];
+        }
+        IsingSpins sp{s8};
+        site_energy_kernel<NB, IsingSpins><<<grid, 256, 0, h->stream>>>(nb, sp, n, ep, d_prop, flip, oe, ode);
+    } else if (h->md.precision == VEGAS_F64) {
+        const double* s[3] = {(const double*)h->g_s[0], (const double*)h->g_s[1], (const double*)h->g_s[2]};
+        if (h->family == FAM_HEIS_STENCIL) {
+            for (int c = 0; c < 3; ++c) CU(cudaMallocAsync(&tmp[c], (size_t)n * 8, h->stream));
+            heis_unpack_kernel<double, double><<<cdiv(n, 256), 256, 0, h->stream>>>((double*)tmp[0], (double*)tmp[1], (double*)tmp[2], 1,
+                (const double*)h->hs[0][0], (const double*)h->hs[0][1], (const double*)h->hs[0][2], (const double*)h->hs[1][0], (const double*)h->hs[1][1], (const double*)h->hs[1][2],
+                (uint32_t)h->ld.nx, (uint32_t)h->ld.ny, (uint32_t)h->ld.nz, (uint32_t)h->z_offset);
+            for (int c = 0; c < 3; ++c) s[c] = (const double*)tmp[c];
+        }
+        HeisSpins<double> sp{s[0], s[1], s[2]};
+        site_energy_kernel<NB, HeisSpins<double>><<<grid, 256, 0, h->stream>>>(nb, sp, n, ep, d_prop, flip, oe, ode);
+    } else {
+        const float* s[3] = {(const float*)h->g_s[0], (const float*)h->g_s[1], (const float*)h->g_s[2]};
+        if (h->family == FAM_HEIS_STENCIL) {
+            for (int c = 0; c < 3; ++c) CU(cudaMallocAsync(&tmp[c], (size_t)n * 4, h->stream));
+            heis_unpack_kernel<float, float><<<cdiv(n, 256), 256, 0, h->stream>>>((float*)tmp[0], (float*)tmp[1], (float*)tmp[2], 1,
+                (const float*)h->hs[0][0], (const float*)h->hs[0][1], (const float*)h->hs[0][2], (const float*)h->hs[1][0], (const float*)h->hs[1][1], (const float*)h->hs[1][2],
+                (uint32_t)h->ld.nx, (uint32_t)h->ld.ny, (uint32_t)h->ld.nz, (uint32_t)h->z_offset);
+            for (int c = 0; c < 3; ++c) s[c] = (const float*)tmp[c];
+        }
+        HeisSpins<float> sp{s[0], s[1], s[2]};
+        site_energy_kernel<NB, HeisSpins<float>><<<grid, 256, 0, h->stream>>>(nb, sp, n, ep, d_prop, flip, oe, ode);
+    }
+    CU(cudaMemcpyAsync(out_host, d_out, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+    for (int c = 0; c < 3; ++c) if (tmp[c]) CU(cudaFreeAsync(tmp[c], h->stream));
+    if (d_prop) CU(cudaFreeAsync(d_prop, h->stream));
+    CU(cudaFreeAsync(d_out, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return VEGAS_OK;
+}
+
+int site_energy_dispatch(vegas_gpu* h, const void* proposal, int want_delta, double* out) {
+    if (h->slab) return fail(h, VEGAS_ERR_STATE, "per-site energies are not available for a slab");
+    if (h->n >= (1ull << 32)) return fail(h, VEGAS_ERR_STATE, "per-site energies support < 2^32 sites");
+    CU(cudaSetDevice(h->device));
+    if (h->csr_input) return site_energy_run(h, csr_nb(h), proposal, want_delta, out);
+    return site_energy_run(h, structured_nb(h), proposal, want_delta, out);
+}
+
+}  // namespace
+
+extern "C" {
+
+int vegas_gpu_site_energies(vegas_gpu_t h, double* out_n) {
+    if (!h || !out_n) return VEGAS_ERR_INVALID;
+    return site_energy_dispatch(h, nullptr, 0, out_n);
+}
+
+int vegas_gpu_delta_energies(vegas_gpu_t h, const void* proposal, double* out_n) {
+    if (!h || !out_n) return VEGAS_ERR_INVALID;
+    return site_energy_dispatch(h, proposal, 1, out_n);
+}
+
+int vegas_gpu_attempt_count(vegas_gpu_t h, uint64_t* attempts, uint64_t* accepted) {
+    if (!h) return VEGAS_ERR_INVALID;
+    CU(cudaSetDevice(h->device));
+    unsigned long long row[OBS_W];
+    CU(cudaMemcpyAsync(row, h->obs + OBS_CAP * OBS_W, sizeof row, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    const Canon c = canon_of(h, row);
+    if (attempts) *attempts = h->attempts;
+    if (accepted) *accepted = h->accepted + c.accepted;
+    return VEGAS_OK;
+}
+
+int vegas_gpu_sweep_count(vegas_gpu_t h, uint64_t* sweeps) {
+    if (!h || !sweeps) return VEGAS_ERR_INVALID;
+    *sweeps = h->sweeps;
+    return VEGAS_OK;
+}
+
+int vegas_gpu_set_sweep_count(vegas_gpu_t h, uint64_t sweeps) {
+    if (!h) return VEGAS_ERR_INVALID;
+    h->sweeps = sweeps;
+    return VEGAS_OK;
+}
+
+int vegas_gpu_ising_thresholds(vegas_gpu_t h, int* n_classes, uint64_t* thr, uint8_t* always) {
+    if (!h) return VEGAS_ERR_INVALID;
+    if (h->family != FAM_ISING_MSC) return fail(h, VEGAS_ERR_STATE, "thresholds are exposed for the ising_msc family only");
+    CU(cudaSetDevice(h->device));
+    int rc = update_tables(h);
+    if (rc) return rc;
+    if (n_classes) *n_classes = 2 * h->ndim + 1;
+    if (thr) memcpy(thr, h->ising_thr.data(), 16 * 8);
+    if (always) memcpy(always, h->ising_always.data(), 16);
+    return VEGAS_OK;
+}
+
+// ---- slab decomposition -------------------------------------------------------------------
+struct SlabBlob {
+    cudaIpcMemHandle_t halo, flags;
+    int device;
+    uint64_t plane_bytes;
+    char pad[VEGAS_IPC_BYTES - 2 * sizeof(cudaIpcMemHandle_t) - sizeof(int) - sizeof(uint64_t)];
+};
+static_assert(sizeof(SlabBlob) <= VEGAS_IPC_BYTES + 8, "blob size");
+
+int vegas_gpu_slab_export(vegas_gpu_t h, void* blob) {
+    if (!h || !blob) return VEGAS_ERR_INVALID;
+    if (!h->slab) return fail(h, VEGAS_ERR_STATE, "handle is not a slab");
+    CU(cudaSetDevice(h->device));
+    SlabBlob b;
+    memset(&b, 0, sizeof b);
+    CU(cudaIpcGetMemHandle(&b.halo, h->halo));
+    CU(cudaIpcGetMemHandle(&b.flags, h->flags));
+    b.device = h->device;
+    b.plane_bytes = h->halo_plane_bytes;
+    memcpy(blob, &b, VEGAS_IPC_BYTES);
+    return VEGAS_OK;
+}
+
+int vegas_gpu_slab_connect(vegas_gpu_t h, const void* lower, const void* upper) {
+    if (!h || !lower || !upper) return VEGAS_ERR_INVALID;
+    if (!h->slab) return fail(h, VEGAS_ERR_STATE, "handle is not a slab");
+    CU(cudaSetDevice(h->device));
+    const void* blobs[2] = {lower, upper};
+    const bool same = memcmp(lower, upper, VEGAS_IPC_BYTES) == 0;  // two ranks: both neighbours are the same peer
+    for (int d = 0; d < 2; ++d) {
+        if (d == 1 && same) { h->peer_halo[1] = h->peer_halo[0]; h->peer_flags[1] = h->peer_flags[0]; break; }
+        SlabBlob b;
+        memcpy(&b, blobs[d], VEGAS_IPC_BYTES);
+        if (b.plane_bytes != h->halo_plane_bytes) return fail(h, VEGAS_ERR_INVALID, "neighbour slab has a different plane size");
+        CU(cudaIpcOpenMemHandle(&h->peer_halo[d], b.halo, cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle((void**)&h->peer_flags[d], b.flags, cudaIpcMemLazyEnablePeerAccess));
+    }
+    h->peer_is_ipc = true;
+    h->connected = true;
+    return push_boundaries(h);
+}
+
+int vegas_gpu_slab_connect_local(vegas_gpu_t h, vegas_gpu_t lower, vegas_gpu_t upper) {
+    if (!h || !lower || !upper) return VEGAS_ERR_INVALID;
+    if (!h->slab || !lower->slab || !upper->slab) return fail(h, VEGAS_ERR_STATE, "handle is not a slab");
+    CU(cudaSetDevice(h->device));
+    vegas_gpu* nbr[2] = {lower, upper};
+    for (int d = 0; d < 2; ++d) {
+        if (nbr[d]->halo_plane_bytes != h->halo_plane_bytes) return fail(h, VEGAS_ERR_INVALID, "neighbour slab has a different plane size");
+        if (nbr[d]->device != h->device) {
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, h->device, nbr[d]->device));
+            if (!can) return fail(h, VEGAS_ERR_CUDA, "no peer access between slab devices");
+            cudaError_t e = cudaDeviceEnablePeerAccess(nbr[d]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
+            cudaGetLastError();
+        }
+        h->peer_halo[d] = nbr[d]->halo;
+        h->peer_flags[d] = nbr[d]->flags;
+    }
+    h->peer_is_ipc = false;
+    h->connected = true;
+    return push_boundaries(h);
+}
+
+// ---- timing hooks -------------------------------------------------------------------------
+int vegas_gpu_timer_start(vegas_gpu_t h) {
+    if (!h) return VEGAS_ERR_INVALID;
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventRecord(h->ev0, h->stream));
+    return VEGAS_OK;
+}
+
+int vegas_gpu_timer_stop(vegas_gpu_t h, float* ms) {
+    if (!h || !ms) return VEGAS_ERR_INVALID;
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaEventSynchronize(h->ev1));
+    CU(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return VEGAS_OK;
+}
+
+}  // extern "C"
