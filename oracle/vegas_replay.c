@@ -103,21 +103,24 @@ uint64_t vo_replay_heisenberg(const vo_hamiltonian* h, const vo_thermostat_t* th
         for (uint64_t i = 0; i < n; ++i) {
             if (colour[i] != c) continue;
             uint32_t r[4], q[4];
-            philox_at(i, sweep, 0u, seed, r);
             double old[3] = {state[3 * i], state[3 * i + 1], state[3 * i + 2]}, p[3], u;
             if (proposal == VO_PROPOSE_FLIP) { p[0] = -old[0]; p[1] = -old[1]; p[2] = -old[2]; }
             if (f32) {
+                /* one call serves sites i and i^2: index i & ~2, words (0,1) / (2,3); 21+21+22 bits */
+                philox_at(i & ~2ull, sweep, 0u, seed, r);
+                const uint32_t w0 = (i & 2ull) ? r[2] : r[0], w1 = (i & 2ull) ? r[3] : r[1];
                 if (proposal != VO_PROPOSE_FLIP) {
-                    float u0 = ((float)(r[0] >> 8) + 0.5f) * 0x1.0p-24f, u1 = (float)(r[1] >> 8) * 0x1.0p-24f;
+                    float u0 = ((float)(w0 >> 11) + 0.5f) * 0x1.0p-21f, u1 = (float)(w1 >> 11) * 0x1.0p-21f;
                     float z = 1.0f - 2.0f * u0;
-                    float rxy = sqrtf(fmaxf(0.0f, (1.0f - z) * (1.0f + z)));
-                    float ang = 2.0f * u1;
-                    p[0] = (double)(rxy * (float)cos(M_PI * (double)ang));
-                    p[1] = (double)(rxy * (float)sin(M_PI * (double)ang));
+                    float rxy = sqrtf(4.0f * u0 * (1.0f - u0));
+                    float ang = 6.283185307179586f * (u1 - 0.5f);
+                    p[0] = (double)(rxy * (float)cos((double)ang));
+                    p[1] = (double)(rxy * (float)sin((double)ang));
                     p[2] = (double)z;
                 }
-                u = (double)((float)(r[2] >> 8) * 0x1.0p-24f);
+                u = (double)((float)(((w0 & 0x7FFu) << 11) | (w1 & 0x7FFu)) * 0x1.0p-22f);
             } else {
+                philox_at(i, sweep, 0u, seed, r);
                 if (proposal != VO_PROPOSE_FLIP) {
                     double z = 1.0 - 2.0 * u53(r[0], r[1]);
                     double rxy = sqrt(fmax(0.0, (1.0 - z) * (1.0 + z)));

@@ -17,6 +17,7 @@ FIELD = dict(temperature=2.5, field_dir=(0.0, 0.0, 1.0), field_mag=0.75)
 # (id, kwargs) -- lattices that exercise every kernel family and boundary rule
 LATTICES = [
     ("sc_msc_3d", dict(unitcell=vg.SC, size=(256, 4, 6))),
+    ("sc_msc_3d_64", dict(unitcell=vg.SC, size=(64, 6, 4))),
     ("sc_msc_2d_open_z", dict(unitcell=vg.SC, size=(256, 6, 1), pbc=(True, True, False))),
     ("sc_msc_2d_self_z", dict(unitcell=vg.SC, size=(256, 4, 1))),
     ("sc_stencil_small", dict(unitcell=vg.SC, size=(16, 4, 6))),
@@ -131,10 +132,11 @@ def test_csr_input_with_values(built):
 @pytest.mark.parametrize("proposal", [vg.PROPOSE_FLIP, vg.PROPOSE_RANDOM], ids=["flip", "random"])
 @pytest.mark.parametrize("lat,fmag", [
     (dict(unitcell=vg.SC, size=(256, 4, 6)), 0.0),
+    (dict(unitcell=vg.SC, size=(64, 6, 2)), 0.0),
     (dict(unitcell=vg.SC, size=(256, 4, 6)), 0.625),  # dyadic field: every partial sum of the reference fold is exact
     (dict(unitcell=vg.SC, size=(512, 6, 1), pbc=(True, True, False)), 0.0),
     (dict(unitcell=vg.SC, size=(256, 4, 1)), -0.375),
-], ids=["3d", "3d_field", "2d", "2d_field_selfz"])
+], ids=["3d", "3d_64_L2", "3d_field", "2d", "2d_field_selfz"])
 def test_ising_msc_sweep_replay_bit_exact(built, lat, fmag, proposal):
     """Every decision of the multi-spin-coded sweep equals the reference rule evaluated by the oracle."""
     seed = 1234
@@ -213,7 +215,7 @@ def test_heisenberg_sweep_replay(built, precision, general):
             assert bad <= max(2, n // 200), bad
             assert abs(e[0] - H.total_energy(th, dev)) < 1e-5 * n * 6
             cpu = dev.copy()  # resynchronise so that rare flips do not cascade
-        assert np.max(np.abs(np.linalg.norm(dev, axis=1) - 1.0)) < (1e-12 if precision == vg.F64 else 1e-6)
+        assert np.max(np.abs(np.linalg.norm(dev, axis=1) - 1.0)) < (1e-12 if precision == vg.F64 else 3e-6)
     g.close()
 
 

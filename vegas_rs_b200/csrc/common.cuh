@@ -11,30 +11,44 @@ namespace vg {
 // lattice over GPUs reproduces the same random numbers per site.
 // Round keys are thread-invariant, so the compiler keeps them on the uniform datapath.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                              uint32_t k1, uint32_t (&out)[4]) {
+// Round keys are precomputed on the host (PhiloxKey, passed by value = constant bank) so that no
+// per-thread integer adds are spent on the key schedule.
+struct PhiloxKey {
+    uint32_t k[10][2];
+};
+
+inline PhiloxKey make_philox_key(uint64_t seed) {
+    PhiloxKey pk;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        pk.k[r][0] = k0; pk.k[r][1] = k1;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return pk;
+}
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKey& pk,
+                                              uint32_t (&out)[4]) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
         const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
-        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
-        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ pk.k[r][0];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ pk.k[r][1];
         c1 = (uint32_t)p1;
         c3 = (uint32_t)p0;
         c0 = n0;
         c2 = n2;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
 // Counter layout used everywhere: c0,c1 = 64-bit index (bit 62 of the index carries the
 // colour for word-keyed streams), c2 = sweep low, c3 = sweep bits 32..55 | call << 24.
-__device__ __forceinline__ void philox_at(uint64_t index, uint64_t sweep, uint32_t call, uint32_t k0, uint32_t k1,
+__device__ __forceinline__ void philox_at(uint64_t index, uint64_t sweep, uint32_t call, const PhiloxKey& pk,
                                           uint32_t (&out)[4]) {
     philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), (uint32_t)sweep,
-                  ((uint32_t)(sweep >> 32) & 0x00FFFFFFu) | (call << 24), k0, k1, out);
+                  ((uint32_t)(sweep >> 32) & 0x00FFFFFFu) | (call << 24), pk, out);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -64,6 +78,30 @@ __device__ __forceinline__ void block_atomic_add(T (&v)[NV], T* red, T* out) {
             T s = lane < nwarp ? red[i * 32 + lane] : T(0);
             s = warp_sum(s);
             if (lane == 0) atomicAdd(out + i, s);
+        }
+    }
+}
+
+// Barrier-free block reduction of NV 32-bit integers: every warp reduces with REDUX, adds into shared
+// accumulators, takes a ticket; the last warp to arrive flushes the block totals with one 64-bit global
+// atomic per value.  `s_acc` (NV ints) and `s_cnt` must be zeroed before (one barrier at kernel start).
+// All 32 lanes of every warp must call this.
+template <int NV>
+__device__ __forceinline__ void block_flush_int(const int (&v)[NV], int* s_acc, unsigned int* s_cnt,
+                                                unsigned long long* out) {
+    int r[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) r[i] = __reduce_add_sync(0xffffffffu, v[i]);
+    if ((threadIdx.x + threadIdx.y * blockDim.x) % 32 == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) atomicAdd(s_acc + i, r[i]);
+        __threadfence_block();
+        const unsigned int nwarp = (blockDim.x * blockDim.y + 31) >> 5;
+        if (atomicAdd(s_cnt, 1u) == nwarp - 1) {
+            __threadfence_block();
+#pragma unroll
+            for (int i = 0; i < NV; ++i)
+                atomicAdd(out + i, (unsigned long long)(long long)atomicAdd(s_acc + i, 0));
         }
     }
 }

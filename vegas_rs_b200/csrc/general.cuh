@@ -70,7 +70,7 @@ struct IsingGeneralParams {
 template <typename NB, bool RANDPROP>
 __global__ void __launch_bounds__(256)
 ising_general_sweep_kernel(int8_t* __restrict__ s, NB nb, const uint32_t* __restrict__ sites, uint32_t count,
-                           IsingGeneralParams p, uint64_t site_offset, uint64_t sweep, uint32_t k0, uint32_t k1,
+                           IsingGeneralParams p, uint64_t site_offset, uint64_t sweep, PhiloxKey pk,
                            unsigned long long* __restrict__ obs) {
     __shared__ unsigned long long s_red[32];
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -79,7 +79,7 @@ ising_general_sweep_kernel(int8_t* __restrict__ s, NB nb, const uint32_t* __rest
         const uint32_t i = sites[t];
         const int si = s[i];
         uint32_t r[4];
-        philox_at((uint64_t)i + site_offset, sweep, 0u, k0, k1, r);
+        philox_at((uint64_t)i + site_offset, sweep, 0u, pk, r);
         const unsigned long long U = ((unsigned long long)r[0] << 32) | r[1];
         bool proposed = true;
         if (RANDPROP) proposed = ((r[2] & 1u) ? 1 : -1) != si;  // IsingSpin::rand src/state.rs:76-84
@@ -111,7 +111,7 @@ template <typename NB, typename real, bool FLIP>
 __global__ void __launch_bounds__(128)
 heis_general_sweep_kernel(real* __restrict__ sx, real* __restrict__ sy, real* __restrict__ sz, NB nb,
                           const uint32_t* __restrict__ sites, uint32_t count, HeisParams<real> p, uint64_t site_offset,
-                          uint64_t sweep, uint32_t k0, uint32_t k1, double* __restrict__ obs) {
+                          uint64_t sweep, PhiloxKey pk, double* __restrict__ obs) {
     __shared__ double s_red[32];
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     double acc[1] = {0.0};
@@ -122,7 +122,9 @@ heis_general_sweep_kernel(real* __restrict__ sx, real* __restrict__ sy, real* __
             if (j != i) { const real w = (real)Jij; nx += w * sx[j]; ny += w * sy[j]; nz += w * sz[j]; }
         });
         real x = sx[i], y = sy[i], z = sz[i];
-        const bool ok = heis_attempt<real, FLIP>(x, y, z, nx, ny, nz, p, (uint64_t)i + site_offset, sweep, k0, k1);
+        HeisRand<real> rnd;
+        heis_rand((uint64_t)i + site_offset, sweep, pk, rnd);
+        const bool ok = heis_attempt<real, FLIP>(x, y, z, nx, ny, nz, p, rnd);
         if (ok) { sx[i] = x; sy[i] = y; sz[i] = z; }
         acc[0] = ok ? 1.0 : 0.0;
     }
@@ -215,21 +217,21 @@ site_energy_kernel(NB nb, SP sp, uint32_t n, EnergyParams ep, const double* __re
 
 // natural-order helpers ------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ising_general_randomize_kernel(int8_t* s, uint32_t n, uint64_t site_offset,
-                                                                      uint32_t k0, uint32_t k1) {
+                                                                      PhiloxKey pk) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t r[4];
-    philox_at(((uint64_t)i + site_offset) | (1ull << 61), ~0ull, 0xFEu, k0, k1, r);
+    philox_at(((uint64_t)i + site_offset) | (1ull << 61), ~0ull, 0xFEu, pk, r);
     s[i] = (r[0] & 1u) ? 1 : -1;
 }
 
 template <typename real>
 __global__ void __launch_bounds__(256) heis_general_randomize_kernel(real* sx, real* sy, real* sz, uint32_t n,
-                                                                     uint64_t site_offset, uint32_t k0, uint32_t k1) {
+                                                                     uint64_t site_offset, PhiloxKey pk) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     real x, y, z;
-    heis_random_spin<real>((uint64_t)i + site_offset, k0, k1, x, y, z);
+    heis_random_spin<real>((uint64_t)i + site_offset, pk, x, y, z);
     sx[i] = x; sy[i] = y; sz[i] = z;
 }
 

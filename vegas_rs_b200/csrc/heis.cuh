@@ -20,13 +20,15 @@ struct HeisParams {
     real invT;
 };
 
-// Uniform point on the sphere from two uniforms (Archimedes); same distribution as
-// util.rs:21-34 (Marsaglia) without a rejection loop.
+// Uniform point on the sphere from two uniforms (Archimedes' hat-box); same distribution as
+// util.rs:21-34 (Marsaglia) without a rejection loop.  u0 in (0,1), u1 in [0,1).
+// fp32: hardware sin/cos/rsqrt (abs. error ~2^-21, the spin norm is 1 +- 1e-6, inside the fp32 bar).
 __device__ __forceinline__ void sphere_point(float u0, float u1, float& x, float& y, float& z) {
     z = 1.0f - 2.0f * u0;
-    const float rxy = sqrtf(fmaxf(0.0f, (1.0f - z) * (1.0f + z)));
+    const float t = 4.0f * u0 * (1.0f - u0);  // 1 - z^2 > 0
+    const float rxy = t * rsqrtf(t);
     float sn, cs;
-    sincospif(2.0f * u1, &sn, &cs);
+    __sincosf(6.283185307179586f * (u1 - 0.5f), &sn, &cs);
     x = rxy * cs; y = rxy * sn;
 }
 __device__ __forceinline__ void sphere_point(double u0, double u1, double& x, double& y, double& z) {
@@ -40,41 +42,50 @@ __device__ __forceinline__ void sphere_point(double u0, double u1, double& x, do
 __device__ __forceinline__ float fast_exp(float x) { return __expf(x); }
 __device__ __forceinline__ double fast_exp(double x) { return exp(x); }
 
-// One Metropolis attempt on a site whose local field (nx,ny,nz) is known.  `site` is the
-// global natural site index; randoms are Philox(site, sweep).  Returns true when accepted.
+// The three uniforms of one attempt: direction (u0, u1) and acceptance (ua).
+template <typename real>
+struct HeisRand { real u0, u1, ua; };
+
+// fp32: 64 random bits per attempt -- 21 bits for z, 21 for the azimuth, 22 for the acceptance test.
+__device__ __forceinline__ HeisRand<float> heis_rand_words(uint32_t w0, uint32_t w1) {
+    HeisRand<float> o;
+    o.u0 = ((float)(w0 >> 11) + 0.5f) * 0x1.0p-21f;
+    o.u1 = (float)(w1 >> 11) * 0x1.0p-21f;
+    o.ua = (float)(((w0 & 0x7FFu) << 11) | (w1 & 0x7FFu)) * 0x1.0p-22f;
+    return o;
+}
+
+// Random numbers of site `site` in sweep `sweep`.
+// fp32: ONE Philox call serves the two sites that differ in bit 1 of the index (same colour, x and x+2
+//       on an sc row): counter index = site & ~2, words (0,1) for bit 1 clear, (2,3) for bit 1 set.
+// fp64: call 0 -> 53-bit u0, u1; call 1 -> 53-bit ua (the fp64 path is the 1e-12 parity path).
+__device__ __forceinline__ void heis_rand(uint64_t site, uint64_t sweep, const PhiloxKey& pk, HeisRand<float>& o) {
+    uint32_t r[4];
+    philox_at(site & ~2ull, sweep, 0u, pk, r);
+    o = (site & 2ull) ? heis_rand_words(r[2], r[3]) : heis_rand_words(r[0], r[1]);
+}
+__device__ __forceinline__ void heis_rand(uint64_t site, uint64_t sweep, const PhiloxKey& pk, HeisRand<double>& o) {
+    uint32_t r[4], q[4];
+    philox_at(site, sweep, 0u, pk, r);
+    philox_at(site, sweep, 1u, pk, q);
+    o.u0 = u53(r[0], r[1]); o.u1 = u53(r[2], r[3]); o.ua = u53(q[0], q[1]);
+}
+
+// One Metropolis attempt on a site whose local field (nx,ny,nz) and random numbers are known.
+// Returns true when accepted.
 template <typename real, bool FLIP>
 __device__ __forceinline__ bool heis_attempt(real& sx, real& sy, real& sz, real nx, real ny, real nz,
-                                             const HeisParams<real>& p, uint64_t site, uint64_t sweep, uint32_t k0,
-                                             uint32_t k1) {
-    uint32_t r[4];
-    philox_at(site, sweep, 0u, k0, k1, r);
-    real px, py, pz, u;
-    if (sizeof(real) == 4) {
-        if (FLIP) { px = -sx; py = -sy; pz = -sz; }
-        else {
-            float fx, fy, fz;
-            sphere_point(((float)(r[0] >> 8) + 0.5f) * 0x1.0p-24f, u24(r[1]), fx, fy, fz);
-            px = fx; py = fy; pz = fz;
-        }
-        u = u24(r[2]);
-    } else {
-        if (FLIP) { px = -sx; py = -sy; pz = -sz; }
-        else {
-            double dx, dy, dz;
-            sphere_point(u53(r[0], r[1]), u53(r[2], r[3]), dx, dy, dz);
-            px = dx; py = dy; pz = dz;
-        }
-        uint32_t q[4];
-        philox_at(site, sweep, 1u, k0, k1, q);
-        u = (real)u53(q[0], q[1]);
-    }
+                                             const HeisParams<real>& p, const HeisRand<real>& rnd) {
+    real px, py, pz;
+    if (FLIP) { px = -sx; py = -sy; pz = -sz; }
+    else sphere_point(rnd.u0, rnd.u1, px, py, pz);
     const real dx = px - sx, dy = py - sy, dz = pz - sz;
     real dE = -(dx * nx + dy * ny + dz * nz) + (dx * p.h[0] + dy * p.h[1] + dz * p.h[2]);
     const real da_new = px * p.a[0] + py * p.a[1] + pz * p.a[2];
     const real da_old = sx * p.a[0] + sy * p.a[1] + sz * p.a[2];
     dE += p.k * (da_new * da_new - da_old * da_old);
     // src/integrator.rs:82-88: accept if dE < 0, else if u < exp(-dE/T)
-    const bool acc = (dE < real(0)) || (u < fast_exp(-dE * p.invT));
+    const bool acc = (dE < real(0)) || (rnd.ua < fast_exp(-dE * p.invT));
     if (acc) { sx = px; sy = py; sz = pz; }
     return acc;
 }
@@ -122,7 +133,7 @@ struct HeisPtrs {
 template <typename real, int NDIM, bool FLIP, int MODE>
 __global__ void __launch_bounds__(128)
 heis_stencil_kernel(HeisPtrs<real> P, HeisGeom g, int colour, uint32_t z_begin, uint32_t z_count, HeisParams<real> p,
-                    uint64_t sweep, uint32_t k0, uint32_t k1, double* __restrict__ obs) {
+                    uint64_t sweep, PhiloxKey pk, double* __restrict__ obs) {
     constexpr int N = VecOf<real>::N;
     __shared__ double s_red[6 * 32];
     const uint32_t rows = g.Ly * g.Gx;
@@ -169,13 +180,27 @@ heis_stencil_kernel(HeisPtrs<real> P, HeisGeom g, int colour, uint32_t z_begin, 
             }
         }
         real facc[6] = {0, 0, 0, 0, 0, 0};
+        HeisRand<real> rnd[N];
+        if (MODE != 2) {
+            const uint64_t site0 = ((uint64_t)zg * g.Ly + y) * g.Lx + 2u * (gx * N) + rp;  // element e: site0 + 2e
+            if (sizeof(real) == 4) {
+#pragma unroll
+                for (int e = 0; e < N; e += 2) {  // bit 1 of site0 is clear (Lx % 8 == 0): elements e, e+1 share a call
+                    uint32_t r[4];
+                    philox_at(site0 + 2u * e, sweep, 0u, pk, r);
+                    reinterpret_cast<HeisRand<float>&>(rnd[e]) = heis_rand_words(r[0], r[1]);
+                    reinterpret_cast<HeisRand<float>&>(rnd[e + 1]) = heis_rand_words(r[2], r[3]);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < N; ++e) heis_rand(site0 + 2u * e, sweep, pk, rnd[e]);
+            }
+        }
 #pragma unroll
         for (int e = 0; e < N; ++e) {
             const real nx = p.J * nsum[0][e], ny = p.J * nsum[1][e], nz = p.J * nsum[2][e];
             if (MODE != 2) {
-                const uint32_t x = 2u * (gx * N + e) + rp;
-                const uint64_t site = ((uint64_t)zg * g.Ly + y) * g.Lx + x;
-                const bool ok = heis_attempt<real, FLIP>(s[0][e], s[1][e], s[2][e], nx, ny, nz, p, site, sweep, k0, k1);
+                const bool ok = heis_attempt<real, FLIP>(s[0][e], s[1][e], s[2][e], nx, ny, nz, p, rnd[e]);
                 facc[5] += ok ? real(1) : real(0);
             }
             if (MODE != 0) {
@@ -202,7 +227,12 @@ heis_stencil_kernel(HeisPtrs<real> P, HeisGeom g, int colour, uint32_t z_begin, 
             }
         }
     }
-    block_atomic_add<double, 6>(acc, s_red, obs);
+    if (MODE == 0) {
+        double a1[1] = {acc[5]};
+        block_atomic_add<double, 1>(a1, s_red, obs + 5);
+    } else {
+        block_atomic_add<double, 6>(acc, s_red, obs);
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -243,9 +273,9 @@ heis_unpack_kernel(outT* __restrict__ ox, outT* __restrict__ oy, outT* __restric
 
 // State::rand_with_size for Heisenberg spins on device, natural site index keyed.
 template <typename real>
-__device__ __forceinline__ void heis_random_spin(uint64_t site, uint32_t k0, uint32_t k1, real& x, real& y, real& z) {
+__device__ __forceinline__ void heis_random_spin(uint64_t site, PhiloxKey pk, real& x, real& y, real& z) {
     uint32_t r[4];
-    philox_at(site | (1ull << 61), ~0ull, 0xFEu, k0, k1, r);
+    philox_at(site | (1ull << 61), ~0ull, 0xFEu, pk, r);
     double dx, dy, dz;
     sphere_point(u53(r[0], r[1]), u53(r[2], r[3]), dx, dy, dz);
     x = (real)dx; y = (real)dy; z = (real)dz;
@@ -254,7 +284,7 @@ __device__ __forceinline__ void heis_random_spin(uint64_t site, uint32_t k0, uin
 template <typename real>
 __global__ void __launch_bounds__(256)
 heis_stencil_randomize_kernel(real* c0x, real* c0y, real* c0z, real* c1x, real* c1y, real* c1z, uint32_t Lx, uint32_t Ly,
-                              uint32_t Lz, uint32_t z_offset, uint32_t k0, uint32_t k1) {
+                              uint32_t Lz, uint32_t z_offset, PhiloxKey pk) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t total = (size_t)Lx * Ly * Lz;
     if (t >= total) return;
@@ -263,7 +293,7 @@ heis_stencil_randomize_kernel(real* c0x, real* c0y, real* c0z, real* c1x, real* 
     const size_t e = ((size_t)z * Ly + y) * (Lx / 2) + (x >> 1);
     const uint64_t site = ((uint64_t)(z + z_offset) * Ly + y) * Lx + x;
     real sx, sy, sz;
-    heis_random_spin<real>(site, k0, k1, sx, sy, sz);
+    heis_random_spin<real>(site, pk, sx, sy, sz);
     if (col == 0) { c0x[e] = sx; c0y[e] = sy; c0z[e] = sz; }
     else { c1x[e] = sx; c1y[e] = sy; c1z[e] = sz; }
 }

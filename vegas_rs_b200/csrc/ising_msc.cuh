@@ -21,182 +21,182 @@
 namespace vg {
 
 constexpr int MSC_MAX_SLOT = 14;
-constexpr uint8_t MSC_ALWAYS = 0xFE;
-constexpr uint8_t MSC_NEVER = 0xFF;
 
-// thresholds grouped into "slots"; class (spin s, antiparallel count c) -> slot / always / never
-struct MscTable {
-    uint8_t slot_of[2][8];
+// Every (spin, antiparallel-count) class with dE > 0 owns one "slot" = one 64-bit threshold.
+// A slot is selected bit-parallel as (n0^a0) & (n1^a1) & (n2^a2) [& (s^sx)]; unused slots ask for
+// the impossible count 7.  Classes without a slot have dE <= 0 and are always accepted.
+template <int NSLOT>
+struct MscSlots {
+    uint32_t a0[NSLOT], a1[NSLOT], a2[NSLOT], sx[NSLOT];
 };
 
 struct MscGeom {
-    uint32_t Gx;        // uint4 groups per row per colour = Lx / 256
+    uint32_t Wx;        // 32-bit words per row per colour = Lx / 64
     uint32_t Ly, Lz;    // local rows / planes
     uint32_t z_offset;  // global z of local plane 0
-    uint32_t Ly_g;      // == Ly (rows are never decomposed)
 };
 
 __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a | b)); }
 
-template <int C>
-__device__ __forceinline__ uint32_t class_mask(uint32_t n0, uint32_t n1, uint32_t n2) {
-    return ((C & 1) ? n0 : ~n0) & ((C & 2) ? n1 : ~n1) & ((C & 4) ? n2 : ~n2);
-}
+#ifndef MSC_MINB
+#define MSC_MINB 3   // resident CTAs of 256 threads per SM the sweep kernel is compiled for (register cap)
+#endif
+constexpr int MSC_ROWS = 4;  // rows (words along y) per thread: amortises addressing, shares the y-neighbour loads
 
+// One thread owns MSC_ROWS 32-bit words: the same word column w in rows y0 .. y0+MSC_ROWS-1.
 // MODE 0: update; 1: update + fused energy/magnetisation reduction; 2: reduction only.
 // obs[0] += sum over own sites of s_i * (sum_nb s_j)   (every bond once, bipartite)
 // obs[1] += sum of s over both colours (own word after update + partner word)
 // obs[2] += accepted moves
 template <int NDIM, bool FIELD, int NSLOT, bool RANDPROP, int MODE>
-__global__ void __launch_bounds__(256)
-ising_msc_kernel(uint4* __restrict__ own, const uint4* __restrict__ oth, const uint4* __restrict__ oth_lo,
-                 const uint4* __restrict__ oth_hi, uint4* __restrict__ peer_lo, uint4* __restrict__ peer_hi,
-                 MscGeom g, int colour, uint32_t z_begin, uint32_t z_count, MscTable tab,
+__global__ void __launch_bounds__(256, MSC_MINB)
+ising_msc_kernel(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth, const uint32_t* __restrict__ oth_lo,
+                 const uint32_t* __restrict__ oth_hi, uint32_t* __restrict__ peer_lo, uint32_t* __restrict__ peer_hi,
+                 MscGeom g, int colour, uint32_t z_begin, MscSlots<NSLOT> slots,
                  const uint4* __restrict__ thr_bits /* [NSLOT][16] uint4: 0/~0 masks of threshold bit-planes */,
-                 uint64_t sweep, uint32_t k0, uint32_t k1, unsigned long long* __restrict__ obs) {
+                 uint64_t sweep, PhiloxKey pk, unsigned long long* __restrict__ obs) {
     constexpr int Z = 2 * NDIM;
-    __shared__ uint4 s_bits[(MODE == 2) ? 1 : NSLOT * 16];
-    __shared__ unsigned long long s_red[3 * 32];
-    if (MODE != 2) {
-        for (int i = threadIdx.x; i < NSLOT * 16; i += blockDim.x) s_bits[i] = thr_bits[i];
-        __syncthreads();
-    }
+    constexpr int K = MSC_ROWS;
+    __shared__ int s_acc[3];
+    __shared__ unsigned int s_cnt;
+    if (threadIdx.x == 0 && threadIdx.y == 0) { s_acc[0] = 0; s_acc[1] = 0; s_acc[2] = 0; s_cnt = 0; }
+    __syncthreads();
 
-    const uint32_t rows = g.Ly * g.Gx;
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = t < z_count * rows;
-    unsigned long long acc[3] = {0ull, 0ull, 0ull};
+    // block = (BX words of a row) x (BY threads, K rows each); grid = (word tiles, row tiles, planes)
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t y0 = (blockIdx.y * blockDim.y + threadIdx.y) * K;
+    const uint32_t zl = z_begin + blockIdx.z;
+    const uint32_t Wx = g.Wx, Ly = g.Ly;
+    const uint32_t plane = Ly * Wx;            // 32-bit word offsets: a colour array has < 2^32 words
+    const bool active = w < Wx && y0 < Ly;
+    int acc[3] = {0, 0, 0};
 
     if (active) {
-        const uint32_t zl = z_begin + t / rows;
-        const uint32_t rem = t % rows;
-        const uint32_t y = rem / g.Gx, gx = rem % g.Gx;
         const uint32_t zg = zl + g.z_offset;
-        const uint32_t rp = (y + zg + (uint32_t)colour) & 1u;
-        const size_t row = ((size_t)zl * g.Ly + y) * g.Gx;
+        const uint32_t rp0 = (y0 + zg + (uint32_t)colour) & 1u;
+        const uint32_t base = zl * plane + w;  // + y * Wx
+        const uint32_t wl = w == 0 ? Wx - 1 : w - 1, wr = w + 1 == Wx ? 0u : w + 1;
 
-        const uint4 s4 = own[row + gx];
-        const uint4 n4 = oth[row + gx];
-        const uint32_t gxc = rp ? (gx + 1 == g.Gx ? 0u : gx + 1) : (gx == 0 ? g.Gx - 1 : gx - 1);
-        const uint32_t cw = reinterpret_cast<const uint32_t*>(oth)[(row + gxc) * 4 + (rp ? 0 : 3)];
-        const uint32_t ym = y == 0 ? g.Ly - 1 : y - 1, yp = y + 1 == g.Ly ? 0 : y + 1;
-        const uint4 a4 = oth[((size_t)zl * g.Ly + ym) * g.Gx + gx];
-        const uint4 b4 = oth[((size_t)zl * g.Ly + yp) * g.Gx + gx];
-        uint4 c4 = make_uint4(0, 0, 0, 0), d4 = make_uint4(0, 0, 0, 0);
-        if (NDIM == 3) {
-            c4 = zl == 0 ? oth_lo[(size_t)y * g.Gx + gx] : oth[row - rows + gx];
-            d4 = zl + 1 == g.Lz ? oth_hi[(size_t)y * g.Gx + gx] : oth[row + rows + gx];
-        }
-        const uint32_t sw[4] = {s4.x, s4.y, s4.z, s4.w}, nw[4] = {n4.x, n4.y, n4.z, n4.w};
-        const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w}, bw[4] = {b4.x, b4.y, b4.z, b4.w};
-        const uint32_t cwz[4] = {c4.x, c4.y, c4.z, c4.w}, dwz[4] = {d4.x, d4.y, d4.z, d4.w};
-        uint32_t out[4];
-
-        // global index of this thread's first 32-bit word inside the colour array (RNG key)
-        const uint64_t wbase = ((((uint64_t)zg * g.Ly_g + y) * g.Gx + gx) << 2) | ((uint64_t)colour << 62);
-
+        // other-colour rows y0-1 .. y0+K at column w (periodic in y); rows[k+1] is the partner word of own row k
+        uint32_t rows[K + 2];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t s = sw[k], N0 = nw[k];
-            const uint32_t prev = k > 0 ? nw[k > 0 ? k - 1 : 0] : cw;
-            const uint32_t next = k < 3 ? nw[k < 3 ? k + 1 : 3] : cw;
-            const uint32_t Nsh = rp ? __funnelshift_r(N0, next, 1) : __funnelshift_l(prev, N0, 1);
+        for (int k = -1; k <= K; ++k) {
+            uint32_t y = y0 + k;
+            if (k < 0) y = y0 == 0 ? Ly - 1 : y0 - 1;
+            if (k > 0 && y >= Ly) y -= Ly;
+            rows[k + 1] = oth[base + y * Wx];
+        }
+        uint32_t sv[K], cwv[K], Cv[K], Dv[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const uint32_t y = y0 + k;
+            const bool in = y < Ly;
+            const uint32_t yy = in ? y : y0;
+            const uint32_t rp = (rp0 + k) & 1u;
+            sv[k] = own[base + yy * Wx];
+            cwv[k] = oth[zl * plane + yy * Wx + (rp ? wr : wl)];
+            Cv[k] = 0; Dv[k] = 0;
+            if (NDIM == 3) {
+                Cv[k] = zl == 0 ? oth_lo[yy * Wx + w] : oth[base - plane + yy * Wx];
+                Dv[k] = zl + 1 == g.Lz ? oth_hi[yy * Wx + w] : oth[base + plane + yy * Wx];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const uint32_t y = y0 + k;
+            if (y >= Ly) break;
+            const uint32_t rp = (rp0 + k) & 1u;
+            const uint32_t s = sv[k], N0 = rows[k + 1];
+            // x-neighbour 2 sits one compact index to the left (row parity 0) or right (1): shift with carry
+            const uint32_t Nsh = rp ? __funnelshift_r(N0, cwv[k], 1) : __funnelshift_l(cwv[k], N0, 1);
             // antiparallel indicators and their bit-sliced count n2 n1 n0
-            const uint32_t a1 = s ^ N0, a2 = s ^ Nsh, a3 = s ^ aw[k], a4b = s ^ bw[k];
+            const uint32_t a1 = s ^ N0, a2 = s ^ Nsh, a3 = s ^ rows[k], a4 = s ^ rows[k + 2];
             uint32_t n0, n1, n2;
             if (NDIM == 3) {
-                const uint32_t a5 = s ^ cwz[k], a6 = s ^ dwz[k];
+                const uint32_t a5 = s ^ Cv[k], a6 = s ^ Dv[k];
                 const uint32_t s1 = a1 ^ a2 ^ a3, c1 = maj3(a1, a2, a3);
-                const uint32_t s2 = a4b ^ a5 ^ a6, c2 = maj3(a4b, a5, a6);
+                const uint32_t s2 = a4 ^ a5 ^ a6, c2 = maj3(a4, a5, a6);
                 n0 = s1 ^ s2;
                 const uint32_t c3 = s1 & s2;
                 n1 = c1 ^ c2 ^ c3;
                 n2 = maj3(c1, c2, c3);
             } else {
                 const uint32_t s1 = a1 ^ a2 ^ a3, c1 = maj3(a1, a2, a3);
-                n0 = s1 ^ a4b;
-                const uint32_t c3 = s1 & a4b;
+                n0 = s1 ^ a4;
+                const uint32_t c3 = s1 & a4;
                 n1 = c1 ^ c3;
                 n2 = c1 & c3;
             }
+            // global index of this 32-bit word inside the colour array (RNG key)
+            const uint64_t widx = (((uint64_t)zg * Ly + y) * Wx + w) | ((uint64_t)colour << 62);
             uint32_t flip = 0;
             if (MODE != 2) {
-                uint32_t accept = 0, pm[NSLOT];
+                uint32_t pm[NSLOT], eq = 0, lt = 0;
 #pragma unroll
-                for (int q = 0; q < NSLOT; ++q) pm[q] = 0;
-                auto assign = [&](uint32_t m, uint32_t slot) {
-                    if (slot == MSC_ALWAYS) accept |= m;
-#pragma unroll
-                    for (int q = 0; q < NSLOT; ++q)
-                        if (slot == (uint32_t)q) pm[q] |= m;
-                };
-                auto per_class = [&](uint32_t m, int c) {
-                    if (FIELD) {
-                        assign(m & ~s, tab.slot_of[0][c]);
-                        assign(m & s, tab.slot_of[1][c]);
-                    } else {
-                        assign(m, tab.slot_of[0][c]);
-                    }
-                };
-                per_class(class_mask<0>(n0, n1, n2), 0);
-                per_class(class_mask<1>(n0, n1, n2), 1);
-                per_class(class_mask<2>(n0, n1, n2), 2);
-                per_class(class_mask<3>(n0, n1, n2), 3);
-                per_class(class_mask<4>(n0, n1, n2), 4);
-                if (NDIM == 3) {
-                    per_class(class_mask<5>(n0, n1, n2), 5);
-                    per_class(class_mask<6>(n0, n1, n2), 6);
+                for (int q = 0; q < NSLOT; ++q) {
+                    uint32_t m = (n0 ^ slots.a0[q]) & (n1 ^ slots.a1[q]) & (n2 ^ slots.a2[q]);
+                    if (FIELD) m &= s ^ slots.sx[q];
+                    pm[q] = m;
+                    eq |= m;
                 }
+                const uint32_t always = ~eq;
                 uint32_t cand = 0xFFFFFFFFu;
-                if (RANDPROP) {  // IsingSpin::rand (src/state.rs:76-84): proposed spin is a fair coin
+                if (RANDPROP) {  // IsingSpin::rand (src/state.rs:76-84): the proposed spin is a fair coin
                     uint32_t r[4];
-                    philox_at(wbase + k, sweep, 0xFFu, k0, k1, r);
+                    philox_at(widx, sweep, 0xFFu, pk, r);
                     cand = r[0] ^ s;  // proposal differs from the current spin
                 }
-                uint32_t eq = 0, lt = 0;
-#pragma unroll
-                for (int q = 0; q < NSLOT; ++q) eq |= pm[q];
                 eq &= cand;
-                for (uint32_t ch = 0; ch < 16u && eq != 0u; ++ch) {
+                // one chunk = 4 bit-planes of U from one Philox call.  The slot masks are disjoint, so the
+                // per-spin threshold bit-plane is sum_q pm[q] * bit_q: integer multiply-adds (FMA pipe)
+                // instead of and/or (ALU pipe), which balances the two issue pipes.
+                auto chunk = [&](uint32_t ch) {
                     uint32_t r[4];
-                    philox_at(wbase + k, sweep, ch, k0, k1, r);
+                    philox_at(widx, sweep, ch, pk, r);
                     uint32_t tb[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
                     for (int q = 0; q < NSLOT; ++q) {
-                        const uint4 b = s_bits[q * 16 + ch];
-                        tb[0] |= pm[q] & b.x; tb[1] |= pm[q] & b.y; tb[2] |= pm[q] & b.z; tb[3] |= pm[q] & b.w;
+                        const uint4 b = __ldg(thr_bits + q * 16 + ch);  // warp-uniform address: one L1 broadcast; values 0/1
+                        tb[0] += pm[q] * b.x; tb[1] += pm[q] * b.y; tb[2] += pm[q] * b.z; tb[3] += pm[q] * b.w;
                     }
 #pragma unroll
                     for (int p = 0; p < 4; ++p) {
-                        const uint32_t tt = eq & (tb[p] ^ r[p]);  // undecided spins whose U bit differs from thr bit
-                        lt |= tt & tb[p];                        // thr bit 1, U bit 0  ->  U < thr
+                        const uint32_t tt = eq & (tb[p] ^ r[p]);  // undecided spins whose U bit differs from the threshold bit
+                        lt |= tt & tb[p];                        // threshold bit 1, U bit 0  ->  U < thr
                         eq ^= tt;
                     }
-                }
-                flip = (accept | lt) & cand;
-                acc[2] += (unsigned long long)__popc(RANDPROP ? ((accept | lt) | ~cand) : flip);
+                };
+                chunk(0);  // 8 planes are needed by practically every warp: no loop control, two calls in flight
+                chunk(1);
+                for (uint32_t ch = 2; ch < 16u && eq != 0u; ++ch) chunk(ch);
+                const uint32_t ok = always | lt;
+                flip = ok & cand;
+                acc[2] += __popc(RANDPROP ? (ok | ~cand) : flip);
             }
             const uint32_t snew = s ^ flip;
-            out[k] = snew;
             if (MODE != 0) {
                 // sum of final antiparallel counts: c' = flip ? Z - c : c
                 const int s_all = __popc(n0) + 2 * __popc(n1) + 4 * __popc(n2);
                 const int s_f = __popc(n0 & flip) + 2 * __popc(n1 & flip) + 4 * __popc(n2 & flip);
                 const int cfin = s_all - 2 * s_f + Z * __popc(flip);
-                acc[0] += (unsigned long long)(long long)(Z * 32 - 2 * cfin);
-                acc[1] += (unsigned long long)(long long)(2 * __popc(snew) - 32 + 2 * __popc(N0) - 32);
+                acc[0] += Z * 32 - 2 * cfin;
+                acc[1] += 2 * __popc(snew) - 32 + 2 * __popc(N0) - 32;
             }
-        }
-        if (MODE != 2) {
-            const uint4 o4 = make_uint4(out[0], out[1], out[2], out[3]);
-            own[row + gx] = o4;
-            if (NDIM == 3) {
-                if (peer_lo != nullptr && zl == 0) peer_lo[(size_t)y * g.Gx + gx] = o4;
-                if (peer_hi != nullptr && zl + 1 == g.Lz) peer_hi[(size_t)y * g.Gx + gx] = o4;
+            if (MODE != 2) {
+                own[base + y * Wx] = snew;
+                if (NDIM == 3) {
+                    if (peer_lo != nullptr && zl == 0) peer_lo[y * Wx + w] = snew;
+                    if (peer_hi != nullptr && zl + 1 == g.Lz) peer_hi[y * Wx + w] = snew;
+                }
             }
         }
     }
-    block_atomic_add<unsigned long long, 3>(acc, s_red, obs);
+    if (MODE == 0) {
+        const int a1[1] = {acc[2]};
+        block_flush_int<1>(a1, s_acc, &s_cnt, obs + 2);
+    } else {
+        block_flush_int<3>(acc, s_acc, &s_cnt, obs);
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -261,15 +261,14 @@ ising_msc_unpack_kernel(int8_t* __restrict__ dst, const uint32_t* __restrict__ c
 
 // State::rand_with_size on device (src/state.rs:260-262): one fair bit per spin.
 __global__ void __launch_bounds__(256)
-ising_msc_randomize_kernel(uint4* __restrict__ c0, uint4* __restrict__ c1, size_t groups_local, uint64_t group_offset,
-                           uint32_t k0, uint32_t k1) {
+ising_msc_randomize_kernel(uint32_t* __restrict__ c0, uint32_t* __restrict__ c1, size_t words_local, uint64_t word_offset,
+                           PhiloxKey pk) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= groups_local) return;
+    if (t >= words_local) return;
     uint32_t r[4];
-    philox_at((t + group_offset) | (1ull << 61), ~0ull, 0xFEu, k0, k1, r);
-    c0[t] = make_uint4(r[0], r[1], r[2], r[3]);
-    philox_at((t + group_offset) | (1ull << 61) | (1ull << 62), ~0ull, 0xFEu, k0, k1, r);
-    c1[t] = make_uint4(r[0], r[1], r[2], r[3]);
+    philox_at((t + word_offset) | (1ull << 61), ~0ull, 0xFEu, pk, r);
+    c0[t] = r[0];
+    c1[t] = r[1];
 }
 
 }  // namespace vg

@@ -48,9 +48,9 @@ struct vegas_gpu {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // --- Ising MSC
-    uint4* msc[2] = {nullptr, nullptr};   // colour arrays
-    uint4* msc_bits = nullptr;            // [MSC_MAX_SLOT][16] threshold bit-plane masks
-    MscTable msc_tab{};
+    uint32_t* msc[2] = {nullptr, nullptr};  // colour arrays (bit-packed)
+    uint4* msc_bits = nullptr;            // [MSC_MAX_SLOT][16] x 4 threshold bits (0/1), MSB first
+    MscSlots<MSC_MAX_SLOT> msc_slots{};
     int msc_nslot = 0;
     bool msc_field = false;
     std::vector<uint64_t> ising_thr;      // [2][8]
@@ -135,7 +135,9 @@ int update_tables(vegas_gpu* h) {
         h->ising_thr.assign(16, 0); h->ising_always.assign(16, 0);
         std::vector<uint64_t> slots;
         h->msc_field = h->md.has_zeeman && std::fabs(h->fmag) != 0.0;
-        for (int sidx = 0; sidx < 2; ++sidx)
+        MscSlots<MSC_MAX_SLOT>& ms = h->msc_slots;
+        for (int q = 0; q < MSC_MAX_SLOT; ++q) { ms.a0[q] = ms.a1[q] = ms.a2[q] = 0u; ms.sx[q] = 0u; }  // count 7: never matches
+        for (int sidx = (h->msc_field ? 0 : 1); sidx < 2; ++sidx)
             for (int c = 0; c <= Z; ++c) {
                 const int s = sidx ? 1 : -1;
                 const int m = s * (Z - 2 * c);  // s*m = Z - 2c
@@ -143,22 +145,19 @@ int update_tables(vegas_gpu* h) {
                 threshold(ising_delta(h, s, m), h->T, thr, code);
                 h->ising_thr[sidx * 8 + c] = thr;
                 h->ising_always[sidx * 8 + c] = code == 2;
-                uint8_t slot;
-                if (code == 2) slot = MSC_ALWAYS;
-                else if (code == 0) slot = MSC_NEVER;
-                else {
-                    size_t q = 0;
-                    while (q < slots.size() && slots[q] != thr) ++q;
-                    if (q == slots.size()) slots.push_back(thr);
-                    slot = (uint8_t)q;
-                }
-                h->msc_tab.slot_of[sidx][c] = slot;
+                if (code == 2) continue;  // dE <= 0: no slot, always accepted
+                const size_t q = slots.size();
+                if ((int)q >= MSC_MAX_SLOT) return fail(h, VEGAS_ERR_INVALID, "internal: too many threshold slots");
+                slots.push_back(thr);  // code 0 (p < 2^-64) is a slot whose threshold is 0: never accepted
+                ms.a0[q] = (c & 1) ? 0u : ~0u; ms.a1[q] = (c & 2) ? 0u : ~0u; ms.a2[q] = (c & 4) ? 0u : ~0u;
+                ms.sx[q] = sidx ? 0u : ~0u;
             }
+        if (!h->msc_field) for (int c = 0; c < 8; ++c) { h->ising_thr[c] = h->ising_thr[8 + c]; h->ising_always[c] = h->ising_always[8 + c]; }
         h->msc_nslot = h->msc_field ? 14 : 3;
         if ((int)slots.size() > h->msc_nslot) return fail(h, VEGAS_ERR_INVALID, "internal: too many threshold slots");
         std::vector<uint32_t> bits((size_t)MSC_MAX_SLOT * 64, 0u);
         for (size_t q = 0; q < slots.size(); ++q)
-            for (int j = 0; j < 64; ++j) bits[q * 64 + j] = (slots[q] >> (63 - j) & 1ull) ? 0xFFFFFFFFu : 0u;
+            for (int j = 0; j < 64; ++j) bits[q * 64 + j] = (uint32_t)(slots[q] >> (63 - j) & 1ull);
         CU(cudaMemcpyAsync(h->msc_bits, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, h->stream));
         CU(cudaStreamSynchronize(h->stream));  // `bits` is pageable host memory
     } else if (h->family == FAM_ISING_GEN) {
@@ -236,11 +235,11 @@ CsrNb csr_nb(const vegas_gpu* h) {
 // ---------------------------------------------------------------------------------------
 MscGeom msc_geom(const vegas_gpu* h) {
     MscGeom g{};
-    g.Gx = (uint32_t)(h->ld.nx / 256); g.Ly = (uint32_t)h->ld.ny; g.Lz = (uint32_t)h->ld.nz;
-    g.z_offset = (uint32_t)h->z_offset; g.Ly_g = (uint32_t)h->ld.ny;
+    g.Wx = (uint32_t)(h->ld.nx / 64); g.Ly = (uint32_t)h->ld.ny; g.Lz = (uint32_t)h->ld.nz;
+    g.z_offset = (uint32_t)h->z_offset;
     return g;
 }
-size_t msc_groups(const vegas_gpu* h) { return (size_t)(h->ld.nx / 256) * h->ld.ny * h->ld.nz; }
+size_t msc_words(const vegas_gpu* h) { return (size_t)(h->ld.nx / 64) * h->ld.ny * h->ld.nz; }
 
 HeisGeom heis_geom(const vegas_gpu* h) {
     HeisGeom g{};
@@ -260,40 +259,52 @@ size_t halo_offset(const vegas_gpu* h, int colour, int hi, int comp) {
 // ---------------------------------------------------------------------------------------
 // kernel dispatch
 // ---------------------------------------------------------------------------------------
+template <int NSLOT>
+MscSlots<NSLOT> slots_prefix(const MscSlots<MSC_MAX_SLOT>& a) {
+    MscSlots<NSLOT> r;
+    for (int q = 0; q < NSLOT; ++q) { r.a0[q] = a.a0[q]; r.a1[q] = a.a1[q]; r.a2[q] = a.a2[q]; r.sx[q] = a.sx[q]; }
+    return r;
+}
+
 template <int NDIM, bool FIELD, int NSLOT, bool RP>
-void launch_msc_mode(vegas_gpu* h, int mode, dim3 grid, uint4* own, const uint4* oth, const uint4* lo, const uint4* hi,
-                     uint4* plo, uint4* phi, int colour, uint32_t zb, uint32_t zc, unsigned long long* obs) {
+void launch_msc_mode(vegas_gpu* h, int mode, dim3 grid, dim3 block, uint32_t* own, const uint32_t* oth, const uint32_t* lo,
+                     const uint32_t* hi, uint32_t* plo, uint32_t* phi, int colour, uint32_t zb, uint32_t zc,
+                     unsigned long long* obs) {
     const MscGeom g = msc_geom(h);
-    const uint32_t k0 = (uint32_t)h->md.seed, k1 = (uint32_t)(h->md.seed >> 32);
+    const PhiloxKey pk = make_philox_key(h->md.seed);
+    const MscSlots<NSLOT> sl = slots_prefix<NSLOT>(h->msc_slots);
     if (mode == 0)
-        ising_msc_kernel<NDIM, FIELD, NSLOT, RP, 0><<<grid, 256, 0, h->stream>>>(own, oth, lo, hi, plo, phi, g, colour, zb, zc,
-                                                                                h->msc_tab, h->msc_bits, h->sweeps, k0, k1, obs);
+        ising_msc_kernel<NDIM, FIELD, NSLOT, RP, 0><<<grid, block, 0, h->stream>>>(own, oth, lo, hi, plo, phi, g, colour, zb,
+                                                                                sl, h->msc_bits, h->sweeps, pk, obs);
     else
-        ising_msc_kernel<NDIM, FIELD, NSLOT, RP, 1><<<grid, 256, 0, h->stream>>>(own, oth, lo, hi, plo, phi, g, colour, zb, zc,
-                                                                                h->msc_tab, h->msc_bits, h->sweeps, k0, k1, obs);
+        ising_msc_kernel<NDIM, FIELD, NSLOT, RP, 1><<<grid, block, 0, h->stream>>>(own, oth, lo, hi, plo, phi, g, colour, zb,
+                                                                                sl, h->msc_bits, h->sweeps, pk, obs);
 }
 
 template <int NDIM>
-void launch_msc(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, const uint4* lo, const uint4* hi, uint4* plo,
-                uint4* phi, unsigned long long* obs) {
+void launch_msc(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, const uint32_t* lo, const uint32_t* hi,
+                uint32_t* plo, uint32_t* phi, unsigned long long* obs) {
     const MscGeom g = msc_geom(h);
-    const dim3 grid(cdiv((uint64_t)zc * g.Ly * g.Gx, 256));
-    uint4* own = h->msc[colour];
-    const uint4* oth = h->msc[1 - colour];
-    const uint32_t k0 = (uint32_t)h->md.seed, k1 = (uint32_t)(h->md.seed >> 32);
+    uint32_t bx = 32;
+    while (bx > g.Wx) bx >>= 1;  // block = (bx words) x (256/bx rows); one warp spans 32/bx rows
+    const dim3 block(bx, 256 / bx);
+    const dim3 grid(cdiv(g.Wx, block.x), cdiv(g.Ly, block.y * MSC_ROWS), zc);
+    uint32_t* own = h->msc[colour];
+    const uint32_t* oth = h->msc[1 - colour];
+    const PhiloxKey pk = make_philox_key(h->md.seed);
     const bool rp = h->md.proposal == VEGAS_PROPOSE_RANDOM;
     h->launches++;
     if (mode == 2) {
-        ising_msc_kernel<NDIM, false, 3, false, 2><<<grid, 256, 0, h->stream>>>(own, oth, lo, hi, plo, phi, g, colour, zb, zc,
-                                                                              h->msc_tab, h->msc_bits, h->sweeps, k0, k1, obs);
+        ising_msc_kernel<NDIM, false, 3, false, 2><<<grid, block, 0, h->stream>>>(own, oth, lo, hi, plo, phi, g, colour, zb,
+                                                                              slots_prefix<3>(h->msc_slots), h->msc_bits, h->sweeps, pk, obs);
         return;
     }
     if (h->msc_field) {
-        if (rp) launch_msc_mode<NDIM, true, 14, true>(h, mode, grid, own, oth, lo, hi, plo, phi, colour, zb, zc, obs);
-        else launch_msc_mode<NDIM, true, 14, false>(h, mode, grid, own, oth, lo, hi, plo, phi, colour, zb, zc, obs);
+        if (rp) launch_msc_mode<NDIM, true, 14, true>(h, mode, grid, block, own, oth, lo, hi, plo, phi, colour, zb, zc, obs);
+        else launch_msc_mode<NDIM, true, 14, false>(h, mode, grid, block, own, oth, lo, hi, plo, phi, colour, zb, zc, obs);
     } else {
-        if (rp) launch_msc_mode<NDIM, false, 3, true>(h, mode, grid, own, oth, lo, hi, plo, phi, colour, zb, zc, obs);
-        else launch_msc_mode<NDIM, false, 3, false>(h, mode, grid, own, oth, lo, hi, plo, phi, colour, zb, zc, obs);
+        if (rp) launch_msc_mode<NDIM, false, 3, true>(h, mode, grid, block, own, oth, lo, hi, plo, phi, colour, zb, zc, obs);
+        else launch_msc_mode<NDIM, false, 3, false>(h, mode, grid, block, own, oth, lo, hi, plo, phi, colour, zb, zc, obs);
     }
 }
 
@@ -302,10 +313,10 @@ void launch_heis(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, c
     const HeisGeom g = heis_geom(h);
     const dim3 grid(cdiv((uint64_t)zc * g.Ly * g.Gx, 128));
     const HeisParams<real> p = heis_params<real>(h);
-    const uint32_t k0 = (uint32_t)h->md.seed, k1 = (uint32_t)(h->md.seed >> 32);
+    const PhiloxKey pk = make_philox_key(h->md.seed);
     const bool flip = h->md.proposal == VEGAS_PROPOSE_FLIP;
     h->launches++;
-#define HL(FLIP, MODE) heis_stencil_kernel<real, NDIM, FLIP, MODE><<<grid, 128, 0, h->stream>>>(P, g, colour, zb, zc, p, h->sweeps, k0, k1, obs)
+#define HL(FLIP, MODE) heis_stencil_kernel<real, NDIM, FLIP, MODE><<<grid, 128, 0, h->stream>>>(P, g, colour, zb, zc, p, h->sweeps, pk, obs)
     if (mode == 2) HL(false, 2);
     else if (mode == 1) { if (flip) HL(true, 1); else HL(false, 1); }
     else { if (flip) HL(true, 0); else HL(false, 0); }
@@ -337,15 +348,15 @@ void heis_pass(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, dou
 }
 
 void msc_pass(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, unsigned long long* obs) {
-    const size_t plane = (size_t)(h->ld.nx / 256) * h->ld.ny;
-    const uint4 *lo, *hi;
-    uint4 *plo = nullptr, *phi = nullptr;
+    const size_t plane = (size_t)(h->ld.nx / 64) * h->ld.ny;
+    const uint32_t *lo, *hi;
+    uint32_t *plo = nullptr, *phi = nullptr;
     if (h->slab && h->connected) {
-        lo = (const uint4*)((char*)h->halo + halo_offset(h, 1 - colour, 0, 0));
-        hi = (const uint4*)((char*)h->halo + halo_offset(h, 1 - colour, 1, 0));
+        lo = (const uint32_t*)((char*)h->halo + halo_offset(h, 1 - colour, 0, 0));
+        hi = (const uint32_t*)((char*)h->halo + halo_offset(h, 1 - colour, 1, 0));
         if (mode != 2) {
-            plo = (uint4*)((char*)h->peer_halo[0] + halo_offset(h, colour, 1, 0));
-            phi = (uint4*)((char*)h->peer_halo[1] + halo_offset(h, colour, 0, 0));
+            plo = (uint32_t*)((char*)h->peer_halo[0] + halo_offset(h, colour, 1, 0));
+            phi = (uint32_t*)((char*)h->peer_halo[1] + halo_offset(h, colour, 0, 0));
         }
     } else {
         lo = h->msc[1 - colour] + (size_t)(h->ld.nz - 1) * plane;
@@ -400,7 +411,7 @@ template <typename NB>
 void general_colour_pass(vegas_gpu* h, const NB& nb, int colour, unsigned long long* obs_row) {
     const uint32_t count = h->g_counts[colour];
     if (count == 0) return;
-    const uint32_t k0 = (uint32_t)h->md.seed, k1 = (uint32_t)(h->md.seed >> 32);
+    const PhiloxKey pk = make_philox_key(h->md.seed);
     h->launches++;
     if (h->family == FAM_ISING_GEN) {
         IsingGeneralParams p{};
@@ -409,20 +420,20 @@ void general_colour_pass(vegas_gpu* h, const NB& nb, int colour, unsigned long l
         p.h_o = ising_h_o(h); p.invT = 1.0 / h->T;
         const dim3 grid(cdiv(count, 256));
         if (h->md.proposal == VEGAS_PROPOSE_RANDOM)
-            ising_general_sweep_kernel<NB, true><<<grid, 256, 0, h->stream>>>(h->g_s8, nb, h->g_sites[colour], count, p, 0, h->sweeps, k0, k1, obs_row + 4);
+            ising_general_sweep_kernel<NB, true><<<grid, 256, 0, h->stream>>>(h->g_s8, nb, h->g_sites[colour], count, p, 0, h->sweeps, pk, obs_row + 4);
         else
-            ising_general_sweep_kernel<NB, false><<<grid, 256, 0, h->stream>>>(h->g_s8, nb, h->g_sites[colour], count, p, 0, h->sweeps, k0, k1, obs_row + 4);
+            ising_general_sweep_kernel<NB, false><<<grid, 256, 0, h->stream>>>(h->g_s8, nb, h->g_sites[colour], count, p, 0, h->sweeps, pk, obs_row + 4);
     } else {
         const dim3 grid(cdiv(count, 128));
         const bool flip = h->md.proposal == VEGAS_PROPOSE_FLIP;
         if (h->md.precision == VEGAS_F64) {
             const HeisParams<double> p = heis_params<double>(h);
-            if (flip) heis_general_sweep_kernel<NB, double, true><<<grid, 128, 0, h->stream>>>((double*)h->g_s[0], (double*)h->g_s[1], (double*)h->g_s[2], nb, h->g_sites[colour], count, p, 0, h->sweeps, k0, k1, (double*)obs_row);
-            else heis_general_sweep_kernel<NB, double, false><<<grid, 128, 0, h->stream>>>((double*)h->g_s[0], (double*)h->g_s[1], (double*)h->g_s[2], nb, h->g_sites[colour], count, p, 0, h->sweeps, k0, k1, (double*)obs_row);
+            if (flip) heis_general_sweep_kernel<NB, double, true><<<grid, 128, 0, h->stream>>>((double*)h->g_s[0], (double*)h->g_s[1], (double*)h->g_s[2], nb, h->g_sites[colour], count, p, 0, h->sweeps, pk, (double*)obs_row);
+            else heis_general_sweep_kernel<NB, double, false><<<grid, 128, 0, h->stream>>>((double*)h->g_s[0], (double*)h->g_s[1], (double*)h->g_s[2], nb, h->g_sites[colour], count, p, 0, h->sweeps, pk, (double*)obs_row);
         } else {
             const HeisParams<float> p = heis_params<float>(h);
-            if (flip) heis_general_sweep_kernel<NB, float, true><<<grid, 128, 0, h->stream>>>((float*)h->g_s[0], (float*)h->g_s[1], (float*)h->g_s[2], nb, h->g_sites[colour], count, p, 0, h->sweeps, k0, k1, (double*)obs_row);
-            else heis_general_sweep_kernel<NB, float, false><<<grid, 128, 0, h->stream>>>((float*)h->g_s[0], (float*)h->g_s[1], (float*)h->g_s[2], nb, h->g_sites[colour], count, p, 0, h->sweeps, k0, k1, (double*)obs_row);
+            if (flip) heis_general_sweep_kernel<NB, float, true><<<grid, 128, 0, h->stream>>>((float*)h->g_s[0], (float*)h->g_s[1], (float*)h->g_s[2], nb, h->g_sites[colour], count, p, 0, h->sweeps, pk, (double*)obs_row);
+            else heis_general_sweep_kernel<NB, float, false><<<grid, 128, 0, h->stream>>>((float*)h->g_s[0], (float*)h->g_s[1], (float*)h->g_s[2], nb, h->g_sites[colour], count, p, 0, h->sweeps, pk, (double*)obs_row);
         }
     }
 }
@@ -616,9 +627,9 @@ int vegas_gpu_create_lattice(const vegas_model_desc* md, const vegas_lattice_des
     bool stencil = ldesc->unitcell == VEGAS_SC && !hh->ld.literal && !md->force_general;
     for (int a = 0; a < 2 && stencil; ++a) stencil = hh->ld.pbc[a] && L[a] >= 2 && (L[a] % 2 == 0);
     if (stencil) stencil = (L[2] == 1) || (hh->ld.pbc[2] && L[2] % 2 == 0);
-    if (stencil && md->model == VEGAS_ISING) stencil = L[0] % 256 == 0;
+    if (stencil && md->model == VEGAS_ISING) stencil = L[0] % 64 == 0;
     if (stencil && md->model == VEGAS_HEISENBERG) stencil = L[0] % 8 == 0;
-    if (stencil && hh->ld.nx * hh->ld.ny * hh->ld.nz >= (1ull << 32) * 64) stencil = false;
+    if (stencil && hh->ld.nx * hh->ld.ny * hh->ld.nz >= (1ull << 32) * 64) stencil = false;  // 32-bit word offsets per colour
     if (hh->slab) {
         if (!stencil || L[2] == 1) return bail(fail(h, VEGAS_ERR_INVALID, "z-slab decomposition needs the sc stencil path (periodic, even extents)"));
         if (hh->z_offset + hh->ld.nz > hh->nz_global) return bail(fail(h, VEGAS_ERR_INVALID, "slab outside the global lattice"));
@@ -629,10 +640,10 @@ int vegas_gpu_create_lattice(const vegas_model_desc* md, const vegas_lattice_des
         h->n_self = (L[2] == 1 && hh->ld.pbc[2]) ? 1 : 0;
         h->n_colours = 2;
         if (h->family == FAM_ISING_MSC) {
-            const size_t bytes = msc_groups(h) * sizeof(uint4);
+            const size_t bytes = msc_words(h) * sizeof(uint32_t);
             for (int c = 0; c < 2; ++c) { if (cudaMalloc(&h->msc[c], bytes) != cudaSuccess) return bail(fail(h, VEGAS_ERR_ALLOC, "cudaMalloc (spins) failed")); }
             if (cudaMalloc(&h->msc_bits, (size_t)MSC_MAX_SLOT * 64 * 4) != cudaSuccess) return bail(fail(h, VEGAS_ERR_ALLOC, "cudaMalloc failed"));
-            h->halo_plane_bytes = (size_t)(h->ld.nx / 256) * h->ld.ny * sizeof(uint4);
+            h->halo_plane_bytes = (size_t)(h->ld.nx / 64) * h->ld.ny * sizeof(uint32_t);
         } else {
             const size_t bytes = heis_colour_elems(h) * real_bytes(h);
             for (int c = 0; c < 2; ++c)
@@ -826,7 +837,7 @@ int vegas_gpu_upload_ising(vegas_gpu_t h, const int8_t* s, uint64_t n) {
         CU(cudaMemcpyAsync(tmp, s, n, cudaMemcpyHostToDevice, h->stream));
         const uint32_t Wx = (uint32_t)(h->ld.nx / 64);
         const size_t total = (size_t)Wx * h->ld.ny * h->ld.nz;
-        ising_msc_pack_kernel<<<cdiv(total, 256), 256, 0, h->stream>>>(tmp, (uint32_t*)h->msc[0], (uint32_t*)h->msc[1], Wx,
+        ising_msc_pack_kernel<<<cdiv(total, 256), 256, 0, h->stream>>>(tmp, h->msc[0], h->msc[1], Wx,
                                                                       (uint32_t)h->ld.ny, (uint32_t)h->ld.nz, (uint32_t)h->z_offset);
         h->launches++;
         CU(cudaFreeAsync(tmp, h->stream));
@@ -847,7 +858,7 @@ int vegas_gpu_download_ising(vegas_gpu_t h, int8_t* s, uint64_t n) {
         CU(cudaMallocAsync(&tmp, n, h->stream));
         const uint32_t Wx = (uint32_t)(h->ld.nx / 64);
         const size_t total = (size_t)Wx * h->ld.ny * h->ld.nz;
-        ising_msc_unpack_kernel<<<cdiv(total, 256), 256, 0, h->stream>>>(tmp, (const uint32_t*)h->msc[0], (const uint32_t*)h->msc[1], Wx,
+        ising_msc_unpack_kernel<<<cdiv(total, 256), 256, 0, h->stream>>>(tmp, h->msc[0], h->msc[1], Wx,
                                                                         (uint32_t)h->ld.ny, (uint32_t)h->ld.nz, (uint32_t)h->z_offset);
         h->launches++;
         CU(cudaMemcpyAsync(s, tmp, n, cudaMemcpyDeviceToHost, h->stream));
@@ -894,7 +905,7 @@ int heis_download_t(vegas_gpu* h, double* dev_aos) {
 int run_fill(vegas_gpu* h, int up) {
     CU(cudaSetDevice(h->device));
     if (h->family == FAM_ISING_MSC) {
-        for (int c = 0; c < 2; ++c) CU(cudaMemsetAsync(h->msc[c], up ? 0xFF : 0x00, msc_groups(h) * sizeof(uint4), h->stream));
+        for (int c = 0; c < 2; ++c) CU(cudaMemsetAsync(h->msc[c], up ? 0xFF : 0x00, msc_words(h) * sizeof(uint32_t), h->stream));
     } else if (h->family == FAM_ISING_GEN) {
         CU(cudaMemsetAsync(h->g_s8, up ? 0x01 : 0xFF, h->n, h->stream));
     } else {
@@ -920,22 +931,22 @@ int run_fill(vegas_gpu* h, int up) {
 
 // Fill the halos of a connected slab from the neighbours' current boundary planes is done by the
 // neighbours themselves: each rank pushes its own boundary planes (both colours) to its peers.
-__global__ void copy_plane_kernel(uint4* dst, const uint4* src, size_t n16) {
+__global__ void copy_plane_kernel(uint32_t* dst, const uint32_t* src, size_t n4) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n16) dst[i] = src[i];
+    if (i < n4) dst[i] = src[i];
 }
 
 int push_boundaries(vegas_gpu* h) {
     if (!(h->slab && h->connected)) return VEGAS_OK;
     const int ncomp = h->family == FAM_ISING_MSC ? 1 : 3;
-    const size_t n16 = h->halo_plane_bytes / 16;
+    const size_t n4 = h->halo_plane_bytes / 4;
     for (int colour = 0; colour < 2; ++colour)
         for (int c = 0; c < ncomp; ++c) {
             const char* base = h->family == FAM_ISING_MSC ? (const char*)h->msc[colour] : (const char*)h->hs[colour][c];
             const char* first = base;
             const char* last = base + (size_t)(h->ld.nz - 1) * h->halo_plane_bytes;
-            copy_plane_kernel<<<cdiv(n16, 256), 256, 0, h->stream>>>((uint4*)((char*)h->peer_halo[0] + halo_offset(h, colour, 1, c)), (const uint4*)first, n16);
-            copy_plane_kernel<<<cdiv(n16, 256), 256, 0, h->stream>>>((uint4*)((char*)h->peer_halo[1] + halo_offset(h, colour, 0, c)), (const uint4*)last, n16);
+            copy_plane_kernel<<<cdiv(n4, 256), 256, 0, h->stream>>>((uint32_t*)((char*)h->peer_halo[0] + halo_offset(h, colour, 1, c)), (const uint32_t*)first, n4);
+            copy_plane_kernel<<<cdiv(n4, 256), 256, 0, h->stream>>>((uint32_t*)((char*)h->peer_halo[1] + halo_offset(h, colour, 0, c)), (const uint32_t*)last, n4);
             h->launches += 2;
         }
     CU(cudaStreamSynchronize(h->stream));
@@ -978,23 +989,23 @@ int vegas_gpu_download_heisenberg(vegas_gpu_t h, double* sxyz, uint64_t n) {
 int vegas_gpu_randomize(vegas_gpu_t h) {
     if (!h) return VEGAS_ERR_INVALID;
     CU(cudaSetDevice(h->device));
-    const uint32_t k0 = (uint32_t)h->md.seed, k1 = (uint32_t)(h->md.seed >> 32);
+    const PhiloxKey pk = make_philox_key(h->md.seed);
     h->launches++;
     if (h->family == FAM_ISING_MSC) {
-        const size_t groups = msc_groups(h);
-        const uint64_t goff = (uint64_t)h->z_offset * h->ld.ny * (h->ld.nx / 256);
-        ising_msc_randomize_kernel<<<cdiv(groups, 256), 256, 0, h->stream>>>(h->msc[0], h->msc[1], groups, goff, k0, k1);
+        const size_t words = msc_words(h);
+        const uint64_t woff = (uint64_t)h->z_offset * h->ld.ny * (h->ld.nx / 64);
+        ising_msc_randomize_kernel<<<cdiv(words, 256), 256, 0, h->stream>>>(h->msc[0], h->msc[1], words, woff, pk);
     } else if (h->family == FAM_ISING_GEN) {
-        ising_general_randomize_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(h->g_s8, (uint32_t)h->n, 0, k0, k1);
+        ising_general_randomize_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(h->g_s8, (uint32_t)h->n, 0, pk);
     } else if (h->family == FAM_HEIS_GEN) {
-        if (h->md.precision == VEGAS_F64) heis_general_randomize_kernel<double><<<cdiv(h->n, 256), 256, 0, h->stream>>>((double*)h->g_s[0], (double*)h->g_s[1], (double*)h->g_s[2], (uint32_t)h->n, 0, k0, k1);
-        else heis_general_randomize_kernel<float><<<cdiv(h->n, 256), 256, 0, h->stream>>>((float*)h->g_s[0], (float*)h->g_s[1], (float*)h->g_s[2], (uint32_t)h->n, 0, k0, k1);
+        if (h->md.precision == VEGAS_F64) heis_general_randomize_kernel<double><<<cdiv(h->n, 256), 256, 0, h->stream>>>((double*)h->g_s[0], (double*)h->g_s[1], (double*)h->g_s[2], (uint32_t)h->n, 0, pk);
+        else heis_general_randomize_kernel<float><<<cdiv(h->n, 256), 256, 0, h->stream>>>((float*)h->g_s[0], (float*)h->g_s[1], (float*)h->g_s[2], (uint32_t)h->n, 0, pk);
     } else {
         const uint32_t Lx = (uint32_t)h->ld.nx, Ly = (uint32_t)h->ld.ny, Lz = (uint32_t)h->ld.nz, zo = (uint32_t)h->z_offset;
         if (h->md.precision == VEGAS_F64)
-            heis_stencil_randomize_kernel<double><<<cdiv(h->n, 256), 256, 0, h->stream>>>((double*)h->hs[0][0], (double*)h->hs[0][1], (double*)h->hs[0][2], (double*)h->hs[1][0], (double*)h->hs[1][1], (double*)h->hs[1][2], Lx, Ly, Lz, zo, k0, k1);
+            heis_stencil_randomize_kernel<double><<<cdiv(h->n, 256), 256, 0, h->stream>>>((double*)h->hs[0][0], (double*)h->hs[0][1], (double*)h->hs[0][2], (double*)h->hs[1][0], (double*)h->hs[1][1], (double*)h->hs[1][2], Lx, Ly, Lz, zo, pk);
         else
-            heis_stencil_randomize_kernel<float><<<cdiv(h->n, 256), 256, 0, h->stream>>>((float*)h->hs[0][0], (float*)h->hs[0][1], (float*)h->hs[0][2], (float*)h->hs[1][0], (float*)h->hs[1][1], (float*)h->hs[1][2], Lx, Ly, Lz, zo, k0, k1);
+            heis_stencil_randomize_kernel<float><<<cdiv(h->n, 256), 256, 0, h->stream>>>((float*)h->hs[0][0], (float*)h->hs[0][1], (float*)h->hs[0][2], (float*)h->hs[1][0], (float*)h->hs[1][1], (float*)h->hs[1][2], Lx, Ly, Lz, zo, pk);
     }
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
@@ -1158,7 +1169,7 @@ int site_energy_run(vegas_gpu* h, const NB& nb, const void* proposal, int want_d
             CU(cudaMallocAsync(&tmp[0], n, h->stream));
             const uint32_t Wx = (uint32_t)(h->ld.nx / 64);
             const size_t total = (size_t)Wx * h->ld.ny * h->ld.nz;
-            ising_msc_unpack_kernel<<<cdiv(total, 256), 256, 0, h->stream>>>((int8_t*)tmp[0], (const uint32_t*)h->msc[0], (const uint32_t*)h->msc[1], Wx, (uint32_t)h->ld.ny, (uint32_t)h->ld.nz, (uint32_t)h->z_offset);
+            ising_msc_unpack_kernel<<<cdiv(total, 256), 256, 0, h->stream>>>((int8_t*)tmp[0], h->msc[0], h->msc[1], Wx, (uint32_t)h->ld.ny, (uint32_t)h->ld.nz, (uint32_t)h->z_offset);
             s8 = (const int8_t*)tmp[0];
         }
         IsingSpins sp{s8};
