@@ -127,105 +127,115 @@ struct HeisPtrs {
     real* peer_hi[3];
 };
 
+// One thread owns one 16-byte vector (4 floats / 2 doubles) of a row and marches over `z_chunk` planes,
+// so index arithmetic and the block reduction are paid once per thread, not once per site.
 // MODE 0: update; 1: update + fused reductions; 2: reductions only.
 // obs[0] += -sum_own s.n (exchange energy, each bond once)   obs[1..3] += sum s (both colours)
 // obs[4] += sum (s.a)^2 (both colours)                         obs[5] += accepted (as double)
+#ifndef HEIS_MINB
+#define HEIS_MINB 6   // resident CTAs of 128 threads per SM the stencil kernel is compiled for (register cap)
+#endif
 template <typename real, int NDIM, bool FLIP, int MODE>
-__global__ void __launch_bounds__(128)
-heis_stencil_kernel(HeisPtrs<real> P, HeisGeom g, int colour, uint32_t z_begin, uint32_t z_count, HeisParams<real> p,
-                    uint64_t sweep, PhiloxKey pk, double* __restrict__ obs) {
+__global__ void __launch_bounds__(128, HEIS_MINB)
+heis_stencil_kernel(HeisPtrs<real> P, HeisGeom g, int colour, uint32_t z_begin, uint32_t z_count, uint32_t z_chunk,
+                    HeisParams<real> p, uint64_t sweep, PhiloxKey pk, double* __restrict__ obs) {
     constexpr int N = VecOf<real>::N;
     __shared__ double s_red[6 * 32];
-    const uint32_t rows = g.Ly * g.Gx;
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = t < z_count * rows;
+    const uint32_t t2 = blockIdx.x * blockDim.x + threadIdx.x;  // (y, gx) inside a plane
+    const bool active = t2 < g.Ly * g.Gx;
     double acc[6] = {0, 0, 0, 0, 0, 0};
     if (active) {
-        const uint32_t zl = z_begin + t / rows;
-        const uint32_t rem = t % rows;
-        const uint32_t y = rem / g.Gx, gx = rem % g.Gx;
-        const uint32_t zg = zl + g.z_offset;
-        const uint32_t rp = (y + zg + (uint32_t)colour) & 1u;
-        const size_t row = ((size_t)zl * g.Ly + y) * g.Hx;
-        const size_t e0 = row + (size_t)gx * N;
+        const uint32_t y = t2 / g.Gx, gx = t2 % g.Gx;
         const uint32_t ym = y == 0 ? g.Ly - 1 : y - 1, yp = y + 1 == g.Ly ? 0 : y + 1;
-        const size_t ea = ((size_t)zl * g.Ly + ym) * g.Hx + (size_t)gx * N;
-        const size_t eb = ((size_t)zl * g.Ly + yp) * g.Hx + (size_t)gx * N;
         const size_t plane = (size_t)g.Ly * g.Hx;
-        // carry element of the x-neighbour that lives in the adjacent group
-        const uint32_t xc_carry = rp ? ((gx + 1 == g.Gx) ? 0u : (gx + 1) * N) : ((gx == 0 ? g.Gx : gx) * N - 1);
-
-        real s[3][N], nsum[3][N], partner[3][N];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            real n0[N], a[N], b[N];
-            vec_load(P.own[c] + e0, s[c]);
-            vec_load(P.oth[c] + e0, n0);
-            vec_load(P.oth[c] + ea, a);
-            vec_load(P.oth[c] + eb, b);
-            const real carry = P.oth[c][row + xc_carry];
-#pragma unroll
-            for (int e = 0; e < N; ++e) {
-                const real sh = rp ? (e + 1 < N ? n0[(e + 1) % N] : carry) : (e > 0 ? n0[(e + N - 1) % N] : carry);
-                nsum[c][e] = (n0[e] + sh) + (a[e] + b[e]);
-                partner[c][e] = n0[e];
-            }
-            if (NDIM == 3) {
-                real lo[N], hi[N];
-                const size_t el = (size_t)y * g.Hx + (size_t)gx * N;
-                vec_load(zl == 0 ? P.oth_lo[c] + el : P.oth[c] + e0 - plane, lo);
-                vec_load(zl + 1 == g.Lz ? P.oth_hi[c] + el : P.oth[c] + e0 + plane, hi);
-#pragma unroll
-                for (int e = 0; e < N; ++e) nsum[c][e] += lo[e] + hi[e];
-            }
-        }
+        const size_t el = (size_t)y * g.Hx + (size_t)gx * N;          // offset inside a plane
+        const size_t ela = (size_t)ym * g.Hx + (size_t)gx * N, elb = (size_t)yp * g.Hx + (size_t)gx * N;
+        const uint32_t z0 = z_begin + blockIdx.y * z_chunk;
+        const uint32_t z1 = min(z0 + z_chunk, z_begin + z_count);
         real facc[6] = {0, 0, 0, 0, 0, 0};
-        HeisRand<real> rnd[N];
-        if (MODE != 2) {
-            const uint64_t site0 = ((uint64_t)zg * g.Ly + y) * g.Lx + 2u * (gx * N) + rp;  // element e: site0 + 2e
-            if (sizeof(real) == 4) {
-#pragma unroll
-                for (int e = 0; e < N; e += 2) {  // bit 1 of site0 is clear (Lx % 8 == 0): elements e, e+1 share a call
-                    uint32_t r[4];
-                    philox_at(site0 + 2u * e, sweep, 0u, pk, r);
-                    reinterpret_cast<HeisRand<float>&>(rnd[e]) = heis_rand_words(r[0], r[1]);
-                    reinterpret_cast<HeisRand<float>&>(rnd[e + 1]) = heis_rand_words(r[2], r[3]);
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < N; ++e) heis_rand(site0 + 2u * e, sweep, pk, rnd[e]);
-            }
-        }
-#pragma unroll
-        for (int e = 0; e < N; ++e) {
-            const real nx = p.J * nsum[0][e], ny = p.J * nsum[1][e], nz = p.J * nsum[2][e];
-            if (MODE != 2) {
-                const bool ok = heis_attempt<real, FLIP>(s[0][e], s[1][e], s[2][e], nx, ny, nz, p, rnd[e]);
-                facc[5] += ok ? real(1) : real(0);
-            }
-            if (MODE != 0) {
-                facc[0] -= s[0][e] * nx + s[1][e] * ny + s[2][e] * nz;
-                facc[1] += s[0][e] + partner[0][e];
-                facc[2] += s[1][e] + partner[1][e];
-                facc[3] += s[2][e] + partner[2][e];
-                const real d1 = s[0][e] * p.a[0] + s[1][e] * p.a[1] + s[2][e] * p.a[2];
-                const real d2 = partner[0][e] * p.a[0] + partner[1][e] * p.a[1] + partner[2][e] * p.a[2];
-                facc[4] += d1 * d1 + d2 * d2;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) acc[i] = (double)facc[i];
-        if (MODE != 2) {
-            const size_t el = (size_t)y * g.Hx + (size_t)gx * N;
+        int accepted = 0;
+        for (uint32_t zl = z0; zl < z1; ++zl) {
+            const uint32_t zg = zl + g.z_offset;
+            const uint32_t rp = (y + zg + (uint32_t)colour) & 1u;
+            const size_t zb = (size_t)zl * plane;
+            const size_t e0 = zb + el;
+            // carry element of the x-neighbour that lives in the adjacent group
+            const uint32_t xc_carry = rp ? ((gx + 1 == g.Gx) ? 0u : (gx + 1) * N) : ((gx == 0 ? g.Gx : gx) * N - 1);
+
+            real s[3][N], nsum[3][N], partner[3][N];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                vec_store(P.own[c] + e0, s[c]);
+                real n0[N], a[N], b[N];
+                vec_load(P.own[c] + e0, s[c]);
+                vec_load(P.oth[c] + e0, n0);
+                vec_load(P.oth[c] + zb + ela, a);
+                vec_load(P.oth[c] + zb + elb, b);
+                const real carry = P.oth[c][zb + (size_t)y * g.Hx + xc_carry];
+#pragma unroll
+                for (int e = 0; e < N; ++e) {
+                    const real sh = rp ? (e + 1 < N ? n0[(e + 1) % N] : carry) : (e > 0 ? n0[(e + N - 1) % N] : carry);
+                    nsum[c][e] = (n0[e] + sh) + (a[e] + b[e]);
+                    partner[c][e] = n0[e];
+                }
                 if (NDIM == 3) {
-                    if (P.peer_lo[c] != nullptr && zl == 0) vec_store(P.peer_lo[c] + el, s[c]);
-                    if (P.peer_hi[c] != nullptr && zl + 1 == g.Lz) vec_store(P.peer_hi[c] + el, s[c]);
+                    real lo[N], hi[N];
+                    vec_load(zl == 0 ? P.oth_lo[c] + el : P.oth[c] + e0 - plane, lo);
+                    vec_load(zl + 1 == g.Lz ? P.oth_hi[c] + el : P.oth[c] + e0 + plane, hi);
+#pragma unroll
+                    for (int e = 0; e < N; ++e) nsum[c][e] += lo[e] + hi[e];
                 }
             }
+            HeisRand<real> rnd[N];
+            if (MODE != 2) {
+                const uint64_t site0 = ((uint64_t)zg * g.Ly + y) * g.Lx + 2u * (gx * N) + rp;  // element e: site0 + 2e
+                if (sizeof(real) == 4) {
+#pragma unroll
+                    for (int e = 0; e < N; e += 2) {  // bit 1 of site0 is clear (Lx % 8 == 0): elements e, e+1 share a call
+                        uint32_t r[4];
+                        philox_at(site0 + 2u * e, sweep, 0u, pk, r);
+                        reinterpret_cast<HeisRand<float>&>(rnd[e]) = heis_rand_words(r[0], r[1]);
+                        reinterpret_cast<HeisRand<float>&>(rnd[e + 1]) = heis_rand_words(r[2], r[3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < N; ++e) heis_rand(site0 + 2u * e, sweep, pk, rnd[e]);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < N; ++e) {
+                const real nx = p.J * nsum[0][e], ny = p.J * nsum[1][e], nz = p.J * nsum[2][e];
+                if (MODE != 2) {
+                    const bool ok = heis_attempt<real, FLIP>(s[0][e], s[1][e], s[2][e], nx, ny, nz, p, rnd[e]);
+                    accepted += ok ? 1 : 0;
+                }
+                if (MODE != 0) {
+                    facc[0] -= s[0][e] * nx + s[1][e] * ny + s[2][e] * nz;
+                    facc[1] += s[0][e] + partner[0][e];
+                    facc[2] += s[1][e] + partner[1][e];
+                    facc[3] += s[2][e] + partner[2][e];
+                    const real d1 = s[0][e] * p.a[0] + s[1][e] * p.a[1] + s[2][e] * p.a[2];
+                    const real d2 = partner[0][e] * p.a[0] + partner[1][e] * p.a[1] + partner[2][e] * p.a[2];
+                    facc[4] += d1 * d1 + d2 * d2;
+                }
+            }
+            if (MODE != 2) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    vec_store(P.own[c] + e0, s[c]);
+                    if (NDIM == 3) {
+                        if (P.peer_lo[c] != nullptr && zl == 0) vec_store(P.peer_lo[c] + el, s[c]);
+                        if (P.peer_hi[c] != nullptr && zl + 1 == g.Lz) vec_store(P.peer_hi[c] + el, s[c]);
+                    }
+                }
+            }
+            if (MODE != 0 && sizeof(real) == 4 && ((zl - z0) & 7u) == 7u) {  // keep fp32 partial sums short
+#pragma unroll
+                for (int i = 0; i < 5; ++i) { acc[i] += (double)facc[i]; facc[i] = 0; }
+            }
         }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) acc[i] += (double)facc[i];
+        acc[5] = (double)accepted;
     }
     if (MODE == 0) {
         double a1[1] = {acc[5]};

@@ -311,12 +311,17 @@ void launch_msc(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, co
 template <typename real, int NDIM>
 void launch_heis(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, const HeisPtrs<real>& P, double* obs) {
     const HeisGeom g = heis_geom(h);
-    const dim3 grid(cdiv((uint64_t)zc * g.Ly * g.Gx, 128));
+    // grid.x tiles one plane, grid.y splits the z range into chunks a thread marches through; aim at ~16 CTAs per SM
+    const uint32_t per_plane = cdiv((uint64_t)g.Ly * g.Gx, 128);
+    uint32_t chunks = std::max<uint32_t>(1, (148u * 16u + per_plane - 1) / per_plane);
+    chunks = std::min(chunks, zc);
+    const uint32_t z_chunk = (zc + chunks - 1) / chunks;
+    const dim3 grid(per_plane, (zc + z_chunk - 1) / z_chunk);
     const HeisParams<real> p = heis_params<real>(h);
     const PhiloxKey pk = make_philox_key(h->md.seed);
     const bool flip = h->md.proposal == VEGAS_PROPOSE_FLIP;
     h->launches++;
-#define HL(FLIP, MODE) heis_stencil_kernel<real, NDIM, FLIP, MODE><<<grid, 128, 0, h->stream>>>(P, g, colour, zb, zc, p, h->sweeps, pk, obs)
+#define HL(FLIP, MODE) heis_stencil_kernel<real, NDIM, FLIP, MODE><<<grid, 128, 0, h->stream>>>(P, g, colour, zb, zc, z_chunk, p, h->sweeps, pk, obs)
     if (mode == 2) HL(false, 2);
     else if (mode == 1) { if (flip) HL(true, 1); else HL(false, 1); }
     else { if (flip) HL(true, 0); else HL(false, 0); }
