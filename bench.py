@@ -175,12 +175,8 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, world: int, devi
     g.randomize()
     g.set_thermostat(w["T"], (0.0, 0.0, 1.0), w["H"])
     if slab:
-        blob = g.slab_export()
-        blobs = [None] * world
-        dist.all_gather_object(blobs, blob)
-        dist.barrier()
-        g.slab_connect(blobs[(rank - 1) % world], blobs[(rank + 1) % world])
-        dist.barrier()
+        from vegas_rs_b200 import distributed as vd
+        vd.connect_slabs(g, dist)
     n_local = g.n_sites
     # ---- device-resident throughput: K steps, fused E/M on, CUDA events on the sweep stream
     g.step_async(warmup, False)
@@ -192,6 +188,9 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, world: int, devi
     if sampler:
         sampler.start()
         time.sleep(0.25)
+    if world > 1:
+        dist.barrier()  # every rank enters the timed region together (slab neighbours spin on each other's flags)
+    torch.cuda.synchronize()
     l0 = g.launches
     g.timer_start()
     g.step_async(steps, True)
@@ -212,18 +211,26 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, world: int, devi
     value = n_local * world * steps / (ms * 1e-3)
     # ---- end to end: Integrator::step's own signature, host State in -> host State out, pinned buffers
     e2e = None
-    if e2e_steps > 0 and not slab:
+    if e2e_steps > 0:
         if w["model"] == "ising":
             host = torch.empty(n_local, dtype=torch.int8, pin_memory=True)
-            arr = host.numpy(); arr[:] = g.download()
         else:
             host = torch.empty((n_local, 3), dtype=torch.float64, pin_memory=True)
-            arr = host.numpy(); arr[:] = g.download()
-        g.step_host(arr)  # warm-up
+        arr = host.numpy(); arr[:] = g.download()
+
+        def host_step():
+            if not slab:
+                g.step_host(arr)  # Integrator::step: host State in -> host State out
+            else:  # a slab's upload pushes its boundary planes to the neighbours: all ranks must have uploaded
+                g.upload(arr); dist.barrier(); g.step(1); arr[:] = g.download(); dist.barrier()
+
+        host_step()  # warm-up
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            g.step_host(arr)
+            host_step()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -233,7 +240,8 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, world: int, devi
         nbytes = arr.nbytes
         e2e = {"value": n_local * world * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": nbytes,
                "d2h_bytes_per_step": nbytes + 32, "steps": e2e_steps,
-               "api": "vegas_gpu_step_host_* (host State in, host State out, E and M back)"}
+               "api": "vegas_gpu_step_host_* (host State in, host State out, E and M back)" if not slab else
+                      "vegas_gpu_upload_* + vegas_gpu_step + vegas_gpu_download_* per slab"}
     peak, peak_src = peaks()
     per_launch_s = ms * 1e-3 / (2 * steps)
     alg_bytes_per_launch = w["bytes_per_attempt"] * n_local / 2

@@ -60,6 +60,7 @@ struct vegas_gpu {
     // --- halos (slab decomposition): per colour lower/upper halo of the *other* ranks' planes
     void* halo = nullptr;                 // one allocation: [colour][lo/hi][comp] planes
     size_t halo_plane_bytes = 0;          // bytes of one colour plane (one component)
+    size_t halo_bytes = 0, slab_bytes = 0; // halos, then flags at halo + halo_bytes; slab_bytes = whole allocation
     unsigned long long* flags = nullptr;  // [2]: pass counters written by lower / upper neighbour
     void* peer_halo[2] = {nullptr, nullptr};            // lower / upper neighbour's halo allocation
     unsigned long long* peer_flags[2] = {nullptr, nullptr};
@@ -658,10 +659,16 @@ int vegas_gpu_create_lattice(const vegas_model_desc* md, const vegas_lattice_des
         }
         if (h->slab) {
             const int ncomp = h->family == FAM_ISING_MSC ? 1 : 3;
-            if (cudaMalloc(&h->halo, h->halo_plane_bytes * 4 * ncomp) != cudaSuccess || cudaMalloc(&h->flags, 2 * 8) != cudaSuccess)
+            // ONE allocation holds the halos and the flags; it is sized in whole 2 MiB pages so that it is not
+            // sub-allocated from a shared page and its CUDA IPC handle maps exactly [halo, halo + slab_bytes).
+            h->halo_bytes = (h->halo_plane_bytes * 4 * ncomp + 255) / 256 * 256;
+            h->slab_bytes = (h->halo_bytes + 256 + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+            if (cudaMalloc(&h->halo, h->slab_bytes) != cudaSuccess)
                 return bail(fail(h, VEGAS_ERR_ALLOC, "cudaMalloc (halo) failed"));
-            cudaMemsetAsync(h->halo, 0, h->halo_plane_bytes * 4 * ncomp, h->stream);
-            cudaMemsetAsync(h->flags, 0, 16, h->stream);
+            h->flags = (unsigned long long*)((char*)h->halo + h->halo_bytes);
+            cudaMemsetAsync(h->halo, 0, h->slab_bytes, h->stream);
+            const unsigned long long magic = 0x76656761735f6770ull ^ h->z_offset;  // checked by the peer after mapping
+            cudaMemcpyAsync(h->flags + 4, &magic, 8, cudaMemcpyHostToDevice, h->stream);
             cudaStreamSynchronize(h->stream);
         }
     } else {
@@ -735,12 +742,10 @@ void vegas_gpu_destroy(vegas_gpu_t h) {
     }
     cudaFree(h->msc_bits);
     if (h->peer_is_ipc) {
-        for (int d = 0; d < 2; ++d) {
-            if (h->peer_halo[d]) cudaIpcCloseMemHandle(h->peer_halo[d]);
-            if (h->peer_flags[d] && !(d == 1 && h->peer_flags[1] == h->peer_flags[0])) cudaIpcCloseMemHandle(h->peer_flags[d]);
-        }
+        if (h->peer_halo[0]) cudaIpcCloseMemHandle(h->peer_halo[0]);
+        if (h->peer_halo[1] && h->peer_halo[1] != h->peer_halo[0]) cudaIpcCloseMemHandle(h->peer_halo[1]);
     }
-    cudaFree(h->halo); cudaFree(h->flags);
+    cudaFree(h->halo);
     cudaFree(h->g_s8);
     for (int k = 0; k < 3; ++k) cudaFree(h->g_s[k]);
     for (uint32_t* p : h->g_sites) cudaFree(p);
@@ -1271,24 +1276,24 @@ int vegas_gpu_ising_thresholds(vegas_gpu_t h, int* n_classes, uint64_t* thr, uin
 
 // ---- slab decomposition -------------------------------------------------------------------
 struct SlabBlob {
-    cudaIpcMemHandle_t halo, flags;
+    cudaIpcMemHandle_t mem;      // the single halo+flags allocation
     int device;
-    uint64_t plane_bytes;
-    char pad[VEGAS_IPC_BYTES - 2 * sizeof(cudaIpcMemHandle_t) - sizeof(int) - sizeof(uint64_t)];
+    uint64_t plane_bytes, halo_bytes, slab_bytes, z_offset;
 };
-static_assert(sizeof(SlabBlob) <= VEGAS_IPC_BYTES + 8, "blob size");
+static_assert(sizeof(SlabBlob) <= VEGAS_IPC_BYTES, "blob size");
 
 int vegas_gpu_slab_export(vegas_gpu_t h, void* blob) {
     if (!h || !blob) return VEGAS_ERR_INVALID;
     if (!h->slab) return fail(h, VEGAS_ERR_STATE, "handle is not a slab");
     CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
     SlabBlob b;
     memset(&b, 0, sizeof b);
-    CU(cudaIpcGetMemHandle(&b.halo, h->halo));
-    CU(cudaIpcGetMemHandle(&b.flags, h->flags));
+    CU(cudaIpcGetMemHandle(&b.mem, h->halo));
     b.device = h->device;
-    b.plane_bytes = h->halo_plane_bytes;
-    memcpy(blob, &b, VEGAS_IPC_BYTES);
+    b.plane_bytes = h->halo_plane_bytes; b.halo_bytes = h->halo_bytes; b.slab_bytes = h->slab_bytes; b.z_offset = h->z_offset;
+    memset(blob, 0, VEGAS_IPC_BYTES);
+    memcpy(blob, &b, sizeof b);
     return VEGAS_OK;
 }
 
@@ -1301,10 +1306,15 @@ int vegas_gpu_slab_connect(vegas_gpu_t h, const void* lower, const void* upper) 
     for (int d = 0; d < 2; ++d) {
         if (d == 1 && same) { h->peer_halo[1] = h->peer_halo[0]; h->peer_flags[1] = h->peer_flags[0]; break; }
         SlabBlob b;
-        memcpy(&b, blobs[d], VEGAS_IPC_BYTES);
-        if (b.plane_bytes != h->halo_plane_bytes) return fail(h, VEGAS_ERR_INVALID, "neighbour slab has a different plane size");
-        CU(cudaIpcOpenMemHandle(&h->peer_halo[d], b.halo, cudaIpcMemLazyEnablePeerAccess));
-        CU(cudaIpcOpenMemHandle((void**)&h->peer_flags[d], b.flags, cudaIpcMemLazyEnablePeerAccess));
+        memcpy(&b, blobs[d], sizeof b);
+        if (b.plane_bytes != h->halo_plane_bytes || b.halo_bytes != h->halo_bytes)
+            return fail(h, VEGAS_ERR_INVALID, "neighbour slab has a different plane size");
+        CU(cudaIpcOpenMemHandle(&h->peer_halo[d], b.mem, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_flags[d] = (unsigned long long*)((char*)h->peer_halo[d] + b.halo_bytes);
+        unsigned long long magic = 0;  // the mapping must start exactly at the neighbour's allocation
+        CU(cudaMemcpy(&magic, h->peer_flags[d] + 4, 8, cudaMemcpyDeviceToHost));
+        if (magic != (0x76656761735f6770ull ^ b.z_offset))
+            return fail(h, VEGAS_ERR_CUDA, "CUDA IPC mapping of the neighbour's halo buffer is not where expected");
     }
     h->peer_is_ipc = true;
     h->connected = true;
