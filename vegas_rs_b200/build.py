@@ -32,9 +32,11 @@ def _stale(target: str, sources: list[str]) -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".hpp", ".cpp", ".h"))]
     srcs.append(os.path.join(INCLUDE, "vegas_gpu.h"))
+    srcs.append(os.path.join(INCLUDE, "vegas_host.h"))
     if force or _stale(LIB, srcs):
         extra = os.environ.get("VEGAS_NVCC_EXTRA", "").split()  # tuning experiments, e.g. -DMSC_MINB=4
-        cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-I", INCLUDE, "-o", LIB, os.path.join(CSRC, "vegas_gpu.cu")]
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-I", INCLUDE, "-o", LIB, os.path.join(CSRC, "vegas_gpu.cu"),
+               os.path.join(CSRC, "vegas_host.cpp")]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.run(cmd, check=True, capture_output=not verbose)
