@@ -166,6 +166,9 @@ def make_handle(name: str, rank: int, world: int, device: int, seed: int = 12345
     else:
         kw["seed"] = seed + rank  # independent replicas (2D: one temperature point per GPU)
     g = vg.GpuMetropolis(model, size=tuple(size), **kw)
+    for kv in filter(None, os.environ.get("VEGAS_TUNE", "").split(",")):  # tuning experiments, e.g. heis_fused=0
+        k, v = kv.split("=")
+        g.set_tuning(k, int(v))
     return g, w
 
 

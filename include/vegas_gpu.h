@@ -164,6 +164,15 @@ int vegas_gpu_slab_connect(vegas_gpu_t, const void* blob_lower_neighbour, const 
 /* single-process variant: both handles live in this process (tests, or one process driving several GPUs) */
 int vegas_gpu_slab_connect_local(vegas_gpu_t self, vegas_gpu_t lower, vegas_gpu_t upper);
 
+/* ---- kernel selection knobs (no reference counterpart; tests and tuning) ----------------
+ * key "heis_fused"    : -1 auto (default), 0 never, 1 whenever the lattice fits  -- the one-launch-per-step
+ *                       two-colour Heisenberg kernel (heis_fused.cuh) instead of two colour passes
+ *     "heis_fused_ty" : interior rows per CTA tile (0 = auto), "heis_fused_cz": planes per z-chunk (0 = auto)
+ * Results do not depend on these knobs (same Philox keys, same arithmetic). */
+int vegas_gpu_set_tuning(vegas_gpu_t, const char* key, long value);
+/* name of the kernel the NEXT step will launch: "heis_fused", "heis_stencil", "ising_msc", ... */
+const char* vegas_gpu_step_kernel(vegas_gpu_t);
+
 /* ---- timing hooks for bench.py (CUDA events on the handle's own stream) --------------- */
 int vegas_gpu_timer_start(vegas_gpu_t);
 int vegas_gpu_timer_stop(vegas_gpu_t, float* elapsed_ms);

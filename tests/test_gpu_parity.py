@@ -323,6 +323,86 @@ def test_heisenberg_stencil_vs_general_statistics(built):
     assert abs(res[0] - res[1]) < 5e-3, res
 
 
+# ------------------------------------------------------------------------------------------ fused two-colour step
+FUSED_CASES = [
+    # (size, ty, cz): several y-tiles, z-chunks that do and do not divide Lz, minimal Ly = ty + 4
+    ((16, 8, 6), 4, 0),
+    ((16, 8, 6), 4, 2),
+    ((32, 12, 8), 4, 3),
+    ((24, 10, 4), 2, 1),
+    ((64, 16, 6), 6, 0),
+]
+
+
+@pytest.mark.parametrize("precision", [vg.F64, vg.F32], ids=["f64", "f32"])
+@pytest.mark.parametrize("size,ty,cz", FUSED_CASES, ids=[f"{c[0][0]}x{c[0][1]}x{c[0][2]}_ty{c[1]}_cz{c[2]}" for c in FUSED_CASES])
+def test_heisenberg_fused_step_replay(built, precision, size, ty, cz):
+    """heis_fused_kernel (one launch per step, both colours, ping-pong buffers) against the oracle's replay of
+    the reference rule with Hamiltonian::energy, and against the two-pass kernels bit for bit."""
+    lat = dict(unitcell=vg.SC, size=size)
+    kw = dict(exchange=1.0, zeeman=True, anisotropy=((0.0, 0.6, 0.8), -0.3))
+    seed = 4242
+    g = vg.GpuMetropolis(vg.HEISENBERG, precision=precision, seed=seed, **kw, **lat)
+    g.set_tuning("heis_fused", 1); g.set_tuning("heis_fused_ty", ty); g.set_tuning("heis_fused_cz", cz)
+    assert g.step_kernel == "heis_fused"
+    two = vg.GpuMetropolis(vg.HEISENBERG, precision=precision, seed=seed, **kw, **lat)
+    two.set_tuning("heis_fused", 0)
+    assert two.step_kernel == "heis_stencil"
+    H, _ = oracle_model(ob.HEISENBERG, **kw, **lat)
+    n = n_sites(lat)
+    s = random_state(ob.HEISENBERG, n, 5)
+    g.upload(s); two.upload(s)
+    cpu = g.download()
+    col = g.colours()
+    for T, hmag in ((1.2, 0.5), (0.4, 0.0)):
+        g.set_thermostat(T, (0, 0.6, 0.8), hmag); two.set_thermostat(T, (0, 0.6, 0.8), hmag)
+        th = H.thermostat(T, (0, 0.6, 0.8), hmag)
+        for _ in range(3):
+            sweep = g.sweeps
+            e, m = g.step(1)
+            e2, m2 = two.step(1)
+            dev = g.download()
+            assert np.array_equal(dev, two.download())          # same keys, same arithmetic order
+            assert abs(e[0] - e2[0]) <= 1e-6 * n and np.max(np.abs(m[0] - m2[0])) <= 1e-6 * n
+            H.replay_heisenberg(th, ob.PROPOSE_RANDOM, precision == vg.F32, seed, sweep, col, 2, cpu)
+            diff = np.max(np.abs(dev - cpu), axis=1)
+            if precision == vg.F64:
+                assert np.max(diff) < 1e-12
+                assert abs(e[0] - H.total_energy(th, cpu)) < 1e-12 * n * 10
+                assert np.max(np.abs(m[0] - cpu.sum(axis=0))) < 1e-12 * n
+            else:
+                assert np.sum(diff > 1e-5) <= max(2, n // 200)
+                assert abs(e[0] - H.total_energy(th, dev)) < 1e-5 * n * 6
+                assert np.max(np.abs(m[0] - dev.sum(axis=0))) < 1e-5 * n
+                cpu = dev.copy()
+        a1, acc1 = g.attempt_count(); a2, acc2 = two.attempt_count()
+        assert (a1, acc1) == (a2, acc2)
+    # unrecorded steps take the same trajectory, and the measure-only path reads the current buffers
+    g.step(3, observe=False); two.step(3, observe=False)
+    assert np.array_equal(g.download(), two.download())
+    assert abs(g.total_energy() - two.total_energy()) <= 1e-9 * n
+    g.close(); two.close()
+
+
+def test_heisenberg_fused_flip_proposal_and_larger(built):
+    """Flip proposal (MetropolisFlipIntegrator, src/integrator.rs:109-138) and an auto-planned tile on 64x64x32."""
+    lat = dict(unitcell=vg.SC, size=(64, 64, 32))
+    for proposal in (vg.PROPOSE_FLIP, vg.PROPOSE_RANDOM):
+        pair = []
+        for fused in (1, 0):
+            g = vg.GpuMetropolis(vg.HEISENBERG, precision=vg.F32, seed=9, proposal=proposal, anisotropy=((0, 0, 1.0), 0.1), **lat)
+            g.set_tuning("heis_fused", fused)
+            assert g.step_kernel == ("heis_fused" if fused else "heis_stencil")
+            g.randomize()
+            g.set_thermostat(1.0, (0, 0, 1.0), 1.0)
+            e, m = g.step(4)
+            pair.append((g.download(), e, m, g.attempt_count()))
+            g.close()
+        assert np.array_equal(pair[0][0], pair[1][0])
+        assert np.allclose(pair[0][1], pair[1][1], rtol=1e-6, atol=1e-3) and np.allclose(pair[0][2], pair[1][2], rtol=1e-6, atol=1e-2)
+        assert pair[0][3] == pair[1][3]
+
+
 # ------------------------------------------------------------------------------------------ slabs
 @pytest.mark.parametrize("model", [vg.ISING, vg.HEISENBERG], ids=["ising", "heisenberg"])
 @pytest.mark.parametrize("nslab", [2, 4])

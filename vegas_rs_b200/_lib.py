@@ -68,6 +68,8 @@ SYMBOLS = [
     ("vegas_gpu_slab_export", _int, [_vp, _vp]),
     ("vegas_gpu_slab_connect", _int, [_vp, _vp, _vp]),
     ("vegas_gpu_slab_connect_local", _int, [_vp, _vp, _vp]),
+    ("vegas_gpu_set_tuning", _int, [_vp, C.c_char_p, C.c_long]),
+    ("vegas_gpu_step_kernel", C.c_char_p, [_vp]),
     ("vegas_gpu_timer_start", _int, [_vp]),
     ("vegas_gpu_timer_stop", _int, [_vp, _vp]),
     ("vegas_gpu_launch_count", _u64, [_vp]),

@@ -124,7 +124,7 @@ heis_general_sweep_kernel(real* __restrict__ sx, real* __restrict__ sy, real* __
         real x = sx[i], y = sy[i], z = sz[i];
         HeisRand<real> rnd;
         heis_rand((uint64_t)i + site_offset, sweep, pk, rnd);
-        const bool ok = heis_attempt<real, FLIP>(x, y, z, nx, ny, nz, p, rnd);
+        const bool ok = heis_attempt<real, FLIP>(x, y, z, nx - p.h[0], ny - p.h[1], nz - p.h[2], p, rnd);
         if (ok) { sx[i] = x; sy[i] = y; sz[i] = z; }
         acc[0] = ok ? 1.0 : 0.0;
     }

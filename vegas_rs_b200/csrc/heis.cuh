@@ -18,19 +18,22 @@ struct HeisParams {
     real k;        // anisotropy strength (0 when absent)
     real a[3];     // anisotropy reference spin
     real invT;
+    real invTl;    // log2(e) / T: the Boltzmann factor is evaluated as 2^(-dE * invTl)
 };
 
 // Uniform point on the sphere from two uniforms (Archimedes' hat-box); same distribution as
-// util.rs:21-34 (Marsaglia) without a rejection loop.  u0 in (0,1), u1 in [0,1).
-// fp32: hardware sin/cos/rsqrt (abs. error ~2^-21, the spin norm is 1 +- 1e-6, inside the fp32 bar).
-__device__ __forceinline__ void sphere_point(float u0, float u1, float& x, float& y, float& z) {
-    z = 1.0f - 2.0f * u0;
-    const float t = 4.0f * u0 * (1.0f - u0);  // 1 - z^2 > 0
+// util.rs:21-34 (Marsaglia) without a rejection loop.
+// fp32: the uniforms arrive as integer-valued floats f0, f1 in [0, 2^21) so that the scalings fold into
+// the multiply-adds; hardware sin/cos/rsqrt (abs. error ~2^-21, spin norm 1 +- 1e-6, inside the fp32 bar).
+//   z = 1 - 2 u0 with u0 = (f0 + 1/2) 2^-21 in (0,1);   azimuth = 2 pi (f1 2^-21 - 1/2)
+__device__ __forceinline__ void sphere_point(float f0, float f1, float& x, float& y, float& z) {
+    z = fmaf(f0, -0x1.0p-20f, 1.0f - 0x1.0p-21f);
+    const float t = (1.0f - z) * (1.0f + z);      // = 4 u0 (1 - u0) > 0, both factors exact
     const float rxy = t * rsqrtf(t);
-    float sn, cs;
-    __sincosf(6.283185307179586f * (u1 - 0.5f), &sn, &cs);
-    x = rxy * cs; y = rxy * sn;
+    const float ang = fmaf(f1, 6.283185307179586f * 0x1.0p-21f, -3.141592653589793f);
+    x = rxy * __cosf(ang); y = rxy * __sinf(ang);
 }
+// fp64: u0 in [0,1), u1 in [0,1)
 __device__ __forceinline__ void sphere_point(double u0, double u1, double& x, double& y, double& z) {
     z = 1.0 - 2.0 * u0;
     const double rxy = sqrt(fmax(0.0, (1.0 - z) * (1.0 + z)));
@@ -39,19 +42,28 @@ __device__ __forceinline__ void sphere_point(double u0, double u1, double& x, do
     x = rxy * cs; y = rxy * sn;
 }
 
-__device__ __forceinline__ float fast_exp(float x) { return __expf(x); }
-__device__ __forceinline__ double fast_exp(double x) { return exp(x); }
+// 2^x; fp32 uses the hardware approximation (rel. error 2^-22)
+__device__ __forceinline__ float fast_exp2(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ double fast_exp2(double x) { return exp2(x); }
 
-// The three uniforms of one attempt: direction (u0, u1) and acceptance (ua).
+// The three random numbers of one attempt: direction (u0, u1) and acceptance (ua).
+// fp32: integer-valued floats, u0, u1 in [0, 2^21), ua in [0, 2^22)  (64 random bits per attempt);
+// fp64: uniforms in [0, 1) with 53 bits.
 template <typename real>
 struct HeisRand { real u0, u1, ua; };
+template <typename real> struct HeisAcceptShift;
+template <> struct HeisAcceptShift<float> { static constexpr float value = 22.0f; };   // ua < 2^22 * exp(-dE/T)
+template <> struct HeisAcceptShift<double> { static constexpr double value = 0.0; };
 
-// fp32: 64 random bits per attempt -- 21 bits for z, 21 for the azimuth, 22 for the acceptance test.
 __device__ __forceinline__ HeisRand<float> heis_rand_words(uint32_t w0, uint32_t w1) {
     HeisRand<float> o;
-    o.u0 = ((float)(w0 >> 11) + 0.5f) * 0x1.0p-21f;
-    o.u1 = (float)(w1 >> 11) * 0x1.0p-21f;
-    o.ua = (float)(((w0 & 0x7FFu) << 11) | (w1 & 0x7FFu)) * 0x1.0p-22f;
+    o.u0 = (float)(w0 >> 11);
+    o.u1 = (float)(w1 >> 11);
+    o.ua = (float)(((w0 & 0x7FFu) << 11) | (w1 & 0x7FFu));
     return o;
 }
 
@@ -71,21 +83,24 @@ __device__ __forceinline__ void heis_rand(uint64_t site, uint64_t sweep, const P
     o.u0 = u53(r[0], r[1]); o.u1 = u53(r[2], r[3]); o.ua = u53(q[0], q[1]);
 }
 
-// One Metropolis attempt on a site whose local field (nx,ny,nz) and random numbers are known.
-// Returns true when accepted.
+// One Metropolis attempt on a site whose effective field f = sum_j J_ij s_j - |H| o (energy units) and random
+// numbers are known:  -dE = (s' - s).f - k[(s'.a)^2 - (s.a)^2]   (reference signs).
+// src/integrator.rs:82-88 accepts if dE < 0, else if u < exp(-dE/T); since u < 1 both cases are
+// u < exp(-dE/T), evaluated as 2^(-dE log2(e)/T).  Returns true when accepted.
 template <typename real, bool FLIP>
-__device__ __forceinline__ bool heis_attempt(real& sx, real& sy, real& sz, real nx, real ny, real nz,
+__device__ __forceinline__ bool heis_attempt(real& sx, real& sy, real& sz, real fx, real fy, real fz,
                                              const HeisParams<real>& p, const HeisRand<real>& rnd) {
     real px, py, pz;
     if (FLIP) { px = -sx; py = -sy; pz = -sz; }
     else sphere_point(rnd.u0, rnd.u1, px, py, pz);
     const real dx = px - sx, dy = py - sy, dz = pz - sz;
-    real dE = -(dx * nx + dy * ny + dz * nz) + (dx * p.h[0] + dy * p.h[1] + dz * p.h[2]);
-    const real da_new = px * p.a[0] + py * p.a[1] + pz * p.a[2];
-    const real da_old = sx * p.a[0] + sy * p.a[1] + sz * p.a[2];
-    dE += p.k * (da_new * da_new - da_old * da_old);
-    // src/integrator.rs:82-88: accept if dE < 0, else if u < exp(-dE/T)
-    const bool acc = (dE < real(0)) || (rnd.ua < fast_exp(-dE * p.invT));
+    real mdE = dx * fx + dy * fy + dz * fz;
+    if (!FLIP) {  // (s.a)^2 is invariant under a flip
+        const real da_new = px * p.a[0] + py * p.a[1] + pz * p.a[2];
+        const real da_old = sx * p.a[0] + sy * p.a[1] + sz * p.a[2];
+        mdE -= p.k * ((da_new - da_old) * (da_new + da_old));
+    }
+    const bool acc = rnd.ua < fast_exp2(mdE * p.invTl + HeisAcceptShift<real>::value);
     if (acc) { sx = px; sy = py; sz = pz; }
     return acc;
 }
@@ -203,13 +218,13 @@ heis_stencil_kernel(HeisPtrs<real> P, HeisGeom g, int colour, uint32_t z_begin, 
             }
 #pragma unroll
             for (int e = 0; e < N; ++e) {
-                const real nx = p.J * nsum[0][e], ny = p.J * nsum[1][e], nz = p.J * nsum[2][e];
                 if (MODE != 2) {
-                    const bool ok = heis_attempt<real, FLIP>(s[0][e], s[1][e], s[2][e], nx, ny, nz, p, rnd[e]);
+                    const bool ok = heis_attempt<real, FLIP>(s[0][e], s[1][e], s[2][e], p.J * nsum[0][e] - p.h[0],
+                                                             p.J * nsum[1][e] - p.h[1], p.J * nsum[2][e] - p.h[2], p, rnd[e]);
                     accepted += ok ? 1 : 0;
                 }
                 if (MODE != 0) {
-                    facc[0] -= s[0][e] * nx + s[1][e] * ny + s[2][e] * nz;
+                    facc[0] -= p.J * (s[0][e] * nsum[0][e] + s[1][e] * nsum[1][e] + s[2][e] * nsum[2][e]);
                     facc[1] += s[0][e] + partner[0][e];
                     facc[2] += s[1][e] + partner[1][e];
                     facc[3] += s[2][e] + partner[2][e];

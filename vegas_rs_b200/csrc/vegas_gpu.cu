@@ -13,6 +13,7 @@
 
 #include "general.cuh"
 #include "heis.cuh"
+#include "heis_fused.cuh"
 #include "ising_msc.cuh"
 #include "lattice.hpp"
 
@@ -57,6 +58,13 @@ struct vegas_gpu {
     std::vector<uint8_t> ising_always;    // [2][8]
     // --- Heisenberg stencil: [colour][component]
     void* hs[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    // --- fused two-colour step (heis_fused.cuh): second buffer set, tile geometry; hs <-> hs_alt swap every fused step
+    void* hs_alt[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    int fused_enable = -1;                // -1 auto, 0 off, 1 on
+    uint32_t fused_ty = 0, fused_cz = 0;  // 0 = auto
+    bool fused_ready = false;
+    FusedGeom fused_geom{};
+    size_t fused_smem = 0;
     // --- halos (slab decomposition): per colour lower/upper halo of the *other* ranks' planes
     void* halo = nullptr;                 // one allocation: [colour][lo/hi][comp] planes
     size_t halo_plane_bytes = 0;          // bytes of one colour plane (one component)
@@ -187,6 +195,7 @@ HeisParams<real> heis_params(const vegas_gpu* h) {
     }
     p.k = (real)(h->md.has_anisotropy ? h->md.anisotropy_k : 0.0);
     p.invT = (real)(1.0 / h->T);
+    p.invTl = (real)(1.4426950408889634 / h->T);
     return p;
 }
 
@@ -463,10 +472,91 @@ void general_reduce(vegas_gpu* h, const NB& nb, double* obs_row) {
     }
 }
 
+// ---- fused two-colour Heisenberg step -------------------------------------------------------
+// Chooses the tile (TY interior rows, full x) and the z-chunking; returns false when the lattice does not fit the
+// fused kernel (the two-pass kernels then run).  Limits: 3-D, single handle (no slab), TY + 4 <= Ly, Ly % TY == 0,
+// (TY + 4) * Lx/8 threads <= 768 and six plane slots of (TY + 4) rows in 227 KB of shared memory.
+bool fused_plan(vegas_gpu* h) {
+    if (h->fused_ready) return true;
+    if (h->family != FAM_HEIS_STENCIL || h->ndim != 3 || h->slab || h->fused_enable != 1) return false;  // opt-in until it beats two passes
+    const size_t rb = real_bytes(h);
+    const uint32_t N = (uint32_t)(16 / rb);
+    FusedGeom g{};
+    g.Lx = (uint32_t)h->ld.nx; g.Ly = (uint32_t)h->ld.ny; g.Lz = (uint32_t)h->ld.nz;
+    g.Hx = g.Lx / 2; g.Gx = g.Hx / N;
+    g.z_offset = (uint32_t)h->z_offset; g.nz_global = (uint32_t)h->nz_global;
+    if (g.Gx == 0 || g.Gx > HEIS_FUSED_THREADS / 5 || g.Lz < 2) return false;
+    int smem_max = 0;
+    if (cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device) != cudaSuccess) return false;
+    const size_t row_bytes = (size_t)6 * 3 * g.Hx * rb;  // six slots x three components
+    uint32_t rows = std::min<uint32_t>(HEIS_FUSED_THREADS / g.Gx, (uint32_t)(((size_t)smem_max - 1024) / row_bytes));
+    rows = std::min(rows, g.Ly);
+    if (rows < 5) return false;
+    uint32_t ty = rows - 4;
+    if (h->fused_ty) { if (h->fused_ty > ty) return false; ty = h->fused_ty; }
+    while (ty > 1 && g.Ly % ty != 0) --ty;
+    if (g.Ly % ty != 0) return false;
+    if (ty < 4 && h->fused_enable != 1) return false;    // too much redundant halo work to pay off
+    g.TY = ty; g.ROWS = ty + 4; g.tiles = g.Ly / ty;
+    uint32_t chunks = cdiv(g.Lz, h->fused_cz ? h->fused_cz : g.Lz);
+    if (!h->fused_cz)  // auto: about seven waves of one CTA per SM, chunks of at least four planes (two warm-up planes each)
+        chunks = std::min(std::max<uint32_t>(1, (148u * 7u + g.tiles / 2) / g.tiles), std::max<uint32_t>(1, g.Lz / 4));
+    g.CZ = cdiv(g.Lz, chunks); g.chunks = cdiv(g.Lz, g.CZ);
+    const size_t bytes = heis_colour_elems(h) * rb;
+    for (int c = 0; c < 2; ++c)
+        for (int k = 0; k < 3; ++k)
+            if (!h->hs_alt[c][k] && cudaMalloc(&h->hs_alt[c][k], bytes) != cudaSuccess) { cudaGetLastError(); return false; }
+    h->fused_geom = g;
+    h->fused_smem = row_bytes * g.ROWS;
+    h->fused_ready = true;
+    return true;
+}
+
+template <typename real, int HX_T>
+int fused_launch(vegas_gpu* h, const FusedPtrs<real>& P, double* obs_row, bool record) {
+    const FusedGeom& g = h->fused_geom;
+    const HeisParams<real> p = heis_params<real>(h);
+    const PhiloxKey pk = make_philox_key(h->md.seed);
+    const bool flip = h->md.proposal == VEGAS_PROPOSE_FLIP;
+    const uint32_t threads = (g.Gx * g.ROWS + 31u) / 32u * 32u;
+    const dim3 grid(g.tiles * g.chunks);
+#define FL(FLIP, REC)                                                                                                   \
+    do {                                                                                                                \
+        CU(cudaFuncSetAttribute(heis_fused_kernel<real, HX_T, FLIP, REC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem)); \
+        heis_fused_kernel<real, HX_T, FLIP, REC><<<grid, threads, h->fused_smem, h->stream>>>(P, g, p, h->sweeps, pk, obs_row); \
+    } while (0)
+    if (record) { if (flip) FL(true, true); else FL(false, true); }
+    else { if (flip) FL(true, false); else FL(false, false); }
+#undef FL
+    return VEGAS_OK;
+}
+
+template <typename real>
+int fused_step_t(vegas_gpu* h, double* obs_row, bool record) {
+    const FusedGeom& g = h->fused_geom;
+    FusedPtrs<real> P{};
+    for (int col = 0; col < 2; ++col)
+        for (int c = 0; c < 3; ++c) { P.src[col][c] = (const real*)h->hs[col][c]; P.dst[col][c] = (real*)h->hs_alt[col][c]; }
+    h->launches++;
+    int rc;
+    // row lengths with a specialised kernel (immediate shared-memory offsets); anything else takes the generic one
+    if (sizeof(real) == 4 && g.Hx == 256) rc = fused_launch<real, 256>(h, P, obs_row, record);
+    else if (g.Hx == 128) rc = fused_launch<real, 128>(h, P, obs_row, record);
+    else if (g.Hx == 64) rc = fused_launch<real, 64>(h, P, obs_row, record);
+    else rc = fused_launch<real, 0>(h, P, obs_row, record);
+    if (rc) return rc;
+    for (int col = 0; col < 2; ++col)
+        for (int c = 0; c < 3; ++c) std::swap(h->hs[col][c], h->hs_alt[col][c]);
+    return VEGAS_OK;
+}
+
 // One Monte Carlo step (= N attempts): every colour once.  obs_row != null records observables.
 void do_step(vegas_gpu* h, void* obs_row, void* scratch_row) {
     const bool rec = obs_row != nullptr;
-    if (h->family == FAM_ISING_MSC || h->family == FAM_HEIS_STENCIL) {
+    if (h->family == FAM_HEIS_STENCIL && fused_plan(h)) {
+        double* row = (double*)(rec ? obs_row : scratch_row);
+        if (h->md.precision == VEGAS_F64) fused_step_t<double>(h, row, rec); else fused_step_t<float>(h, row, rec);
+    } else if (h->family == FAM_ISING_MSC || h->family == FAM_HEIS_STENCIL) {
         for (int c = 0; c < 2; ++c) {
             const int mode = (rec && c == 1) ? 1 : 0;
             stencil_colour_pass(h, mode, c, rec ? obs_row : scratch_row);
@@ -738,7 +828,7 @@ void vegas_gpu_destroy(vegas_gpu_t h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (int c = 0; c < 2; ++c) {
         cudaFree(h->msc[c]);
-        for (int k = 0; k < 3; ++k) cudaFree(h->hs[c][k]);
+        for (int k = 0; k < 3; ++k) { cudaFree(h->hs[c][k]); cudaFree(h->hs_alt[c][k]); }
     }
     cudaFree(h->msc_bits);
     if (h->peer_is_ipc) {
@@ -1342,6 +1432,24 @@ int vegas_gpu_slab_connect_local(vegas_gpu_t h, vegas_gpu_t lower, vegas_gpu_t u
     h->peer_is_ipc = false;
     h->connected = true;
     return push_boundaries(h);
+}
+
+// ---- tuning knobs ---------------------------------------------------------------------------
+int vegas_gpu_set_tuning(vegas_gpu_t h, const char* key, long value) {
+    if (!h || !key) return VEGAS_ERR_INVALID;
+    const std::string k(key);
+    if (k == "heis_fused") h->fused_enable = (int)value;
+    else if (k == "heis_fused_ty") h->fused_ty = (uint32_t)value;
+    else if (k == "heis_fused_cz") h->fused_cz = (uint32_t)value;
+    else return fail(h, VEGAS_ERR_INVALID, "unknown tuning key: " + k);
+    h->fused_ready = false;  // re-plan at the next step
+    return VEGAS_OK;
+}
+
+const char* vegas_gpu_step_kernel(vegas_gpu_t h) {
+    if (!h) return "";
+    if (h->family == FAM_HEIS_STENCIL && cudaSetDevice(h->device) == cudaSuccess && fused_plan(h)) return "heis_fused";
+    return FAMILY_NAME[h->family];
 }
 
 // ---- timing hooks -------------------------------------------------------------------------

@@ -253,6 +253,11 @@ class GpuMetropolis:
     def slab_connect_local(self, lower: "GpuMetropolis", upper: "GpuMetropolis"):
         self._check(self._lib.vegas_gpu_slab_connect_local(self._h, lower._h, upper._h))
 
+    def set_tuning(self, key: str, value: int): self._check(self._lib.vegas_gpu_set_tuning(self._h, key.encode(), int(value)))
+
+    @property
+    def step_kernel(self) -> str: return self._lib.vegas_gpu_step_kernel(self._h).decode()
+
     def timer_start(self): self._check(self._lib.vegas_gpu_timer_start(self._h))
 
     def timer_stop(self) -> float:
