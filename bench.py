@@ -33,6 +33,12 @@ WORKLOADS = {
     "heis3d_512": dict(model="heisenberg", size=(512, 512, 512), pbc=(True, True, True), T=1.0, H=1.0, bytes_per_attempt=24.0,
                        dtype="f32", cpu_L=(128, 128, 128), anisotropy=((0.0, 0.0, 1.0), 0.1)),
 }
+# dram__bytes_read.sum + dram__bytes_write.sum per colour-pass launch from the committed `ncu --set full` captures
+# (profiles/r01a_*.metrics.txt, cold cache): (bytes, source)
+NCU_TRAFFIC = {
+    "ising3d_1024": (134.38e6 + 35.52e6, "profiles/r01a_ising_msc.metrics.txt"),
+    "heis3d_512": (1.6439e9 + 0.7726e9, "profiles/r01a_heis_stencil.metrics.txt"),
+}
 METRIC = "spin-flip attempts/sec"
 UNIT = "attempts/s"
 
@@ -46,35 +52,40 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Polls NVML (SM clock, max clock, power, throttle reasons) as fast as it can while the timed region runs;
+    nvidia-smi's own polling (>= 100 ms) is too coarse for a region of a few milliseconds."""
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+        self.index, self.rows, self.stop_flag, self.ready = index, [], False, threading.Event()
+        self.mark0 = self.mark1 = None
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                          str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([x.strip() for x in line.split(",")])
-                if self.stop_flag:
-                    break
-        except Exception:
-            pass
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+            while not self.stop_flag:
+                t = time.perf_counter()
+                mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.rows.append((t, mhz, [k for k, b in bits.items() if mask & b]))
+                self.ready.set()
+        except Exception as e:  # no NVML: report nothing rather than a wrong number
+            self.error = repr(e)
+            self.ready.set()
 
     def finish(self):
         self.stop_flag = True
-        if self.proc:
-            self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower() == "active"})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        self.join(timeout=2.0)
+        inside = [r for r in self.rows if self.mark0 is not None and self.mark0 <= r[0] <= self.mark1] or self.rows[-3:]
+        sm = [r[1] for r in inside]
+        reasons = sorted({x for r in inside for x in r[2]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": getattr(self, "max_mhz", None),
+                "reasons": reasons, "samples": len(sm), "source": "NVML polled during the timed region"}
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
@@ -190,14 +201,18 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, world: int, devi
     sampler = ClockSampler(device) if rank == 0 else None
     if sampler:
         sampler.start()
-        time.sleep(0.25)
+        sampler.ready.wait(5.0)
     if world > 1:
         dist.barrier()  # every rank enters the timed region together (slab neighbours spin on each other's flags)
     torch.cuda.synchronize()
     l0 = g.launches
+    if sampler:
+        sampler.mark0 = time.perf_counter()
     g.timer_start()
     g.step_async(steps, True)
     ms = g.timer_stop()
+    if sampler:
+        sampler.mark1 = time.perf_counter()
     launches = g.launches - l0
     torch.cuda.synchronize()
     if world > 1:
@@ -252,7 +267,8 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, world: int, devi
     res = {"value": value, "ms_per_step": ms / steps, "launches": launches, "clocks": clocks, "e2e": e2e,
            "family": g.kernel_family, "n_local": n_local,
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": None, "peak_source": peak_src, "kernel": f"{g.kernel_family} colour pass",
+                        "traffic": NCU_TRAFFIC.get(name, (None, None))[0], "traffic_source": NCU_TRAFFIC.get(name, (None, None))[1],
+                        "algorithmic_bytes_per_launch": alg_bytes_per_launch, "peak_source": peak_src, "kernel": f"{g.kernel_family} colour pass",
                         "algorithmic_bytes_per_attempt": w["bytes_per_attempt"]},
            "energy_per_site_last": float(e_series[-1] / (n_local * (world if slab else 1)))}
     g.close()
@@ -262,7 +278,7 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, world: int, devi
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ising3d_1024", choices=sorted(WORKLOADS))

@@ -384,6 +384,21 @@ def test_heisenberg_fused_step_replay(built, precision, size, ty, cz):
     g.close(); two.close()
 
 
+def test_heisenberg_wave_chunked_passes_identical(built):
+    """tuning key heis_wave_c: colour passes interleaved in z-chunks (L2 reuse experiment) give the same trajectory."""
+    lat = dict(unitcell=vg.SC, size=(16, 8, 12))
+    res = []
+    for c in (0, 2, 3, 5):
+        g = vg.GpuMetropolis(vg.HEISENBERG, precision=vg.F32, seed=5, anisotropy=((0, 0, 1.0), 0.1), **lat)
+        g.set_tuning("heis_wave_c", c)
+        g.randomize(); g.set_thermostat(0.9, (0, 0, 1.0), 0.3)
+        e, m = g.step(3)
+        res.append((g.download(), e))
+        g.close()
+    for d, e in res[1:]:
+        assert np.array_equal(d, res[0][0]) and np.allclose(e, res[0][1], rtol=1e-6)
+
+
 def test_heisenberg_fused_flip_proposal_and_larger(built):
     """Flip proposal (MetropolisFlipIntegrator, src/integrator.rs:109-138) and an auto-planned tile on 64x64x32."""
     lat = dict(unitcell=vg.SC, size=(64, 64, 32))

@@ -47,7 +47,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 #ifndef HEIS_FUSED_THREADS
-#define HEIS_FUSED_THREADS 768
+#define HEIS_FUSED_THREADS 640   // (ROWS - 2) rows x up to 64 sixteen-byte groups: every thread owns a column that colour 0 updates
 #endif
 
 // obs layout as heis_stencil_kernel: [0] -sum_{colour 1} s.n  [1..3] sum s  [4] sum (s.a)^2  [5] accepted
@@ -68,13 +68,16 @@ heis_fused_kernel(FusedPtrs<real> P, FusedGeom g, HeisParams<real> p, uint64_t s
 
     const uint32_t tile = blockIdx.x % g.tiles, chunk = blockIdx.x / g.tiles;
     const int z0 = (int)(chunk * g.CZ), z1 = min((int)g.Lz, z0 + (int)g.CZ);
-    const uint32_t r = threadIdx.x / GX, gx = threadIdx.x - r * GX;   // tile row (0 .. ROWS-1) and 16-byte group
-    const bool in_tile = r < g.ROWS;
+    // threads cover tile rows 1 .. ROWS-2 (the rows whose colour-0 update this CTA computes); the threads of rows 1 and
+    // ROWS-2 also stage the outermost colour-1 rows 0 and ROWS-1, which are only read
+    const uint32_t r = 1u + threadIdx.x / GX, gx = threadIdx.x % GX;
+    const bool a_row = r + 1 < g.ROWS;
+    const bool b_row = a_row && r >= 2 && r + 2 < g.ROWS;    // interior rows: written by this CTA
+    const int outer = !a_row ? 0 : (r == 1 ? -1 : (r + 2 == g.ROWS ? 1 : 0));   // also stages the colour-1 row r + outer
     const uint32_t y = (tile * g.TY + g.Ly - 2u + r) % g.Ly; // lattice row of tile row r
-    const bool a_row = in_tile && r >= 1 && r + 1 < g.ROWS;  // rows whose colour-0 update this CTA computes
-    const bool b_row = in_tile && r >= 2 && r + 2 < g.ROWS;  // interior rows: written by this CTA
     const size_t plane = (size_t)g.Ly * HX;
     const size_t e_row = (size_t)y * HX + (size_t)gx * N;    // element offset inside a plane
+    const size_t e_outer = (size_t)((y + g.Ly + outer) % g.Ly) * HX + (size_t)gx * N;
     const uint32_t own = r * ROWB + gx * (N * RB);           // byte offset of the own 16 bytes inside a slot (component 0)
     // x-neighbour 2 of element 0 / N-1 lives in the adjacent group of the same row (periodic in x)
     const int dl = (gx == 0 ? (int)(CB - RB) : -(int)RB);                          // byte delta to the left carry
@@ -89,14 +92,24 @@ heis_fused_kernel(FusedPtrs<real> P, FusedGeom g, HeisParams<real> p, uint64_t s
     auto lds1 = [&](uint32_t off) { return *reinterpret_cast<const real*>(smem + off); };
     auto sts = [&](uint32_t off, const real (&v)[N]) { vec_store(reinterpret_cast<real*>(smem + off), v); };
     auto wrapz = [&](int zl) { return (size_t)(zl < 0 ? zl + (int)g.Lz : (zl >= (int)g.Lz ? zl - (int)g.Lz : zl)); };
-    auto stage = [&](int colour, uint32_t off, int zl) {     // async copy of this thread's 16 bytes x 3 components of plane zl
-        const size_t e = wrapz(zl) * plane + e_row;
+    auto stageB = [&](uint32_t off, int zl) {                // async copy of this thread's 16 bytes x 3 components of plane zl
+        const size_t zo = wrapz(zl) * plane;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) cp_async16(smem_base + off + c * CB, P.src[colour][c] + e);
+        for (int c = 0; c < 3; ++c) cp_async16(smem_base + off + c * CB, P.src[1][c] + zo + e_row);
+        if (outer != 0) {
+            const uint32_t off2 = outer < 0 ? off - ROWB : off + ROWB;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) cp_async16(smem_base + off2 + c * CB, P.src[1][c] + zo + e_outer);
+        }
+    };
+    auto stageA = [&](uint32_t off, int zl) {
+        const size_t zo = wrapz(zl) * plane + e_row;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) cp_async16(smem_base + off + c * CB, P.src[0][c] + zo);
     };
 
     real Bm2[3][N], Am3[3][N];                               // B[k-2], Anew[k-3] of the own column
-    real facc[5] = {0, 0, 0, 0, 0};                          // per-thread partial sums, flushed every 8 planes
+    real facc[5] = {0, 0, 0, 0, 0};                          // per-thread partial sums, flushed every 16 planes
     int accepted = 0;
     auto flush = [&]() {                                     // all threads of the CTA call this together
 #pragma unroll
@@ -112,15 +125,13 @@ heis_fused_kernel(FusedPtrs<real> P, FusedGeom g, HeisParams<real> p, uint64_t s
         for (int e = 0; e < N; ++e) { Bm2[c][e] = 0; Am3[c][e] = 0; }
 
     // prologue: B[z0-2] -> registers; B[z0-1], B[z0], A[z0-1] -> shared
-    if (in_tile) {
-        if (a_row) {
-            const size_t e = wrapz(z0 - 2) * plane + e_row;
+    if (a_row) {
+        const size_t e = wrapz(z0 - 2) * plane + e_row;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) vec_load(P.src[1][c] + e, Bm2[c]);
-        }
-        stage(1, oB0, z0 - 1);
-        stage(1, oB1, z0);
-        if (a_row) stage(0, oA1, z0 - 1);
+        for (int c = 0; c < 3; ++c) vec_load(P.src[1][c] + e, Bm2[c]);
+        stageB(oB0, z0 - 1);
+        stageB(oB1, z0);
+        stageA(oA1, z0 - 1);
     }
     cp_async_commit();
 
@@ -156,88 +167,86 @@ heis_fused_kernel(FusedPtrs<real> P, FusedGeom g, HeisParams<real> p, uint64_t s
         }
     };
 
-    // the arithmetic of one march step for a row whose x-neighbour 2 sits to the right (RP = 1) or left (RP = 0)
-    auto body = [&](auto rp_tag, int k, uint32_t zgA, uint32_t zgB) {
+    // The arithmetic of one march step for a row whose x-neighbour 2 sits to the right (RP = 1) or left (RP = 0).
+    // INTERIOR rows run colour 0 on plane k-1 and colour 1 on plane k-2 as ONE straight-line block (the warm-up steps
+    // compute on not-yet-valid planes and simply do not store), so that the scheduler can overlap the two.
+    auto body = [&](auto rp_tag, auto interior_tag, int k, uint32_t zgA, uint32_t zgB) {
         constexpr int RP = decltype(rp_tag)::value;
+        constexpr bool INTERIOR = decltype(interior_tag)::value;
         const int dc = RP ? dr : dl;
+        real nA[3][N], s[3][N], bk1[3][N];
         // ---- colour 0 on plane k-1
-        if (a_row) {
-            real nsum[3][N], s[3][N];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                real n0[N], up[N], dn[N], zp[N];
-                lds(oB0 + c * CB, n0);
-                lds(oB0 + c * CB - ROWB, up);
-                lds(oB0 + c * CB + ROWB, dn);
-                lds(oB1 + c * CB, zp);
-                lds(oA1 + c * CB, s[c]);
-                const real carry = lds1(oB0 + c * CB + dc);
+        for (int c = 0; c < 3; ++c) {
+            real up[N], dn[N], zp[N];
+            lds(oB0 + c * CB, bk1[c]);
+            lds(oB0 + c * CB - ROWB, up);
+            lds(oB0 + c * CB + ROWB, dn);
+            lds(oB1 + c * CB, zp);
+            lds(oA1 + c * CB, s[c]);
+            const real carry = lds1(oB0 + c * CB + dc);
 #pragma unroll
-                for (int e = 0; e < N; ++e) {
-                    const real sh = RP ? (e + 1 < N ? n0[(e + 1) % N] : carry) : (e > 0 ? n0[(e + N - 1) % N] : carry);
-                    nsum[c][e] = ((n0[e] + sh) + (up[e] + dn[e])) + (Bm2[c][e] + zp[e]);
-                }
+            for (int e = 0; e < N; ++e) {
+                const real sh = RP ? (e + 1 < N ? bk1[c][(e + 1) % N] : carry) : (e > 0 ? bk1[c][(e + N - 1) % N] : carry);
+                nA[c][e] = ((bk1[c][e] + sh) + (up[e] + dn[e])) + (Bm2[c][e] + zp[e]);
             }
-            const bool mine = b_row && k - 1 >= z0 && k - 1 < z1;  // not a redundant halo update
-            update(s, nsum, zgA, RP, mine);
+        }
+        const bool mineA = INTERIOR && k - 1 >= z0 && k - 1 < z1;  // not a redundant halo update
+        update(s, nA, zgA, RP, mineA);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) sts(oA1 + c * CB, s[c]);
-            if (mine) {
-                const size_t e = (size_t)(k - 1) * plane + e_row;
+        for (int c = 0; c < 3; ++c) sts(oA1 + c * CB, s[c]);
+        if (mineA) {
+            const size_t e = (size_t)(k - 1) * plane + e_row;
 #pragma unroll
-                for (int c = 0; c < 3; ++c) vec_store(P.dst[0][c] + e, s[c]);
-                if (RECORD) {
+            for (int c = 0; c < 3; ++c) vec_store(P.dst[0][c] + e, s[c]);
+            if (RECORD) {
 #pragma unroll
-                    for (int e2 = 0; e2 < N; ++e2) {
-                        facc[1] += s[0][e2]; facc[2] += s[1][e2]; facc[3] += s[2][e2];
-                        const real d1 = s[0][e2] * p.a[0] + s[1][e2] * p.a[1] + s[2][e2] * p.a[2];
-                        facc[4] += d1 * d1;
-                    }
+                for (int e2 = 0; e2 < N; ++e2) {
+                    facc[1] += s[0][e2]; facc[2] += s[1][e2]; facc[3] += s[2][e2];
+                    const real d1 = s[0][e2] * p.a[0] + s[1][e2] * p.a[1] + s[2][e2] * p.a[2];
+                    facc[4] += d1 * d1;
                 }
             }
         }
         // ---- colour 1 on plane k-2 (its x-neighbour 2 sits on the same side: (y + z + colour) has the same parity)
-        if (b_row) {
-            if (k - 2 >= z0) {
-                real nsum[3][N];
+        if (INTERIOR) {
+            real nB[3][N];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    real n0[N], up[N], dn[N], zp[N];
-                    lds(oA0 + c * CB, n0);
-                    lds(oA0 + c * CB - ROWB, up);
-                    lds(oA0 + c * CB + ROWB, dn);
-                    lds(oA1 + c * CB, zp);                   // Anew[k-1], written by this thread above
-                    const real carry = lds1(oA0 + c * CB + dc);
+            for (int c = 0; c < 3; ++c) {
+                real n0[N], up[N], dn[N];
+                lds(oA0 + c * CB, n0);
+                lds(oA0 + c * CB - ROWB, up);
+                lds(oA0 + c * CB + ROWB, dn);
+                const real carry = lds1(oA0 + c * CB + dc);
 #pragma unroll
-                    for (int e = 0; e < N; ++e) {
-                        const real sh = RP ? (e + 1 < N ? n0[(e + 1) % N] : carry) : (e > 0 ? n0[(e + N - 1) % N] : carry);
-                        nsum[c][e] = ((n0[e] + sh) + (up[e] + dn[e])) + (Am3[c][e] + zp[e]);
-                        Am3[c][e] = n0[e];                   // Anew[k-2] is next step's Anew[k-3]
-                    }
+                for (int e = 0; e < N; ++e) {
+                    const real sh = RP ? (e + 1 < N ? n0[(e + 1) % N] : carry) : (e > 0 ? n0[(e + N - 1) % N] : carry);
+                    nB[c][e] = ((n0[e] + sh) + (up[e] + dn[e])) + (Am3[c][e] + s[c][e]);   // s = Anew[k-1] of the own column
+                    Am3[c][e] = n0[e];                       // Anew[k-2] is next step's Anew[k-3]
                 }
-                update(Bm2, nsum, zgB, RP, true);
+            }
+            const bool mineB = k - 2 >= z0;
+            update(Bm2, nB, zgB, RP, mineB);
+            if (mineB) {
                 const size_t e = (size_t)(k - 2) * plane + e_row;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) vec_store(P.dst[1][c] + e, Bm2[c]);
                 if (RECORD) {
 #pragma unroll
                     for (int e2 = 0; e2 < N; ++e2) {
-                        facc[0] -= p.J * (Bm2[0][e2] * nsum[0][e2] + Bm2[1][e2] * nsum[1][e2] + Bm2[2][e2] * nsum[2][e2]);
+                        facc[0] -= p.J * (Bm2[0][e2] * nB[0][e2] + Bm2[1][e2] * nB[1][e2] + Bm2[2][e2] * nB[2][e2]);
                         facc[1] += Bm2[0][e2]; facc[2] += Bm2[1][e2]; facc[3] += Bm2[2][e2];
                         const real d1 = Bm2[0][e2] * p.a[0] + Bm2[1][e2] * p.a[1] + Bm2[2][e2] * p.a[2];
                         facc[4] += d1 * d1;
                     }
                 }
-            } else {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) lds(oA0 + c * CB, Am3[c]);   // warm-up steps: Anew[z0-1] -> Am3
             }
         }
         // ---- B[k-1] becomes next step's B[k-2] (own column)
-        if (a_row) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) lds(oB0 + c * CB, Bm2[c]);
-        }
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int e = 0; e < N; ++e) Bm2[c][e] = bk1[c][e];
     };
 
     const uint32_t nzg = g.nz_global;
@@ -245,15 +254,23 @@ heis_fused_kernel(FusedPtrs<real> P, FusedGeom g, HeisParams<real> p, uint64_t s
     for (int k = z0; k <= z1 + 1; ++k) {
         cp_async_wait_all();
         __syncthreads();                                     // planes B[k], A[k-1] have landed; the previous step is complete
-        if (in_tile) {                                       // prefetch for step k+1
-            if (k + 1 <= z1 + 1) stage(1, oB2, k + 1);
-            if (a_row && k <= z1) stage(0, oA2, k);
+        if (a_row) {                                         // prefetch for step k+1
+            if (k + 1 <= z1 + 1) stageB(oB2, k + 1);
+            if (k <= z1) stageA(oA2, k);
         }
         cp_async_commit();
         const uint32_t zgB = zgA == 0 ? nzg - 1 : zgA - 1;
-        if ((y + zgA) & 1u) body(std::integral_constant<int, 1>{}, k, zgA, zgB);
-        else body(std::integral_constant<int, 0>{}, k, zgA, zgB);
-        if (RECORD && ((k - z0) & 7) == 7) flush();          // keep the fp32 partial sums short
+        if (a_row) {
+            const bool rp = (y + zgA) & 1u;
+            if (b_row) {
+                if (rp) body(std::integral_constant<int, 1>{}, std::true_type{}, k, zgA, zgB);
+                else body(std::integral_constant<int, 0>{}, std::true_type{}, k, zgA, zgB);
+            } else {
+                if (rp) body(std::integral_constant<int, 1>{}, std::false_type{}, k, zgA, zgB);
+                else body(std::integral_constant<int, 0>{}, std::false_type{}, k, zgA, zgB);
+            }
+        }
+        if (RECORD && ((k - z0) & 15) == 15) flush();        // keep the fp32 partial sums short
         // rotate the rings
         { const uint32_t t = oB0; oB0 = oB1; oB1 = oB2; oB2 = t; }
         { const uint32_t t = oA0; oA0 = oA1; oA1 = oA2; oA2 = t; }

@@ -62,6 +62,7 @@ struct vegas_gpu {
     void* hs_alt[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     int fused_enable = -1;                // -1 auto, 0 off, 1 on
     uint32_t fused_ty = 0, fused_cz = 0;  // 0 = auto
+    uint32_t wave_c = 0;                  // experiment: interleave the two colour passes in chunks of wave_c planes
     bool fused_ready = false;
     FusedGeom fused_geom{};
     size_t fused_smem = 0;
@@ -489,7 +490,7 @@ bool fused_plan(vegas_gpu* h) {
     int smem_max = 0;
     if (cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device) != cudaSuccess) return false;
     const size_t row_bytes = (size_t)6 * 3 * g.Hx * rb;  // six slots x three components
-    uint32_t rows = std::min<uint32_t>(HEIS_FUSED_THREADS / g.Gx, (uint32_t)(((size_t)smem_max - 1024) / row_bytes));
+    uint32_t rows = std::min<uint32_t>(HEIS_FUSED_THREADS / g.Gx + 2, (uint32_t)(((size_t)smem_max - 1024) / row_bytes));
     rows = std::min(rows, g.Ly);
     if (rows < 5) return false;
     uint32_t ty = rows - 4;
@@ -518,7 +519,7 @@ int fused_launch(vegas_gpu* h, const FusedPtrs<real>& P, double* obs_row, bool r
     const HeisParams<real> p = heis_params<real>(h);
     const PhiloxKey pk = make_philox_key(h->md.seed);
     const bool flip = h->md.proposal == VEGAS_PROPOSE_FLIP;
-    const uint32_t threads = (g.Gx * g.ROWS + 31u) / 32u * 32u;
+    const uint32_t threads = (g.Gx * (g.ROWS - 2) + 31u) / 32u * 32u;
     const dim3 grid(g.tiles * g.chunks);
 #define FL(FLIP, REC)                                                                                                   \
     do {                                                                                                                \
@@ -556,6 +557,26 @@ void do_step(vegas_gpu* h, void* obs_row, void* scratch_row) {
     if (h->family == FAM_HEIS_STENCIL && fused_plan(h)) {
         double* row = (double*)(rec ? obs_row : scratch_row);
         if (h->md.precision == VEGAS_F64) fused_step_t<double>(h, row, rec); else fused_step_t<float>(h, row, rec);
+    } else if (h->family == FAM_HEIS_STENCIL && h->wave_c > 0 && h->ndim == 3 && !h->slab && h->ld.nz >= 2 * h->wave_c) {
+        // EXPERIMENT (tuning key "heis_wave_c"): the two colour passes interleaved in chunks of wave_c planes so that the
+        // second pass finds the planes of the first in L2.  Colour 1 on planes [z, z+C) needs colour 0 on [z-1, z+C],
+        // and colour 0 on plane Lz-1 reads the OLD colour 1 on plane 0, so colour-1 plane 0 goes last.
+        const uint32_t Lz = (uint32_t)h->ld.nz, C = h->wave_c;
+        void* row = rec ? obs_row : scratch_row;
+        auto pass = [&](int colour, uint32_t zb, uint32_t zc) {
+            if (zc == 0) return;
+            const int mode = (rec && colour == 1) ? 1 : 0;
+            if (h->md.precision == VEGAS_F64) heis_pass<double>(h, mode, colour, zb, zc, (double*)row);
+            else heis_pass<float>(h, mode, colour, zb, zc, (double*)row);
+        };
+        uint32_t a_done = 0, b_done = 1;                 // colour 0 done on [0, a_done); colour 1 done on [1, b_done)
+        while (a_done < Lz) {
+            const uint32_t n = std::min(C, Lz - a_done);
+            pass(0, a_done, n); a_done += n;
+            const uint32_t b_to = a_done == Lz ? Lz : a_done - 1;   // colour 1 may advance to plane a_done - 2
+            if (b_to > b_done) { pass(1, b_done, b_to - b_done); b_done = b_to; }
+        }
+        pass(1, 0, 1);
     } else if (h->family == FAM_ISING_MSC || h->family == FAM_HEIS_STENCIL) {
         for (int c = 0; c < 2; ++c) {
             const int mode = (rec && c == 1) ? 1 : 0;
@@ -1441,6 +1462,7 @@ int vegas_gpu_set_tuning(vegas_gpu_t h, const char* key, long value) {
     if (k == "heis_fused") h->fused_enable = (int)value;
     else if (k == "heis_fused_ty") h->fused_ty = (uint32_t)value;
     else if (k == "heis_fused_cz") h->fused_cz = (uint32_t)value;
+    else if (k == "heis_wave_c") h->wave_c = (uint32_t)value;
     else return fail(h, VEGAS_ERR_INVALID, "unknown tuning key: " + k);
     h->fused_ready = false;  // re-plan at the next step
     return VEGAS_OK;
