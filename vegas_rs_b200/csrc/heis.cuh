@@ -153,6 +153,7 @@ struct HeisPtrs {
 template <typename real, int NDIM, bool FLIP, int MODE>
 __global__ void __launch_bounds__(128, HEIS_MINB)
 heis_stencil_kernel(HeisPtrs<real> P, HeisGeom g, int colour, uint32_t z_begin, uint32_t z_count, uint32_t z_chunk,
+                    uint32_t z_stride /* distance between the chunk starts of consecutive blockIdx.y */,
                     HeisParams<real> p, uint64_t sweep, PhiloxKey pk, double* __restrict__ obs) {
     constexpr int N = VecOf<real>::N;
     __shared__ double s_red[6 * 32];
@@ -165,7 +166,7 @@ heis_stencil_kernel(HeisPtrs<real> P, HeisGeom g, int colour, uint32_t z_begin, 
         const size_t plane = (size_t)g.Ly * g.Hx;
         const size_t el = (size_t)y * g.Hx + (size_t)gx * N;          // offset inside a plane
         const size_t ela = (size_t)ym * g.Hx + (size_t)gx * N, elb = (size_t)yp * g.Hx + (size_t)gx * N;
-        const uint32_t z0 = z_begin + blockIdx.y * z_chunk;
+        const uint32_t z0 = z_begin + blockIdx.y * z_stride;
         const uint32_t z1 = min(z0 + z_chunk, z_begin + z_count);
         real facc[6] = {0, 0, 0, 0, 0, 0};
         int accepted = 0;

@@ -30,6 +30,13 @@ struct MscSlots {
     uint32_t a0[NSLOT], a1[NSLOT], a2[NSLOT], sx[NSLOT];
 };
 
+// Bit-planes of the slot thresholds, MSB first: bit[q][j] = bit (63 - j) of slot q's 64-bit threshold, as 0/1.
+// Passed by value (constant bank): with a compile-time plane index the bits are immediate-like operands.
+template <int NSLOT>
+struct MscThr {
+    uint32_t bit[NSLOT][64];
+};
+
 struct MscGeom {
     uint32_t Wx;        // 32-bit words per row per colour = Lx / 64
     uint32_t Ly, Lz;    // local rows / planes
@@ -48,145 +55,231 @@ constexpr int MSC_ROWS = 4;  // rows (words along y) per thread: amortises addre
 // obs[0] += sum over own sites of s_i * (sum_nb s_j)   (every bond once, bipartite)
 // obs[1] += sum of s over both colours (own word after update + partner word)
 // obs[2] += accepted moves
-template <int NDIM, bool FIELD, int NSLOT, bool RANDPROP, int MODE>
+// FERRO: the slots are exactly "count == q" for q < Z/2 (uniform J > 0, no field): the class masks need no operands.
+// HALO:  planes z-1 / z+1 outside the local range come from oth_lo / oth_hi and boundary words are also stored into the
+//        neighbours' halos (connected slab); otherwise the periodic wrap of `oth` itself is used and those four
+//        pointers are never touched (fewer uniform registers: the Philox round keys and threshold bits stay resident).
+template <int NDIM, bool FIELD, int NSLOT, bool RANDPROP, int MODE, bool FERRO = false, bool HALO = true>
 __global__ void __launch_bounds__(256, MSC_MINB)
 ising_msc_kernel(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth, const uint32_t* __restrict__ oth_lo,
                  const uint32_t* __restrict__ oth_hi, uint32_t* __restrict__ peer_lo, uint32_t* __restrict__ peer_hi,
-                 MscGeom g, int colour, uint32_t z_begin, MscSlots<NSLOT> slots,
-                 const uint4* __restrict__ thr_bits /* [NSLOT][16] uint4: 0/~0 masks of threshold bit-planes */,
+                 MscGeom g, int colour, uint32_t z_begin, uint32_t z_step, MscSlots<NSLOT> slots, MscThr<NSLOT> thr,
                  uint64_t sweep, PhiloxKey pk, unsigned long long* __restrict__ obs) {
     constexpr int Z = 2 * NDIM;
     constexpr int K = MSC_ROWS;
     __shared__ int s_acc[3];
     __shared__ unsigned int s_cnt;
+    // straggler records of the warp-compacted tail (NSLOT <= 3): one per word that still holds an undecided spin after
+    // 8 bit-planes: {eq, pm0, pm1, pm2, widx lo, widx hi, n0, n1, n2, word offset, cand}; at most K * 32 per warp
+    constexpr int REC_W = 11;
+    __shared__ uint32_t s_rec[NSLOT <= 3 ? 8 : 1][NSLOT <= 3 ? K * 32 : 1][NSLOT <= 3 ? REC_W : 1];
+    uint32_t n_rec = 0;  // warp-uniform
     if (threadIdx.x == 0 && threadIdx.y == 0) { s_acc[0] = 0; s_acc[1] = 0; s_acc[2] = 0; s_cnt = 0; }
     __syncthreads();
 
     // block = (BX words of a row) x (BY threads, K rows each); grid = (word tiles, row tiles, planes)
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t y0 = (blockIdx.y * blockDim.y + threadIdx.y) * K;
-    const uint32_t zl = z_begin + blockIdx.z;
+    const uint32_t zl = z_begin + blockIdx.z * z_step;   // z_step > 1: the two boundary planes of a slab in one launch
     const uint32_t Wx = g.Wx, Ly = g.Ly;
     const uint32_t plane = Ly * Wx;            // 32-bit word offsets: a colour array has < 2^32 words
     const bool active = w < Wx && y0 < Ly;
     int acc[3] = {0, 0, 0};
+    const uint32_t lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31u, warp = (threadIdx.y * blockDim.x + threadIdx.x) >> 5;
 
-    if (active) {
-        const uint32_t zg = zl + g.z_offset;
-        const uint32_t rp0 = (y0 + zg + (uint32_t)colour) & 1u;
-        const uint32_t base = zl * plane + w;  // + y * Wx
-        const uint32_t wl = w == 0 ? Wx - 1 : w - 1, wr = w + 1 == Wx ? 0u : w + 1;
+    const uint32_t zg = zl + g.z_offset;
+    const uint32_t rp0 = (y0 + zg + (uint32_t)colour) & 1u;
+    const uint32_t base = zl * plane + w;      // + y * Wx
+    const uint32_t wl = w == 0 ? Wx - 1 : w - 1, wr = w + 1 == Wx ? 0u : w + 1;
 
-        // other-colour rows y0-1 .. y0+K at column w (periodic in y); rows[k+1] is the partner word of own row k
-        uint32_t rows[K + 2];
+    // other-colour rows y0-1 .. y0+K at column w (periodic in y); rows[k+1] is the partner word of own row k.
+    // Inactive lanes (ragged grids) load nothing and carry zero masks through the warp-collective code below.
+    uint32_t rows[K + 2];
+    uint32_t sv[K], cwv[K], Cv[K], Dv[K];
 #pragma unroll
-        for (int k = -1; k <= K; ++k) {
-            uint32_t y = y0 + k;
-            if (k < 0) y = y0 == 0 ? Ly - 1 : y0 - 1;
-            if (k > 0 && y >= Ly) y -= Ly;
-            rows[k + 1] = oth[base + y * Wx];
-        }
-        uint32_t sv[K], cwv[K], Cv[K], Dv[K];
+    for (int k = -1; k <= K; ++k) {
+        uint32_t y = y0 + k;
+        if (k < 0) y = y0 == 0 ? Ly - 1 : y0 - 1;
+        if (k > 0 && y >= Ly) y -= Ly;
+        rows[k + 1] = active ? oth[base + y * Wx] : 0u;
+    }
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const uint32_t y = y0 + k;
-            const bool in = y < Ly;
-            const uint32_t yy = in ? y : y0;
-            const uint32_t rp = (rp0 + k) & 1u;
+    for (int k = 0; k < K; ++k) {
+        const uint32_t y = y0 + k;
+        const bool in = active && y < Ly;
+        const uint32_t yy = y < Ly ? y : y0;
+        const uint32_t rp = (rp0 + k) & 1u;
+        sv[k] = 0; cwv[k] = 0; Cv[k] = 0; Dv[k] = 0;
+        if (in) {
             sv[k] = own[base + yy * Wx];
             cwv[k] = oth[zl * plane + yy * Wx + (rp ? wr : wl)];
-            Cv[k] = 0; Dv[k] = 0;
             if (NDIM == 3) {
-                Cv[k] = zl == 0 ? oth_lo[yy * Wx + w] : oth[base - plane + yy * Wx];
-                Dv[k] = zl + 1 == g.Lz ? oth_hi[yy * Wx + w] : oth[base + plane + yy * Wx];
+                if (HALO) {
+                    Cv[k] = zl == 0 ? oth_lo[yy * Wx + w] : oth[base - plane + yy * Wx];
+                    Dv[k] = zl + 1 == g.Lz ? oth_hi[yy * Wx + w] : oth[base + plane + yy * Wx];
+                } else {
+                    Cv[k] = oth[(zl == 0 ? (g.Lz - 1) * plane : (zl - 1) * plane) + yy * Wx + w];
+                    Dv[k] = oth[(zl + 1 == g.Lz ? 0u : (zl + 1) * plane) + yy * Wx + w];
+                }
             }
         }
+    }
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const uint32_t y = y0 + k;
-            if (y >= Ly) break;
-            const uint32_t rp = (rp0 + k) & 1u;
-            const uint32_t s = sv[k], N0 = rows[k + 1];
-            // x-neighbour 2 sits one compact index to the left (row parity 0) or right (1): shift with carry
-            const uint32_t Nsh = rp ? __funnelshift_r(N0, cwv[k], 1) : __funnelshift_l(cwv[k], N0, 1);
-            // antiparallel indicators and their bit-sliced count n2 n1 n0
-            const uint32_t a1 = s ^ N0, a2 = s ^ Nsh, a3 = s ^ rows[k], a4 = s ^ rows[k + 2];
-            uint32_t n0, n1, n2;
-            if (NDIM == 3) {
-                const uint32_t a5 = s ^ Cv[k], a6 = s ^ Dv[k];
-                const uint32_t s1 = a1 ^ a2 ^ a3, c1 = maj3(a1, a2, a3);
-                const uint32_t s2 = a4 ^ a5 ^ a6, c2 = maj3(a4, a5, a6);
-                n0 = s1 ^ s2;
-                const uint32_t c3 = s1 & s2;
-                n1 = c1 ^ c2 ^ c3;
-                n2 = maj3(c1, c2, c3);
-            } else {
-                const uint32_t s1 = a1 ^ a2 ^ a3, c1 = maj3(a1, a2, a3);
-                n0 = s1 ^ a4;
-                const uint32_t c3 = s1 & a4;
-                n1 = c1 ^ c3;
-                n2 = c1 & c3;
+    for (int k = 0; k < K; ++k) {
+        const uint32_t y = y0 + k;
+        const bool in = active && y < Ly;
+        const uint32_t rp = (rp0 + k) & 1u;
+        const uint32_t s = sv[k], N0 = rows[k + 1];
+        // x-neighbour 2 sits one compact index to the left (row parity 0) or right (1): shift with carry
+        const uint32_t Nsh = rp ? __funnelshift_r(N0, cwv[k], 1) : __funnelshift_l(cwv[k], N0, 1);
+        // antiparallel indicators and their bit-sliced count n2 n1 n0
+        const uint32_t a1 = s ^ N0, a2 = s ^ Nsh, a3 = s ^ rows[k], a4 = s ^ rows[k + 2];
+        uint32_t n0, n1, n2;
+        if (NDIM == 3) {
+            const uint32_t a5 = s ^ Cv[k], a6 = s ^ Dv[k];
+            const uint32_t s1 = a1 ^ a2 ^ a3, c1 = maj3(a1, a2, a3);
+            const uint32_t s2 = a4 ^ a5 ^ a6, c2 = maj3(a4, a5, a6);
+            n0 = s1 ^ s2;
+            const uint32_t c3 = s1 & s2;
+            n1 = c1 ^ c2 ^ c3;
+            n2 = maj3(c1, c2, c3);
+        } else {
+            const uint32_t s1 = a1 ^ a2 ^ a3, c1 = maj3(a1, a2, a3);
+            n0 = s1 ^ a4;
+            const uint32_t c3 = s1 & a4;
+            n1 = c1 ^ c3;
+            n2 = c1 & c3;
+        }
+        // global index of this 32-bit word inside the colour array (RNG key)
+        const uint64_t widx = (((uint64_t)zg * Ly + y) * Wx + w) | ((uint64_t)colour << 62);
+        uint32_t flip = 0;
+        if (MODE != 2) {
+            uint32_t pm[NSLOT], eq = 0, lt = 0;
+#pragma unroll
+            for (int q = 0; q < NSLOT; ++q) {
+                uint32_t m;
+                if (FERRO) m = q >= Z / 2 ? 0u : ((q & 1 ? n0 : ~n0) & (q & 2 ? n1 : ~n1) & ~n2);
+                else m = (n0 ^ slots.a0[q]) & (n1 ^ slots.a1[q]) & (n2 ^ slots.a2[q]);
+                if (FIELD) m &= s ^ slots.sx[q];
+                pm[q] = m;
+                eq |= m;
             }
-            // global index of this 32-bit word inside the colour array (RNG key)
-            const uint64_t widx = (((uint64_t)zg * Ly + y) * Wx + w) | ((uint64_t)colour << 62);
-            uint32_t flip = 0;
-            if (MODE != 2) {
-                uint32_t pm[NSLOT], eq = 0, lt = 0;
+            const uint32_t always = ~eq;
+            uint32_t cand = in ? 0xFFFFFFFFu : 0u;
+            if (RANDPROP) {  // IsingSpin::rand (src/state.rs:76-84): the proposed spin is a fair coin
+                uint32_t r[4];
+                philox_at(widx, sweep, 0xFFu, pk, r);
+                cand &= r[0] ^ s;  // proposal differs from the current spin
+            }
+            eq &= cand;
+            // One chunk = 4 bit-planes of U from one Philox call.  The slot masks are disjoint, so the per-spin
+            // threshold bit-plane is sum_q pm[q] * bit_q: integer multiply-adds (FMA pipe) instead of and/or (ALU pipe),
+            // which balances the two issue pipes; with a compile-time chunk the bits are constant-bank operands.
+            auto planes = [&](uint32_t ch, const uint32_t (&r)[4], const uint32_t (&m)[NSLOT], uint32_t& e, uint32_t& l) {
+                uint32_t tb[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
                 for (int q = 0; q < NSLOT; ++q) {
-                    uint32_t m = (n0 ^ slots.a0[q]) & (n1 ^ slots.a1[q]) & (n2 ^ slots.a2[q]);
-                    if (FIELD) m &= s ^ slots.sx[q];
-                    pm[q] = m;
-                    eq |= m;
-                }
-                const uint32_t always = ~eq;
-                uint32_t cand = 0xFFFFFFFFu;
-                if (RANDPROP) {  // IsingSpin::rand (src/state.rs:76-84): the proposed spin is a fair coin
-                    uint32_t r[4];
-                    philox_at(widx, sweep, 0xFFu, pk, r);
-                    cand = r[0] ^ s;  // proposal differs from the current spin
-                }
-                eq &= cand;
-                // one chunk = 4 bit-planes of U from one Philox call.  The slot masks are disjoint, so the
-                // per-spin threshold bit-plane is sum_q pm[q] * bit_q: integer multiply-adds (FMA pipe)
-                // instead of and/or (ALU pipe), which balances the two issue pipes.
-                auto chunk = [&](uint32_t ch) {
-                    uint32_t r[4];
-                    philox_at(widx, sweep, ch, pk, r);
-                    uint32_t tb[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-                    for (int q = 0; q < NSLOT; ++q) {
-                        const uint4 b = __ldg(thr_bits + q * 16 + ch);  // warp-uniform address: one L1 broadcast; values 0/1
-                        tb[0] += pm[q] * b.x; tb[1] += pm[q] * b.y; tb[2] += pm[q] * b.z; tb[3] += pm[q] * b.w;
-                    }
+                    for (int pl = 0; pl < 4; ++pl) tb[pl] += m[q] * thr.bit[q][4 * ch + pl];
+                }
 #pragma unroll
-                    for (int p = 0; p < 4; ++p) {
-                        const uint32_t tt = eq & (tb[p] ^ r[p]);  // undecided spins whose U bit differs from the threshold bit
-                        lt |= tt & tb[p];                        // threshold bit 1, U bit 0  ->  U < thr
-                        eq ^= tt;
-                    }
-                };
-                chunk(0);  // 8 planes are needed by practically every warp: no loop control, two calls in flight
-                chunk(1);
+                for (int pl = 0; pl < 4; ++pl) {
+                    const uint32_t tt = e & (tb[pl] ^ r[pl]);  // undecided spins whose U bit differs from the threshold bit
+                    l |= tt & tb[pl];                          // threshold bit 1, U bit 0  ->  U < thr
+                    e ^= tt;
+                }
+            };
+            auto chunk = [&](uint32_t ch) {
+                uint32_t r[4];
+                philox_at(widx, sweep, ch, pk, r);
+                planes(ch, r, pm, eq, lt);
+            };
+            chunk(0);  // 8 planes are needed by practically every word: no loop control, two calls in flight
+            chunk(1);
+            if constexpr (NSLOT <= 3) {
+                // Tail.  After 8 planes about 6 % of the words still hold an undecided spin.  Running every lane through
+                // more chunks would cost the whole warp a Philox call per word; instead the word is finished
+                // provisionally (undecided = rejected) and a record goes to the warp's list in shared memory.  After the
+                // K words the list is compacted over the lanes (one record per lane) and resolved there, with the SAME
+                // random numbers (keyed by the word index), so the decisions are exactly those of the plain loop.
+                const uint32_t need = __ballot_sync(0xffffffffu, eq != 0u);
+                if (eq != 0u) {
+                    uint32_t* q = s_rec[warp][n_rec + __popc(need & ((1u << lane) - 1u))];
+                    q[0] = eq;
+#pragma unroll
+                    for (int i = 0; i < NSLOT; ++i) q[1 + i] = pm[i];
+                    q[4] = (uint32_t)widx; q[5] = (uint32_t)(widx >> 32);
+                    q[6] = n0; q[7] = n1; q[8] = n2; q[9] = base + y * Wx; q[10] = cand;
+                }
+                n_rec += __popc(need);
+            } else {
                 for (uint32_t ch = 2; ch < 16u && eq != 0u; ++ch) chunk(ch);
-                const uint32_t ok = always | lt;
-                flip = ok & cand;
-                acc[2] += __popc(RANDPROP ? (ok | ~cand) : flip);
             }
-            const uint32_t snew = s ^ flip;
-            if (MODE != 0) {
-                // sum of final antiparallel counts: c' = flip ? Z - c : c
-                const int s_all = __popc(n0) + 2 * __popc(n1) + 4 * __popc(n2);
-                const int s_f = __popc(n0 & flip) + 2 * __popc(n1 & flip) + 4 * __popc(n2 & flip);
-                const int cfin = s_all - 2 * s_f + Z * __popc(flip);
-                acc[0] += Z * 32 - 2 * cfin;
-                acc[1] += 2 * __popc(snew) - 32 + 2 * __popc(N0) - 32;
+            const uint32_t ok = always | lt;
+            flip = ok & cand;
+            acc[2] += __popc(RANDPROP ? ((ok | ~cand) & (in ? 0xFFFFFFFFu : 0u)) : flip);
+        }
+        const uint32_t snew = s ^ flip;
+        if (MODE != 0 && in) {
+            // sum of final antiparallel counts: c' = flip ? Z - c : c
+            const int s_all = __popc(n0) + 2 * __popc(n1) + 4 * __popc(n2);
+            const int s_f = __popc(n0 & flip) + 2 * __popc(n1 & flip) + 4 * __popc(n2 & flip);
+            const int cfin = s_all - 2 * s_f + Z * __popc(flip);
+            acc[0] += Z * 32 - 2 * cfin;
+            acc[1] += 2 * __popc(snew) - 32 + 2 * __popc(N0) - 32;
+        }
+        if (MODE != 2 && in) {
+            own[base + y * Wx] = snew;
+            if (NDIM == 3 && HALO) {
+                if (peer_lo != nullptr && zl == 0) peer_lo[y * Wx + w] = snew;
+                if (peer_hi != nullptr && zl + 1 == g.Lz) peer_hi[y * Wx + w] = snew;
             }
-            if (MODE != 2) {
-                own[base + y * Wx] = snew;
-                if (NDIM == 3) {
-                    if (peer_lo != nullptr && zl == 0) peer_lo[y * Wx + w] = snew;
-                    if (peer_hi != nullptr && zl + 1 == g.Lz) peer_hi[y * Wx + w] = snew;
+        }
+    }
+    if constexpr (NSLOT <= 3) {
+        if (MODE != 2) {
+            __syncwarp();
+            for (uint32_t b0 = 0; b0 < n_rec; b0 += 32u) {
+                const uint32_t idx = b0 + lane;
+                if (idx < n_rec) {
+                    const uint32_t* q = s_rec[warp][idx];
+                    uint32_t e = q[0], l = 0u, m[NSLOT];
+#pragma unroll
+                    for (int i = 0; i < NSLOT; ++i) m[i] = q[1 + i];
+                    const uint64_t wi = (uint64_t)q[4] | ((uint64_t)q[5] << 32);
+                    for (uint32_t ch = 2; e != 0u && ch < 16u; ++ch) {
+                        uint32_t r[4], tb[4] = {0u, 0u, 0u, 0u};
+                        philox_at(wi, sweep, ch, pk, r);
+#pragma unroll
+                        for (int qq = 0; qq < NSLOT; ++qq) {
+#pragma unroll
+                            for (int pl = 0; pl < 4; ++pl) tb[pl] += m[qq] * thr.bit[qq][4 * ch + pl];
+                        }
+#pragma unroll
+                        for (int pl = 0; pl < 4; ++pl) {
+                            const uint32_t tt = e & (tb[pl] ^ r[pl]);
+                            l |= tt & tb[pl];
+                            e ^= tt;
+                        }
+                    }
+                    const uint32_t f = l & q[10];  // spins accepted after all: flip them on top of the provisional word
+                    if (f != 0u) {
+                        const uint32_t off = q[9];
+                        const uint32_t prov = own[off], fin = prov ^ f;
+                        own[off] = fin;
+                        if (NDIM == 3 && HALO) {
+                            const uint32_t in_plane = off - zl * plane;
+                            if (peer_lo != nullptr && zl == 0) peer_lo[in_plane] = fin;
+                            if (peer_hi != nullptr && zl + 1 == g.Lz) peer_hi[in_plane] = fin;
+                        }
+                        acc[2] += __popc(f);
+                        if (MODE != 0) {
+                            // a flipped spin with antiparallel count c ends with Z - c: the sum of final counts moves by Z - 2c
+                            const int dc = Z * __popc(f) - 2 * (__popc(q[6] & f) + 2 * __popc(q[7] & f) + 4 * __popc(q[8] & f));
+                            acc[0] -= 2 * dc;
+                            acc[1] += 2 * (__popc(f & ~prov) - __popc(f & prov));
+                        }
+                    }
                 }
             }
         }

@@ -46,14 +46,15 @@ struct vegas_gpu {
     int econv = VEGAS_E_REFERENCE_COMPOUND;
     // device
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream_b = nullptr;   // sweep stream; boundary-plane stream of a connected slab
+    cudaEvent_t ev_main = nullptr, ev_bnd = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // --- Ising MSC
     uint32_t* msc[2] = {nullptr, nullptr};  // colour arrays (bit-packed)
-    uint4* msc_bits = nullptr;            // [MSC_MAX_SLOT][16] x 4 threshold bits (0/1), MSB first
+    MscThr<MSC_MAX_SLOT> msc_thr{};       // threshold bit-planes (0/1), MSB first; passed to the kernel by value
     MscSlots<MSC_MAX_SLOT> msc_slots{};
     int msc_nslot = 0;
-    bool msc_field = false;
+    bool msc_field = false, msc_ferro = false;   // ferro: the slots are exactly count == q for q < Z/2 (J > 0, no field)
     std::vector<uint64_t> ising_thr;      // [2][8]
     std::vector<uint8_t> ising_always;    // [2][8]
     // --- Heisenberg stencil: [colour][component]
@@ -164,12 +165,13 @@ int update_tables(vegas_gpu* h) {
             }
         if (!h->msc_field) for (int c = 0; c < 8; ++c) { h->ising_thr[c] = h->ising_thr[8 + c]; h->ising_always[c] = h->ising_always[8 + c]; }
         h->msc_nslot = h->msc_field ? 14 : 3;
+        h->msc_ferro = !h->msc_field && (int)slots.size() == Z / 2;
+        for (int q = 0; q < Z / 2 && h->msc_ferro; ++q)
+            h->msc_ferro = ms.a0[q] == ((q & 1) ? 0u : ~0u) && ms.a1[q] == ((q & 2) ? 0u : ~0u) && ms.a2[q] == ~0u;
         if ((int)slots.size() > h->msc_nslot) return fail(h, VEGAS_ERR_INVALID, "internal: too many threshold slots");
-        std::vector<uint32_t> bits((size_t)MSC_MAX_SLOT * 64, 0u);
+        memset(&h->msc_thr, 0, sizeof h->msc_thr);
         for (size_t q = 0; q < slots.size(); ++q)
-            for (int j = 0; j < 64; ++j) bits[q * 64 + j] = (uint32_t)(slots[q] >> (63 - j) & 1ull);
-        CU(cudaMemcpyAsync(h->msc_bits, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, h->stream));
-        CU(cudaStreamSynchronize(h->stream));  // `bits` is pageable host memory
+            for (int j = 0; j < 64; ++j) h->msc_thr.bit[q][j] = (uint32_t)(slots[q] >> (63 - j) & 1ull);
     } else if (h->family == FAM_ISING_GEN) {
         const int W = 2 * ISING_ZMAX + 1;
         std::vector<uint64_t> thr((size_t)2 * W);
@@ -271,30 +273,38 @@ size_t halo_offset(const vegas_gpu* h, int colour, int hi, int comp) {
 // kernel dispatch
 // ---------------------------------------------------------------------------------------
 template <int NSLOT>
+MscThr<NSLOT> thr_prefix(const MscThr<MSC_MAX_SLOT>& a) {
+    MscThr<NSLOT> r;
+    memcpy(&r, &a, sizeof r);  // bit[q][64] rows are contiguous: the first NSLOT slots
+    return r;
+}
+
+template <int NSLOT>
 MscSlots<NSLOT> slots_prefix(const MscSlots<MSC_MAX_SLOT>& a) {
     MscSlots<NSLOT> r;
     for (int q = 0; q < NSLOT; ++q) { r.a0[q] = a.a0[q]; r.a1[q] = a.a1[q]; r.a2[q] = a.a2[q]; r.sx[q] = a.sx[q]; }
     return r;
 }
 
-template <int NDIM, bool FIELD, int NSLOT, bool RP>
+template <int NDIM, bool FIELD, int NSLOT, bool RP, bool FERRO, bool HALO>
 void launch_msc_mode(vegas_gpu* h, int mode, dim3 grid, dim3 block, uint32_t* own, const uint32_t* oth, const uint32_t* lo,
-                     const uint32_t* hi, uint32_t* plo, uint32_t* phi, int colour, uint32_t zb, uint32_t zc,
-                     unsigned long long* obs) {
+                     const uint32_t* hi, uint32_t* plo, uint32_t* phi, int colour, uint32_t zb, uint32_t zstep,
+                     unsigned long long* obs, cudaStream_t st) {
     const MscGeom g = msc_geom(h);
     const PhiloxKey pk = make_philox_key(h->md.seed);
     const MscSlots<NSLOT> sl = slots_prefix<NSLOT>(h->msc_slots);
+    const MscThr<NSLOT> th = thr_prefix<NSLOT>(h->msc_thr);
     if (mode == 0)
-        ising_msc_kernel<NDIM, FIELD, NSLOT, RP, 0><<<grid, block, 0, h->stream>>>(own, oth, lo, hi, plo, phi, g, colour, zb,
-                                                                                sl, h->msc_bits, h->sweeps, pk, obs);
+        ising_msc_kernel<NDIM, FIELD, NSLOT, RP, 0, FERRO, HALO><<<grid, block, 0, st>>>(own, oth, lo, hi, plo, phi, g, colour, zb, zstep,
+                                                                                      sl, th, h->sweeps, pk, obs);
     else
-        ising_msc_kernel<NDIM, FIELD, NSLOT, RP, 1><<<grid, block, 0, h->stream>>>(own, oth, lo, hi, plo, phi, g, colour, zb,
-                                                                                sl, h->msc_bits, h->sweeps, pk, obs);
+        ising_msc_kernel<NDIM, FIELD, NSLOT, RP, 1, FERRO, HALO><<<grid, block, 0, st>>>(own, oth, lo, hi, plo, phi, g, colour, zb, zstep,
+                                                                                      sl, th, h->sweeps, pk, obs);
 }
 
 template <int NDIM>
-void launch_msc(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, const uint32_t* lo, const uint32_t* hi,
-                uint32_t* plo, uint32_t* phi, unsigned long long* obs) {
+void launch_msc(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, uint32_t zstep, const uint32_t* lo, const uint32_t* hi,
+                uint32_t* plo, uint32_t* phi, unsigned long long* obs, cudaStream_t st) {
     const MscGeom g = msc_geom(h);
     uint32_t bx = 32;
     while (bx > g.Wx) bx >>= 1;  // block = (bx words) x (256/bx rows); one warp spans 32/bx rows
@@ -304,35 +314,41 @@ void launch_msc(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, co
     const uint32_t* oth = h->msc[1 - colour];
     const PhiloxKey pk = make_philox_key(h->md.seed);
     const bool rp = h->md.proposal == VEGAS_PROPOSE_RANDOM;
+    const bool halo = h->slab && h->connected;   // otherwise lo / hi are the periodic wrap of `oth` itself
     h->launches++;
     if (mode == 2) {
-        ising_msc_kernel<NDIM, false, 3, false, 2><<<grid, block, 0, h->stream>>>(own, oth, lo, hi, plo, phi, g, colour, zb,
-                                                                              slots_prefix<3>(h->msc_slots), h->msc_bits, h->sweeps, pk, obs);
+        ising_msc_kernel<NDIM, false, 3, false, 2><<<grid, block, 0, st>>>(own, oth, lo, hi, plo, phi, g, colour, zb, zstep,
+                                                                       slots_prefix<3>(h->msc_slots), thr_prefix<3>(h->msc_thr), h->sweeps, pk, obs);
         return;
     }
+#define ML(FIELD, NSLOT, RP, FERRO, HALO) launch_msc_mode<NDIM, FIELD, NSLOT, RP, FERRO, HALO>(h, mode, grid, block, own, oth, lo, hi, plo, phi, colour, zb, zstep, obs, st)
     if (h->msc_field) {
-        if (rp) launch_msc_mode<NDIM, true, 14, true>(h, mode, grid, block, own, oth, lo, hi, plo, phi, colour, zb, zc, obs);
-        else launch_msc_mode<NDIM, true, 14, false>(h, mode, grid, block, own, oth, lo, hi, plo, phi, colour, zb, zc, obs);
+        if (rp) ML(true, 14, true, false, true); else ML(true, 14, false, false, true);
+    } else if (h->msc_ferro) {
+        if (halo) { if (rp) ML(false, 3, true, true, true); else ML(false, 3, false, true, true); }
+        else { if (rp) ML(false, 3, true, true, false); else ML(false, 3, false, true, false); }
     } else {
-        if (rp) launch_msc_mode<NDIM, false, 3, true>(h, mode, grid, block, own, oth, lo, hi, plo, phi, colour, zb, zc, obs);
-        else launch_msc_mode<NDIM, false, 3, false>(h, mode, grid, block, own, oth, lo, hi, plo, phi, colour, zb, zc, obs);
+        if (rp) ML(false, 3, true, false, true); else ML(false, 3, false, false, true);
     }
+#undef ML
 }
 
 template <typename real, int NDIM>
-void launch_heis(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, const HeisPtrs<real>& P, double* obs) {
+void launch_heis(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, uint32_t zstep, const HeisPtrs<real>& P, double* obs,
+                 cudaStream_t st) {
     const HeisGeom g = heis_geom(h);
     // grid.x tiles one plane, grid.y splits the z range into chunks a thread marches through; aim at ~16 CTAs per SM
     const uint32_t per_plane = cdiv((uint64_t)g.Ly * g.Gx, 128);
     uint32_t chunks = std::max<uint32_t>(1, (148u * 16u + per_plane - 1) / per_plane);
     chunks = std::min(chunks, zc);
-    const uint32_t z_chunk = (zc + chunks - 1) / chunks;
-    const dim3 grid(per_plane, (zc + z_chunk - 1) / z_chunk);
+    uint32_t z_chunk = (zc + chunks - 1) / chunks, z_stride = z_chunk;
+    dim3 grid(per_plane, (zc + z_chunk - 1) / z_chunk);
+    if (zstep > 1) { z_chunk = 1; z_stride = zstep; grid.y = zc; zc = (zc - 1) * zstep + 1; }  // zc single planes, zstep apart
     const HeisParams<real> p = heis_params<real>(h);
     const PhiloxKey pk = make_philox_key(h->md.seed);
     const bool flip = h->md.proposal == VEGAS_PROPOSE_FLIP;
     h->launches++;
-#define HL(FLIP, MODE) heis_stencil_kernel<real, NDIM, FLIP, MODE><<<grid, 128, 0, h->stream>>>(P, g, colour, zb, zc, z_chunk, p, h->sweeps, pk, obs)
+#define HL(FLIP, MODE) heis_stencil_kernel<real, NDIM, FLIP, MODE><<<grid, 128, 0, st>>>(P, g, colour, zb, zc, z_chunk, z_stride, p, h->sweeps, pk, obs)
     if (mode == 2) HL(false, 2);
     else if (mode == 1) { if (flip) HL(true, 1); else HL(false, 1); }
     else { if (flip) HL(true, 0); else HL(false, 0); }
@@ -341,7 +357,8 @@ void launch_heis(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, c
 
 // One colour pass of a stencil family over local planes [zb, zb+zc).
 template <typename real>
-void heis_pass(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, double* obs) {
+void heis_pass(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, double* obs, uint32_t zstep = 1, cudaStream_t st = nullptr) {
+    if (!st) st = h->stream;
     HeisPtrs<real> P{};
     const size_t plane = (size_t)(h->ld.nx / 2) * h->ld.ny;
     for (int c = 0; c < 3; ++c) {
@@ -359,11 +376,13 @@ void heis_pass(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, dou
             P.peer_lo[c] = nullptr; P.peer_hi[c] = nullptr;
         }
     }
-    if (h->ndim == 3) launch_heis<real, 3>(h, mode, colour, zb, zc, P, obs);
-    else launch_heis<real, 2>(h, mode, colour, zb, zc, P, obs);
+    if (h->ndim == 3) launch_heis<real, 3>(h, mode, colour, zb, zc, zstep, P, obs, st);
+    else launch_heis<real, 2>(h, mode, colour, zb, zc, zstep, P, obs, st);
 }
 
-void msc_pass(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, unsigned long long* obs) {
+void msc_pass(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, unsigned long long* obs, uint32_t zstep = 1,
+              cudaStream_t st = nullptr) {
+    if (!st) st = h->stream;
     const size_t plane = (size_t)(h->ld.nx / 64) * h->ld.ny;
     const uint32_t *lo, *hi;
     uint32_t *plo = nullptr, *phi = nullptr;
@@ -378,8 +397,8 @@ void msc_pass(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, unsi
         lo = h->msc[1 - colour] + (size_t)(h->ld.nz - 1) * plane;
         hi = h->msc[1 - colour];
     }
-    if (h->ndim == 3) launch_msc<3>(h, mode, colour, zb, zc, lo, hi, plo, phi, obs);
-    else launch_msc<2>(h, mode, colour, zb, zc, lo, hi, plo, phi, obs);
+    if (h->ndim == 3) launch_msc<3>(h, mode, colour, zb, zc, zstep, lo, hi, plo, phi, obs, st);
+    else launch_msc<2>(h, mode, colour, zb, zc, zstep, lo, hi, plo, phi, obs, st);
 }
 
 // ---- slab flags: tiny kernels on the sweep stream (no host sync per colour) -------------
@@ -403,23 +422,43 @@ __global__ void wait_kernel(const unsigned long long* flags, unsigned long long 
 
 void stencil_colour_pass(vegas_gpu* h, int mode, int colour, void* obs_row) {
     const uint32_t Lz = (uint32_t)h->ld.nz;
-    auto run = [&](uint32_t zb, uint32_t zc) {
+    auto run = [&](uint32_t zb, uint32_t zc, uint32_t zstep, cudaStream_t st) {
         if (zc == 0) return;
-        if (h->family == FAM_ISING_MSC) msc_pass(h, mode, colour, zb, zc, (unsigned long long*)obs_row);
-        else if (h->md.precision == VEGAS_F64) heis_pass<double>(h, mode, colour, zb, zc, (double*)obs_row);
-        else heis_pass<float>(h, mode, colour, zb, zc, (double*)obs_row);
+        if (h->family == FAM_ISING_MSC) msc_pass(h, mode, colour, zb, zc, (unsigned long long*)obs_row, zstep, st);
+        else if (h->md.precision == VEGAS_F64) heis_pass<double>(h, mode, colour, zb, zc, (double*)obs_row, zstep, st);
+        else heis_pass<float>(h, mode, colour, zb, zc, (double*)obs_row, zstep, st);
     };
-    if (h->slab && h->connected && mode != 2) {
-        // boundary planes first (they feed the neighbours), then signal, then the interior
+    if (h->slab && h->connected && mode != 2 && !h->peer_is_ipc) {
+        // all slabs in one process (tests, or one process driving several GPUs): one stream, boundary planes first.
+        // (A second stream per handle could alias hardware queues with another handle's spinning wait kernel.)
         h->pass_counter++;
         if (h->pass_counter > 1) { wait_kernel<<<1, 32, 0, h->stream>>>(h->flags, h->pass_counter - 1); h->launches++; }
-        if (Lz >= 2) { run(0, 1); run(Lz - 1, 1); } else run(0, 1);
+        if (Lz >= 2) run(0, 2, Lz - 1, h->stream); else run(0, 1, 1, h->stream);
         signal_kernel<<<1, 32, 0, h->stream>>>(h->peer_flags[0], h->peer_flags[1], h->pass_counter);
         h->launches++;
-        if (Lz > 2) run(1, Lz - 2);
+        if (Lz > 2) run(1, Lz - 2, 1, h->stream);
+    } else if (h->slab && h->connected && mode != 2) {
+        // One process per GPU.  The two boundary planes (ONE launch) feed the neighbours: they run on the boundary stream -- wait for the
+        // neighbours' previous pass, update, store into the peers' halos, signal -- while the interior planes run
+        // on the main stream.  Both streams first wait for the whole previous pass (it wrote the other colour).
+        h->pass_counter++;
+        cudaEventRecord(h->ev_main, h->stream);
+        cudaStreamWaitEvent(h->stream_b, h->ev_main, 0);
+        cudaStreamWaitEvent(h->stream, h->ev_bnd, 0);
+        if (h->pass_counter > 1) { wait_kernel<<<1, 32, 0, h->stream_b>>>(h->flags, h->pass_counter - 1); h->launches++; }
+        if (Lz >= 2) run(0, 2, Lz - 1, h->stream_b); else run(0, 1, 1, h->stream_b);
+        signal_kernel<<<1, 32, 0, h->stream_b>>>(h->peer_flags[0], h->peer_flags[1], h->pass_counter);
+        h->launches++;
+        cudaEventRecord(h->ev_bnd, h->stream_b);
+        if (Lz > 2) run(1, Lz - 2, 1, h->stream);
     } else {
-        run(0, Lz);
+        run(0, Lz, 1, h->stream);
     }
+}
+
+// the main stream joins the boundary stream (slabs): later main-stream work sees both
+void join_boundary_stream(vegas_gpu* h) {
+    if (h->slab && h->connected && h->peer_is_ipc && h->stream_b) cudaStreamWaitEvent(h->stream, h->ev_bnd, 0);
 }
 
 // ---- general family ---------------------------------------------------------------------
@@ -593,6 +632,7 @@ void do_step(vegas_gpu* h, void* obs_row, void* scratch_row) {
             else general_reduce(h, structured_nb(h), (double*)obs_row);
         }
     }
+    join_boundary_stream(h);
     h->sweeps++;
     h->attempts += h->n;
 }
@@ -664,6 +704,13 @@ int common_init(vegas_gpu* h) {
     h->device = h->md.device;
     CU(cudaSetDevice(h->device));
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    {
+        int lo_prio = 0, hi_prio = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+        CU(cudaStreamCreateWithPriority(&h->stream_b, cudaStreamNonBlocking, hi_prio));
+        CU(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_bnd, cudaEventDisableTiming));
+    }
     CU(cudaEventCreate(&h->ev0));
     CU(cudaEventCreate(&h->ev1));
     CU(cudaMalloc(&h->obs, (OBS_CAP + 2) * OBS_W * 8));
@@ -759,7 +806,6 @@ int vegas_gpu_create_lattice(const vegas_model_desc* md, const vegas_lattice_des
         if (h->family == FAM_ISING_MSC) {
             const size_t bytes = msc_words(h) * sizeof(uint32_t);
             for (int c = 0; c < 2; ++c) { if (cudaMalloc(&h->msc[c], bytes) != cudaSuccess) return bail(fail(h, VEGAS_ERR_ALLOC, "cudaMalloc (spins) failed")); }
-            if (cudaMalloc(&h->msc_bits, (size_t)MSC_MAX_SLOT * 64 * 4) != cudaSuccess) return bail(fail(h, VEGAS_ERR_ALLOC, "cudaMalloc failed"));
             h->halo_plane_bytes = (size_t)(h->ld.nx / 64) * h->ld.ny * sizeof(uint32_t);
         } else {
             const size_t bytes = heis_colour_elems(h) * real_bytes(h);
@@ -851,7 +897,6 @@ void vegas_gpu_destroy(vegas_gpu_t h) {
         cudaFree(h->msc[c]);
         for (int k = 0; k < 3; ++k) { cudaFree(h->hs[c][k]); cudaFree(h->hs_alt[c][k]); }
     }
-    cudaFree(h->msc_bits);
     if (h->peer_is_ipc) {
         if (h->peer_halo[0]) cudaIpcCloseMemHandle(h->peer_halo[0]);
         if (h->peer_halo[1] && h->peer_halo[1] != h->peer_halo[0]) cudaIpcCloseMemHandle(h->peer_halo[1]);
@@ -863,6 +908,9 @@ void vegas_gpu_destroy(vegas_gpu_t h) {
     cudaFree(h->d_row_ptr); cudaFree(h->d_col); cudaFree(h->d_val);
     cudaFree(h->g_thr); cudaFree(h->g_code);
     cudaFree(h->obs);
+    if (h->stream_b) { cudaStreamSynchronize(h->stream_b); cudaStreamDestroy(h->stream_b); }
+    if (h->ev_main) cudaEventDestroy(h->ev_main);
+    if (h->ev_bnd) cudaEventDestroy(h->ev_bnd);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
