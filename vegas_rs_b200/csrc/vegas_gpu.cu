@@ -314,7 +314,9 @@ void launch_msc(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, ui
     const uint32_t* oth = h->msc[1 - colour];
     const PhiloxKey pk = make_philox_key(h->md.seed);
     const bool rp = h->md.proposal == VEGAS_PROPOSE_RANDOM;
-    const bool halo = h->slab && h->connected;   // otherwise lo / hi are the periodic wrap of `oth` itself
+    // halo pointers matter only for launches that touch local plane 0 or Lz-1 of a connected slab; everything else
+    // (single handle: periodic wrap of `oth` itself; interior planes of a slab) takes the leaner variant
+    const bool halo = h->slab && h->connected && (zb == 0 || zb + (zc - 1) * zstep + 1 >= g.Lz);
     h->launches++;
     if (mode == 2) {
         ising_msc_kernel<NDIM, false, 3, false, 2><<<grid, block, 0, st>>>(own, oth, lo, hi, plo, phi, g, colour, zb, zstep,
