@@ -32,6 +32,10 @@ WORKLOADS = {
                          bytes_per_attempt=0.25, dtype="u32 bit-packed (1 bit/spin)", cpu_L=(1024, 1024, 1)),
     "heis3d_512": dict(model="heisenberg", size=(512, 512, 512), pbc=(True, True, True), T=1.0, H=1.0, bytes_per_attempt=24.0,
                        dtype="f32", cpu_L=(128, 128, 128), anisotropy=((0.0, 0.0, 1.0), 0.1)),
+    # cfg[4]: fcc (4 sites per cell, z = 12), greedy/basis 4-colouring, general-adjacency kernel with the implicit
+    # unit-cell stencil; single GPU only (z-slabs exist for the sc stencil kernels only)
+    "heis_fcc_384": dict(model="heisenberg", unitcell="fcc", size=(384, 384, 384), pbc=(True, True, True), T=3.2, H=0.0,
+                         bytes_per_attempt=24.0, dtype="f32", cpu_L=(48, 48, 48)),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per colour-pass launch from the committed `ncu --set full` captures
 # (profiles/r01a_*.metrics.txt, cold cache): (bytes, source)
@@ -97,7 +101,7 @@ def cpu_replica(args):
     w = WORKLOADS[name]
     L = w["cpu_L"]
     model = ob.ISING if w["model"] == "ising" else ob.HEISENBERG
-    lat = ob.Lattice(ob.SC, *L, pbc=w["pbc"])
+    lat = ob.Lattice(ob.FCC if w.get("unitcell") == "fcc" else ob.SC, *L, pbc=w["pbc"])
     csr = ob.Csr.from_lattice(lat, 1.0, False)
     terms = [ob.TERM_EXCHANGE, ob.TERM_ZEEMAN]
     kw = {}
@@ -105,7 +109,7 @@ def cpu_replica(args):
         terms.append(ob.TERM_ANISOTROPY); kw = dict(aniso_axis=w["anisotropy"][0], aniso_k=w["anisotropy"][1])
     H = ob.Hamiltonian(model, terms, csr, **kw)
     rng = ob.OracleRng(seed)
-    n = L[0] * L[1] * L[2]
+    n = L[0] * L[1] * L[2] * (4 if w.get("unitcell") == "fcc" else 1)
     state = H.rand_state(rng, n)
     m = ob.Machine(H, ob.PROPOSE_FLIP if model == ob.ISING else ob.PROPOSE_RANDOM, rng, state, n_sensors=2)
     m.set_thermostat(H.thermostat(w["T"], (0, 0, 1.0), w["H"]))
@@ -130,7 +134,7 @@ def cpu_run(name: str, steps: int, replicas: int):
 
 def cpu_steps_for(name: str, budget_s: float) -> int:
     L = WORKLOADS[name]["cpu_L"]
-    n = L[0] * L[1] * L[2]
+    n = L[0] * L[1] * L[2] * (4 if WORKLOADS[name].get("unitcell") == "fcc" else 1)
     return max(2, int(budget_s * 1.5e6 / n))  # ~1.5e6 attempts/s/core out of cache with two sensors
 
 
@@ -165,13 +169,13 @@ def make_handle(name: str, rank: int, world: int, device: int, seed: int = 12345
     import vegas_rs_b200 as vg
     w = WORKLOADS[name]
     size = list(w["size"])
-    kw = dict(unitcell=vg.SC, pbc=w["pbc"], seed=seed, device=device)
+    kw = dict(unitcell=vg.FCC if w.get("unitcell") == "fcc" else vg.SC, pbc=w["pbc"], seed=seed, device=device)
     if w["model"] == "ising":
         model = vg.ISING
     else:
         model = vg.HEISENBERG
-        kw.update(precision=vg.F32, anisotropy=w["anisotropy"])
-    if world > 1 and size[2] > 1:
+        kw.update(precision=vg.F32, anisotropy=w.get("anisotropy"))
+    if world > 1 and size[2] > 1 and "unitcell" not in w:
         # weak scaling: every rank owns a full-size slab of a lattice that is `world` times taller
         kw.update(nz_global=size[2] * world, z_offset=size[2] * rank)
     else:
@@ -185,7 +189,7 @@ def make_handle(name: str, rank: int, world: int, device: int, seed: int = 12345
 
 def run_workload(name: str, steps: int, warmup: int, rank: int, world: int, device: int, dist, torch, e2e_steps: int):
     g, w = make_handle(name, rank, world, device)
-    slab = world > 1 and w["size"][2] > 1
+    slab = world > 1 and w["size"][2] > 1 and "unitcell" not in w
     g.randomize()
     g.set_thermostat(w["T"], (0.0, 0.0, 1.0), w["H"])
     if slab:
@@ -261,8 +265,9 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, world: int, devi
                "api": "vegas_gpu_step_host_* (host State in, host State out, E and M back)" if not slab else
                       "vegas_gpu_upload_* + vegas_gpu_step + vegas_gpu_download_* per slab"}
     peak, peak_src = peaks()
-    per_launch_s = ms * 1e-3 / (2 * steps)
-    alg_bytes_per_launch = w["bytes_per_attempt"] * n_local / 2
+    passes = g.n_colours                      # colour passes (= sweep launches) per step
+    per_launch_s = ms * 1e-3 / (passes * steps)
+    alg_bytes_per_launch = w["bytes_per_attempt"] * n_local / passes
     achieved = alg_bytes_per_launch / per_launch_s / 1e9
     res = {"value": value, "ms_per_step": ms / steps, "launches": launches, "clocks": clocks, "e2e": e2e,
            "family": g.kernel_family, "n_local": n_local,
@@ -306,11 +311,14 @@ def main():
     also = {}
     if not args.no_also:
         for other in WORKLOADS:
-            if other != args.workload:
-                r = run_workload(other, args.steps, args.warmup, rank, world, device, dist, torch, args.e2e_steps)
+            if other != args.workload and not (world > 1 and "unitcell" in WORKLOADS[other]):
+                heavy = "unitcell" in WORKLOADS[other]   # 226 M sites: fewer steps, no 5 GB host round trip
+                r = run_workload(other, min(args.steps, 10) if heavy else args.steps, args.warmup, rank, world, device, dist, torch,
+                                 0 if heavy else args.e2e_steps)
                 also[other] = {"value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "roofline": r["roofline"],
                                "e2e": r["e2e"], "family": r["family"],
-                               "note": "8 MiB state is L2 resident: not an HBM measurement" if other == "ising2d_8192" else ""}
+                               "note": {"ising2d_8192": "8 MiB state is L2 resident: not an HBM measurement",
+                                        "heis_fcc_384": "general-adjacency (gather) kernel, 4 colours; correctness path, not a tuned stencil"}.get(other, "")}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         k = cpu_steps_for(args.workload, 12.0)

@@ -143,10 +143,14 @@ struct HeisPtrs {
 };
 
 // One thread owns one 16-byte vector (4 floats / 2 doubles) of a row and marches over `z_chunk` planes,
-// so index arithmetic and the block reduction are paid once per thread, not once per site.
-// MODE 0: update; 1: update + fused reductions; 2: reductions only.
-// obs[0] += -sum_own s.n (exchange energy, each bond once)   obs[1..3] += sum s (both colours)
-// obs[4] += sum (s.a)^2 (both colours)                         obs[5] += accepted (as double)
+// so index arithmetic and the block reduction are paid once per thread, not once per site.  All element offsets are
+// 32-bit (a colour/component array holds < 2^32 elements: checked when the family is chosen), so that every address
+// is one IMAD.WIDE from a base pointer.
+// MODE 0: update.  1: update + observables of the OWN colour + exchange energy (last colour pass of a recorded step).
+//      3: update + observables of the own colour only (first colour pass of a recorded step).
+//      2: no update; energy and the observables of BOTH colours (measure-only entry points).
+// obs[0] += -sum_own s.n (exchange energy, each bond once)   obs[1..3] += sum s
+// obs[4] += sum (s.a)^2                                       obs[5] += accepted (as double)
 #ifndef HEIS_MINB
 #define HEIS_MINB 6   // resident CTAs of 128 threads per SM the stencil kernel is compiled for (register cap)
 #endif
@@ -156,27 +160,40 @@ heis_stencil_kernel(HeisPtrs<real> P, HeisGeom g, int colour, uint32_t z_begin, 
                     uint32_t z_stride /* distance between the chunk starts of consecutive blockIdx.y */,
                     HeisParams<real> p, uint64_t sweep, PhiloxKey pk, double* __restrict__ obs) {
     constexpr int N = VecOf<real>::N;
-    __shared__ double s_red[6 * 32];
+    constexpr bool OBS = MODE != 0, ENERGY = MODE == 1 || MODE == 2, BOTH = MODE == 2;
+    __shared__ double s_acc[6];
+    if (threadIdx.x < 6) s_acc[threadIdx.x] = 0.0;
+    __syncthreads();
     const uint32_t t2 = blockIdx.x * blockDim.x + threadIdx.x;  // (y, gx) inside a plane
     const bool active = t2 < g.Ly * g.Gx;
-    double acc[6] = {0, 0, 0, 0, 0, 0};
-    if (active) {
-        const uint32_t y = t2 / g.Gx, gx = t2 % g.Gx;
-        const uint32_t ym = y == 0 ? g.Ly - 1 : y - 1, yp = y + 1 == g.Ly ? 0 : y + 1;
-        const size_t plane = (size_t)g.Ly * g.Hx;
-        const size_t el = (size_t)y * g.Hx + (size_t)gx * N;          // offset inside a plane
-        const size_t ela = (size_t)ym * g.Hx + (size_t)gx * N, elb = (size_t)yp * g.Hx + (size_t)gx * N;
-        const uint32_t z0 = z_begin + blockIdx.y * z_stride;
-        const uint32_t z1 = min(z0 + z_chunk, z_begin + z_count);
-        real facc[6] = {0, 0, 0, 0, 0, 0};
-        int accepted = 0;
-        for (uint32_t zl = z0; zl < z1; ++zl) {
+    real facc[5] = {0, 0, 0, 0, 0};
+    int accepted = 0;
+    auto flush = [&]() {  // every thread of the CTA calls this (warp shuffles); fp32 partial sums -> f64 block sums
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            if (i == 0 && !ENERGY) continue;
+            const double v = warp_sum((double)facc[i]);
+            if ((threadIdx.x & 31u) == 0) atomicAdd(&s_acc[i], v);
+            facc[i] = 0;
+        }
+    };
+    const uint32_t z0 = z_begin + blockIdx.y * z_stride;
+    const uint32_t z1 = min(z0 + z_chunk, z_begin + z_count);
+    const uint32_t y = active ? t2 / g.Gx : 0u, gx = active ? t2 % g.Gx : 0u;
+    const uint32_t ym = y == 0 ? g.Ly - 1 : y - 1, yp = y + 1 == g.Ly ? 0 : y + 1;
+    const uint32_t plane = g.Ly * g.Hx;
+    const uint32_t el = y * g.Hx + gx * N;                          // offsets inside a plane
+    const uint32_t ela = ym * g.Hx + gx * N, elb = yp * g.Hx + gx * N;
+    const uint32_t row0 = y * g.Hx;
+    // carry element of the x-neighbour that lives in the adjacent group (periodic in x)
+    const uint32_t c_right = row0 + ((gx + 1 == g.Gx) ? 0u : (gx + 1) * N), c_left = row0 + (gx == 0 ? g.Gx : gx) * N - 1;
+    for (uint32_t zl = z0; zl < z1; ++zl) {
+        if (active) {
             const uint32_t zg = zl + g.z_offset;
             const uint32_t rp = (y + zg + (uint32_t)colour) & 1u;
-            const size_t zb = (size_t)zl * plane;
-            const size_t e0 = zb + el;
-            // carry element of the x-neighbour that lives in the adjacent group
-            const uint32_t xc_carry = rp ? ((gx + 1 == g.Gx) ? 0u : (gx + 1) * N) : ((gx == 0 ? g.Gx : gx) * N - 1);
+            const uint32_t zb = zl * plane;
+            const uint32_t e0 = zb + el;
+            const uint32_t e_carry = zb + (rp ? c_right : c_left);
 
             real s[3][N], nsum[3][N], partner[3][N];
 #pragma unroll
@@ -184,26 +201,26 @@ heis_stencil_kernel(HeisPtrs<real> P, HeisGeom g, int colour, uint32_t z_begin, 
                 real n0[N], a[N], b[N];
                 vec_load(P.own[c] + e0, s[c]);
                 vec_load(P.oth[c] + e0, n0);
-                vec_load(P.oth[c] + zb + ela, a);
-                vec_load(P.oth[c] + zb + elb, b);
-                const real carry = P.oth[c][zb + (size_t)y * g.Hx + xc_carry];
+                vec_load(P.oth[c] + (zb + ela), a);
+                vec_load(P.oth[c] + (zb + elb), b);
+                const real carry = P.oth[c][e_carry];
 #pragma unroll
                 for (int e = 0; e < N; ++e) {
                     const real sh = rp ? (e + 1 < N ? n0[(e + 1) % N] : carry) : (e > 0 ? n0[(e + N - 1) % N] : carry);
                     nsum[c][e] = (n0[e] + sh) + (a[e] + b[e]);
-                    partner[c][e] = n0[e];
+                    if (BOTH) partner[c][e] = n0[e];
                 }
                 if (NDIM == 3) {
                     real lo[N], hi[N];
-                    vec_load(zl == 0 ? P.oth_lo[c] + el : P.oth[c] + e0 - plane, lo);
-                    vec_load(zl + 1 == g.Lz ? P.oth_hi[c] + el : P.oth[c] + e0 + plane, hi);
+                    vec_load(zl == 0 ? P.oth_lo[c] + el : P.oth[c] + (e0 - plane), lo);
+                    vec_load(zl + 1 == g.Lz ? P.oth_hi[c] + el : P.oth[c] + (e0 + plane), hi);
 #pragma unroll
                     for (int e = 0; e < N; ++e) nsum[c][e] += lo[e] + hi[e];
                 }
             }
             HeisRand<real> rnd[N];
             if (MODE != 2) {
-                const uint64_t site0 = ((uint64_t)zg * g.Ly + y) * g.Lx + 2u * (gx * N) + rp;  // element e: site0 + 2e
+                const uint64_t site0 = (uint64_t)(zg * g.Ly + y) * g.Lx + 2u * (gx * N) + rp;  // element e: site0 + 2e
                 if (sizeof(real) == 4) {
 #pragma unroll
                     for (int e = 0; e < N; e += 2) {  // bit 1 of site0 is clear (Lx % 8 == 0): elements e, e+1 share a call
@@ -224,14 +241,16 @@ heis_stencil_kernel(HeisPtrs<real> P, HeisGeom g, int colour, uint32_t z_begin, 
                                                              p.J * nsum[1][e] - p.h[1], p.J * nsum[2][e] - p.h[2], p, rnd[e]);
                     accepted += ok ? 1 : 0;
                 }
-                if (MODE != 0) {
-                    facc[0] -= p.J * (s[0][e] * nsum[0][e] + s[1][e] * nsum[1][e] + s[2][e] * nsum[2][e]);
-                    facc[1] += s[0][e] + partner[0][e];
-                    facc[2] += s[1][e] + partner[1][e];
-                    facc[3] += s[2][e] + partner[2][e];
+                if (OBS) {
+                    if (ENERGY) facc[0] -= p.J * (s[0][e] * nsum[0][e] + s[1][e] * nsum[1][e] + s[2][e] * nsum[2][e]);
+                    facc[1] += s[0][e]; facc[2] += s[1][e]; facc[3] += s[2][e];
                     const real d1 = s[0][e] * p.a[0] + s[1][e] * p.a[1] + s[2][e] * p.a[2];
-                    const real d2 = partner[0][e] * p.a[0] + partner[1][e] * p.a[1] + partner[2][e] * p.a[2];
-                    facc[4] += d1 * d1 + d2 * d2;
+                    facc[4] += d1 * d1;
+                    if (BOTH) {
+                        facc[1] += partner[0][e]; facc[2] += partner[1][e]; facc[3] += partner[2][e];
+                        const real d2 = partner[0][e] * p.a[0] + partner[1][e] * p.a[1] + partner[2][e] * p.a[2];
+                        facc[4] += d2 * d2;
+                    }
                 }
             }
             if (MODE != 2) {
@@ -244,21 +263,16 @@ heis_stencil_kernel(HeisPtrs<real> P, HeisGeom g, int colour, uint32_t z_begin, 
                     }
                 }
             }
-            if (MODE != 0 && sizeof(real) == 4 && ((zl - z0) & 7u) == 7u) {  // keep fp32 partial sums short
-#pragma unroll
-                for (int i = 0; i < 5; ++i) { acc[i] += (double)facc[i]; facc[i] = 0; }
-            }
         }
-#pragma unroll
-        for (int i = 0; i < 5; ++i) acc[i] += (double)facc[i];
-        acc[5] = (double)accepted;
+        if (OBS && ((zl - z0) & 15u) == 15u) flush();  // keep the fp32 partial sums short (uniform branch)
     }
-    if (MODE == 0) {
-        double a1[1] = {acc[5]};
-        block_atomic_add<double, 1>(a1, s_red, obs + 5);
-    } else {
-        block_atomic_add<double, 6>(acc, s_red, obs);
+    if (OBS) flush();
+    if (MODE != 2) {
+        const int a = __reduce_add_sync(0xffffffffu, accepted);
+        if ((threadIdx.x & 31u) == 0 && a != 0) atomicAdd(&s_acc[5], (double)a);
     }
+    __syncthreads();
+    if (threadIdx.x < 6 && s_acc[threadIdx.x] != 0.0) atomicAdd(obs + threadIdx.x, s_acc[threadIdx.x]);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -353,6 +353,7 @@ void launch_heis(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, u
 #define HL(FLIP, MODE) heis_stencil_kernel<real, NDIM, FLIP, MODE><<<grid, 128, 0, st>>>(P, g, colour, zb, zc, z_chunk, z_stride, p, h->sweeps, pk, obs)
     if (mode == 2) HL(false, 2);
     else if (mode == 1) { if (flip) HL(true, 1); else HL(false, 1); }
+    else if (mode == 3) { if (flip) HL(true, 3); else HL(false, 3); }
     else { if (flip) HL(true, 0); else HL(false, 0); }
 #undef HL
 }
@@ -606,7 +607,7 @@ void do_step(vegas_gpu* h, void* obs_row, void* scratch_row) {
         void* row = rec ? obs_row : scratch_row;
         auto pass = [&](int colour, uint32_t zb, uint32_t zc) {
             if (zc == 0) return;
-            const int mode = (rec && colour == 1) ? 1 : 0;
+            const int mode = !rec ? 0 : (colour == 1 ? 1 : 3);
             if (h->md.precision == VEGAS_F64) heis_pass<double>(h, mode, colour, zb, zc, (double*)row);
             else heis_pass<float>(h, mode, colour, zb, zc, (double*)row);
         };
@@ -620,7 +621,9 @@ void do_step(vegas_gpu* h, void* obs_row, void* scratch_row) {
         pass(1, 0, 1);
     } else if (h->family == FAM_ISING_MSC || h->family == FAM_HEIS_STENCIL) {
         for (int c = 0; c < 2; ++c) {
-            const int mode = (rec && c == 1) ? 1 : 0;
+            // recorded step: the Ising kernel reduces both colours in the last pass; the Heisenberg kernel reduces the
+            // own colour in each pass (mode 3 / 1) and the exchange energy in the last one
+            const int mode = !rec ? 0 : (c == 1 ? 1 : (h->family == FAM_HEIS_STENCIL ? 3 : 0));
             stencil_colour_pass(h, mode, c, rec ? obs_row : scratch_row);
         }
     } else {
@@ -795,7 +798,7 @@ int vegas_gpu_create_lattice(const vegas_model_desc* md, const vegas_lattice_des
     if (stencil) stencil = (L[2] == 1) || (hh->ld.pbc[2] && L[2] % 2 == 0);
     if (stencil && md->model == VEGAS_ISING) stencil = L[0] % 64 == 0;
     if (stencil && md->model == VEGAS_HEISENBERG) stencil = L[0] % 8 == 0;
-    if (stencil && hh->ld.nx * hh->ld.ny * hh->ld.nz >= (1ull << 32) * 64) stencil = false;  // 32-bit word offsets per colour
+    if (stencil && hh->ld.nx * hh->ld.ny * hh->ld.nz >= (1ull << 32) * (md->model == VEGAS_ISING ? 64 : 2)) stencil = false;  // 32-bit offsets per colour array
     if (hh->slab) {
         if (!stencil || L[2] == 1) return bail(fail(h, VEGAS_ERR_INVALID, "z-slab decomposition needs the sc stencil path (periodic, even extents)"));
         if (hh->z_offset + hh->ld.nz > hh->nz_global) return bail(fail(h, VEGAS_ERR_INVALID, "slab outside the global lattice"));
