@@ -46,3 +46,54 @@ def test_slab_extent_validation():
     with pytest.raises(ValueError):
         vd.slab_extent(6, 0, 2)
     assert vd.neighbours(0, 8) == (7, 1) and vd.neighbours(7, 8) == (6, 0)
+
+
+def test_cooldown_point_list_matches_reference_quirks():
+    """src/program.rs:202-211 accumulates T in f64."""
+    from vegas_rs_b200 import distributed as vd
+    pts = vd.cooldown_temperatures(6.0, 1.0, 0.05)
+    assert len(pts) == 101 and pts[0] == 6.0 and pts[-1] == 1.0000000000000133
+    pts = vd.cooldown_temperatures(4.0, 0.1, 0.1)
+    assert len(pts) == 39 and pts[-1] == 0.1999999999999976
+    assert len(vd.cooldown_temperatures(3.0, 0.05, 0.1)) == 30
+    with pytest.raises(ValueError):
+        vd.cooldown_temperatures(1.0, 2.0, 0.1)
+    with pytest.raises(ValueError):
+        vd.cooldown_temperatures(2.0, 1.0, 0.0)
+    shards = [vd.shard_points(pts, r, 8) for r in range(8)]
+    assert sorted(t for s in shards for t in s) == sorted(pts) and max(map(len, shards)) - min(map(len, shards)) <= 1
+    assert all(s[0] > 3.0 and s[-1] < 1.0 for s in shards)  # every rank spans the range
+
+
+def _points_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vegas_rs_b200 import distributed as vd
+
+    class FakeMachine:  # records the one-point CoolDown calls a rank issues
+        def __init__(self): self.lines = []
+        def cooldown(self, tmax, tmin, rate, relax, steps):
+            assert tmax == tmin
+            self.lines.append(f"{tmax:.16f} 0.0 {relax} {steps}")
+
+    pts = vd.cooldown_temperatures(3.0, 2.0, 0.25)
+    m = FakeMachine()
+    vd.sharded_cooldown(m, vd.shard_points(pts, rank, world), 0.25, 10, 20)
+    merged = vd.gather_lines(m.lines, dist)
+    q.put((rank, len(m.lines), merged))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_cooldown_points_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29800 + os.getpid() % 150
+    procs = [ctx.Process(target=_points_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs: p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs: p.join(60)
+    assert all(p.exitcode == 0 for p in procs)
+    assert [r[1] for r in res] == [3, 2]
+    temps = [float(ln.split()[0]) for ln in res[0][2]]
+    assert temps == [3.0, 2.75, 2.5, 2.25, 2.0] and res[0][2] == res[1][2]

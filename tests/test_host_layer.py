@@ -134,3 +134,25 @@ def test_run_toml_end_to_end(built, tmp_path):
     st = pq.read_table(tmp_path / "state.parquet")
     assert st.schema.names == ["relax", "stage", "step", "temperature", "field", "id", "sx", "sy", "sz"]
     assert st.num_rows % 1000 == 0 and set(st.column("sz").to_pylist()) <= {1.0, -1.0}
+
+
+@pytest.mark.gpu
+def test_sharded_cooldown_points_through_machine(built):
+    """distributed.sharded_cooldown: a rank's temperature points as one-point CoolDowns on the real Machine."""
+    import vegas_rs_b200 as vg
+    from vegas_rs_b200 import distributed as vd
+    from vegas_rs_b200.machine import Machine
+    pts = vd.cooldown_temperatures(3.0, 2.0, 0.25)
+    lines_by_rank = []
+    for rank in range(2):  # what two ranks would do, one after the other on this GPU
+        g = vg.GpuMetropolis(vg.ISING, unitcell=vg.SC, size=(64, 8, 8), seed=40 + rank)
+        g.randomize()
+        m = Machine(g)
+        lines = []
+        m.add_stat_sensor(lambda line, row: lines.append(line))
+        mine = vd.shard_points(pts, rank, 2)
+        vd.sharded_cooldown(m, mine, 0.25, 30, 40)
+        assert [float(l.split()[0]) for l in lines] == mine and m.steps_done == len(mine) * 70
+        lines_by_rank.append(lines)
+        m.close(); g.close()
+    assert len(lines_by_rank[0]) == 3 and len(lines_by_rank[1]) == 2

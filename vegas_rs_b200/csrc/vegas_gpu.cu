@@ -718,6 +718,13 @@ int common_init(vegas_gpu* h) {
     }
     CU(cudaEventCreate(&h->ev0));
     CU(cudaEventCreate(&h->ev1));
+    {   // staging buffers of the host-layout entry points come from the stream-ordered pool: keep freed blocks cached,
+        // otherwise every Integrator::step-style call pays a fresh 1-3 GB driver allocation
+        cudaMemPool_t pool;
+        CU(cudaDeviceGetDefaultMemPool(&pool, h->device));
+        unsigned long long keep = ~0ull;
+        CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     CU(cudaMalloc(&h->obs, (OBS_CAP + 2) * OBS_W * 8));
     CU(cudaMemsetAsync(h->obs, 0, (OBS_CAP + 2) * OBS_W * 8, h->stream));
     return VEGAS_OK;

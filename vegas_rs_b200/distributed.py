@@ -51,3 +51,46 @@ def reduce_observables(energy: np.ndarray, mag: np.ndarray, dist, device, group=
     out = t.cpu().numpy()
     n = len(energy)
     return out[:n], out[n:].reshape(n, 3)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Point sharding: independent temperature points of a CoolDown, one subset per GPU.
+# The reference anneals (the state is carried from point to point, src/program.rs:203-211); sharded points
+# are equilibrium estimates that start from the rank's own state and need their own `relax`.
+# HysteresisLoop points are history dependent and are NOT sharded (shard whole loops / seeds instead).
+# ---------------------------------------------------------------------------------------------------
+def cooldown_temperatures(max_temperature: float, min_temperature: float, cool_rate: float):
+    """The point list CoolDown visits: `T -= cool_rate` in f64, stop once T < min (src/program.rs:202-211).
+    6.0 -> 1.0 @ 0.05 gives 101 points (last 1.0000000000000133); 4.0 -> 0.1 @ 0.1 gives 39 (the 0.1 point is lost)."""
+    if cool_rate <= 0.0:
+        raise ValueError("cool_rate must be positive")  # ProgramError::ZeroCoolRate
+    if max_temperature < min_temperature:
+        raise ValueError("max_temperature < min_temperature")  # ProgramError::MaxTemperatureLessThanMin
+    out, t = [], float(max_temperature)
+    while True:
+        out.append(t)
+        t -= cool_rate
+        if t < min_temperature:
+            return out
+
+
+def shard_points(points, rank: int, world: int):
+    """Interleaved shard (rank, rank+world, ...) so that every rank spans the whole temperature range."""
+    return list(points[rank::world])
+
+
+def sharded_cooldown(machine, temperatures, cool_rate: float, relax: int, steps: int):
+    """Run this rank's points through the host Machine: each is a one-point CoolDown (relax, then measure),
+    so the StatSensor / ObservableSensor hooks fire exactly as in the reference program."""
+    for t in temperatures:
+        machine.cooldown(t, t, cool_rate, relax, steps)
+
+
+def gather_lines(lines, dist, group=None):
+    """All ranks' StatSensor lines on rank 0, sorted by temperature descending (the order CoolDown prints them)."""
+    world = dist.get_world_size(group)
+    parts = [None] * world
+    dist.all_gather_object(parts, list(lines), group=group)
+    merged = [ln for p in parts for ln in p]
+    merged.sort(key=lambda ln: -float(ln.split()[0]))
+    return merged
