@@ -399,6 +399,34 @@ def test_heisenberg_wave_chunked_passes_identical(built):
         assert np.array_equal(d, res[0][0]) and np.allclose(e, res[0][1], rtol=1e-6)
 
 
+@pytest.mark.parametrize("precision", [vg.F64, vg.F32], ids=["f64", "f32"])
+def test_heisenberg_wave_kernel_identical(built, precision):
+    """heis_wave_kernel (both colour passes in one persistent launch, dependency-counted wave order) takes the same
+    trajectory as the two separate passes, for several chunk sizes / lags, recorded and unrecorded steps."""
+    lat = dict(unitcell=vg.SC, size=(32, 12, 12))
+    kw = dict(precision=precision, seed=21, anisotropy=((0, 0.6, 0.8), 0.2))
+    ref = vg.GpuMetropolis(vg.HEISENBERG, **kw, **lat)
+    ref.randomize(); ref.set_thermostat(0.8, (0, 0, 1.0), 0.4)
+    e0, m0 = ref.step(3)
+    ref.step(2, observe=False)
+    e1, m1 = ref.step(1)
+    want = ref.download(); acc = ref.attempt_count()
+    ref.close()
+    for planes, lag in ((1, 1), (2, 1), (3, 2), (4, 2), (5, 7)):
+        g = vg.GpuMetropolis(vg.HEISENBERG, **kw, **lat)
+        g.set_tuning("heis_wave", 1); g.set_tuning("heis_wave_planes", planes); g.set_tuning("heis_wave_lag", lag)
+        assert g.step_kernel == "heis_wave"
+        g.randomize(); g.set_thermostat(0.8, (0, 0, 1.0), 0.4)
+        e, m = g.step(3)
+        g.step(2, observe=False)
+        e2, m2 = g.step(1)
+        g.synchronize()
+        assert np.array_equal(g.download(), want), (planes, lag)
+        assert np.allclose(e, e0, rtol=1e-6) and np.allclose(e2, e1, rtol=1e-6) and np.allclose(m, m0, rtol=1e-5, atol=1e-3)
+        assert g.attempt_count() == acc
+        g.close()
+
+
 def test_heisenberg_fused_flip_proposal_and_larger(built):
     """Flip proposal (MetropolisFlipIntegrator, src/integrator.rs:109-138) and an auto-planned tile on 64x64x32."""
     lat = dict(unitcell=vg.SC, size=(64, 64, 32))

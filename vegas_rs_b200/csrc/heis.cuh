@@ -154,31 +154,18 @@ struct HeisPtrs {
 #ifndef HEIS_MINB
 #define HEIS_MINB 6   // resident CTAs of 128 threads per SM the stencil kernel is compiled for (register cap)
 #endif
-template <typename real, int NDIM, bool FLIP, int MODE>
-__global__ void __launch_bounds__(128, HEIS_MINB)
-heis_stencil_kernel(HeisPtrs<real> P, HeisGeom g, int colour, uint32_t z_begin, uint32_t z_count, uint32_t z_chunk,
-                    uint32_t z_stride /* distance between the chunk starts of consecutive blockIdx.y */,
-                    HeisParams<real> p, uint64_t sweep, PhiloxKey pk, double* __restrict__ obs) {
+// The march of one thread: vector (y, gx) = t2 of colour `colour`, planes [z0, z1).
+//   UPDATE  attempt the moves and store (false: measure only)
+//   OBS     accumulate observables into facc: [1..3] sum s, [4] sum (s.a)^2 of the own colour, and, when `energy`,
+//           [0] -sum s.n (exchange energy, each bond once);  BOTH adds the other colour's s and (s.a)^2 as well
+// `every16` is called (by all threads of the CTA, uniformly) after every 16th plane so that the caller can shorten the
+// fp32 partial sums.
+template <typename real, int NDIM, bool FLIP, bool UPDATE, bool OBS, bool BOTH, typename F>
+__device__ __forceinline__ void heis_march(const HeisPtrs<real>& P, const HeisGeom& g, int colour, uint32_t t2, uint32_t z0,
+                                           uint32_t z1, bool energy, const HeisParams<real>& p, uint64_t sweep,
+                                           const PhiloxKey& pk, real (&facc)[5], int& accepted, F&& every16) {
     constexpr int N = VecOf<real>::N;
-    constexpr bool OBS = MODE != 0, ENERGY = MODE == 1 || MODE == 2, BOTH = MODE == 2;
-    __shared__ double s_acc[6];
-    if (threadIdx.x < 6) s_acc[threadIdx.x] = 0.0;
-    __syncthreads();
-    const uint32_t t2 = blockIdx.x * blockDim.x + threadIdx.x;  // (y, gx) inside a plane
     const bool active = t2 < g.Ly * g.Gx;
-    real facc[5] = {0, 0, 0, 0, 0};
-    int accepted = 0;
-    auto flush = [&]() {  // every thread of the CTA calls this (warp shuffles); fp32 partial sums -> f64 block sums
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            if (i == 0 && !ENERGY) continue;
-            const double v = warp_sum((double)facc[i]);
-            if ((threadIdx.x & 31u) == 0) atomicAdd(&s_acc[i], v);
-            facc[i] = 0;
-        }
-    };
-    const uint32_t z0 = z_begin + blockIdx.y * z_stride;
-    const uint32_t z1 = min(z0 + z_chunk, z_begin + z_count);
     const uint32_t y = active ? t2 / g.Gx : 0u, gx = active ? t2 % g.Gx : 0u;
     const uint32_t ym = y == 0 ? g.Ly - 1 : y - 1, yp = y + 1 == g.Ly ? 0 : y + 1;
     const uint32_t plane = g.Ly * g.Hx;
@@ -195,6 +182,9 @@ heis_stencil_kernel(HeisPtrs<real> P, HeisGeom g, int colour, uint32_t z_begin, 
             const uint32_t e0 = zb + el;
             const uint32_t e_carry = zb + (rp ? c_right : c_left);
 
+            // planes z-1 / z+1: the base pointer choice is uniform over the CTA, the offset is one select per thread
+            const bool at_lo = NDIM == 3 && zl == 0, at_hi = NDIM == 3 && zl + 1 == g.Lz;
+            const uint32_t e_lo = at_lo ? el : e0 - plane, e_hi = at_hi ? el : e0 + plane;
             real s[3][N], nsum[3][N], partner[3][N];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -206,20 +196,28 @@ heis_stencil_kernel(HeisPtrs<real> P, HeisGeom g, int colour, uint32_t z_begin, 
                 const real carry = P.oth[c][e_carry];
 #pragma unroll
                 for (int e = 0; e < N; ++e) {
-                    const real sh = rp ? (e + 1 < N ? n0[(e + 1) % N] : carry) : (e > 0 ? n0[(e + N - 1) % N] : carry);
-                    nsum[c][e] = (n0[e] + sh) + (a[e] + b[e]);
+                    nsum[c][e] = n0[e] + (a[e] + b[e]);
                     if (BOTH) partner[c][e] = n0[e];
+                }
+                // x-neighbour 2: the row shifted by one element towards the carry side (a real branch, warp-uniform when a
+                // warp lies inside one row: both sides are plain adds, no per-element selects)
+                if (rp) {
+#pragma unroll
+                    for (int e = 0; e < N; ++e) nsum[c][e] += e + 1 < N ? n0[(e + 1) % N] : carry;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < N; ++e) nsum[c][e] += e > 0 ? n0[(e + N - 1) % N] : carry;
                 }
                 if (NDIM == 3) {
                     real lo[N], hi[N];
-                    vec_load(zl == 0 ? P.oth_lo[c] + el : P.oth[c] + (e0 - plane), lo);
-                    vec_load(zl + 1 == g.Lz ? P.oth_hi[c] + el : P.oth[c] + (e0 + plane), hi);
+                    vec_load((at_lo ? P.oth_lo[c] : P.oth[c]) + e_lo, lo);
+                    vec_load((at_hi ? P.oth_hi[c] : P.oth[c]) + e_hi, hi);
 #pragma unroll
                     for (int e = 0; e < N; ++e) nsum[c][e] += lo[e] + hi[e];
                 }
             }
             HeisRand<real> rnd[N];
-            if (MODE != 2) {
+            if (UPDATE) {
                 const uint64_t site0 = (uint64_t)(zg * g.Ly + y) * g.Lx + 2u * (gx * N) + rp;  // element e: site0 + 2e
                 if (sizeof(real) == 4) {
 #pragma unroll
@@ -236,13 +234,13 @@ heis_stencil_kernel(HeisPtrs<real> P, HeisGeom g, int colour, uint32_t z_begin, 
             }
 #pragma unroll
             for (int e = 0; e < N; ++e) {
-                if (MODE != 2) {
+                if (UPDATE) {
                     const bool ok = heis_attempt<real, FLIP>(s[0][e], s[1][e], s[2][e], p.J * nsum[0][e] - p.h[0],
                                                              p.J * nsum[1][e] - p.h[1], p.J * nsum[2][e] - p.h[2], p, rnd[e]);
                     accepted += ok ? 1 : 0;
                 }
                 if (OBS) {
-                    if (ENERGY) facc[0] -= p.J * (s[0][e] * nsum[0][e] + s[1][e] * nsum[1][e] + s[2][e] * nsum[2][e]);
+                    if (energy) facc[0] -= p.J * (s[0][e] * nsum[0][e] + s[1][e] * nsum[1][e] + s[2][e] * nsum[2][e]);
                     facc[1] += s[0][e]; facc[2] += s[1][e]; facc[3] += s[2][e];
                     const real d1 = s[0][e] * p.a[0] + s[1][e] * p.a[1] + s[2][e] * p.a[2];
                     facc[4] += d1 * d1;
@@ -253,7 +251,7 @@ heis_stencil_kernel(HeisPtrs<real> P, HeisGeom g, int colour, uint32_t z_begin, 
                     }
                 }
             }
-            if (MODE != 2) {
+            if (UPDATE) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     vec_store(P.own[c] + e0, s[c]);
@@ -264,10 +262,107 @@ heis_stencil_kernel(HeisPtrs<real> P, HeisGeom g, int colour, uint32_t z_begin, 
                 }
             }
         }
-        if (OBS && ((zl - z0) & 15u) == 15u) flush();  // keep the fp32 partial sums short (uniform branch)
+        if (OBS && ((zl - z0) & 15u) == 15u) every16();  // uniform branch
     }
-    if (OBS) flush();
-    if (MODE != 2) {
+}
+
+// fp32 per-thread partial sums -> f64 sums of the CTA in shared memory (every thread of the CTA calls this)
+template <typename real>
+__device__ __forceinline__ void heis_flush(real (&facc)[5], double* s_acc) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const double v = warp_sum((double)facc[i]);
+        if ((threadIdx.x & 31u) == 0 && v != 0.0) atomicAdd(&s_acc[i], v);
+        facc[i] = 0;
+    }
+}
+
+template <typename real, int NDIM, bool FLIP, int MODE>
+__global__ void __launch_bounds__(128, HEIS_MINB)
+heis_stencil_kernel(HeisPtrs<real> P, HeisGeom g, int colour, uint32_t z_begin, uint32_t z_count, uint32_t z_chunk,
+                    uint32_t z_stride /* distance between the chunk starts of consecutive blockIdx.y */,
+                    HeisParams<real> p, uint64_t sweep, PhiloxKey pk, double* __restrict__ obs) {
+    constexpr bool OBS = MODE != 0, ENERGY = MODE == 1 || MODE == 2, BOTH = MODE == 2, UPDATE = MODE != 2;
+    __shared__ double s_acc[6];
+    if (threadIdx.x < 6) s_acc[threadIdx.x] = 0.0;
+    __syncthreads();
+    const uint32_t t2 = blockIdx.x * blockDim.x + threadIdx.x;  // (y, gx) inside a plane
+    real facc[5] = {0, 0, 0, 0, 0};
+    int accepted = 0;
+    const uint32_t z0 = z_begin + blockIdx.y * z_stride;
+    const uint32_t z1 = min(z0 + z_chunk, z_begin + z_count);
+    heis_march<real, NDIM, FLIP, UPDATE, OBS, BOTH>(P, g, colour, t2, z0, z1, ENERGY, p, sweep, pk, facc, accepted,
+                                                    [&]() { heis_flush(facc, s_acc); });
+    if (OBS) heis_flush(facc, s_acc);
+    if (UPDATE) {
+        const int a = __reduce_add_sync(0xffffffffu, accepted);
+        if ((threadIdx.x & 31u) == 0 && a != 0) atomicAdd(&s_acc[5], (double)a);
+    }
+    __syncthreads();
+    if (threadIdx.x < 6 && s_acc[threadIdx.x] != 0.0) atomicAdd(obs + threadIdx.x, s_acc[threadIdx.x]);
+}
+
+// ---------------------------------------------------------------------------------------
+// K3w: the two colour passes of one step as ONE persistent launch in wave order, so that the second pass finds the
+// planes of the first in L2 (36 -> ~27 B/attempt of DRAM traffic).  Work items = (unit, tile); a unit is one colour
+// on a chunk of C planes; `units` lists them in an order in which colour 1 on chunk j comes `lag` chunks behind the
+// colour-0 front (colour-1 chunk 0 last: it needs colour 0 on the last chunk, and colour 0 on the last chunk reads the
+// OLD colour 1 of plane 0).  Items are dealt round-robin to the co-resident CTAs (static, in order: an item only waits
+// for lower-numbered items, so the lowest unfinished item can always run).  A colour-1 item waits until colour 0 is
+// complete on its own and the two adjacent chunks (per-chunk counters of finished tiles, release/acquire fences).
+// ---------------------------------------------------------------------------------------
+struct WaveSched {
+    const uint32_t* units;       // [n_units]: colour << 31 | chunk
+    uint32_t n_units, tiles, C, n_chunks;
+    unsigned long long* done;    // [n_chunks] colour-0 tiles finished on the chunk, monotone over the steps
+    unsigned long long target;   // value of done[] when colour 0 is complete on a chunk in THIS step
+    unsigned int* error;         // != 0: a dependency wait timed out (results invalid)
+};
+
+template <typename real, bool FLIP, bool RECORD>
+__global__ void __launch_bounds__(128, HEIS_MINB)
+heis_wave_kernel(HeisPtrs<real> P0, HeisPtrs<real> P1, HeisGeom g, WaveSched ws, HeisParams<real> p, uint64_t sweep,
+                 PhiloxKey pk, double* __restrict__ obs) {
+    __shared__ double s_acc[6];
+    if (threadIdx.x < 6) s_acc[threadIdx.x] = 0.0;
+    __syncthreads();
+    real facc[5] = {0, 0, 0, 0, 0};
+    int accepted = 0;
+    const uint32_t n_items = ws.n_units * ws.tiles;
+    uint32_t since_flush = 0;
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const uint32_t u = item / ws.tiles, tile = item - u * ws.tiles;
+        const uint32_t unit = ws.units[u];
+        const int colour = (int)(unit >> 31);
+        const uint32_t chunk = unit & 0x7FFFFFFFu;
+        const uint32_t z0 = chunk * ws.C, z1 = min(z0 + ws.C, g.Lz);
+        if (colour == 1) {
+            if (threadIdx.x < 3) {
+                const uint32_t dep = threadIdx.x == 0 ? (chunk == 0 ? ws.n_chunks - 1 : chunk - 1)
+                                   : threadIdx.x == 1 ? chunk : (chunk + 1 == ws.n_chunks ? 0u : chunk + 1);
+                const volatile unsigned long long* d = ws.done + dep;
+                uint32_t spins = 0;
+                while (*d < ws.target) {
+                    __nanosleep(256);
+                    if (++spins > (1u << 22)) { atomicExch(ws.error, 1u); break; }  // never hang the GPU
+                }
+                __threadfence();
+            }
+            __syncthreads();
+        }
+        const uint32_t t2 = tile * blockDim.x + threadIdx.x;
+        if (colour == 0)
+            heis_march<real, 3, FLIP, true, RECORD, false>(P0, g, 0, t2, z0, z1, false, p, sweep, pk, facc, accepted, [] {});
+        else
+            heis_march<real, 3, FLIP, true, RECORD, false>(P1, g, 1, t2, z0, z1, true, p, sweep, pk, facc, accepted, [] {});
+        if (colour == 0) {
+            __syncthreads();  // every thread's stores of this tile are issued
+            if (threadIdx.x == 0) { __threadfence(); atomicAdd(ws.done + chunk, 1ull); }
+        }
+        if (RECORD && ++since_flush == 8) { heis_flush(facc, s_acc); since_flush = 0; }
+    }
+    if (RECORD) heis_flush(facc, s_acc);
+    {
         const int a = __reduce_add_sync(0xffffffffu, accepted);
         if ((threadIdx.x & 31u) == 0 && a != 0) atomicAdd(&s_acc[5], (double)a);
     }

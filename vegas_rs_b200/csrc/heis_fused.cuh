@@ -188,7 +188,7 @@ heis_fused_kernel(FusedPtrs<real> P, FusedGeom g, HeisParams<real> p, uint64_t s
 #pragma unroll
             for (int e = 0; e < N; ++e) {
                 const real sh = RP ? (e + 1 < N ? bk1[c][(e + 1) % N] : carry) : (e > 0 ? bk1[c][(e + N - 1) % N] : carry);
-                nA[c][e] = ((bk1[c][e] + sh) + (up[e] + dn[e])) + (Bm2[c][e] + zp[e]);
+                nA[c][e] = ((bk1[c][e] + (up[e] + dn[e])) + sh) + (Bm2[c][e] + zp[e]);  // same order as heis_march
             }
         }
         const bool mineA = INTERIOR && k - 1 >= z0 && k - 1 < z1;  // not a redundant halo update
@@ -221,7 +221,7 @@ heis_fused_kernel(FusedPtrs<real> P, FusedGeom g, HeisParams<real> p, uint64_t s
 #pragma unroll
                 for (int e = 0; e < N; ++e) {
                     const real sh = RP ? (e + 1 < N ? n0[(e + 1) % N] : carry) : (e > 0 ? n0[(e + N - 1) % N] : carry);
-                    nB[c][e] = ((n0[e] + sh) + (up[e] + dn[e])) + (Am3[c][e] + s[c][e]);   // s = Anew[k-1] of the own column
+                    nB[c][e] = ((n0[e] + (up[e] + dn[e])) + sh) + (Am3[c][e] + s[c][e]);   // s = Anew[k-1] of the own column
                     Am3[c][e] = n0[e];                       // Anew[k-2] is next step's Anew[k-3]
                 }
             }

@@ -64,6 +64,16 @@ struct vegas_gpu {
     int fused_enable = -1;                // -1 auto, 0 off, 1 on
     uint32_t fused_ty = 0, fused_cz = 0;  // 0 = auto
     uint32_t wave_c = 0;                  // experiment: interleave the two colour passes in chunks of wave_c planes
+    // --- persistent wave kernel (heis_wave_kernel): both colour passes in one launch, L2-friendly order
+    int wave_enable = 0;                  // tuning key heis_wave
+    uint32_t wave_planes = 4, wave_lag = 2;
+    bool wave_ready = false;
+    WaveSched wave_sched{};
+    uint32_t* wave_units = nullptr;
+    unsigned long long* wave_done = nullptr;
+    unsigned int* wave_error = nullptr;
+    unsigned long long wave_steps = 0;
+    int wave_grid = 0;
     bool fused_ready = false;
     FusedGeom fused_geom{};
     size_t fused_smem = 0;
@@ -593,10 +603,84 @@ int fused_step_t(vegas_gpu* h, double* obs_row, bool record) {
     return VEGAS_OK;
 }
 
+// ---- persistent wave step (heis_wave_kernel) ------------------------------------------------------
+bool wave_plan(vegas_gpu* h) {
+    if (h->wave_ready) return true;
+    if (h->family != FAM_HEIS_STENCIL || h->ndim != 3 || h->slab || h->wave_enable != 1) return false;
+    const uint32_t Lz = (uint32_t)h->ld.nz, C = std::max<uint32_t>(1, h->wave_planes);
+    const uint32_t n = cdiv(Lz, C);
+    if (n < 2) return false;
+    const uint32_t D = std::max<uint32_t>(1, std::min(h->wave_lag, n - 1));
+    // colour 0 on chunk a, then colour 1 on chunk a - D (chunk 0 of colour 1 goes last)
+    std::vector<uint32_t> units;
+    for (uint32_t a = 0; a < n; ++a) {
+        units.push_back(a);
+        if (a >= D && a - D >= 1) units.push_back(0x80000000u | (a - D));
+    }
+    for (uint32_t j = std::max<uint32_t>(1, n - D); j < n; ++j) units.push_back(0x80000000u | j);
+    units.push_back(0x80000000u);
+    if (units.size() != 2 * (size_t)n) return false;
+    cudaFree(h->wave_units); cudaFree(h->wave_done); cudaFree(h->wave_error);
+    h->wave_units = nullptr; h->wave_done = nullptr; h->wave_error = nullptr;
+    if (cudaMalloc(&h->wave_units, units.size() * 4) != cudaSuccess || cudaMalloc(&h->wave_done, (size_t)n * 8) != cudaSuccess ||
+        cudaMalloc(&h->wave_error, 4) != cudaSuccess) { cudaGetLastError(); return false; }
+    cudaMemcpy(h->wave_units, units.data(), units.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemset(h->wave_done, 0, (size_t)n * 8);
+    cudaMemset(h->wave_error, 0, 4);
+    h->wave_steps = 0;
+    const HeisGeom g = heis_geom(h);
+    WaveSched ws{};
+    ws.units = h->wave_units; ws.n_units = (uint32_t)units.size(); ws.tiles = cdiv((uint64_t)g.Ly * g.Gx, 128);
+    ws.C = C; ws.n_chunks = n; ws.done = h->wave_done; ws.error = h->wave_error;
+    h->wave_sched = ws;
+    // every CTA of the grid must be resident at once (static round-robin over the items)
+    int per_sm = 0, sms = 0;
+    const bool f64 = h->md.precision == VEGAS_F64;
+    cudaError_t e = f64 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, heis_wave_kernel<double, false, true>, 128, 0)
+                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, heis_wave_kernel<float, false, true>, 128, 0);
+    if (e != cudaSuccess || per_sm < 1 || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) != cudaSuccess) return false;
+    h->wave_grid = per_sm * sms;
+    h->wave_ready = true;
+    return true;
+}
+
+template <typename real>
+void wave_ptrs(vegas_gpu* h, int colour, HeisPtrs<real>& P) {
+    const size_t plane = (size_t)(h->ld.nx / 2) * h->ld.ny;
+    for (int c = 0; c < 3; ++c) {
+        P.own[c] = (real*)h->hs[colour][c];
+        P.oth[c] = (const real*)h->hs[1 - colour][c];
+        P.oth_lo[c] = P.oth[c] + (size_t)(h->ld.nz - 1) * plane;   // periodic wrap of the single handle
+        P.oth_hi[c] = P.oth[c];
+        P.peer_lo[c] = nullptr; P.peer_hi[c] = nullptr;
+    }
+}
+
+template <typename real>
+void wave_step_t(vegas_gpu* h, double* obs_row, bool record) {
+    HeisPtrs<real> P0{}, P1{};
+    wave_ptrs<real>(h, 0, P0); wave_ptrs<real>(h, 1, P1);
+    WaveSched ws = h->wave_sched;
+    ws.target = (unsigned long long)ws.tiles * (++h->wave_steps);
+    const HeisGeom g = heis_geom(h);
+    const HeisParams<real> p = heis_params<real>(h);
+    const PhiloxKey pk = make_philox_key(h->md.seed);
+    const bool flip = h->md.proposal == VEGAS_PROPOSE_FLIP;
+    const int grid = (int)std::min<uint64_t>((uint64_t)h->wave_grid, (uint64_t)ws.n_units * ws.tiles);
+    h->launches++;
+#define WL(FLIP, REC) heis_wave_kernel<real, FLIP, REC><<<grid, 128, 0, h->stream>>>(P0, P1, g, ws, p, h->sweeps, pk, obs_row)
+    if (record) { if (flip) WL(true, true); else WL(false, true); }
+    else { if (flip) WL(true, false); else WL(false, false); }
+#undef WL
+}
+
 // One Monte Carlo step (= N attempts): every colour once.  obs_row != null records observables.
 void do_step(vegas_gpu* h, void* obs_row, void* scratch_row) {
     const bool rec = obs_row != nullptr;
-    if (h->family == FAM_HEIS_STENCIL && fused_plan(h)) {
+    if (h->family == FAM_HEIS_STENCIL && wave_plan(h)) {
+        double* row = (double*)(rec ? obs_row : scratch_row);
+        if (h->md.precision == VEGAS_F64) wave_step_t<double>(h, row, rec); else wave_step_t<float>(h, row, rec);
+    } else if (h->family == FAM_HEIS_STENCIL && fused_plan(h)) {
         double* row = (double*)(rec ? obs_row : scratch_row);
         if (h->md.precision == VEGAS_F64) fused_step_t<double>(h, row, rec); else fused_step_t<float>(h, row, rec);
     } else if (h->family == FAM_HEIS_STENCIL && h->wave_c > 0 && h->ndim == 3 && !h->slab && h->ld.nz >= 2 * h->wave_c) {
@@ -920,6 +1004,7 @@ void vegas_gpu_destroy(vegas_gpu_t h) {
     cudaFree(h->d_row_ptr); cudaFree(h->d_col); cudaFree(h->d_val);
     cudaFree(h->g_thr); cudaFree(h->g_code);
     cudaFree(h->obs);
+    cudaFree(h->wave_units); cudaFree(h->wave_done); cudaFree(h->wave_error);
     if (h->stream_b) { cudaStreamSynchronize(h->stream_b); cudaStreamDestroy(h->stream_b); }
     if (h->ev_main) cudaEventDestroy(h->ev_main);
     if (h->ev_bnd) cudaEventDestroy(h->ev_bnd);
@@ -1271,6 +1356,11 @@ int vegas_gpu_synchronize(vegas_gpu_t h) {
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
+    if (h->wave_error) {
+        unsigned int werr = 0;
+        CU(cudaMemcpy(&werr, h->wave_error, 4, cudaMemcpyDeviceToHost));
+        if (werr) return fail(h, VEGAS_ERR_CUDA, "heis_wave_kernel: a dependency wait timed out");
+    }
     return VEGAS_OK;
 }
 
@@ -1523,13 +1613,18 @@ int vegas_gpu_set_tuning(vegas_gpu_t h, const char* key, long value) {
     else if (k == "heis_fused_ty") h->fused_ty = (uint32_t)value;
     else if (k == "heis_fused_cz") h->fused_cz = (uint32_t)value;
     else if (k == "heis_wave_c") h->wave_c = (uint32_t)value;
+    else if (k == "heis_wave") h->wave_enable = (int)value;
+    else if (k == "heis_wave_planes") h->wave_planes = (uint32_t)value;
+    else if (k == "heis_wave_lag") h->wave_lag = (uint32_t)value;
     else return fail(h, VEGAS_ERR_INVALID, "unknown tuning key: " + k);
     h->fused_ready = false;  // re-plan at the next step
+    h->wave_ready = false;
     return VEGAS_OK;
 }
 
 const char* vegas_gpu_step_kernel(vegas_gpu_t h) {
     if (!h) return "";
+    if (h->family == FAM_HEIS_STENCIL && cudaSetDevice(h->device) == cudaSuccess && wave_plan(h)) return "heis_wave";
     if (h->family == FAM_HEIS_STENCIL && cudaSetDevice(h->device) == cudaSuccess && fused_plan(h)) return "heis_fused";
     return FAMILY_NAME[h->family];
 }
