@@ -32,8 +32,8 @@ WORKLOADS = {
                          bytes_per_attempt=0.25, dtype="u32 bit-packed (1 bit/spin)", cpu_L=(1024, 1024, 1)),
     "heis3d_512": dict(model="heisenberg", size=(512, 512, 512), pbc=(True, True, True), T=1.0, H=1.0, bytes_per_attempt=24.0,
                        dtype="f32", cpu_L=(128, 128, 128), anisotropy=((0.0, 0.0, 1.0), 0.1)),
-    # cfg[4]: fcc (4 sites per cell, z = 12), greedy/basis 4-colouring, general-adjacency kernel with the implicit
-    # unit-cell stencil; single GPU only (z-slabs exist for the sc stencil kernels only)
+    # cfg[4]: fcc (4 sites per cell, z = 12), basis 4-colouring, heis_basis kernel (basis-split SoA, compile-time
+    # neighbour table); single GPU only (z-slabs exist for the sc stencil kernels only)
     "heis_fcc_384": dict(model="heisenberg", unitcell="fcc", size=(384, 384, 384), pbc=(True, True, True), T=3.2, H=0.0,
                          bytes_per_attempt=24.0, dtype="f32", cpu_L=(48, 48, 48)),
 }
@@ -318,7 +318,7 @@ def main():
                 also[other] = {"value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "roofline": r["roofline"],
                                "e2e": r["e2e"], "family": r["family"],
                                "note": {"ising2d_8192": "8 MiB state is L2 resident: not an HBM measurement",
-                                        "heis_fcc_384": "general-adjacency (gather) kernel, 4 colours; correctness path, not a tuned stencil"}.get(other, "")}
+                                        "heis_fcc_384": "heis_basis kernel (scalar loads, one Philox call per site), 4 colours, single GPU"}.get(other, "")}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         k = cpu_steps_for(args.workload, 12.0)

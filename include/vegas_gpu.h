@@ -98,7 +98,7 @@ const char* vegas_gpu_version(void);
 /* ---- introspection -------------------------------------------------------------------- */
 uint64_t vegas_gpu_n_sites(vegas_gpu_t);            /* State::len, src/state.rs:279-281 (local sites) */
 int vegas_gpu_n_colours(vegas_gpu_t);
-/* kernel family in use: "ising_msc", "heis_stencil", "ising_csr", "heis_csr" */
+/* kernel family in use: "ising_msc", "heis_stencil", "heis_basis" (periodic bcc / fcc), "ising_general", "heis_general" */
 const char* vegas_gpu_kernel_family(vegas_gpu_t);
 /* the host-side adjacency this handle was built with, in the reference's CSR form (tests/oracle parity).
  * Pass NULL arrays to query sizes. Not available (VEGAS_ERR_STATE) for stencil handles above 2^27 sites. */

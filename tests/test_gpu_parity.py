@@ -219,6 +219,48 @@ def test_heisenberg_sweep_replay(built, precision, general):
     g.close()
 
 
+@pytest.mark.parametrize("name", ["bcc", "fcc", "fcc_open", "bcc_literal"])
+@pytest.mark.parametrize("precision", [vg.F64, vg.F32], ids=["f64", "f32"])
+def test_heisenberg_basis_lattices_recorded_step(built, name, precision):
+    """bcc / fcc: the recorded step reduces E and M inside the colour passes (each bond once, towards the lower colours);
+    they must equal the dedicated reduction over the final state and the oracle's Hamiltonian::total_energy."""
+    lat = dict(LATTICES)[name]
+    kw = dict(exchange=1.0, zeeman=True, anisotropy=((0.6, 0.0, 0.8), 0.25))
+    g = vg.GpuMetropolis(vg.HEISENBERG, precision=precision, seed=12, **kw, **lat)
+    # periodic bcc / fcc take the basis-split kernel with compile-time neighbour tables, the rest the general one
+    assert g.kernel_family == ("heis_basis" if name in ("bcc", "fcc") else "heis_general")
+    H, _ = oracle_model(ob.HEISENBERG, **kw, **lat)
+    n = n_sites(lat)
+    s0 = random_state(ob.HEISENBERG, n, 3)
+    g.upload(s0)
+    assert np.max(np.abs(g.download() - s0)) <= (0 if precision == vg.F64 else 1e-7)
+    g.set_thermostat(1.5, (0, 0, 1.0), 0.7)
+    th = H.thermostat(1.5, (0, 0, 1.0), 0.7)
+    tol = 1e-12 if precision == vg.F64 else 1e-5
+    # every decision of a sweep against the oracle's replay with Hamiltonian::energy
+    cpu = g.download(); col = g.colours()
+    for _ in range(2):
+        sweep = g.sweeps
+        g.step(1)
+        H.replay_heisenberg(th, ob.PROPOSE_RANDOM, precision == vg.F32, 12, sweep, col, g.n_colours, cpu)
+        dev = g.download()
+        diff = np.max(np.abs(dev - cpu), axis=1)
+        if precision == vg.F64:
+            assert np.max(diff) < 1e-12
+        else:
+            assert np.sum(diff > 1e-5) <= max(2, n // 200)
+            cpu = dev.copy()
+    for conv in (vg.E_REFERENCE_COMPOUND, vg.E_PHYSICAL):
+        g.set_energy_convention(conv)
+        e, m = g.step(2)
+        dev = g.download()
+        assert abs(e[-1] - g.total_energy()) <= tol * n * 10
+        assert np.max(np.abs(m[-1] - g.magnetization())) <= tol * n
+        if conv == vg.E_REFERENCE_COMPOUND:
+            assert abs(e[-1] - H.total_energy(th, dev)) <= tol * n * 10
+    g.close()
+
+
 def test_stencil_equals_general_ising_state_evolution(built):
     """ising_msc and ising_general are both exact restatements of the rule; on a field-free run their
     equilibrium statistics must agree (different random-number mappings, so not bitwise)."""

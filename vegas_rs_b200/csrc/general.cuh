@@ -40,6 +40,22 @@ struct StructuredNb {
             f(j, J);
         }
     }
+    // same enumeration, also handing out the neighbour's basis index (= its colour for bcc / fcc)
+    template <typename F>
+    __device__ __forceinline__ void for_each_b(uint32_t i, F&& f) const {
+        const uint32_t cell = i / (uint32_t)nb, b = i - cell * (uint32_t)nb;
+        const uint32_t ix = cell % nx, iy = (cell / nx) % ny, iz = cell / (nx * ny);
+        for (int q = 0; q < count[b]; ++q) {
+            const NbEntry en = e[b][q];
+            int tx = (int)ix + en.dx, ty = (int)iy + en.dy, tz = (int)iz + en.dz;
+            if (tx < 0 || tx >= (int)nx) { if (!pbc[0]) continue; tx = tx < 0 ? tx + (int)nx : tx - (int)nx; }
+            if (ty < 0 || ty >= (int)ny) { if (!pbc[1]) continue; ty = ty < 0 ? ty + (int)ny : ty - (int)ny; }
+            if (tz < 0 || tz >= (int)nz) { if (!pbc[2]) continue; tz = tz < 0 ? tz + (int)nz : tz - (int)nz; }
+            const uint32_t j = (((uint32_t)tz * ny + (uint32_t)ty) * nx + (uint32_t)tx) * (uint32_t)nb + (uint32_t)en.tb;
+            if (literal && (en.fwd ? !(i <= j) : !(j <= i))) continue;
+            f(j, J, (int)en.tb);
+        }
+    }
 };
 
 struct CsrNb {
@@ -129,6 +145,42 @@ heis_general_sweep_kernel(real* __restrict__ sx, real* __restrict__ sy, real* __
         acc[0] = ok ? 1.0 : 0.0;
     }
     block_atomic_add<double, 1>(acc, s_red, obs + 5);
+}
+
+// Recorded step on a bcc / fcc lattice (colour = basis index): the colour pass also reduces its own colour --
+// obs[1..3] += s, obs[4] += (s.a)^2 -- and the exchange bonds towards the LOWER colours, which are final by now, so
+// that every bond is counted once over the step; obs[0] receives twice that (the layout general_reduce_kernel fills:
+// sum_i sum_j J_ij s_i.s_j with every bond twice).  No separate reduction launch.
+template <typename real, bool FLIP>
+__global__ void __launch_bounds__(128)
+heis_basis_sweep_obs_kernel(real* __restrict__ sx, real* __restrict__ sy, real* __restrict__ sz, StructuredNb nb,
+                            const uint32_t* __restrict__ sites, uint32_t count, int colour, HeisParams<real> p,
+                            uint64_t site_offset, uint64_t sweep, PhiloxKey pk, double* __restrict__ obs) {
+    __shared__ double s_red[6 * 32];
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    if (t < count) {
+        const uint32_t i = sites[t];
+        real nx = 0, ny = 0, nz = 0, lx = 0, ly = 0, lz = 0;
+        nb.for_each_b(i, [&](uint32_t j, double Jij, int tb) {
+            if (j != i) {
+                const real w = (real)Jij, u = w * sx[j], v = w * sy[j], q = w * sz[j];
+                nx += u; ny += v; nz += q;
+                if (tb < colour) { lx += u; ly += v; lz += q; }
+            }
+        });
+        real x = sx[i], y = sy[i], z = sz[i];
+        HeisRand<real> rnd;
+        heis_rand((uint64_t)i + site_offset, sweep, pk, rnd);
+        const bool ok = heis_attempt<real, FLIP>(x, y, z, nx - p.h[0], ny - p.h[1], nz - p.h[2], p, rnd);
+        if (ok) { sx[i] = x; sy[i] = y; sz[i] = z; }
+        acc[0] = 2.0 * ((double)x * lx + (double)y * ly + (double)z * lz);
+        acc[1] = x; acc[2] = y; acc[3] = z;
+        const double d = (double)x * p.a[0] + (double)y * p.a[1] + (double)z * p.a[2];
+        acc[4] = d * d;
+        acc[5] = ok ? 1.0 : 0.0;
+    }
+    block_atomic_add<double, 6>(acc, s_red, obs);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -13,6 +13,7 @@
 
 #include "general.cuh"
 #include "heis.cuh"
+#include "heis_basis.cuh"
 #include "heis_fused.cuh"
 #include "ising_msc.cuh"
 #include "lattice.hpp"
@@ -21,8 +22,8 @@ using namespace vg;
 
 namespace {
 
-enum Family { FAM_ISING_MSC = 0, FAM_HEIS_STENCIL = 1, FAM_ISING_GEN = 2, FAM_HEIS_GEN = 3 };
-const char* const FAMILY_NAME[4] = {"ising_msc", "heis_stencil", "ising_general", "heis_general"};
+enum Family { FAM_ISING_MSC = 0, FAM_HEIS_STENCIL = 1, FAM_ISING_GEN = 2, FAM_HEIS_GEN = 3, FAM_HEIS_BASIS = 4 };
+const char* const FAMILY_NAME[5] = {"ising_msc", "heis_stencil", "ising_general", "heis_general", "heis_basis"};
 
 constexpr uint64_t OBS_CAP = 4096;  // steps of observables kept on the device per batch
 constexpr int OBS_W = 8;            // 8 x 8-byte slots per step
@@ -59,6 +60,8 @@ struct vegas_gpu {
     std::vector<uint8_t> ising_always;    // [2][8]
     // --- Heisenberg stencil: [colour][component]
     void* hs[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    // --- periodic bcc / fcc Heisenberg (heis_basis.cuh): basis-split SoA [basis][component][cell]
+    void* hb[4][3] = {};
     // --- fused two-colour step (heis_fused.cuh): second buffer set, tile geometry; hs <-> hs_alt swap every fused step
     void* hs_alt[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     int fused_enable = -1;                // -1 auto, 0 off, 1 on
@@ -475,6 +478,30 @@ void join_boundary_stream(vegas_gpu* h) {
 }
 
 // ---- general family ---------------------------------------------------------------------
+// bcc / fcc Heisenberg: the colour passes of a recorded step reduce the observables themselves
+bool basis_fused_obs(const vegas_gpu* h) {
+    return h->family == FAM_HEIS_GEN && !h->csr_input && vgl::basis_count(h->ld.unitcell) > 1;
+}
+
+void basis_obs_pass(vegas_gpu* h, int colour, double* obs_row) {
+    const uint32_t count = h->g_counts[colour];
+    if (count == 0) return;
+    const PhiloxKey pk = make_philox_key(h->md.seed);
+    const StructuredNb nb = structured_nb(h);
+    const dim3 grid(cdiv(count, 128));
+    const bool flip = h->md.proposal == VEGAS_PROPOSE_FLIP;
+    h->launches++;
+    if (h->md.precision == VEGAS_F64) {
+        const HeisParams<double> p = heis_params<double>(h);
+        if (flip) heis_basis_sweep_obs_kernel<double, true><<<grid, 128, 0, h->stream>>>((double*)h->g_s[0], (double*)h->g_s[1], (double*)h->g_s[2], nb, h->g_sites[colour], count, colour, p, 0, h->sweeps, pk, obs_row);
+        else heis_basis_sweep_obs_kernel<double, false><<<grid, 128, 0, h->stream>>>((double*)h->g_s[0], (double*)h->g_s[1], (double*)h->g_s[2], nb, h->g_sites[colour], count, colour, p, 0, h->sweeps, pk, obs_row);
+    } else {
+        const HeisParams<float> p = heis_params<float>(h);
+        if (flip) heis_basis_sweep_obs_kernel<float, true><<<grid, 128, 0, h->stream>>>((float*)h->g_s[0], (float*)h->g_s[1], (float*)h->g_s[2], nb, h->g_sites[colour], count, colour, p, 0, h->sweeps, pk, obs_row);
+        else heis_basis_sweep_obs_kernel<float, false><<<grid, 128, 0, h->stream>>>((float*)h->g_s[0], (float*)h->g_s[1], (float*)h->g_s[2], nb, h->g_sites[colour], count, colour, p, 0, h->sweeps, pk, obs_row);
+    }
+}
+
 template <typename NB>
 void general_colour_pass(vegas_gpu* h, const NB& nb, int colour, unsigned long long* obs_row) {
     const uint32_t count = h->g_counts[colour];
@@ -523,6 +550,56 @@ void general_reduce(vegas_gpu* h, const NB& nb, double* obs_row) {
         HeisSpins<float> sp{(const float*)h->g_s[0], (const float*)h->g_s[1], (const float*)h->g_s[2]};
         general_reduce_kernel<NB, HeisSpins<float>><<<grid, 256, 0, h->stream>>>(nb, sp, n, ax, ay, az, obs_row);
     }
+}
+
+// ---- periodic bcc / fcc Heisenberg (heis_basis.cuh) ----------------------------------------------
+template <typename real>
+BasisPtrs<real> basis_ptrs(const vegas_gpu* h) {
+    BasisPtrs<real> P{};
+    for (int b = 0; b < 4; ++b) for (int c = 0; c < 3; ++c) P.s[b][c] = (real*)h->hb[b][c];
+    return P;
+}
+BasisGeom basis_geom(const vegas_gpu* h) {
+    BasisGeom g{};
+    g.nx = (uint32_t)h->ld.nx; g.ny = (uint32_t)h->ld.ny; g.nz = (uint32_t)h->ld.nz; g.ncells = g.nx * g.ny * g.nz;
+    return g;
+}
+
+template <typename real, int UC, int B>
+void basis_launch(vegas_gpu* h, int mode, double* obs) {
+    const BasisGeom g = basis_geom(h);
+    // rows per CTA: enough CTAs to fill the GPU (~16 per SM), at most 64 rows (fp32 partial sums stay short)
+    const uint64_t ctas_per_row_set = (uint64_t)cdiv(g.nx, 128) * g.nz;
+    uint32_t rows = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, (uint64_t)g.ny * ctas_per_row_set / (148u * 16u)));
+    const dim3 grid(cdiv(g.nx, 128), cdiv(g.ny, rows), g.nz);
+    const HeisParams<real> p = heis_params<real>(h);
+    const PhiloxKey pk = make_philox_key(h->md.seed);
+    const BasisPtrs<real> P = basis_ptrs<real>(h);
+    const bool flip = h->md.proposal == VEGAS_PROPOSE_FLIP;
+    h->launches++;
+#define BL(FLIP, MODE) heis_basis_kernel<real, UC, B, FLIP, MODE><<<grid, 128, 0, h->stream>>>(P, g, rows, p, h->sweeps, pk, obs)
+    if (mode == 2) BL(false, 2);
+    else if (mode == 1) { if (flip) BL(true, 1); else BL(false, 1); }
+    else { if (flip) BL(true, 0); else BL(false, 0); }
+#undef BL
+}
+
+// one colour (= basis) pass; mode as heis_basis_kernel
+template <typename real>
+void basis_pass(vegas_gpu* h, int mode, int b, double* obs) {
+    if (h->ld.unitcell == VEGAS_BCC) {
+        if (b == 0) basis_launch<real, 1, 0>(h, mode, obs); else basis_launch<real, 1, 1>(h, mode, obs);
+    } else {
+        switch (b) {
+            case 0: basis_launch<real, 2, 0>(h, mode, obs); break;
+            case 1: basis_launch<real, 2, 1>(h, mode, obs); break;
+            case 2: basis_launch<real, 2, 2>(h, mode, obs); break;
+            default: basis_launch<real, 2, 3>(h, mode, obs); break;
+        }
+    }
+}
+void basis_pass_any(vegas_gpu* h, int mode, int b, double* obs) {
+    if (h->md.precision == VEGAS_F64) basis_pass<double>(h, mode, b, obs); else basis_pass<float>(h, mode, b, obs);
 }
 
 // ---- fused two-colour Heisenberg step -------------------------------------------------------
@@ -677,7 +754,9 @@ void wave_step_t(vegas_gpu* h, double* obs_row, bool record) {
 // One Monte Carlo step (= N attempts): every colour once.  obs_row != null records observables.
 void do_step(vegas_gpu* h, void* obs_row, void* scratch_row) {
     const bool rec = obs_row != nullptr;
-    if (h->family == FAM_HEIS_STENCIL && wave_plan(h)) {
+    if (h->family == FAM_HEIS_BASIS) {
+        for (int b = 0; b < h->n_colours; ++b) basis_pass_any(h, rec ? 1 : 0, b, (double*)(rec ? obs_row : scratch_row));
+    } else if (h->family == FAM_HEIS_STENCIL && wave_plan(h)) {
         double* row = (double*)(rec ? obs_row : scratch_row);
         if (h->md.precision == VEGAS_F64) wave_step_t<double>(h, row, rec); else wave_step_t<float>(h, row, rec);
     } else if (h->family == FAM_HEIS_STENCIL && fused_plan(h)) {
@@ -712,11 +791,13 @@ void do_step(vegas_gpu* h, void* obs_row, void* scratch_row) {
         }
     } else {
         unsigned long long* row = (unsigned long long*)(rec ? obs_row : scratch_row);
+        const bool fused_obs = rec && basis_fused_obs(h);
         for (int c = 0; c < h->n_colours; ++c) {
-            if (h->csr_input) general_colour_pass(h, csr_nb(h), c, row);
+            if (fused_obs) basis_obs_pass(h, c, (double*)row);
+            else if (h->csr_input) general_colour_pass(h, csr_nb(h), c, row);
             else general_colour_pass(h, structured_nb(h), c, row);
         }
-        if (rec) {
+        if (rec && !fused_obs) {
             if (h->csr_input) general_reduce(h, csr_nb(h), (double*)obs_row);
             else general_reduce(h, structured_nb(h), (double*)obs_row);
         }
@@ -772,6 +853,7 @@ int measure_now(vegas_gpu* h, Canon& out) {
     unsigned long long* row = h->obs + (OBS_CAP + 1) * OBS_W;
     CU(cudaMemsetAsync(row, 0, OBS_W * 8, h->stream));
     if (h->family == FAM_ISING_MSC || h->family == FAM_HEIS_STENCIL) stencil_colour_pass(h, 2, 1, row);
+    else if (h->family == FAM_HEIS_BASIS) { for (int b = 0; b < h->n_colours; ++b) basis_pass_any(h, 2, b, (double*)row); }
     else if (h->csr_input) general_reduce(h, csr_nb(h), (double*)row);
     else general_reduce(h, structured_nb(h), (double*)row);
     unsigned long long host[OBS_W];
@@ -924,6 +1006,17 @@ int vegas_gpu_create_lattice(const vegas_model_desc* md, const vegas_lattice_des
             cudaMemcpyAsync(h->flags + 4, &magic, 8, cudaMemcpyHostToDevice, h->stream);
             cudaStreamSynchronize(h->stream);
         }
+    } else if (md->model == VEGAS_HEISENBERG && ldesc->unitcell != VEGAS_SC && !hh->ld.literal && !md->force_general &&
+               hh->ld.pbc[0] && hh->ld.pbc[1] && hh->ld.pbc[2] && !hh->slab && h->n < (1ull << 32)) {
+        // periodic bcc / fcc: basis-split arrays, colour = basis, compile-time neighbour tables (heis_basis.cuh)
+        h->family = FAM_HEIS_BASIS;
+        h->n_colours = vgl::basis_count(ldesc->unitcell);
+        h->h_colour.resize(h->n);
+        for (uint64_t i = 0; i < h->n; ++i) h->h_colour[i] = (uint8_t)(i % (uint64_t)h->n_colours);
+        const size_t bytes = (size_t)(h->n / h->n_colours) * real_bytes(h);
+        for (int b = 0; b < h->n_colours; ++b)
+            for (int k = 0; k < 3; ++k)
+                if (cudaMalloc(&h->hb[b][k], bytes) != cudaSuccess) return bail(fail(h, VEGAS_ERR_ALLOC, "cudaMalloc (spins) failed"));
     } else {
         h->family = md->model == VEGAS_ISING ? FAM_ISING_GEN : FAM_HEIS_GEN;
         if (h->n >= (1ull << 32)) return bail(fail(h, VEGAS_ERR_INVALID, "general-adjacency path supports < 2^32 sites"));
@@ -998,6 +1091,7 @@ void vegas_gpu_destroy(vegas_gpu_t h) {
         if (h->peer_halo[1] && h->peer_halo[1] != h->peer_halo[0]) cudaIpcCloseMemHandle(h->peer_halo[1]);
     }
     cudaFree(h->halo);
+    for (int b = 0; b < 4; ++b) for (int k = 0; k < 3; ++k) cudaFree(h->hb[b][k]);
     cudaFree(h->g_s8);
     for (int k = 0; k < 3; ++k) cudaFree(h->g_s[k]);
     for (uint32_t* p : h->g_sites) cudaFree(p);
@@ -1142,7 +1236,9 @@ namespace {
 template <typename real>
 int heis_upload_t(vegas_gpu* h, const double* dev_aos) {
     const uint32_t n = (uint32_t)h->n;
-    if (h->family == FAM_HEIS_GEN) {
+    if (h->family == FAM_HEIS_BASIS) {
+        basis_pack_kernel<real><<<cdiv(h->n, 256), 256, 0, h->stream>>>(dev_aos, basis_ptrs<real>(h), (uint32_t)h->n_colours, (size_t)h->n);
+    } else if (h->family == FAM_HEIS_GEN) {
         aos_to_soa_kernel<real><<<cdiv(n, 256), 256, 0, h->stream>>>(dev_aos, (real*)h->g_s[0], (real*)h->g_s[1], (real*)h->g_s[2], n);
     } else {
         heis_pack_kernel<real><<<cdiv(h->n, 256), 256, 0, h->stream>>>(dev_aos, (real*)h->hs[0][0], (real*)h->hs[0][1], (real*)h->hs[0][2],
@@ -1156,7 +1252,10 @@ int heis_upload_t(vegas_gpu* h, const double* dev_aos) {
 template <typename real>
 int heis_download_t(vegas_gpu* h, double* dev_aos) {
     const uint32_t n = (uint32_t)h->n;
-    if (h->family == FAM_HEIS_GEN) {
+    if (h->family == FAM_HEIS_BASIS) {
+        basis_unpack_kernel<real, double><<<cdiv(h->n, 256), 256, 0, h->stream>>>(dev_aos, dev_aos + 1, dev_aos + 2, 3, basis_ptrs<real>(h),
+                                                                                 (uint32_t)h->n_colours, (size_t)h->n);
+    } else if (h->family == FAM_HEIS_GEN) {
         soa_to_aos_kernel<real><<<cdiv(n, 256), 256, 0, h->stream>>>(dev_aos, (const real*)h->g_s[0], (const real*)h->g_s[1], (const real*)h->g_s[2], n);
     } else {
         heis_unpack_kernel<real, double><<<cdiv(h->n, 256), 256, 0, h->stream>>>(
@@ -1183,6 +1282,9 @@ int run_fill(vegas_gpu* h, int up) {
         };
         if (h->family == FAM_HEIS_GEN) {
             fill(h->g_s[0], h->n, 0.0); fill(h->g_s[1], h->n, 0.0); fill(h->g_s[2], h->n, up ? 1.0 : -1.0);
+        } else if (h->family == FAM_HEIS_BASIS) {
+            const size_t cells = h->n / h->n_colours;
+            for (int b = 0; b < h->n_colours; ++b) { fill(h->hb[b][0], cells, 0.0); fill(h->hb[b][1], cells, 0.0); fill(h->hb[b][2], cells, up ? 1.0 : -1.0); }
         } else {
             for (int c = 0; c < 2; ++c) {
                 fill(h->hs[c][0], heis_colour_elems(h), 0.0); fill(h->hs[c][1], heis_colour_elems(h), 0.0);
@@ -1263,6 +1365,9 @@ int vegas_gpu_randomize(vegas_gpu_t h) {
         ising_msc_randomize_kernel<<<cdiv(words, 256), 256, 0, h->stream>>>(h->msc[0], h->msc[1], words, woff, pk);
     } else if (h->family == FAM_ISING_GEN) {
         ising_general_randomize_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(h->g_s8, (uint32_t)h->n, 0, pk);
+    } else if (h->family == FAM_HEIS_BASIS) {
+        if (h->md.precision == VEGAS_F64) basis_randomize_kernel<double><<<cdiv(h->n, 256), 256, 0, h->stream>>>(basis_ptrs<double>(h), (uint32_t)h->n_colours, (size_t)h->n, pk);
+        else basis_randomize_kernel<float><<<cdiv(h->n, 256), 256, 0, h->stream>>>(basis_ptrs<float>(h), (uint32_t)h->n_colours, (size_t)h->n, pk);
     } else if (h->family == FAM_HEIS_GEN) {
         if (h->md.precision == VEGAS_F64) heis_general_randomize_kernel<double><<<cdiv(h->n, 256), 256, 0, h->stream>>>((double*)h->g_s[0], (double*)h->g_s[1], (double*)h->g_s[2], (uint32_t)h->n, 0, pk);
         else heis_general_randomize_kernel<float><<<cdiv(h->n, 256), 256, 0, h->stream>>>((float*)h->g_s[0], (float*)h->g_s[1], (float*)h->g_s[2], (uint32_t)h->n, 0, pk);
@@ -1447,6 +1552,12 @@ int site_energy_run(vegas_gpu* h, const NB& nb, const void* proposal, int want_d
         site_energy_kernel<NB, IsingSpins><<<grid, 256, 0, h->stream>>>(nb, sp, n, ep, d_prop, flip, oe, ode);
     } else if (h->md.precision == VEGAS_F64) {
         const double* s[3] = {(const double*)h->g_s[0], (const double*)h->g_s[1], (const double*)h->g_s[2]};
+        if (h->family == FAM_HEIS_BASIS) {
+            for (int c = 0; c < 3; ++c) CU(cudaMallocAsync(&tmp[c], (size_t)n * 8, h->stream));
+            basis_unpack_kernel<double, double><<<cdiv(n, 256), 256, 0, h->stream>>>((double*)tmp[0], (double*)tmp[1], (double*)tmp[2], 1,
+                                                                                    basis_ptrs<double>(h), (uint32_t)h->n_colours, (size_t)n);
+            for (int c = 0; c < 3; ++c) s[c] = (const double*)tmp[c];
+        }
         if (h->family == FAM_HEIS_STENCIL) {
             for (int c = 0; c < 3; ++c) CU(cudaMallocAsync(&tmp[c], (size_t)n * 8, h->stream));
             heis_unpack_kernel<double, double><<<cdiv(n, 256), 256, 0, h->stream>>>((double*)tmp[0], (double*)tmp[1], (double*)tmp[2], 1,
@@ -1458,6 +1569,12 @@ int site_energy_run(vegas_gpu* h, const NB& nb, const void* proposal, int want_d
         site_energy_kernel<NB, HeisSpins<double>><<<grid, 256, 0, h->stream>>>(nb, sp, n, ep, d_prop, flip, oe, ode);
     } else {
         const float* s[3] = {(const float*)h->g_s[0], (const float*)h->g_s[1], (const float*)h->g_s[2]};
+        if (h->family == FAM_HEIS_BASIS) {
+            for (int c = 0; c < 3; ++c) CU(cudaMallocAsync(&tmp[c], (size_t)n * 4, h->stream));
+            basis_unpack_kernel<float, float><<<cdiv(n, 256), 256, 0, h->stream>>>((float*)tmp[0], (float*)tmp[1], (float*)tmp[2], 1,
+                                                                                  basis_ptrs<float>(h), (uint32_t)h->n_colours, (size_t)n);
+            for (int c = 0; c < 3; ++c) s[c] = (const float*)tmp[c];
+        }
         if (h->family == FAM_HEIS_STENCIL) {
             for (int c = 0; c < 3; ++c) CU(cudaMallocAsync(&tmp[c], (size_t)n * 4, h->stream));
             heis_unpack_kernel<float, float><<<cdiv(n, 256), 256, 0, h->stream>>>((float*)tmp[0], (float*)tmp[1], (float*)tmp[2], 1,
