@@ -160,7 +160,10 @@ struct HeisPtrs {
 //           [0] -sum s.n (exchange energy, each bond once);  BOTH adds the other colour's s and (s.a)^2 as well
 // `every16` is called (by all threads of the CTA, uniformly) after every 16th plane so that the caller can shorten the
 // fp32 partial sums.
-template <typename real, int NDIM, bool FLIP, bool UPDATE, bool OBS, bool BOTH, typename F>
+// HALO: planes outside the local z range come from P.oth_lo / P.oth_hi and boundary planes are also stored into the
+// neighbours' halos (connected slab); otherwise the periodic wrap of P.oth itself is used and those twelve pointers
+// are never touched (they would crowd the Philox round keys out of the uniform registers).
+template <typename real, int NDIM, bool FLIP, bool UPDATE, bool OBS, bool BOTH, bool HALO, typename F>
 __device__ __forceinline__ void heis_march(const HeisPtrs<real>& P, const HeisGeom& g, int colour, uint32_t t2, uint32_t z0,
                                            uint32_t z1, bool energy, const HeisParams<real>& p, uint64_t sweep,
                                            const PhiloxKey& pk, real (&facc)[5], int& accepted, F&& every16) {
@@ -184,7 +187,7 @@ __device__ __forceinline__ void heis_march(const HeisPtrs<real>& P, const HeisGe
 
             // planes z-1 / z+1: the base pointer choice is uniform over the CTA, the offset is one select per thread
             const bool at_lo = NDIM == 3 && zl == 0, at_hi = NDIM == 3 && zl + 1 == g.Lz;
-            const uint32_t e_lo = at_lo ? el : e0 - plane, e_hi = at_hi ? el : e0 + plane;
+            const uint32_t e_lo = at_lo ? (HALO ? el : (g.Lz - 1) * plane + el) : e0 - plane, e_hi = at_hi ? el : e0 + plane;
             real s[3][N], nsum[3][N], partner[3][N];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -210,8 +213,8 @@ __device__ __forceinline__ void heis_march(const HeisPtrs<real>& P, const HeisGe
                 }
                 if (NDIM == 3) {
                     real lo[N], hi[N];
-                    vec_load((at_lo ? P.oth_lo[c] : P.oth[c]) + e_lo, lo);
-                    vec_load((at_hi ? P.oth_hi[c] : P.oth[c]) + e_hi, hi);
+                    vec_load((HALO && at_lo ? P.oth_lo[c] : P.oth[c]) + e_lo, lo);
+                    vec_load((HALO && at_hi ? P.oth_hi[c] : P.oth[c]) + e_hi, hi);
 #pragma unroll
                     for (int e = 0; e < N; ++e) nsum[c][e] += lo[e] + hi[e];
                 }
@@ -255,7 +258,7 @@ __device__ __forceinline__ void heis_march(const HeisPtrs<real>& P, const HeisGe
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     vec_store(P.own[c] + e0, s[c]);
-                    if (NDIM == 3) {
+                    if (NDIM == 3 && HALO) {
                         if (P.peer_lo[c] != nullptr && zl == 0) vec_store(P.peer_lo[c] + el, s[c]);
                         if (P.peer_hi[c] != nullptr && zl + 1 == g.Lz) vec_store(P.peer_hi[c] + el, s[c]);
                     }
@@ -277,7 +280,7 @@ __device__ __forceinline__ void heis_flush(real (&facc)[5], double* s_acc) {
     }
 }
 
-template <typename real, int NDIM, bool FLIP, int MODE>
+template <typename real, int NDIM, bool FLIP, int MODE, bool HALO = true>
 __global__ void __launch_bounds__(128, HEIS_MINB)
 heis_stencil_kernel(HeisPtrs<real> P, HeisGeom g, int colour, uint32_t z_begin, uint32_t z_count, uint32_t z_chunk,
                     uint32_t z_stride /* distance between the chunk starts of consecutive blockIdx.y */,
@@ -291,7 +294,7 @@ heis_stencil_kernel(HeisPtrs<real> P, HeisGeom g, int colour, uint32_t z_begin, 
     int accepted = 0;
     const uint32_t z0 = z_begin + blockIdx.y * z_stride;
     const uint32_t z1 = min(z0 + z_chunk, z_begin + z_count);
-    heis_march<real, NDIM, FLIP, UPDATE, OBS, BOTH>(P, g, colour, t2, z0, z1, ENERGY, p, sweep, pk, facc, accepted,
+    heis_march<real, NDIM, FLIP, UPDATE, OBS, BOTH, HALO>(P, g, colour, t2, z0, z1, ENERGY, p, sweep, pk, facc, accepted,
                                                     [&]() { heis_flush(facc, s_acc); });
     if (OBS) heis_flush(facc, s_acc);
     if (UPDATE) {
@@ -352,9 +355,9 @@ heis_wave_kernel(HeisPtrs<real> P0, HeisPtrs<real> P1, HeisGeom g, WaveSched ws,
         }
         const uint32_t t2 = tile * blockDim.x + threadIdx.x;
         if (colour == 0)
-            heis_march<real, 3, FLIP, true, RECORD, false>(P0, g, 0, t2, z0, z1, false, p, sweep, pk, facc, accepted, [] {});
+            heis_march<real, 3, FLIP, true, RECORD, false, false>(P0, g, 0, t2, z0, z1, false, p, sweep, pk, facc, accepted, [] {});
         else
-            heis_march<real, 3, FLIP, true, RECORD, false>(P1, g, 1, t2, z0, z1, true, p, sweep, pk, facc, accepted, [] {});
+            heis_march<real, 3, FLIP, true, RECORD, false, false>(P1, g, 1, t2, z0, z1, true, p, sweep, pk, facc, accepted, [] {});
         if (colour == 0) {
             __syncthreads();  // every thread's stores of this tile are issued
             if (threadIdx.x == 0) { __threadfence(); atomicAdd(ws.done + chunk, 1ull); }

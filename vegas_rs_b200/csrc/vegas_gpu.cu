@@ -363,7 +363,13 @@ void launch_heis(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, u
     const PhiloxKey pk = make_philox_key(h->md.seed);
     const bool flip = h->md.proposal == VEGAS_PROPOSE_FLIP;
     h->launches++;
-#define HL(FLIP, MODE) heis_stencil_kernel<real, NDIM, FLIP, MODE><<<grid, 128, 0, st>>>(P, g, colour, zb, zc, z_chunk, z_stride, p, h->sweeps, pk, obs)
+    // halo / peer pointers only matter for launches that touch local plane 0 or Lz-1 of a connected slab
+    const bool halo = h->slab && h->connected && (zb == 0 || zb + zc >= g.Lz);
+#define HL(FLIP, MODE)                                                                                                             \
+    do {                                                                                                                           \
+        if (halo) heis_stencil_kernel<real, NDIM, FLIP, MODE, true><<<grid, 128, 0, st>>>(P, g, colour, zb, zc, z_chunk, z_stride, p, h->sweeps, pk, obs); \
+        else heis_stencil_kernel<real, NDIM, FLIP, MODE, false><<<grid, 128, 0, st>>>(P, g, colour, zb, zc, z_chunk, z_stride, p, h->sweeps, pk, obs);    \
+    } while (0)
     if (mode == 2) HL(false, 2);
     else if (mode == 1) { if (flip) HL(true, 1); else HL(false, 1); }
     else if (mode == 3) { if (flip) HL(true, 3); else HL(false, 3); }
@@ -434,6 +440,43 @@ __global__ void wait_kernel(const unsigned long long* flags, unsigned long long 
         } while (v < value);
     }
     __threadfence_system();
+}
+
+// CUDA loads kernels lazily, and loading one while a spinning wait_kernel is resident can block the launching host
+// thread -- fatal when that thread is also the one that must enqueue the neighbour slab's work (all slabs in one
+// process).  A connected slab therefore loads every kernel variant it can launch up front.
+template <typename K>
+void preload(K kernel) {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, kernel);
+}
+template <typename real>
+void preload_heis_slab() {
+    preload(heis_stencil_kernel<real, 3, false, 0, true>); preload(heis_stencil_kernel<real, 3, false, 0, false>);
+    preload(heis_stencil_kernel<real, 3, false, 1, true>); preload(heis_stencil_kernel<real, 3, false, 1, false>);
+    preload(heis_stencil_kernel<real, 3, false, 3, true>); preload(heis_stencil_kernel<real, 3, false, 3, false>);
+    preload(heis_stencil_kernel<real, 3, true, 0, true>); preload(heis_stencil_kernel<real, 3, true, 0, false>);
+    preload(heis_stencil_kernel<real, 3, true, 1, true>); preload(heis_stencil_kernel<real, 3, true, 1, false>);
+    preload(heis_stencil_kernel<real, 3, true, 3, true>); preload(heis_stencil_kernel<real, 3, true, 3, false>);
+    preload(heis_stencil_kernel<real, 3, false, 2, true>); preload(heis_stencil_kernel<real, 3, false, 2, false>);
+}
+template <bool RP>
+void preload_msc_slab() {
+    preload(ising_msc_kernel<3, true, 14, RP, 0, false, true>); preload(ising_msc_kernel<3, true, 14, RP, 1, false, true>);
+    preload(ising_msc_kernel<3, false, 3, RP, 0, true, true>); preload(ising_msc_kernel<3, false, 3, RP, 1, true, true>);
+    preload(ising_msc_kernel<3, false, 3, RP, 0, true, false>); preload(ising_msc_kernel<3, false, 3, RP, 1, true, false>);
+    preload(ising_msc_kernel<3, false, 3, RP, 0, false, true>); preload(ising_msc_kernel<3, false, 3, RP, 1, false, true>);
+}
+__global__ void signal_kernel(unsigned long long*, unsigned long long*, unsigned long long);
+__global__ void wait_kernel(const unsigned long long*, unsigned long long);
+__global__ void copy_plane_kernel(uint32_t*, const uint32_t*, size_t);
+void preload_slab_kernels(vegas_gpu* h) {
+    preload(signal_kernel); preload(wait_kernel); preload(copy_plane_kernel);
+    if (h->family == FAM_ISING_MSC) {
+        preload_msc_slab<false>(); preload_msc_slab<true>();
+        preload(ising_msc_kernel<3, false, 3, false, 2>);
+    } else if (h->md.precision == VEGAS_F64) preload_heis_slab<double>();
+    else preload_heis_slab<float>();
 }
 
 void stencil_colour_pass(vegas_gpu* h, int mode, int colour, void* obs_row) {
@@ -1696,6 +1739,7 @@ int vegas_gpu_slab_connect(vegas_gpu_t h, const void* lower, const void* upper) 
     }
     h->peer_is_ipc = true;
     h->connected = true;
+    preload_slab_kernels(h);
     return push_boundaries(h);
 }
 
@@ -1719,6 +1763,7 @@ int vegas_gpu_slab_connect_local(vegas_gpu_t h, vegas_gpu_t lower, vegas_gpu_t u
     }
     h->peer_is_ipc = false;
     h->connected = true;
+    preload_slab_kernels(h);
     return push_boundaries(h);
 }
 
