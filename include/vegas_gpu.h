@@ -168,6 +168,10 @@ int vegas_gpu_slab_connect_local(vegas_gpu_t self, vegas_gpu_t lower, vegas_gpu_
  * key "heis_fused"    : -1 auto (default), 0 never, 1 whenever the lattice fits  -- the one-launch-per-step
  *                       two-colour Heisenberg kernel (heis_fused.cuh) instead of two colour passes
  *     "heis_fused_ty" : interior rows per CTA tile (0 = auto), "heis_fused_cz": planes per z-chunk (0 = auto)
+ *     "heis_wave"     : -1 auto (default: lattices with >= 32 planes), 0 never, 1 always -- both colour passes of a
+ *                       Heisenberg step as ONE persistent launch in wave order (second pass finds the first in L2);
+ *                       "heis_wave_planes" (planes per chunk, default 4), "heis_wave_lag" (chunks, default 4)
+ *     "heis_wave_c"   : experiment: the two passes as separate launches interleaved in chunks of C planes
  * Results do not depend on these knobs (same Philox keys, same arithmetic). */
 int vegas_gpu_set_tuning(vegas_gpu_t, const char* key, long value);
 /* name of the kernel the NEXT step will launch: "heis_fused", "heis_stencil", "ising_msc", ... */

@@ -68,8 +68,8 @@ struct vegas_gpu {
     uint32_t fused_ty = 0, fused_cz = 0;  // 0 = auto
     uint32_t wave_c = 0;                  // experiment: interleave the two colour passes in chunks of wave_c planes
     // --- persistent wave kernel (heis_wave_kernel): both colour passes in one launch, L2-friendly order
-    int wave_enable = 0;                  // tuning key heis_wave
-    uint32_t wave_planes = 4, wave_lag = 2;
+    int wave_enable = -1;                 // tuning key heis_wave: -1 auto (lattices with >= 32 planes), 0 never, 1 always
+    uint32_t wave_planes = 4, wave_lag = 4;
     bool wave_ready = false;
     WaveSched wave_sched{};
     uint32_t* wave_units = nullptr;
@@ -726,7 +726,8 @@ int fused_step_t(vegas_gpu* h, double* obs_row, bool record) {
 // ---- persistent wave step (heis_wave_kernel) ------------------------------------------------------
 bool wave_plan(vegas_gpu* h) {
     if (h->wave_ready) return true;
-    if (h->family != FAM_HEIS_STENCIL || h->ndim != 3 || h->slab || h->wave_enable != 1) return false;
+    if (h->family != FAM_HEIS_STENCIL || h->ndim != 3 || h->slab || h->wave_enable == 0) return false;
+    if (h->wave_enable < 0 && (h->ld.nz < 32 || h->fused_enable == 1 || h->wave_c > 0)) return false;  // auto: big lattices only
     const uint32_t Lz = (uint32_t)h->ld.nz, C = std::max<uint32_t>(1, h->wave_planes);
     const uint32_t n = cdiv(Lz, C);
     if (n < 2) return false;
