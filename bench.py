@@ -37,11 +37,12 @@ WORKLOADS = {
     "heis_fcc_384": dict(model="heisenberg", unitcell="fcc", size=(384, 384, 384), pbc=(True, True, True), T=3.2, H=0.0,
                          bytes_per_attempt=24.0, dtype="f32", cpu_L=(48, 48, 48)),
 }
-# dram__bytes_read.sum + dram__bytes_write.sum per colour-pass launch from the committed `ncu --set full` captures
-# (profiles/r01a_*.metrics.txt, cold cache): (bytes, source)
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from the committed `ncu --set full`
+# captures (cold cache): (bytes, source)
 NCU_TRAFFIC = {
-    "ising3d_1024": (134.38e6 + 35.52e6, "profiles/r01a_ising_msc.metrics.txt"),
-    "heis3d_512": (1.6439e9 + 0.7726e9, "profiles/r01a_heis_stencil.metrics.txt"),
+    "ising3d_1024": (134.37e6 + 30.83e6, "profiles/r01o_ising_msc.metrics.txt (one colour pass)"),
+    "heis3d_512": (2.887e9 + 1.562e9, "profiles/r01u_heis_wave.metrics.txt (one step = both colours)"),
+    "heis_fcc_384": (2.753e9 + 0.662e9, "profiles/r01s_heis_basis.metrics.txt (one colour pass)"),
 }
 METRIC = "spin-flip attempts/sec"
 UNIT = "attempts/s"
@@ -196,6 +197,7 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, world: int, devi
         from vegas_rs_b200 import distributed as vd
         vd.connect_slabs(g, dist)
     n_local = g.n_sites
+    step_kernel = g.step_kernel
     # ---- device-resident throughput: K steps, fused E/M on, CUDA events on the sweep stream
     g.step_async(warmup, False)
     g.synchronize()
@@ -265,15 +267,17 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, world: int, devi
                "api": "vegas_gpu_step_host_* (host State in, host State out, E and M back)" if not slab else
                       "vegas_gpu_upload_* + vegas_gpu_step + vegas_gpu_download_* per slab"}
     peak, peak_src = peaks()
-    passes = g.n_colours                      # colour passes (= sweep launches) per step
+    # sweep launches per step: one per colour, or ONE for the persistent wave kernel (both colours); a connected slab
+    # adds wait / signal / boundary launches, so count colours there
+    passes = g.n_colours if slab else max(1, round(launches / steps))
     per_launch_s = ms * 1e-3 / (passes * steps)
     alg_bytes_per_launch = w["bytes_per_attempt"] * n_local / passes
     achieved = alg_bytes_per_launch / per_launch_s / 1e9
     res = {"value": value, "ms_per_step": ms / steps, "launches": launches, "clocks": clocks, "e2e": e2e,
-           "family": g.kernel_family, "n_local": n_local,
+           "family": step_kernel, "n_local": n_local,
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": NCU_TRAFFIC.get(name, (None, None))[0], "traffic_source": NCU_TRAFFIC.get(name, (None, None))[1],
-                        "algorithmic_bytes_per_launch": alg_bytes_per_launch, "peak_source": peak_src, "kernel": f"{g.kernel_family} colour pass",
+                        "algorithmic_bytes_per_launch": alg_bytes_per_launch, "peak_source": peak_src, "kernel": f"{step_kernel} " + ("step (both colours, one launch)" if passes == 1 else "colour pass"),
                         "algorithmic_bytes_per_attempt": w["bytes_per_attempt"]},
            "energy_per_site_last": float(e_series[-1] / (n_local * (world if slab else 1)))}
     g.close()
