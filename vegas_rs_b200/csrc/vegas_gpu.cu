@@ -322,7 +322,7 @@ void launch_msc(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, ui
     uint32_t bx = 32;
     while (bx > g.Wx) bx >>= 1;  // block = (bx words) x (256/bx rows); one warp spans 32/bx rows
     const dim3 block(bx, 256 / bx);
-    const dim3 grid(cdiv(g.Wx, block.x), cdiv(g.Ly, block.y * MSC_ROWS), zc);
+    const dim3 grid(cdiv(g.Wx, block.x), cdiv(g.Ly, block.y * msc_rows(NDIM)), zc);
     uint32_t* own = h->msc[colour];
     const uint32_t* oth = h->msc[1 - colour];
     const PhiloxKey pk = make_philox_key(h->md.seed);
