@@ -111,6 +111,9 @@ int vegas_gpu_colours(vegas_gpu_t, uint8_t* colour_of_site);
 int vegas_gpu_lattice_adjacency(const vegas_lattice_desc*, double exchange, uint64_t* n, uint64_t* nnz,
                                 uint64_t* row_ptr, uint32_t* col_idx, double* values);
 int vegas_gpu_lattice_colours(const vegas_lattice_desc*, int* n_colours, uint8_t* colour_of_site);
+/* host-only self check: the compile-time bcc / fcc neighbour tables of the heis_basis kernel equal the unit-cell edge
+ * list the adjacency export above is built from (0 = identical) */
+int vegas_gpu_check_basis_tables(void);
 
 /* ---- state I/O in the REFERENCE's host layouts (src/state.rs:60-63,133-134,245-246) ---- */
 int vegas_gpu_upload_ising(vegas_gpu_t, const int8_t* s, uint64_t n);          /* +1 Up / -1 Down per site */

@@ -71,3 +71,10 @@ def test_host_lattice_matches_oracle(built, uc):
                 rows = np.repeat(np.arange(len(rp) - 1), np.diff(rp.astype(np.int64)))
                 assert not np.any((col[rows] == col[ci]) & (rows != ci)), (uc, size, pbc, lit)
                 assert nc <= 4 and col.max() < nc
+
+
+def test_basis_kernel_neighbour_tables_match_lattice(built):
+    """heis_basis.cuh bakes the bcc / fcc unit-cell bonds into the kernel at compile time; the same library checks
+    them (on the host, no GPU) against the edge list its adjacency export and the oracle comparison are built from."""
+    from vegas_rs_b200 import _lib
+    assert _lib.load().vegas_gpu_check_basis_tables() == 0

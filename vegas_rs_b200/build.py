@@ -39,7 +39,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
                os.path.join(CSRC, "vegas_host.cpp")]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
-        subprocess.run(cmd, check=True, capture_output=not verbose)
+        res = subprocess.run(cmd, capture_output=not verbose, text=True)
+        if res.returncode != 0:  # fail loudly with the compiler's own words
+            tail = "" if verbose else "\n".join((res.stderr or "").splitlines()[-40:])
+            raise RuntimeError(f"nvcc failed ({res.returncode}): {' '.join(cmd)}\n{tail}")
     return LIB
 
 

@@ -595,6 +595,22 @@ void general_reduce(vegas_gpu* h, const NB& nb, double* obs_row) {
     }
 }
 
+// ---- host-only self check: the compile-time neighbour tables of heis_basis.cuh against lattice.hpp -------------
+template <int UC, int B>
+int check_basis_table() {
+    StructuredNb nb{};
+    for (int b = 0; b < 4; ++b) nb.count[b] = 0;
+    for (const vgl::UcEdge& e : vgl::unitcell_edges(UC)) { NbEntry f{}; f.tb = (int8_t)e.t; f.dx = (int8_t)e.dx; f.dy = (int8_t)e.dy; f.dz = (int8_t)e.dz; nb.e[e.s][nb.count[e.s]++] = f; }
+    for (const vgl::UcEdge& e : vgl::unitcell_edges(UC)) { NbEntry r{}; r.tb = (int8_t)e.s; r.dx = (int8_t)-e.dx; r.dy = (int8_t)-e.dy; r.dz = (int8_t)-e.dz; nb.e[e.t][nb.count[e.t]++] = r; }
+    if (nb.count[B] != BasisCell<UC>::Z) return 1;
+    for (int q = 0; q < BasisCell<UC>::Z; ++q) {
+        const BasisNb t = basis_neighbour<UC, B>(q);
+        const NbEntry& w = nb.e[B][q];
+        if (t.tb != w.tb || t.dx != w.dx || t.dy != w.dy || t.dz != w.dz) return 1;
+    }
+    return 0;
+}
+
 // ---- periodic bcc / fcc Heisenberg (heis_basis.cuh) ----------------------------------------------
 template <typename real>
 BasisPtrs<real> basis_ptrs(const vegas_gpu* h) {
@@ -1766,6 +1782,11 @@ int vegas_gpu_slab_connect_local(vegas_gpu_t h, vegas_gpu_t lower, vegas_gpu_t u
     h->connected = true;
     preload_slab_kernels(h);
     return push_boundaries(h);
+}
+
+int vegas_gpu_check_basis_tables(void) {
+    return check_basis_table<1, 0>() + check_basis_table<1, 1>() + check_basis_table<2, 0>() + check_basis_table<2, 1>() +
+           check_basis_table<2, 2>() + check_basis_table<2, 3>();
 }
 
 // ---- tuning knobs ---------------------------------------------------------------------------
