@@ -33,7 +33,7 @@ WORKLOADS = {
     "heis3d_512": dict(model="heisenberg", size=(512, 512, 512), pbc=(True, True, True), T=1.0, H=1.0, bytes_per_attempt=24.0,
                        dtype="f32", cpu_L=(128, 128, 128), anisotropy=((0.0, 0.0, 1.0), 0.1)),
     # cfg[4]: fcc (4 sites per cell, z = 12), basis 4-colouring, heis_basis kernel (basis-split SoA, compile-time
-    # neighbour table); single GPU only (z-slabs exist for the sc stencil kernels only)
+    # neighbour table); z-slabs of 384 cell planes per GPU at N > 1 (weak scaling)
     "heis_fcc_384": dict(model="heisenberg", unitcell="fcc", size=(384, 384, 384), pbc=(True, True, True), T=3.2, H=0.0,
                          bytes_per_attempt=24.0, dtype="f32", cpu_L=(48, 48, 48)),
 }
@@ -176,7 +176,7 @@ def make_handle(name: str, rank: int, world: int, device: int, seed: int = 12345
     else:
         model = vg.HEISENBERG
         kw.update(precision=vg.F32, anisotropy=w.get("anisotropy"))
-    if world > 1 and size[2] > 1 and "unitcell" not in w:
+    if world > 1 and size[2] > 1:
         # weak scaling: every rank owns a full-size slab of a lattice that is `world` times taller
         kw.update(nz_global=size[2] * world, z_offset=size[2] * rank)
     else:
@@ -190,7 +190,7 @@ def make_handle(name: str, rank: int, world: int, device: int, seed: int = 12345
 
 def run_workload(name: str, steps: int, warmup: int, rank: int, world: int, device: int, dist, torch, e2e_steps: int):
     g, w = make_handle(name, rank, world, device)
-    slab = world > 1 and w["size"][2] > 1 and "unitcell" not in w
+    slab = world > 1 and w["size"][2] > 1
     g.randomize()
     g.set_thermostat(w["T"], (0.0, 0.0, 1.0), w["H"])
     if slab:

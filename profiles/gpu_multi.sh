@@ -5,7 +5,8 @@ nvidia-smi topo -m > $out/topo.txt 2>&1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 timeout 300 $TR --master-port 29501 tests/mp_slab_check.py ising 2>&1 | grep -E "mp_slab_check|Error|error" | head -5
 timeout 300 $TR --master-port 29502 tests/mp_slab_check.py heisenberg 2>&1 | grep -E "mp_slab_check|Error|error" | head -5
-for w in ising3d_1024 heis3d_512; do
+timeout 300 $TR --master-port 29504 tests/mp_slab_check.py fcc 2>&1 | grep -E "mp_slab_check|Error|error" | head -5
+for w in ising3d_1024 heis3d_512 heis_fcc_384; do
   timeout 600 $TR --master-port 29503 bench.py --gpus $N --steps 50 --warmup 5 --workload $w --no-also --e2e-steps 1 > $out/bench_${w}_n$N.json 2> $out/bench_${w}_n$N.err
   python -c "
 import json,sys

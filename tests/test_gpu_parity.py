@@ -490,18 +490,29 @@ def test_heisenberg_fused_flip_proposal_and_larger(built):
 
 
 # ------------------------------------------------------------------------------------------ slabs
-@pytest.mark.parametrize("model", [vg.ISING, vg.HEISENBERG], ids=["ising", "heisenberg"])
+SLAB_KINDS = {
+    # kind: (model, unitcell, (nx, ny, nz) in cells, sites per cell)
+    "ising": (vg.ISING, vg.SC, (256, 4, 8), 1),
+    "heisenberg": (vg.HEISENBERG, vg.SC, (16, 4, 8), 1),
+    "heisenberg_bcc": (vg.HEISENBERG, vg.BCC, (5, 3, 8), 2),
+    "heisenberg_fcc": (vg.HEISENBERG, vg.FCC, (4, 3, 8), 4),
+}
+
+
+@pytest.mark.parametrize("kind", list(SLAB_KINDS))
 @pytest.mark.parametrize("nslab", [2, 4])
-def test_slab_decomposition_bit_identical(built, model, nslab):
-    """z-slabs with peer-written halos reproduce the single-handle run bit for bit (same Philox keys)."""
-    Lx, Ly, Lz = (256, 4, 8) if model == vg.ISING else (16, 4, 8)
+def test_slab_decomposition_bit_identical(built, kind, nslab):
+    """z-slabs with peer-written halos reproduce the single-handle run bit for bit (same Philox keys): sc stencil
+    kernels (Ising, Heisenberg) and the bcc / fcc basis kernel."""
+    model, uc, (Lx, Ly, Lz), nb = SLAB_KINDS[kind]
     kw = dict(seed=314, precision=vg.F32)
-    whole = vg.GpuMetropolis(model, unitcell=vg.SC, size=(Lx, Ly, Lz), **kw)
-    s = random_state(model, Lx * Ly * Lz, 61)
+    whole = vg.GpuMetropolis(model, unitcell=uc, size=(Lx, Ly, Lz), **kw)
+    s = random_state(model, Lx * Ly * Lz * nb, 61)
     whole.upload(s)
     nz = Lz // nslab
-    slabs = [vg.GpuMetropolis(model, unitcell=vg.SC, size=(Lx, Ly, nz), nz_global=Lz, z_offset=r * nz, **kw) for r in range(nslab)]
-    plane = Lx * Ly
+    slabs = [vg.GpuMetropolis(model, unitcell=uc, size=(Lx, Ly, nz), nz_global=Lz, z_offset=r * nz, **kw) for r in range(nslab)]
+    assert all(sl.kernel_family == whole.kernel_family for sl in slabs)
+    plane = Lx * Ly * nb
     for r, sl in enumerate(slabs):
         sl.upload(s[r * nz * plane:(r + 1) * nz * plane])
     for r, sl in enumerate(slabs):
@@ -520,6 +531,16 @@ def test_slab_decomposition_bit_identical(built, model, nslab):
         assert np.array_equal(ref, got)
         e_sum = sum(p[0][0] for p in parts)
         assert abs(e_sum - e[-1]) <= (0 if model == vg.ISING else 1e-6 * abs(e[-1]) + 1e-6)
+        m_sum = sum(p[1][0] for p in parts)
+        assert np.max(np.abs(m_sum - m[-1])) <= (0 if model == vg.ISING else 1e-4)
+        # the measure-only entry points of a slab reduce its own sites (halo planes are read, not counted)
+        e_now = sum(sl.total_energy() for sl in slabs)
+        assert abs(e_now - whole.total_energy()) <= (0 if model == vg.ISING else 1e-6 * abs(e[-1]) + 1e-6)
+    # a fresh random state keyed by the GLOBAL site index is the same with and without slabs
+    whole.randomize()
+    for sl in slabs:
+        sl.randomize()
+    assert np.array_equal(whole.download(), np.concatenate([sl.download() for sl in slabs]))
     for sl in slabs:
         sl.close()
     whole.close()

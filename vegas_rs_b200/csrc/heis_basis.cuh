@@ -64,16 +64,22 @@ __device__ __forceinline__ void basis_for_each(F&& f, std::index_sequence<Q...>)
 template <typename real>
 struct BasisPtrs { real* s[4][3]; };  // [basis][component][cell]
 
-struct BasisGeom { uint32_t nx, ny, nz, ncells; };
+// z-slab (multi-GPU): the handle owns cell planes [z_offset, z_offset + nz) of nz_global; every array then carries one
+// halo plane below (index -1) and above (index nz), filled by the z-neighbours, and `ext` = (nz + 2) * ny * nx is the
+// element distance between consecutive arrays of the single allocation (used for the stores into the peers' halos).
+struct BasisGeom { uint32_t nx, ny, nz, ncells, z_offset, nz_global; size_t ext; };
+
+template <typename real>
+struct BasisPeers { real* lo; real* hi; };  // bases of the lower / upper neighbour's allocation (null: not a slab)
 
 // MODE 0: update.  1: update + observables of this colour: obs[1..3] += s, obs[4] += (s.a)^2 and the exchange bonds
 // towards the LOWER colours (final by now) so that a step counts every bond once; obs[0] receives twice that sum
 // (layout of general_reduce_kernel: sum_i sum_j J s_i.s_j, every bond twice).  2: the same reductions, no update.
 // obs[5] += accepted.
-template <typename real, int UC, int B, bool FLIP, int MODE>
+template <typename real, int UC, int B, bool FLIP, int MODE, bool SLAB = false>
 __global__ void __launch_bounds__(128)
-heis_basis_kernel(BasisPtrs<real> P, BasisGeom g, uint32_t rows_per_cta, HeisParams<real> p, uint64_t sweep, PhiloxKey pk,
-                  double* __restrict__ obs) {
+heis_basis_kernel(BasisPtrs<real> P, BasisPeers<real> peers, BasisGeom g, uint32_t rows_per_cta, HeisParams<real> p,
+                  uint64_t sweep, PhiloxKey pk, double* __restrict__ obs) {
     constexpr int NB = BasisCell<UC>::NB, Z = BasisCell<UC>::Z;
     __shared__ double s_red[6 * 32];
     // a thread owns one ix and marches over rows_per_cta rows of plane iz: one block reduction per CTA
@@ -81,7 +87,9 @@ heis_basis_kernel(BasisPtrs<real> P, BasisGeom g, uint32_t rows_per_cta, HeisPar
     const uint32_t y0 = blockIdx.y * rows_per_cta, y1 = min(y0 + rows_per_cta, g.ny);
     double acc[6] = {0, 0, 0, 0, 0, 0};
     if (ix < g.nx) {
-        const uint32_t zs[3] = {iz == 0 ? g.nz - 1 : iz - 1, iz, iz + 1 == g.nz ? 0u : iz + 1};
+        // slab: planes -1 and nz are the halo planes of the same array (signed plane index); else periodic wrap
+        const int zs[3] = {SLAB ? (int)iz - 1 : (int)(iz == 0 ? g.nz - 1 : iz - 1), (int)iz,
+                           SLAB ? (int)iz + 1 : (int)(iz + 1 == g.nz ? 0u : iz + 1)};
         const uint32_t xs[3] = {ix == 0 ? g.nx - 1 : ix - 1, ix, ix + 1 == g.nx ? 0u : ix + 1};
         real fs[5] = {0, 0, 0, 0, 0};
         int accepted = 0;
@@ -92,7 +100,7 @@ heis_basis_kernel(BasisPtrs<real> P, BasisGeom g, uint32_t rows_per_cta, HeisPar
             auto gather = [&](auto qtag) {
                 constexpr int Q = decltype(qtag)::value;
                 constexpr BasisNb nb = basis_neighbour<UC, B>(Q);
-                const uint32_t j = (zs[nb.dz + 1] * g.ny + ys[nb.dy + 1]) * g.nx + xs[nb.dx + 1];
+                const int j = (zs[nb.dz + 1] * (int)g.ny + (int)ys[nb.dy + 1]) * (int)g.nx + (int)xs[nb.dx + 1];
                 const real u = P.s[nb.tb][0][j], v = P.s[nb.tb][1][j], w = P.s[nb.tb][2][j];
                 nx += u; ny += v; nz += w;
                 if (MODE != 0 && nb.tb < B) { lx += u; ly += v; lz += w; }
@@ -101,9 +109,21 @@ heis_basis_kernel(BasisPtrs<real> P, BasisGeom g, uint32_t rows_per_cta, HeisPar
             real x = P.s[B][0][cell], y = P.s[B][1][cell], z = P.s[B][2][cell];
             if (MODE != 2) {
                 HeisRand<real> rnd;
-                heis_rand((uint64_t)cell * NB + B, sweep, pk, rnd);
+                const uint64_t gcell = ((uint64_t)(iz + g.z_offset) * g.ny + iy) * g.nx + ix;  // global cell: slab-independent keys
+                heis_rand(gcell * NB + B, sweep, pk, rnd);
                 const bool ok = heis_attempt<real, FLIP>(x, y, z, p.J * nx - p.h[0], p.J * ny - p.h[1], p.J * nz - p.h[2], p, rnd);
                 if (ok) { P.s[B][0][cell] = x; P.s[B][1][cell] = y; P.s[B][2][cell] = z; }
+                if (SLAB) {  // boundary planes also go straight into the neighbours' halo planes (peer memory over NVLink)
+                    const size_t in_plane = (size_t)iy * g.nx + ix, pl = (size_t)g.ny * g.nx;
+                    if (iz == 0 && peers.lo != nullptr) {
+                        real* q = peers.lo + (size_t)(B * 3) * g.ext + (size_t)(g.nz + 1) * pl + in_plane;  // their plane "nz"
+                        q[0] = x; q[g.ext] = y; q[2 * g.ext] = z;
+                    }
+                    if (iz + 1 == g.nz && peers.hi != nullptr) {
+                        real* q = peers.hi + (size_t)(B * 3) * g.ext + in_plane;                            // their plane "-1"
+                        q[0] = x; q[g.ext] = y; q[2 * g.ext] = z;
+                    }
+                }
                 accepted += ok ? 1 : 0;
             }
             if (MODE != 0) {
@@ -149,12 +169,12 @@ __global__ void __launch_bounds__(256) basis_unpack_kernel(outT* __restrict__ ox
 }
 
 template <typename real>
-__global__ void __launch_bounds__(256) basis_randomize_kernel(BasisPtrs<real> P, uint32_t nb, size_t n, PhiloxKey pk) {
+__global__ void __launch_bounds__(256) basis_randomize_kernel(BasisPtrs<real> P, uint32_t nb, size_t n, uint64_t site_offset, PhiloxKey pk) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const size_t cell = i / nb; const uint32_t b = (uint32_t)(i - cell * nb);
     real x, y, z;
-    heis_random_spin<real>((uint64_t)i, pk, x, y, z);  // keyed by the natural site index, as the general kernels
+    heis_random_spin<real>((uint64_t)i + site_offset, pk, x, y, z);  // keyed by the natural GLOBAL site index, as the general kernels
     P.s[b][0][cell] = x; P.s[b][1][cell] = y; P.s[b][2][cell] = z;
 }
 

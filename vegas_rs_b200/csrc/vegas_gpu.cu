@@ -460,6 +460,17 @@ void preload_heis_slab() {
     preload(heis_stencil_kernel<real, 3, true, 3, true>); preload(heis_stencil_kernel<real, 3, true, 3, false>);
     preload(heis_stencil_kernel<real, 3, false, 2, true>); preload(heis_stencil_kernel<real, 3, false, 2, false>);
 }
+template <typename real, int UC, int B>
+void preload_basis_one() {
+    preload(heis_basis_kernel<real, UC, B, false, 0, true>); preload(heis_basis_kernel<real, UC, B, false, 1, true>);
+    preload(heis_basis_kernel<real, UC, B, true, 0, true>); preload(heis_basis_kernel<real, UC, B, true, 1, true>);
+    preload(heis_basis_kernel<real, UC, B, false, 2, true>);
+}
+template <typename real>
+void preload_basis_slab() {
+    preload_basis_one<real, 1, 0>(); preload_basis_one<real, 1, 1>();
+    preload_basis_one<real, 2, 0>(); preload_basis_one<real, 2, 1>(); preload_basis_one<real, 2, 2>(); preload_basis_one<real, 2, 3>();
+}
 template <bool RP>
 void preload_msc_slab() {
     preload(ising_msc_kernel<3, true, 14, RP, 0, false, true>); preload(ising_msc_kernel<3, true, 14, RP, 1, false, true>);
@@ -475,6 +486,8 @@ void preload_slab_kernels(vegas_gpu* h) {
     if (h->family == FAM_ISING_MSC) {
         preload_msc_slab<false>(); preload_msc_slab<true>();
         preload(ising_msc_kernel<3, false, 3, false, 2>);
+    } else if (h->family == FAM_HEIS_BASIS) {
+        if (h->md.precision == VEGAS_F64) preload_basis_slab<double>(); else preload_basis_slab<float>();
     } else if (h->md.precision == VEGAS_F64) preload_heis_slab<double>();
     else preload_heis_slab<float>();
 }
@@ -621,6 +634,8 @@ BasisPtrs<real> basis_ptrs(const vegas_gpu* h) {
 BasisGeom basis_geom(const vegas_gpu* h) {
     BasisGeom g{};
     g.nx = (uint32_t)h->ld.nx; g.ny = (uint32_t)h->ld.ny; g.nz = (uint32_t)h->ld.nz; g.ncells = g.nx * g.ny * g.nz;
+    g.z_offset = (uint32_t)h->z_offset; g.nz_global = (uint32_t)h->nz_global;
+    g.ext = (size_t)(g.nz + 2) * g.ny * g.nx;
     return g;
 }
 
@@ -635,8 +650,15 @@ void basis_launch(vegas_gpu* h, int mode, double* obs) {
     const PhiloxKey pk = make_philox_key(h->md.seed);
     const BasisPtrs<real> P = basis_ptrs<real>(h);
     const bool flip = h->md.proposal == VEGAS_PROPOSE_FLIP;
+    const bool slab = h->slab && h->connected;
+    BasisPeers<real> peers{};
+    if (slab && mode != 2) { peers.lo = (real*)h->peer_halo[0]; peers.hi = (real*)h->peer_halo[1]; }
     h->launches++;
-#define BL(FLIP, MODE) heis_basis_kernel<real, UC, B, FLIP, MODE><<<grid, 128, 0, h->stream>>>(P, g, rows, p, h->sweeps, pk, obs)
+#define BL(FLIP, MODE)                                                                                                          \
+    do {                                                                                                                        \
+        if (slab) heis_basis_kernel<real, UC, B, FLIP, MODE, true><<<grid, 128, 0, h->stream>>>(P, peers, g, rows, p, h->sweeps, pk, obs); \
+        else heis_basis_kernel<real, UC, B, FLIP, MODE, false><<<grid, 128, 0, h->stream>>>(P, peers, g, rows, p, h->sweeps, pk, obs);    \
+    } while (0)
     if (mode == 2) BL(false, 2);
     else if (mode == 1) { if (flip) BL(true, 1); else BL(false, 1); }
     else { if (flip) BL(true, 0); else BL(false, 0); }
@@ -657,8 +679,21 @@ void basis_pass(vegas_gpu* h, int mode, int b, double* obs) {
         }
     }
 }
+__global__ void signal_kernel(unsigned long long*, unsigned long long*, unsigned long long);
+__global__ void wait_kernel(const unsigned long long*, unsigned long long);
 void basis_pass_any(vegas_gpu* h, int mode, int b, double* obs) {
+    // connected slab: the pass reads halo planes the z-neighbours wrote in their previous pass and writes its own
+    // boundary planes into theirs (same flag protocol as the sc stencil kernels; one launch covers all planes)
+    const bool exchange = h->slab && h->connected && mode != 2;
+    if (exchange) {
+        h->pass_counter++;
+        if (h->pass_counter > 1) { wait_kernel<<<1, 32, 0, h->stream>>>(h->flags, h->pass_counter - 1); h->launches++; }
+    }
     if (h->md.precision == VEGAS_F64) basis_pass<double>(h, mode, b, obs); else basis_pass<float>(h, mode, b, obs);
+    if (exchange) {
+        signal_kernel<<<1, 32, 0, h->stream>>>(h->peer_flags[0], h->peer_flags[1], h->pass_counter);
+        h->launches++;
+    }
 }
 
 // ---- fused two-colour Heisenberg step -------------------------------------------------------
@@ -1032,8 +1067,11 @@ int vegas_gpu_create_lattice(const vegas_model_desc* md, const vegas_lattice_des
     if (stencil && md->model == VEGAS_ISING) stencil = L[0] % 64 == 0;
     if (stencil && md->model == VEGAS_HEISENBERG) stencil = L[0] % 8 == 0;
     if (stencil && hh->ld.nx * hh->ld.ny * hh->ld.nz >= (1ull << 32) * (md->model == VEGAS_ISING ? 64 : 2)) stencil = false;  // 32-bit offsets per colour array
+    const bool basis_family = md->model == VEGAS_HEISENBERG && ldesc->unitcell != VEGAS_SC && !hh->ld.literal && !md->force_general &&
+                              hh->ld.pbc[0] && hh->ld.pbc[1] && hh->ld.pbc[2] && h->n < (1ull << 31);
     if (hh->slab) {
-        if (!stencil || L[2] == 1) return bail(fail(h, VEGAS_ERR_INVALID, "z-slab decomposition needs the sc stencil path (periodic, even extents)"));
+        if (!(basis_family || (stencil && L[2] != 1)))
+            return bail(fail(h, VEGAS_ERR_INVALID, "z-slab decomposition needs the sc stencil path (periodic, even extents) or periodic Heisenberg bcc/fcc"));
         if (hh->z_offset + hh->ld.nz > hh->nz_global) return bail(fail(h, VEGAS_ERR_INVALID, "slab outside the global lattice"));
     }
     if (stencil) {
@@ -1066,17 +1104,33 @@ int vegas_gpu_create_lattice(const vegas_model_desc* md, const vegas_lattice_des
             cudaMemcpyAsync(h->flags + 4, &magic, 8, cudaMemcpyHostToDevice, h->stream);
             cudaStreamSynchronize(h->stream);
         }
-    } else if (md->model == VEGAS_HEISENBERG && ldesc->unitcell != VEGAS_SC && !hh->ld.literal && !md->force_general &&
-               hh->ld.pbc[0] && hh->ld.pbc[1] && hh->ld.pbc[2] && !hh->slab && h->n < (1ull << 32)) {
+    } else if (basis_family) {
         // periodic bcc / fcc: basis-split arrays, colour = basis, compile-time neighbour tables (heis_basis.cuh)
         h->family = FAM_HEIS_BASIS;
         h->n_colours = vgl::basis_count(ldesc->unitcell);
         h->h_colour.resize(h->n);
         for (uint64_t i = 0; i < h->n; ++i) h->h_colour[i] = (uint8_t)(i % (uint64_t)h->n_colours);
-        const size_t bytes = (size_t)(h->n / h->n_colours) * real_bytes(h);
-        for (int b = 0; b < h->n_colours; ++b)
-            for (int k = 0; k < 3; ++k)
-                if (cudaMalloc(&h->hb[b][k], bytes) != cudaSuccess) return bail(fail(h, VEGAS_ERR_ALLOC, "cudaMalloc (spins) failed"));
+        const size_t cells = (size_t)(h->n / h->n_colours), pl = (size_t)h->ld.nx * h->ld.ny;
+        if (!h->slab) {
+            for (int b = 0; b < h->n_colours; ++b)
+                for (int k = 0; k < 3; ++k)
+                    if (cudaMalloc(&h->hb[b][k], cells * real_bytes(h)) != cudaSuccess) return bail(fail(h, VEGAS_ERR_ALLOC, "cudaMalloc (spins) failed"));
+        } else {
+            // ONE 2 MiB-granular allocation (its CUDA IPC handle maps exactly this range in the neighbour): the arrays
+            // [basis][component], each with a halo plane below and above its nz local planes, then the flags
+            const size_t ext = cells + 2 * pl;
+            h->halo_plane_bytes = pl * real_bytes(h);
+            h->halo_bytes = ((size_t)h->n_colours * 3 * ext * real_bytes(h) + 255) / 256 * 256;
+            h->slab_bytes = (h->halo_bytes + 256 + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+            if (cudaMalloc(&h->halo, h->slab_bytes) != cudaSuccess) return bail(fail(h, VEGAS_ERR_ALLOC, "cudaMalloc (spins + halos) failed"));
+            for (int b = 0; b < h->n_colours; ++b)
+                for (int k = 0; k < 3; ++k) h->hb[b][k] = (char*)h->halo + ((size_t)(b * 3 + k) * ext + pl) * real_bytes(h);
+            h->flags = (unsigned long long*)((char*)h->halo + h->halo_bytes);
+            cudaMemsetAsync(h->halo, 0, h->slab_bytes, h->stream);
+            const unsigned long long magic = 0x76656761735f6770ull ^ h->z_offset;  // checked by the peer after mapping
+            cudaMemcpyAsync(h->flags + 4, &magic, 8, cudaMemcpyHostToDevice, h->stream);
+            cudaStreamSynchronize(h->stream);
+        }
     } else {
         h->family = md->model == VEGAS_ISING ? FAM_ISING_GEN : FAM_HEIS_GEN;
         if (h->n >= (1ull << 32)) return bail(fail(h, VEGAS_ERR_INVALID, "general-adjacency path supports < 2^32 sites"));
@@ -1151,7 +1205,7 @@ void vegas_gpu_destroy(vegas_gpu_t h) {
         if (h->peer_halo[1] && h->peer_halo[1] != h->peer_halo[0]) cudaIpcCloseMemHandle(h->peer_halo[1]);
     }
     cudaFree(h->halo);
-    for (int b = 0; b < 4; ++b) for (int k = 0; k < 3; ++k) cudaFree(h->hb[b][k]);
+    if (!(h->family == FAM_HEIS_BASIS && h->slab)) for (int b = 0; b < 4; ++b) for (int k = 0; k < 3; ++k) cudaFree(h->hb[b][k]);
     cudaFree(h->g_s8);
     for (int k = 0; k < 3; ++k) cudaFree(h->g_s[k]);
     for (uint32_t* p : h->g_sites) cudaFree(p);
@@ -1366,6 +1420,22 @@ __global__ void copy_plane_kernel(uint32_t* dst, const uint32_t* src, size_t n4)
 
 int push_boundaries(vegas_gpu* h) {
     if (!(h->slab && h->connected)) return VEGAS_OK;
+    if (h->family == FAM_HEIS_BASIS) {
+        // my first / last local plane of every array -> the lower neighbour's plane "nz" / the upper neighbour's plane "-1"
+        const size_t n4 = h->halo_plane_bytes / 4, pl = (size_t)h->ld.nx * h->ld.ny, rb = real_bytes(h);
+        const size_t ext = (size_t)(h->n / h->n_colours) + 2 * pl;
+        for (int a = 0; a < h->n_colours * 3; ++a) {
+            const char* mine = (const char*)h->hb[a / 3][a % 3];
+            char* lo_dst = (char*)h->peer_halo[0] + ((size_t)a * ext + (size_t)(h->ld.nz + 1) * pl) * rb;
+            char* hi_dst = (char*)h->peer_halo[1] + ((size_t)a * ext) * rb;
+            copy_plane_kernel<<<cdiv(n4, 256), 256, 0, h->stream>>>((uint32_t*)lo_dst, (const uint32_t*)mine, n4);
+            copy_plane_kernel<<<cdiv(n4, 256), 256, 0, h->stream>>>((uint32_t*)hi_dst, (const uint32_t*)(mine + (size_t)(h->ld.nz - 1) * pl * rb), n4);
+            h->launches += 2;
+        }
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaGetLastError());
+        return VEGAS_OK;
+    }
     const int ncomp = h->family == FAM_ISING_MSC ? 1 : 3;
     const size_t n4 = h->halo_plane_bytes / 4;
     for (int colour = 0; colour < 2; ++colour)
@@ -1426,8 +1496,8 @@ int vegas_gpu_randomize(vegas_gpu_t h) {
     } else if (h->family == FAM_ISING_GEN) {
         ising_general_randomize_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(h->g_s8, (uint32_t)h->n, 0, pk);
     } else if (h->family == FAM_HEIS_BASIS) {
-        if (h->md.precision == VEGAS_F64) basis_randomize_kernel<double><<<cdiv(h->n, 256), 256, 0, h->stream>>>(basis_ptrs<double>(h), (uint32_t)h->n_colours, (size_t)h->n, pk);
-        else basis_randomize_kernel<float><<<cdiv(h->n, 256), 256, 0, h->stream>>>(basis_ptrs<float>(h), (uint32_t)h->n_colours, (size_t)h->n, pk);
+        if (h->md.precision == VEGAS_F64) basis_randomize_kernel<double><<<cdiv(h->n, 256), 256, 0, h->stream>>>(basis_ptrs<double>(h), (uint32_t)h->n_colours, (size_t)h->n, (uint64_t)h->z_offset * h->ld.ny * h->ld.nx * h->n_colours, pk);
+        else basis_randomize_kernel<float><<<cdiv(h->n, 256), 256, 0, h->stream>>>(basis_ptrs<float>(h), (uint32_t)h->n_colours, (size_t)h->n, (uint64_t)h->z_offset * h->ld.ny * h->ld.nx * h->n_colours, pk);
     } else if (h->family == FAM_HEIS_GEN) {
         if (h->md.precision == VEGAS_F64) heis_general_randomize_kernel<double><<<cdiv(h->n, 256), 256, 0, h->stream>>>((double*)h->g_s[0], (double*)h->g_s[1], (double*)h->g_s[2], (uint32_t)h->n, 0, pk);
         else heis_general_randomize_kernel<float><<<cdiv(h->n, 256), 256, 0, h->stream>>>((float*)h->g_s[0], (float*)h->g_s[1], (float*)h->g_s[2], (uint32_t)h->n, 0, pk);
