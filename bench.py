@@ -240,13 +240,13 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, world: int, devi
             host = torch.empty(n_local, dtype=torch.int8, pin_memory=True)
         else:
             host = torch.empty((n_local, 3), dtype=torch.float64, pin_memory=True)
-        arr = host.numpy(); arr[:] = g.download()
+        arr = host.numpy(); g.download_into(arr)
 
         def host_step():
             if not slab:
                 g.step_host(arr)  # Integrator::step: host State in -> host State out
             else:  # a slab's upload pushes its boundary planes to the neighbours: all ranks must have uploaded
-                g.upload(arr); dist.barrier(); g.step(1); arr[:] = g.download(); dist.barrier()
+                g.upload(arr); dist.barrier(); g.step(1); g.download_into(arr); dist.barrier()
 
         host_step()  # warm-up
         torch.cuda.synchronize()

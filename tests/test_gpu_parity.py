@@ -45,6 +45,7 @@ def test_ising_energies_bit_exact(built, name, lat):
     s = random_state(ob.ISING, n_sites(lat), 11)
     g.upload(s)
     assert np.array_equal(g.download(), s)
+    assert np.array_equal(g.download_into(np.empty(n_sites(lat), np.int8)), s)
     for fmag, fdir in ((0.0, (0, 0, 1.0)), (0.75, (0, 0, 1.0)), (-1.5, (0, 0, -1.0))):
         g.set_thermostat(2.5, fdir, fmag)
         th = H.thermostat(2.5, fdir, fmag)

@@ -159,6 +159,17 @@ class GpuMetropolis:
             self._check(self._lib.vegas_gpu_download_heisenberg(self._h, _ptr(a), a.shape[0]))
         return a
 
+    def download_into(self, out):
+        """download() into a caller-owned buffer (e.g. pinned host memory): int8[n] or float64[n,3], C-contiguous."""
+        assert out.flags["C_CONTIGUOUS"] and out.dtype == (np.int8 if self.model == ISING else np.float64)
+        if self.model == ISING:
+            assert out.size == self.n_sites
+            self._check(self._lib.vegas_gpu_download_ising(self._h, _ptr(out), out.size))
+        else:
+            assert out.size == 3 * self.n_sites
+            self._check(self._lib.vegas_gpu_download_heisenberg(self._h, _ptr(out), self.n_sites))
+        return out
+
     def randomize(self): self._check(self._lib.vegas_gpu_randomize(self._h))
     def fill(self, up: bool = True): self._check(self._lib.vegas_gpu_fill(self._h, int(up)))
 
