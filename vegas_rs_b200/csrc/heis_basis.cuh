@@ -78,12 +78,13 @@ struct BasisPeers { real* lo; real* hi; };  // bases of the lower / upper neighb
 // obs[5] += accepted.
 template <typename real, int UC, int B, bool FLIP, int MODE, bool SLAB = false>
 __global__ void __launch_bounds__(128)
-heis_basis_kernel(BasisPtrs<real> P, BasisPeers<real> peers, BasisGeom g, uint32_t rows_per_cta, HeisParams<real> p,
-                  uint64_t sweep, PhiloxKey pk, double* __restrict__ obs) {
+heis_basis_kernel(BasisPtrs<real> P, BasisPeers<real> peers, BasisGeom g, uint32_t rows_per_cta, uint32_t z_begin, uint32_t z_step,
+                  HeisParams<real> p, uint64_t sweep, PhiloxKey pk, double* __restrict__ obs) {
     constexpr int NB = BasisCell<UC>::NB, Z = BasisCell<UC>::Z;
     __shared__ double s_red[6 * 32];
     // a thread owns one ix and marches over rows_per_cta rows of plane iz: one block reduction per CTA
-    const uint32_t ix = blockIdx.x * blockDim.x + threadIdx.x, iz = blockIdx.z;
+    // plane of this CTA: z_begin + blockIdx.z * z_step (z_step > 1: the two boundary planes of a slab in one launch)
+    const uint32_t ix = blockIdx.x * blockDim.x + threadIdx.x, iz = z_begin + blockIdx.z * z_step;
     const uint32_t y0 = blockIdx.y * rows_per_cta, y1 = min(y0 + rows_per_cta, g.ny);
     double acc[6] = {0, 0, 0, 0, 0, 0};
     if (ix < g.nx) {

@@ -640,12 +640,12 @@ BasisGeom basis_geom(const vegas_gpu* h) {
 }
 
 template <typename real, int UC, int B>
-void basis_launch(vegas_gpu* h, int mode, double* obs) {
+void basis_launch(vegas_gpu* h, int mode, double* obs, uint32_t zb, uint32_t zc, uint32_t zstep, cudaStream_t st) {
     const BasisGeom g = basis_geom(h);
     // rows per CTA: enough CTAs to fill the GPU (~16 per SM), at most 64 rows (fp32 partial sums stay short)
-    const uint64_t ctas_per_row_set = (uint64_t)cdiv(g.nx, 128) * g.nz;
+    const uint64_t ctas_per_row_set = (uint64_t)cdiv(g.nx, 128) * zc;
     uint32_t rows = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, (uint64_t)g.ny * ctas_per_row_set / (148u * 16u)));
-    const dim3 grid(cdiv(g.nx, 128), cdiv(g.ny, rows), g.nz);
+    const dim3 grid(cdiv(g.nx, 128), cdiv(g.ny, rows), zc);
     const HeisParams<real> p = heis_params<real>(h);
     const PhiloxKey pk = make_philox_key(h->md.seed);
     const BasisPtrs<real> P = basis_ptrs<real>(h);
@@ -656,8 +656,8 @@ void basis_launch(vegas_gpu* h, int mode, double* obs) {
     h->launches++;
 #define BL(FLIP, MODE)                                                                                                          \
     do {                                                                                                                        \
-        if (slab) heis_basis_kernel<real, UC, B, FLIP, MODE, true><<<grid, 128, 0, h->stream>>>(P, peers, g, rows, p, h->sweeps, pk, obs); \
-        else heis_basis_kernel<real, UC, B, FLIP, MODE, false><<<grid, 128, 0, h->stream>>>(P, peers, g, rows, p, h->sweeps, pk, obs);    \
+        if (slab) heis_basis_kernel<real, UC, B, FLIP, MODE, true><<<grid, 128, 0, st>>>(P, peers, g, rows, zb, zstep, p, h->sweeps, pk, obs); \
+        else heis_basis_kernel<real, UC, B, FLIP, MODE, false><<<grid, 128, 0, st>>>(P, peers, g, rows, zb, zstep, p, h->sweeps, pk, obs);    \
     } while (0)
     if (mode == 2) BL(false, 2);
     else if (mode == 1) { if (flip) BL(true, 1); else BL(false, 1); }
@@ -665,35 +665,52 @@ void basis_launch(vegas_gpu* h, int mode, double* obs) {
 #undef BL
 }
 
-// one colour (= basis) pass; mode as heis_basis_kernel
+// one colour (= basis) pass over planes zb, zb + zstep, ... (zc of them); mode as heis_basis_kernel
 template <typename real>
-void basis_pass(vegas_gpu* h, int mode, int b, double* obs) {
+void basis_pass(vegas_gpu* h, int mode, int b, double* obs, uint32_t zb, uint32_t zc, uint32_t zstep, cudaStream_t st) {
+    if (zc == 0) return;
     if (h->ld.unitcell == VEGAS_BCC) {
-        if (b == 0) basis_launch<real, 1, 0>(h, mode, obs); else basis_launch<real, 1, 1>(h, mode, obs);
+        if (b == 0) basis_launch<real, 1, 0>(h, mode, obs, zb, zc, zstep, st); else basis_launch<real, 1, 1>(h, mode, obs, zb, zc, zstep, st);
     } else {
         switch (b) {
-            case 0: basis_launch<real, 2, 0>(h, mode, obs); break;
-            case 1: basis_launch<real, 2, 1>(h, mode, obs); break;
-            case 2: basis_launch<real, 2, 2>(h, mode, obs); break;
-            default: basis_launch<real, 2, 3>(h, mode, obs); break;
+            case 0: basis_launch<real, 2, 0>(h, mode, obs, zb, zc, zstep, st); break;
+            case 1: basis_launch<real, 2, 1>(h, mode, obs, zb, zc, zstep, st); break;
+            case 2: basis_launch<real, 2, 2>(h, mode, obs, zb, zc, zstep, st); break;
+            default: basis_launch<real, 2, 3>(h, mode, obs, zb, zc, zstep, st); break;
         }
     }
 }
 __global__ void signal_kernel(unsigned long long*, unsigned long long*, unsigned long long);
 __global__ void wait_kernel(const unsigned long long*, unsigned long long);
 void basis_pass_any(vegas_gpu* h, int mode, int b, double* obs) {
+    const uint32_t nz = (uint32_t)h->ld.nz;
+    auto run = [&](uint32_t zb, uint32_t zc, uint32_t zstep, cudaStream_t st) {
+        if (h->md.precision == VEGAS_F64) basis_pass<double>(h, mode, b, obs, zb, zc, zstep, st);
+        else basis_pass<float>(h, mode, b, obs, zb, zc, zstep, st);
+    };
     // connected slab: the pass reads halo planes the z-neighbours wrote in their previous pass and writes its own
-    // boundary planes into theirs (same flag protocol as the sc stencil kernels; one launch covers all planes)
+    // boundary planes into theirs (same flag protocol and stream structure as the sc stencil kernels)
     const bool exchange = h->slab && h->connected && mode != 2;
-    if (exchange) {
-        h->pass_counter++;
+    if (!exchange) { run(0, nz, 1, h->stream); return; }
+    h->pass_counter++;
+    if (!h->peer_is_ipc) {  // all slabs in one process: one stream (see stencil_colour_pass)
         if (h->pass_counter > 1) { wait_kernel<<<1, 32, 0, h->stream>>>(h->flags, h->pass_counter - 1); h->launches++; }
-    }
-    if (h->md.precision == VEGAS_F64) basis_pass<double>(h, mode, b, obs); else basis_pass<float>(h, mode, b, obs);
-    if (exchange) {
+        if (nz >= 2) run(0, 2, nz - 1, h->stream); else run(0, 1, 1, h->stream);
         signal_kernel<<<1, 32, 0, h->stream>>>(h->peer_flags[0], h->peer_flags[1], h->pass_counter);
         h->launches++;
+        if (nz > 2) run(1, nz - 2, 1, h->stream);
+        return;
     }
+    // one process per GPU: boundary planes (wait, update, peer stores, signal) on the boundary stream, interior on the main one
+    cudaEventRecord(h->ev_main, h->stream);
+    cudaStreamWaitEvent(h->stream_b, h->ev_main, 0);
+    cudaStreamWaitEvent(h->stream, h->ev_bnd, 0);
+    if (h->pass_counter > 1) { wait_kernel<<<1, 32, 0, h->stream_b>>>(h->flags, h->pass_counter - 1); h->launches++; }
+    if (nz >= 2) run(0, 2, nz - 1, h->stream_b); else run(0, 1, 1, h->stream_b);
+    signal_kernel<<<1, 32, 0, h->stream_b>>>(h->peer_flags[0], h->peer_flags[1], h->pass_counter);
+    h->launches++;
+    cudaEventRecord(h->ev_bnd, h->stream_b);
+    if (nz > 2) run(1, nz - 2, 1, h->stream);
 }
 
 // ---- fused two-colour Heisenberg step -------------------------------------------------------
