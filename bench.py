@@ -44,6 +44,13 @@ NCU_TRAFFIC = {
     "heis3d_512": (2.887e9 + 1.562e9, "profiles/r01u_heis_wave.metrics.txt (one step = both colours)"),
     "heis_fcc_384": (2.753e9 + 0.662e9, "profiles/r01s_heis_basis.metrics.txt (one colour pass)"),
 }
+# cfg[0] (docs/metropolis.toml, the reference's own CPU-runnable case): 1000 sites, latency bound; runs on the
+# shared-memory-resident kernel (one launch per batch of steps), reported in "also" without a roofline
+SMALL_WORKLOADS = {
+    "ising_sc10_cfg0": dict(model="ising", size=(10, 10, 10), pbc=(True, True, True), T=4.5, H=0.0, cpu_L=(10, 10, 10),
+                            dtype="int8 in shared memory"),
+}
+ALL_WORKLOADS = {**WORKLOADS, **SMALL_WORKLOADS}
 METRIC = "spin-flip attempts/sec"
 UNIT = "attempts/s"
 
@@ -96,10 +103,11 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------ CPU arm
 def cpu_replica(args):
     """One single-threaded run of the oracle port of the reference Metropolis (machine.rs:91-101 loop
-    with StatSensor + ObservableSensor as `vegas run` configures them, input.rs:324-345)."""
-    name, steps, seed = args
+    with StatSensor + ObservableSensor as `vegas run` configures them, input.rs:324-345): the model is built once,
+    then `samples` timed samples of `steps` Monte Carlo steps each.  Returns [(attempts, seconds)] per sample."""
+    name, steps, samples, seed = args
     from oracle import binding as ob
-    w = WORKLOADS[name]
+    w = ALL_WORKLOADS[name]
     L = w["cpu_L"]
     model = ob.ISING if w["model"] == "ising" else ob.HEISENBERG
     lat = ob.Lattice(ob.FCC if w.get("unitcell") == "fcc" else ob.SC, *L, pbc=w["pbc"])
@@ -110,33 +118,44 @@ def cpu_replica(args):
         terms.append(ob.TERM_ANISOTROPY); kw = dict(aniso_axis=w["anisotropy"][0], aniso_k=w["anisotropy"][1])
     H = ob.Hamiltonian(model, terms, csr, **kw)
     rng = ob.OracleRng(seed)
-    n = L[0] * L[1] * L[2] * (4 if w.get("unitcell") == "fcc" else 1)
+    n = cpu_sites(name)
     state = H.rand_state(rng, n)
     m = ob.Machine(H, ob.PROPOSE_FLIP if model == ob.ISING else ob.PROPOSE_RANDOM, rng, state, n_sensors=2)
     m.set_thermostat(H.thermostat(w["T"], (0, 0, 1.0), w["H"]))
     m.relax_for(1)  # warm caches
-    t0 = time.perf_counter()
-    m.measure_for(steps)
-    dt = time.perf_counter() - t0
-    return n * steps, dt
+    out = []
+    for _ in range(samples):
+        t0 = time.perf_counter()
+        m.measure_for(steps)
+        out.append((n * steps, time.perf_counter() - t0))
+    return out
 
 
-def cpu_run(name: str, steps: int, replicas: int):
+def cpu_run(name: str, steps: int, replicas: int, samples: int = 1):
+    """`replicas` independent single-threaded copies (the reference has no intra-run parallelism); per sample:
+    (attempts of all replicas / slowest replica's time, that time)."""
     if replicas == 1:
-        res = [cpu_replica((name, steps, 12345))]
+        res = [cpu_replica((name, steps, samples, 12345))]
     else:
         import multiprocessing as mp
         with mp.get_context("fork").Pool(replicas) as pool:
-            res = pool.map(cpu_replica, [(name, steps, 12345 + r) for r in range(replicas)])
-    attempts = sum(r[0] for r in res)
-    wall = max(r[1] for r in res)
-    return attempts / wall, wall
+            res = pool.map(cpu_replica, [(name, steps, samples, 12345 + r) for r in range(replicas)])
+    out = []
+    for k in range(samples):
+        attempts = sum(r[k][0] for r in res)
+        wall = max(r[k][1] for r in res)
+        out.append((attempts / wall, wall))
+    return out
+
+
+def cpu_sites(name: str) -> int:
+    L = ALL_WORKLOADS[name]["cpu_L"]
+    return L[0] * L[1] * L[2] * (4 if ALL_WORKLOADS[name].get("unitcell") == "fcc" else 1)
 
 
 def cpu_steps_for(name: str, budget_s: float) -> int:
-    L = WORKLOADS[name]["cpu_L"]
-    n = L[0] * L[1] * L[2] * (4 if WORKLOADS[name].get("unitcell") == "fcc" else 1)
-    return max(2, int(budget_s * 1.5e6 / n))  # ~1.5e6 attempts/s/core out of cache with two sensors
+    n = cpu_sites(name)
+    return max(1, int(budget_s * (6e6 if n <= 4096 else 1.5e6) / n))  # ~1.5e6 attempts/s/core out of cache with two sensors
 
 
 def reference_arm(args):
@@ -145,16 +164,15 @@ def reference_arm(args):
         return
     name = args.workload
     cores = min(os.cpu_count() or 1, 32)
-    per_step = cpu_steps_for(name, 6.0)
-    vals = []
-    for i in range(args.warmup + args.steps):
-        v, wall = cpu_run(name, per_step, cores)
-        if i >= args.warmup:
-            vals.append((v, wall))
+    # every timed "step" is a bounded sample of the workload; the whole --steps/--warmup run stays within ~3 minutes
+    budget = max(0.25, min(6.0, 150.0 / max(1, args.warmup + args.steps)))
+    per_step = cpu_steps_for(name, budget)
+    vals = cpu_run(name, per_step, cores, args.warmup + args.steps)[args.warmup:]
     value = float(np.mean([v for v, _ in vals]))
-    w = WORKLOADS[name]
+    w = ALL_WORKLOADS[name]
     sample = (f"{cores} independent single-threaded replicas (the reference has no intra-run parallelism) of the oracle port, "
-              f"sc {w['cpu_L']} sub-lattice of the workload (the reference CSR layout, 16 B/nnz, cannot hold the full size), "
+              f"{'fcc' if w.get('unitcell') == 'fcc' else 'sc'} {w['cpu_L']} sub-lattice of the workload (the reference CSR "
+              f"layout, 16 B/nnz, cannot hold the full size), "
               f"{per_step} MC steps per timed step, StatSensor+ObservableSensor per-step E/M as `vegas run`")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": float(np.mean([wl for _, wl in vals]) * 1e3), "higher_is_better": True, "scaling": "weak",
@@ -188,7 +206,8 @@ def make_handle(name: str, rank: int, world: int, device: int, seed: int = 12345
     return g, w
 
 
-def run_workload(name: str, steps: int, warmup: int, rank: int, world: int, device: int, dist, torch, e2e_steps: int):
+def run_workload(name: str, steps: int, warmup: int, rank: int, world: int, device: int, dist, torch, e2e_steps: int,
+                 machine_e2e: bool = True):
     g, w = make_handle(name, rank, world, device)
     slab = world > 1 and w["size"][2] > 1
     g.randomize()
@@ -266,6 +285,28 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, world: int, devi
                "d2h_bytes_per_step": nbytes + 32, "steps": e2e_steps,
                "api": "vegas_gpu_step_host_* (host State in, host State out, E and M back)" if not slab else
                       "vegas_gpu_upload_* + vegas_gpu_step + vegas_gpu_download_* per slab"}
+    # ---- the same steps through the host layer: Machine::measure_for with StatSensor + ObservableSensor fed from the
+    # device-reduced per-step (E, M); the State stays in HBM (it only crosses PCIe for a StateSensor dump)
+    e2e_machine = None
+    if machine_e2e and not slab:
+        from vegas_rs_b200.machine import Machine
+        m = Machine(g)
+        m.add_stat_sensor(lambda line, row: None)
+        m.add_observable_sensor(lambda *a: None)
+        m.set_thermostat(w["T"], (0.0, 0.0, 1.0), w["H"])
+        m.measure_for(3)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        m.measure_for(steps)
+        dt = time.perf_counter() - t0
+        m.close()
+        if world > 1:
+            t = torch.tensor([dt], device=f"cuda:{device}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e_machine = {"value": n_local * world * steps / dt, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 64,
+                       "steps": steps, "api": "vegas_machine_measure_for (Machine::measure_for, src/machine.rs:116-125) with "
+                                              "StatSensor + ObservableSensor; host wall clock"}
     peak, peak_src = peaks()
     # sweep launches per step: one per colour, or ONE for the persistent wave kernel (both colours); a connected slab
     # adds wait / signal / boundary launches, so count colours there
@@ -273,7 +314,7 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, world: int, devi
     per_launch_s = ms * 1e-3 / (passes * steps)
     alg_bytes_per_launch = w["bytes_per_attempt"] * n_local / passes
     achieved = alg_bytes_per_launch / per_launch_s / 1e9
-    res = {"value": value, "ms_per_step": ms / steps, "launches": launches, "clocks": clocks, "e2e": e2e,
+    res = {"value": value, "ms_per_step": ms / steps, "launches": launches, "clocks": clocks, "e2e": e2e, "e2e_machine": e2e_machine,
            "family": step_kernel, "n_local": n_local,
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": NCU_TRAFFIC.get(name, (None, None))[0], "traffic_source": NCU_TRAFFIC.get(name, (None, None))[1],
@@ -284,13 +325,57 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, world: int, devi
     return res
 
 
+def run_small_workload(name: str, device: int, torch, with_cpu: bool):
+    """cfg[0]-sized lattice: batches of 4096 recorded steps on the shared-memory-resident kernel (one launch per batch),
+    then the same through Machine::measure_for, next to the oracle port on ONE host core on the SAME lattice."""
+    import vegas_rs_b200 as vg
+    from vegas_rs_b200.machine import Machine
+    w = SMALL_WORKLOADS[name]
+    g = vg.GpuMetropolis(vg.ISING, unitcell=vg.SC, size=w["size"], pbc=w["pbc"], seed=12345, device=device)
+    g.randomize()
+    g.set_thermostat(w["T"], (0.0, 0.0, 1.0), w["H"])
+    batch, reps = 4096, 8
+    g.step_async(batch, True)
+    g.synchronize()
+    l0 = g.launches
+    g.timer_start()
+    for _ in range(reps):
+        g.step_async(batch, True)
+    ms = g.timer_stop()
+    launches = g.launches - l0
+    family = g.step_kernel
+    m = Machine(g)
+    m.add_stat_sensor(lambda line, row: None)
+    m.add_observable_sensor(lambda *a: None)
+    m.set_thermostat(w["T"], (0.0, 0.0, 1.0), w["H"])
+    m.measure_for(batch)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    m.measure_for(batch * reps)
+    dt = time.perf_counter() - t0
+    m.close()
+    n = g.n_sites
+    g.close()
+    res = {"value": n * batch * reps / (ms * 1e-3), "unit": UNIT, "us_per_step": ms * 1e3 / (batch * reps), "gpu_launches": launches,
+           "steps": batch * reps, "family": family, "roofline": None,
+           "e2e": {"value": n * batch * reps / dt, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 64,
+                   "api": "vegas_machine_measure_for with StatSensor + ObservableSensor; host wall clock"},
+           "note": "docs/metropolis.toml lattice (1000 sites): latency bound, one CTA, State resident in shared memory; no HBM roofline"}
+    if with_cpu:
+        k = cpu_steps_for(name, 3.0)
+        v, wall = cpu_run(name, k, 1)[0]
+        res["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                               "sample": f"oracle port, the same sc {w['size']} lattice, {k} MC steps, two sensors, {wall:.1f} s"}
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="ising3d_1024", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="ising3d_1024", choices=sorted(ALL_WORKLOADS))
     ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -299,6 +384,8 @@ def main():
     if args.impl == "reference":
         reference_arm(args)
         return
+    if args.workload in SMALL_WORKLOADS:
+        raise SystemExit(f"bench.py: {args.workload} is reported inside \"also\" (and by --impl reference); pick a BASELINE workload")
     import torch
     import torch.distributed as dist
     from vegas_rs_b200 import _lib
@@ -311,22 +398,26 @@ def main():
     torch.cuda.set_device(device)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{device}"))
-    main_res = run_workload(args.workload, args.steps, args.warmup, rank, world, device, dist, torch, args.e2e_steps)
+    main_res = run_workload(args.workload, args.steps, args.warmup, rank, world, device, dist, torch, args.e2e_steps,
+                            args.e2e_steps > 0)
     also = {}
     if not args.no_also:
         for other in WORKLOADS:
             if other != args.workload and not (world > 1 and "unitcell" in WORKLOADS[other]):
                 heavy = "unitcell" in WORKLOADS[other]   # 226 M sites: fewer steps, no 5 GB host round trip
                 r = run_workload(other, min(args.steps, 10) if heavy else args.steps, args.warmup, rank, world, device, dist, torch,
-                                 0 if heavy else args.e2e_steps)
+                                 0 if heavy else args.e2e_steps, args.e2e_steps > 0)
                 also[other] = {"value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "roofline": r["roofline"],
-                               "e2e": r["e2e"], "family": r["family"],
+                               "e2e": r["e2e"], "e2e_machine": r["e2e_machine"], "family": r["family"],
                                "note": {"ising2d_8192": "8 MiB state is L2 resident: not an HBM measurement",
                                         "heis_fcc_384": "heis_basis kernel (scalar loads, one Philox call per site), 4 colours, single GPU"}.get(other, "")}
+        if world == 1 and args.e2e_steps > 0:
+            for small in SMALL_WORKLOADS:
+                also[small] = run_small_workload(small, device, torch, not args.no_cpu)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         k = cpu_steps_for(args.workload, 12.0)
-        v, wall = cpu_run(args.workload, k, 1)
+        v, wall = cpu_run(args.workload, k, 1)[0]
         w = WORKLOADS[args.workload]
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"oracle port of the reference Metropolis, sc {w['cpu_L']} sub-lattice, {k} MC steps, "
@@ -344,7 +435,7 @@ def main():
                                              ("independent replicas" if world > 1 else "single GPU")),
                            "observers": "energy+magnetisation fused in the last colour pass, every step",
                            "l2": "state (2 x 64 MiB colour arrays) exceeds L2; no flush" if args.workload == "ising3d_1024" else "see note"},
-                "roofline": main_res["roofline"], "cpu_baseline": cpu, "e2e": main_res["e2e"], "gpu_launches": main_res["launches"],
+                "roofline": main_res["roofline"], "cpu_baseline": cpu, "e2e": main_res["e2e"], "e2e_machine": main_res["e2e_machine"], "gpu_launches": main_res["launches"],
                 "clocks": main_res["clocks"], "kernel_family": main_res["family"], "also": also}
         print(json.dumps(line), flush=True)
     if world > 1:

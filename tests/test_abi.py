@@ -78,3 +78,20 @@ def test_basis_kernel_neighbour_tables_match_lattice(built):
     them (on the host, no GPU) against the edge list its adjacency export and the oracle comparison are built from."""
     from vegas_rs_b200 import _lib
     assert _lib.load().vegas_gpu_check_basis_tables() == 0
+
+
+def test_bench_reference_arm_line(built):
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the contract's keys,
+    on the reference's own config[0] lattice so that it finishes in seconds."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                          "--workload", "ising_sc10_cfg0"], capture_output=True, text=True, timeout=300, check=True).stdout
+    line = json.loads(out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "spin-flip attempts/sec" and line["unit"] == "attempts/s"
+    assert line["steps"] == 2 and line["warmup"] == 1 and line["higher_is_better"] is True
+    assert line["value"] > 1e5 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "attempts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["workload"] == "ising_sc10_cfg0"

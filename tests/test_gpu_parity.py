@@ -335,6 +335,30 @@ def test_ising_2d_onsager_magnetisation(built):
     g.close()
 
 
+def test_ising_2d_cooldown_peaks_at_onsager_tc(built):
+    """BASELINE config[1] in miniature (north_star check 3): a CoolDown of the 2D Ising model across Tc; the specific heat
+    Var(E)/(N T^2) and the susceptibility Var(|M|)/(N T) (StatSensor formulas, src/instrument.rs:98-131) must peak at
+    Onsager's Tc = 2/ln(1+sqrt 2) up to the finite-size shift of a 64 x 64 lattice (Tc(L) - Tc ~ 0.4 Tc/L for Cv,
+    ~ 1.1 Tc / L for chi') and the 0.05 temperature grid."""
+    L, Tc = 64, 2.269185314213022
+    g = vg.GpuMetropolis(vg.ISING, unitcell=vg.SC, size=(L, L, 1), pbc=(True, True, False), seed=41)
+    g.set_energy_convention(vg.E_PHYSICAL)
+    g.randomize()
+    temps = [2.7 - 0.05 * i for i in range(17)]              # 2.70 ... 1.90, annealed like CoolDown (program.rs:203-211)
+    cv, chi = [], []
+    for T in temps:
+        g.set_thermostat(T)
+        g.step(5000, observe=False)
+        e, m = g.step(60000)
+        mag = np.abs(m[:, 2])
+        cv.append(e.var() / (L * L * T * T)); chi.append(mag.var() / (L * L * T))
+    t_cv, t_chi = temps[int(np.argmax(cv))], temps[int(np.argmax(chi))]
+    assert abs(t_cv - Tc) <= 0.085, (t_cv, cv)
+    assert -0.03 <= t_chi - Tc <= 0.135, (t_chi, chi)
+    assert max(cv) > 1.5 and max(cv) > 2.0 * cv[0] and max(cv) > 2.0 * cv[-1]   # a peak, not a slope
+    g.close()
+
+
 @pytest.mark.parametrize("precision", [vg.F32, vg.F64], ids=["f32", "f64"])
 def test_heisenberg_free_spins_langevin(built, precision):
     """No exchange: independent spins in a field, reference sign +|H| s.o (src/energy.rs:147-151)
@@ -593,4 +617,30 @@ def test_full_size_heisenberg_512(built):
     e, m = g.step(2)
     assert abs(g.total_energy() - e[-1]) < 1e-5 * abs(e[-1]) + 1e-5 * N
     assert np.max(np.abs(g.magnetization() - m[-1])) < 1e-5 * N
+    g.close()
+
+
+def test_full_size_heisenberg_fcc_384(built):
+    """BASELINE config[4] size: fcc 384^3 cells = 226,492,416 sites, z = 12, four colours (heis_basis kernel)."""
+    L = 384
+    g = vg.GpuMetropolis(vg.HEISENBERG, unitcell=vg.FCC, size=(L, L, L), seed=4)
+    assert g.kernel_family == "heis_basis" and g.n_colours == 4
+    N = 4 * L**3
+    assert g.n_sites == N
+    g.fill(True)
+    g.set_thermostat(3.2, (0, 0, 1.0), 0.5)
+    # all-up: energy(i) = -12 J + |H| (Exchange fold over z = 12 neighbours, Zeeman +|H| s.o); compound total = sum_i
+    assert abs(g.total_energy() - N * (-12 + 0.5)) < 1e-5 * N
+    g.set_energy_convention(vg.E_PHYSICAL)
+    assert abs(g.total_energy() - N * (-6 - 0.5)) < 1e-5 * N
+    assert abs(g.magnetization()[2] - N) < 1e-5 * N
+    g.set_energy_convention(vg.E_REFERENCE_COMPOUND)
+    g.randomize()
+    assert np.max(np.abs(g.magnetization())) < 6 * np.sqrt(N)
+    e, m = g.step(2)
+    assert abs(g.total_energy() - e[-1]) < 1e-5 * abs(e[-1]) + 1e-5 * N
+    assert np.max(np.abs(g.magnetization() - m[-1])) < 1e-5 * N
+    assert e[-1] < e[0] < 0                                   # quench from T = inf towards T = 3.2
+    a, acc = g.attempt_count()
+    assert a == 2 * N and 0 < acc < a
     g.close()

@@ -156,3 +156,71 @@ def test_sharded_cooldown_points_through_machine(built):
         lines_by_rank.append(lines)
         m.close(); g.close()
     assert len(lines_by_rank[0]) == 3 and len(lines_by_rank[1]) == 2
+
+
+@pytest.mark.gpu
+def test_machine_on_fcc_heisenberg_reports_vector_magnetisation(built):
+    """config[4] shape through the Machine: periodic fcc takes the heis_basis family, whose |M| is the norm of three
+    projections (HeisenbergSpin::from_projections, src/state.rs:150-160) and whose StateSensor dump is [f64;3] per site."""
+    import vegas_rs_b200 as vg
+    from vegas_rs_b200.machine import Machine
+    g = vg.GpuMetropolis(vg.HEISENBERG, unitcell=vg.FCC, size=(4, 4, 4), precision=vg.F64, seed=8)
+    assert g.kernel_family == "heis_basis"
+    v = np.tile(np.array([[0.6, 0.8, 0.0]]), (g.n_sites, 1))      # magnetised in the xy plane: Mz = 0, |M| = N
+    g.upload(v)
+    m = Machine(g)
+    batches, dumps = [], []
+    m.add_observable_sensor(lambda *a: batches.append(a))
+    m.add_state_sensor(5, lambda *a: dumps.append(a))
+    m.relax(6, 0.05)                                              # cold: the state stays close to the initial one
+    mag = batches[0][6]
+    assert mag.shape == (6,) and np.all(mag > 0.9 * g.n_sites)    # |M| from all three projections, not |Mz|
+    assert dumps[0][5].shape == (g.n_sites, 3)
+    assert np.max(np.abs(np.linalg.norm(dumps[1][5], axis=1) - 1.0)) < 1e-12
+    # the dumped state is the state after that step: its energy is the recorded one
+    from oracle import binding as ob
+    from helpers import oracle_model
+    H, _ = oracle_model(ob.HEISENBERG, unitcell=ob.FCC, size=(4, 4, 4))
+    assert abs(H.total_energy(H.thermostat(0.05), dumps[1][5]) - batches[0][5][5]) < 1e-9
+    m.close(); g.close()
+
+
+@pytest.mark.gpu
+def test_run_toml_hysteresis_heisenberg(built, tmp_path):
+    """config[3] shape in miniature: Heisenberg sc HysteresisLoop through the TOML front end; the field column is
+    |magnitude| (Field::magnitude, src/state.rs:219-221) and the point list overshoots max_field (App. A Q11)."""
+    import pyarrow.parquet as pq
+    from vegas_rs_b200 import run
+    text = f"""
+model = "Heisenberg"
+algorithm = "Metropolis"
+exchange = 1.0
+
+[sample]
+unitcell = {{ name = "sc" }}
+size = {{ x = 16, y = 8, z = 8 }}
+pbc = {{ x = true, y = true, z = true }}
+
+[[stages]]
+program = "Hysteresis"
+steps = 20
+relax = 10
+temperature = 1.0
+max_field = 1.0
+field_step = 0.5
+
+[output]
+observables = "{tmp_path / 'hyst.parquet'}"
+"""
+    cfg = run.parse_input(text)
+    out = io.StringIO()
+    run.run_input(cfg, seed=3, out=out)
+    lines = out.getvalue().strip().split("\n")
+    fields = [float(l.split()[1]) for l in lines]
+    # 0, .5, 1 | 1.5, 1, .5, 0, -.5, -1 | -1.5, -1, ..., 1  with |.| applied (program.rs:303-332)
+    assert fields == [0.0, 0.5, 1.0, 1.5, 1.0, 0.5, 0.0, 0.5, 1.0, 1.5, 1.0, 0.5, 0.0, 0.5, 1.0]
+    obs = pq.read_table(tmp_path / "hyst.parquet")
+    assert obs.num_rows == len(fields) * 30 and set(obs.column("n").to_pylist()) == {1024}
+    # reference sign (+|H| s.o, src/energy.rs:147-151): the spins turn AGAINST the field orientation
+    mags = np.array(obs.column("magnetization").to_pylist())
+    assert np.all(mags >= 0)

@@ -83,6 +83,36 @@ struct IsingGeneralParams {
     double invT;
 };
 
+// One attempt on site i (the body of src/integrator.rs:121-135 / :75-89 for IsingSpin); `s` may live in global or
+// shared memory.  Returns true when the move counts as accepted.
+template <typename NB, bool RANDPROP>
+__device__ __forceinline__ bool ising_general_attempt(int8_t* s, const NB& nb, uint32_t i, const IsingGeneralParams& p,
+                                                      uint64_t site_offset, uint64_t sweep, const PhiloxKey& pk) {
+    const int si = s[i];
+    uint32_t r[4];
+    philox_at((uint64_t)i + site_offset, sweep, 0u, pk, r);
+    const unsigned long long U = ((unsigned long long)r[0] << 32) | r[1];
+    bool proposed = true;
+    if (RANDPROP) proposed = ((r[2] & 1u) ? 1 : -1) != si;  // IsingSpin::rand src/state.rs:76-84
+    bool ok;
+    if (p.uniform) {
+        int m = 0;
+        nb.for_each(i, [&](uint32_t j, double) { if (j != i) m += s[j]; });
+        const int idx = (si > 0 ? 1 : 0) * (2 * ISING_ZMAX + 1) + (m + ISING_ZMAX);
+        const uint8_t c = p.code[idx];
+        ok = c == 2 || (c == 1 && U < p.thr[idx]);
+    } else {
+        double ex = 0.0;  // Exchange::energy fold src/energy.rs:197-201 without the constant diagonal
+        nb.for_each(i, [&](uint32_t j, double Jij) { if (j != i) ex = ex + (-Jij * (double)(si * s[j])); });
+        const double dE = -2.0 * (ex + p.h_o * (double)si);
+        const double pr = exp(-dE * p.invT);
+        ok = !(pr < 1.0) || U < __double2ull_rd(pr * 18446744073709551616.0);
+    }
+    if (!proposed) ok = true;
+    if (ok && proposed) s[i] = (int8_t)-si;
+    return ok;
+}
+
 template <typename NB, bool RANDPROP>
 __global__ void __launch_bounds__(256)
 ising_general_sweep_kernel(int8_t* __restrict__ s, NB nb, const uint32_t* __restrict__ sites, uint32_t count,
@@ -91,38 +121,30 @@ ising_general_sweep_kernel(int8_t* __restrict__ s, NB nb, const uint32_t* __rest
     __shared__ unsigned long long s_red[32];
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long acc[1] = {0ull};
-    if (t < count) {
-        const uint32_t i = sites[t];
-        const int si = s[i];
-        uint32_t r[4];
-        philox_at((uint64_t)i + site_offset, sweep, 0u, pk, r);
-        const unsigned long long U = ((unsigned long long)r[0] << 32) | r[1];
-        bool proposed = true;
-        if (RANDPROP) proposed = ((r[2] & 1u) ? 1 : -1) != si;  // IsingSpin::rand src/state.rs:76-84
-        bool ok;
-        if (p.uniform) {
-            int m = 0;
-            nb.for_each(i, [&](uint32_t j, double) { if (j != i) m += s[j]; });
-            const int idx = (si > 0 ? 1 : 0) * (2 * ISING_ZMAX + 1) + (m + ISING_ZMAX);
-            const uint8_t c = p.code[idx];
-            ok = c == 2 || (c == 1 && U < p.thr[idx]);
-        } else {
-            double ex = 0.0;  // Exchange::energy fold src/energy.rs:197-201 without the constant diagonal
-            nb.for_each(i, [&](uint32_t j, double Jij) { if (j != i) ex = ex + (-Jij * (double)(si * s[j])); });
-            const double dE = -2.0 * (ex + p.h_o * (double)si);
-            const double pr = exp(-dE * p.invT);
-            ok = !(pr < 1.0) || U < __double2ull_rd(pr * 18446744073709551616.0);
-        }
-        if (!proposed) ok = true;
-        if (ok && proposed) s[i] = (int8_t)-si;
-        acc[0] = ok ? 1ull : 0ull;
-    }
+    if (t < count) acc[0] = ising_general_attempt<NB, RANDPROP>(s, nb, sites[t], p, site_offset, sweep, pk) ? 1ull : 0ull;
     block_atomic_add<unsigned long long, 1>(acc, s_red, obs + 2);
 }
 
 // ---------------------------------------------------------------------------------------
 // Heisenberg
 // ---------------------------------------------------------------------------------------
+// One attempt on site i for HeisenbergSpin; the SoA arrays may live in global or shared memory.
+template <typename NB, typename real, bool FLIP>
+__device__ __forceinline__ bool heis_general_attempt(real* sx, real* sy, real* sz, const NB& nb, uint32_t i,
+                                                     const HeisParams<real>& p, uint64_t site_offset, uint64_t sweep,
+                                                     const PhiloxKey& pk) {
+    real nx = 0, ny = 0, nz = 0;
+    nb.for_each(i, [&](uint32_t j, double Jij) {
+        if (j != i) { const real w = (real)Jij; nx += w * sx[j]; ny += w * sy[j]; nz += w * sz[j]; }
+    });
+    real x = sx[i], y = sy[i], z = sz[i];
+    HeisRand<real> rnd;
+    heis_rand((uint64_t)i + site_offset, sweep, pk, rnd);
+    const bool ok = heis_attempt<real, FLIP>(x, y, z, nx - p.h[0], ny - p.h[1], nz - p.h[2], p, rnd);
+    if (ok) { sx[i] = x; sy[i] = y; sz[i] = z; }
+    return ok;
+}
+
 template <typename NB, typename real, bool FLIP>
 __global__ void __launch_bounds__(128)
 heis_general_sweep_kernel(real* __restrict__ sx, real* __restrict__ sy, real* __restrict__ sz, NB nb,
@@ -131,19 +153,7 @@ heis_general_sweep_kernel(real* __restrict__ sx, real* __restrict__ sy, real* __
     __shared__ double s_red[32];
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     double acc[1] = {0.0};
-    if (t < count) {
-        const uint32_t i = sites[t];
-        real nx = 0, ny = 0, nz = 0;
-        nb.for_each(i, [&](uint32_t j, double Jij) {
-            if (j != i) { const real w = (real)Jij; nx += w * sx[j]; ny += w * sy[j]; nz += w * sz[j]; }
-        });
-        real x = sx[i], y = sy[i], z = sz[i];
-        HeisRand<real> rnd;
-        heis_rand((uint64_t)i + site_offset, sweep, pk, rnd);
-        const bool ok = heis_attempt<real, FLIP>(x, y, z, nx - p.h[0], ny - p.h[1], nz - p.h[2], p, rnd);
-        if (ok) { sx[i] = x; sy[i] = y; sz[i] = z; }
-        acc[0] = ok ? 1.0 : 0.0;
-    }
+    if (t < count) acc[0] = heis_general_attempt<NB, real, FLIP>(sx, sy, sz, nb, sites[t], p, site_offset, sweep, pk) ? 1.0 : 0.0;
     block_atomic_add<double, 1>(acc, s_red, obs + 5);
 }
 
@@ -207,24 +217,30 @@ struct EnergyParams {
     int has_exchange, has_zeeman, has_aniso, has_gauge;
 };
 
+// Site i's share of the K5 sums (acc[0..4] as general_reduce_kernel documents them).
+template <typename NB, typename SP>
+__device__ __forceinline__ void general_site_terms(const NB& nb, const SP& sp, uint32_t i, double ax, double ay, double az,
+                                                   double (&acc)[5]) {
+    double x, y, z;
+    sp.get(i, x, y, z);
+    double e = 0.0;
+    nb.for_each(i, [&](uint32_t j, double Jij) {
+        double u, v, w;
+        sp.get(j, u, v, w);
+        e += Jij * (x * u + y * v + z * w);
+    });
+    acc[0] += e; acc[1] += x; acc[2] += y; acc[3] += z;
+    const double d = x * ax + y * ay + z * az;
+    acc[4] += d * d;
+}
+
 template <typename NB, typename SP>
 __global__ void __launch_bounds__(256)
 general_reduce_kernel(NB nb, SP sp, uint32_t n, double ax, double ay, double az, double* __restrict__ obs) {
     __shared__ double s_red[5 * 32];
     double acc[5] = {0, 0, 0, 0, 0};
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        double x, y, z;
-        sp.get(i, x, y, z);
-        double e = 0.0;
-        nb.for_each(i, [&](uint32_t j, double Jij) {
-            double u, v, w;
-            sp.get(j, u, v, w);
-            e += Jij * (x * u + y * v + z * w);
-        });
-        acc[0] += e; acc[1] += x; acc[2] += y; acc[3] += z;
-        const double d = x * ax + y * ay + z * az;
-        acc[4] += d * d;
-    }
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        general_site_terms(nb, sp, i, ax, ay, az, acc);
     block_atomic_add<double, 5>(acc, s_red, obs);
 }
 

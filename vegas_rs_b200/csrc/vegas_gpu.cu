@@ -1,8 +1,9 @@
 // vegas_gpu.cu -- C ABI (include/vegas_gpu.h) of the B200-native Metropolis sweep.
 // Host logic only: handle, layout selection, thermostat tables, launch sequencing.
-// Kernels live in ising_msc.cuh (K1), heis.cuh (K3), general.cuh (K2/K4/K5).
+// Kernels live in ising_msc.cuh (K1), heis.cuh (K3), general.cuh (K2/K4/K5), resident.cuh (K2r), heis_basis.cuh (K4b).
 #include "../../include/vegas_gpu.h"
 
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
@@ -17,6 +18,7 @@
 #include "heis_fused.cuh"
 #include "ising_msc.cuh"
 #include "lattice.hpp"
+#include "resident.cuh"
 
 using namespace vg;
 
@@ -98,6 +100,8 @@ struct vegas_gpu {
     unsigned long long* g_thr = nullptr; uint8_t* g_code = nullptr;
     std::vector<uint64_t> h_row_ptr; std::vector<uint32_t> h_col; std::vector<double> h_val;  // csr input copy
     std::vector<uint8_t> h_colour;
+    // --- shared-memory-resident batches of steps for small general-family lattices (resident.cuh)
+    uint32_t resident_max = 8192;         // tuning key "resident_max": largest site count that takes this path (0: never)
     // --- observables
     unsigned long long* obs = nullptr;    // [OBS_CAP + 2][OBS_W]; row OBS_CAP = scratch, OBS_CAP+1 = query
     // --- counters
@@ -863,6 +867,66 @@ void wave_step_t(vegas_gpu* h, double* obs_row, bool record) {
 #undef WL
 }
 
+// ---- K2r: a batch of steps of a small general-family lattice in ONE launch (state resident in shared memory) ----
+size_t resident_smem(const vegas_gpu* h) {
+    const size_t per_site = h->family == FAM_ISING_GEN ? 1 : 3 * real_bytes(h);
+    return RES_RED * sizeof(double) + per_site * h->n;
+}
+
+bool resident_plan(const vegas_gpu* h) {
+    if (h->family != FAM_ISING_GEN && h->family != FAM_HEIS_GEN) return false;
+    if (h->slab || h->n == 0 || h->n > h->resident_max || h->n_colours > RES_MAX_COLOURS) return false;
+    return resident_smem(h) <= 200 * 1024;
+}
+
+template <typename K, typename... Args>
+int resident_launch(vegas_gpu* h, K kernel, uint32_t threads, Args... args) {
+    const size_t smem = resident_smem(h);
+    // the attribute is per kernel instantiation and cheap to set; the variants of one handle never change
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<1, threads, smem, h->stream>>>(args...);
+    h->launches++;
+    return VEGAS_OK;
+}
+
+template <typename NB>
+int resident_steps(vegas_gpu* h, const NB& nb, uint32_t n_steps, bool record) {
+    ResidentPlan rp{};
+    rp.n_colours = h->n_colours;
+    rp.n = (uint32_t)h->n;
+    uint32_t widest = 1;
+    for (int c = 0; c < h->n_colours; ++c) {
+        rp.sites[c] = h->g_sites[c];
+        rp.counts[c] = h->g_counts[c];
+        widest = std::max(widest, h->g_counts[c]);
+    }
+    const uint32_t threads = std::min<uint32_t>(1024, std::max<uint32_t>(128, (widest + 31) / 32 * 32));
+    const PhiloxKey pk = make_philox_key(h->md.seed);
+    unsigned long long* rows = record ? h->obs : nullptr;
+    unsigned long long* scratch = h->obs + OBS_CAP * OBS_W;
+    if (h->family == FAM_ISING_GEN) {
+        IsingGeneralParams p{};
+        p.thr = h->g_thr; p.code = h->g_code;
+        p.uniform = (h->csr_input && h->d_val) ? 0 : 1;
+        p.h_o = ising_h_o(h); p.invT = 1.0 / h->T;
+        if (h->md.proposal == VEGAS_PROPOSE_RANDOM)
+            return resident_launch(h, ising_resident_kernel<NB, true>, threads, h->g_s8, nb, rp, p, h->sweeps, n_steps, pk, rows, OBS_W, scratch);
+        return resident_launch(h, ising_resident_kernel<NB, false>, threads, h->g_s8, nb, rp, p, h->sweeps, n_steps, pk, rows, OBS_W, scratch);
+    }
+    const bool flip = h->md.proposal == VEGAS_PROPOSE_FLIP;
+    const double ax = h->md.anisotropy_axis[0], ay = h->md.anisotropy_axis[1], az = h->md.anisotropy_axis[2];
+    if (h->md.precision == VEGAS_F64) {
+        const HeisParams<double> p = heis_params<double>(h);
+        double *x = (double*)h->g_s[0], *y = (double*)h->g_s[1], *z = (double*)h->g_s[2];
+        if (flip) return resident_launch(h, heis_resident_kernel<NB, double, true>, threads, x, y, z, nb, rp, p, ax, ay, az, h->sweeps, n_steps, pk, (double*)rows, OBS_W, (double*)scratch);
+        return resident_launch(h, heis_resident_kernel<NB, double, false>, threads, x, y, z, nb, rp, p, ax, ay, az, h->sweeps, n_steps, pk, (double*)rows, OBS_W, (double*)scratch);
+    }
+    const HeisParams<float> p = heis_params<float>(h);
+    float *x = (float*)h->g_s[0], *y = (float*)h->g_s[1], *z = (float*)h->g_s[2];
+    if (flip) return resident_launch(h, heis_resident_kernel<NB, float, true>, threads, x, y, z, nb, rp, p, ax, ay, az, h->sweeps, n_steps, pk, (double*)rows, OBS_W, (double*)scratch);
+    return resident_launch(h, heis_resident_kernel<NB, float, false>, threads, x, y, z, nb, rp, p, ax, ay, az, h->sweeps, n_steps, pk, (double*)rows, OBS_W, (double*)scratch);
+}
+
 // One Monte Carlo step (= N attempts): every colour once.  obs_row != null records observables.
 void do_step(vegas_gpu* h, void* obs_row, void* scratch_row) {
     const bool rec = obs_row != nullptr;
@@ -1563,6 +1627,19 @@ int vegas_gpu_step_async(vegas_gpu_t h, uint64_t n_steps, int record) {
     if (rc) return rc;
     unsigned long long* scratch = h->obs + OBS_CAP * OBS_W;
     if (record) CU(cudaMemsetAsync(h->obs, 0, n_steps * OBS_W * 8, h->stream));
+    if (resident_plan(h)) {  // small lattice: the whole batch is one launch with the State in shared memory
+        uint64_t done = 0;
+        while (done < n_steps) {
+            const uint32_t batch = (uint32_t)std::min<uint64_t>(n_steps - done, OBS_CAP);
+            rc = h->csr_input ? resident_steps(h, csr_nb(h), batch, record != 0) : resident_steps(h, structured_nb(h), batch, record != 0);
+            if (rc) return rc;
+            h->sweeps += batch;
+            h->attempts += h->n * batch;
+            done += batch;
+        }
+        CU(cudaGetLastError());
+        return VEGAS_OK;
+    }
     for (uint64_t s = 0; s < n_steps; ++s) do_step(h, record ? (void*)(h->obs + s * OBS_W) : nullptr, scratch);
     CU(cudaGetLastError());
     return VEGAS_OK;
@@ -1887,6 +1964,7 @@ int vegas_gpu_set_tuning(vegas_gpu_t h, const char* key, long value) {
     else if (k == "heis_wave") h->wave_enable = (int)value;
     else if (k == "heis_wave_planes") h->wave_planes = (uint32_t)value;
     else if (k == "heis_wave_lag") h->wave_lag = (uint32_t)value;
+    else if (k == "resident_max") h->resident_max = (uint32_t)value;
     else return fail(h, VEGAS_ERR_INVALID, "unknown tuning key: " + k);
     h->fused_ready = false;  // re-plan at the next step
     h->wave_ready = false;
@@ -1897,6 +1975,7 @@ const char* vegas_gpu_step_kernel(vegas_gpu_t h) {
     if (!h) return "";
     if (h->family == FAM_HEIS_STENCIL && cudaSetDevice(h->device) == cudaSuccess && wave_plan(h)) return "heis_wave";
     if (h->family == FAM_HEIS_STENCIL && cudaSetDevice(h->device) == cudaSuccess && fused_plan(h)) return "heis_fused";
+    if (resident_plan(h)) return h->family == FAM_ISING_GEN ? "ising_resident" : "heis_resident";
     return FAMILY_NAME[h->family];
 }
 

@@ -22,8 +22,9 @@ int Machine::set_thermostat(const Thermostat& th) {
 // are then replayed in the reference's order with the recorded per-step (E, |M|).
 int Machine::run(uint64_t steps) {
     const uint64_t n = n_sites();
-    const bool heis = std::strcmp(vegas_gpu_kernel_family(gpu_), "heis_stencil") == 0 ||
-                      std::strcmp(vegas_gpu_kernel_family(gpu_), "heis_general") == 0;
+    // every Heisenberg family (heis_stencil, heis_general, heis_basis) reports |M| from three projections and dumps
+    // 24-byte spins
+    const bool heis = std::strncmp(vegas_gpu_kernel_family(gpu_), "heis", 4) == 0;
     std::vector<double> e, m;
     std::vector<char> state;
     uint64_t remaining = steps;
