@@ -51,6 +51,7 @@ SMALL_WORKLOADS = {
                             dtype="int8 in shared memory"),
 }
 ALL_WORKLOADS = {**WORKLOADS, **SMALL_WORKLOADS}
+POLL_S = float(os.environ.get("VEGAS_BENCH_POLL_MS", "0")) * 1e-3  # pause between NVML polls of the clock sampler
 METRIC = "spin-flip attempts/sec"
 UNIT = "attempts/s"
 
@@ -86,6 +87,8 @@ class ClockSampler(threading.Thread):
                 mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 self.rows.append((t, mhz, [k for k, b in bits.items() if mask & b]))
                 self.ready.set()
+                if POLL_S > 0:
+                    time.sleep(POLL_S)
         except Exception as e:  # no NVML: report nothing rather than a wrong number
             self.error = repr(e)
             self.ready.set()

@@ -83,6 +83,15 @@ struct IsingGeneralParams {
     double invT;
 };
 
+// Uniform-J decision for a spin si whose neighbour sum m = sum_j s_j is known: threshold table lookup with the 64-bit
+// uniform U (thr / code may live in global or shared memory).
+__device__ __forceinline__ bool ising_table_decision(int si, int m, unsigned long long U, const unsigned long long* thr,
+                                                     const uint8_t* code) {
+    const int idx = (si > 0 ? 1 : 0) * (2 * ISING_ZMAX + 1) + (m + ISING_ZMAX);
+    const uint8_t c = code[idx];
+    return c == 2 || (c == 1 && U < thr[idx]);
+}
+
 // One attempt on site i (the body of src/integrator.rs:121-135 / :75-89 for IsingSpin); `s` may live in global or
 // shared memory.  Returns true when the move counts as accepted.
 template <typename NB, bool RANDPROP>
@@ -98,9 +107,7 @@ __device__ __forceinline__ bool ising_general_attempt(int8_t* s, const NB& nb, u
     if (p.uniform) {
         int m = 0;
         nb.for_each(i, [&](uint32_t j, double) { if (j != i) m += s[j]; });
-        const int idx = (si > 0 ? 1 : 0) * (2 * ISING_ZMAX + 1) + (m + ISING_ZMAX);
-        const uint8_t c = p.code[idx];
-        ok = c == 2 || (c == 1 && U < p.thr[idx]);
+        ok = ising_table_decision(si, m, U, p.thr, p.code);
     } else {
         double ex = 0.0;  // Exchange::energy fold src/energy.rs:197-201 without the constant diagonal
         nb.for_each(i, [&](uint32_t j, double Jij) { if (j != i) ex = ex + (-Jij * (double)(si * s[j])); });
@@ -128,7 +135,21 @@ ising_general_sweep_kernel(int8_t* __restrict__ s, NB nb, const uint32_t* __rest
 // ---------------------------------------------------------------------------------------
 // Heisenberg
 // ---------------------------------------------------------------------------------------
-// One attempt on site i for HeisenbergSpin; the SoA arrays may live in global or shared memory.
+// The Metropolis decision for site i once its neighbour sum n = sum_j J_ij s_j is known (shared by every gather
+// policy); the SoA arrays may live in global or shared memory.
+template <typename real, bool FLIP>
+__device__ __forceinline__ bool heis_site_update(real* sx, real* sy, real* sz, uint32_t i, real nx, real ny, real nz,
+                                                 const HeisParams<real>& p, uint64_t site_offset, uint64_t sweep,
+                                                 const PhiloxKey& pk) {
+    real x = sx[i], y = sy[i], z = sz[i];
+    HeisRand<real> rnd;
+    heis_rand((uint64_t)i + site_offset, sweep, pk, rnd);
+    const bool ok = heis_attempt<real, FLIP>(x, y, z, nx - p.h[0], ny - p.h[1], nz - p.h[2], p, rnd);
+    if (ok) { sx[i] = x; sy[i] = y; sz[i] = z; }
+    return ok;
+}
+
+// One attempt on site i for HeisenbergSpin, neighbours enumerated by the policy NB.
 template <typename NB, typename real, bool FLIP>
 __device__ __forceinline__ bool heis_general_attempt(real* sx, real* sy, real* sz, const NB& nb, uint32_t i,
                                                      const HeisParams<real>& p, uint64_t site_offset, uint64_t sweep,
@@ -137,12 +158,7 @@ __device__ __forceinline__ bool heis_general_attempt(real* sx, real* sy, real* s
     nb.for_each(i, [&](uint32_t j, double Jij) {
         if (j != i) { const real w = (real)Jij; nx += w * sx[j]; ny += w * sy[j]; nz += w * sz[j]; }
     });
-    real x = sx[i], y = sy[i], z = sz[i];
-    HeisRand<real> rnd;
-    heis_rand((uint64_t)i + site_offset, sweep, pk, rnd);
-    const bool ok = heis_attempt<real, FLIP>(x, y, z, nx - p.h[0], ny - p.h[1], nz - p.h[2], p, rnd);
-    if (ok) { sx[i] = x; sy[i] = y; sz[i] = z; }
-    return ok;
+    return heis_site_update<real, FLIP>(sx, sy, sz, i, nx, ny, nz, p, site_offset, sweep, pk);
 }
 
 template <typename NB, typename real, bool FLIP>

@@ -76,8 +76,11 @@ struct BasisPeers { real* lo; real* hi; };  // bases of the lower / upper neighb
 // towards the LOWER colours (final by now) so that a step counts every bond once; obs[0] receives twice that sum
 // (layout of general_reduce_kernel: sum_i sum_j J s_i.s_j, every bond twice).  2: the same reductions, no update.
 // obs[5] += accepted.
+#ifndef BASIS_MINB
+#define BASIS_MINB 1   // no register cap: capping the recorded-step variants at 40 registers (12 CTAs per SM) spills and
+#endif                 // was measured slower (4.02 vs 3.42 ms per fcc 384^3 step), 32 registers slower still (4.27 ms)
 template <typename real, int UC, int B, bool FLIP, int MODE, bool SLAB = false>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, BASIS_MINB)
 heis_basis_kernel(BasisPtrs<real> P, BasisPeers<real> peers, BasisGeom g, uint32_t rows_per_cta, uint32_t z_begin, uint32_t z_step,
                   HeisParams<real> p, uint64_t sweep, PhiloxKey pk, double* __restrict__ obs) {
     constexpr int NB = BasisCell<UC>::NB, Z = BasisCell<UC>::Z;

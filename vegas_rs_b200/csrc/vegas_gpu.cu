@@ -10,6 +10,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "general.cuh"
@@ -102,6 +103,7 @@ struct vegas_gpu {
     std::vector<uint8_t> h_colour;
     // --- shared-memory-resident batches of steps for small general-family lattices (resident.cuh)
     uint32_t resident_max = 8192;         // tuning key "resident_max": largest site count that takes this path (0: never)
+    int resident_cols = -2;               // cached resident_columns(): -2 not planned yet, -1 no, 0 direct, > 0 table columns
     // --- observables
     unsigned long long* obs = nullptr;    // [OBS_CAP + 2][OBS_W]; row OBS_CAP = scratch, OBS_CAP+1 = query
     // --- counters
@@ -868,20 +870,43 @@ void wave_step_t(vegas_gpu* h, double* obs_row, bool record) {
 }
 
 // ---- K2r: a batch of steps of a small general-family lattice in ONE launch (state resident in shared memory) ----
-size_t resident_smem(const vegas_gpu* h) {
-    const size_t per_site = h->family == FAM_ISING_GEN ? 1 : 3 * real_bytes(h);
-    return RES_RED * sizeof(double) + per_site * h->n;
+constexpr size_t RES_SMEM_LIMIT = 226 * 1024;  // of the 227 KB a CTA may opt in to
+constexpr uint32_t RES_DIRECT_MAX = 2048;      // the direct variant (per-bond values) only pays off on tiny lattices
+
+// widest neighbour row (self entries included: an upper bound for the table columns); 0 when the rows are unknown
+int resident_row_width(const vegas_gpu* h) {
+    if (h->csr_input) {
+        uint64_t w = 0;
+        for (size_t i = 0; i + 1 < h->h_row_ptr.size(); ++i) w = std::max<uint64_t>(w, h->h_row_ptr[i + 1] - h->h_row_ptr[i]);
+        return (int)std::min<uint64_t>(w, 1u << 20);
+    }
+    const StructuredNb nb = structured_nb(h);
+    int w = 0;
+    for (int b = 0; b < nb.nb; ++b) w = std::max(w, nb.count[b]);
+    return w;
 }
 
-bool resident_plan(const vegas_gpu* h) {
-    if (h->family != FAM_ISING_GEN && h->family != FAM_HEIS_GEN) return false;
-    if (h->slab || h->n == 0 || h->n > h->resident_max || h->n_colours > RES_MAX_COLOURS) return false;
-    return resident_smem(h) <= 200 * 1024;
+// table columns of the resident launch: > 0 table variant, 0 direct variant, -1 no resident path for this handle
+int resident_columns(const vegas_gpu* h) {
+    if (h->family != FAM_ISING_GEN && h->family != FAM_HEIS_GEN) return -1;
+    if (h->slab || h->n == 0 || h->n > h->resident_max || h->n > 16384 || h->n_colours > RES_MAX_COLOURS) return -1;
+    const size_t per_site = h->family == FAM_ISING_GEN ? 1 : 3 * real_bytes(h);
+    const bool uniform = !(h->csr_input && h->d_val);
+    if (uniform) {
+        const int z = std::max(1, resident_row_width(h));
+        if (z <= RES_MAX_Z && resident_smem_bytes((uint32_t)h->n, z, per_site) <= RES_SMEM_LIMIT) return z;
+    }
+    if (h->n <= RES_DIRECT_MAX && resident_smem_bytes((uint32_t)h->n, 0, per_site) <= RES_SMEM_LIMIT) return 0;
+    return -1;
+}
+
+bool resident_plan(vegas_gpu* h) {
+    if (h->resident_cols == -2) h->resident_cols = resident_columns(h);
+    return h->resident_cols >= 0;
 }
 
 template <typename K, typename... Args>
-int resident_launch(vegas_gpu* h, K kernel, uint32_t threads, Args... args) {
-    const size_t smem = resident_smem(h);
+int resident_launch(vegas_gpu* h, K kernel, uint32_t threads, size_t smem, Args... args) {
     // the attribute is per kernel instantiation and cheap to set; the variants of one handle never change
     CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kernel<<<1, threads, smem, h->stream>>>(args...);
@@ -889,11 +914,12 @@ int resident_launch(vegas_gpu* h, K kernel, uint32_t threads, Args... args) {
     return VEGAS_OK;
 }
 
-template <typename NB>
-int resident_steps(vegas_gpu* h, const NB& nb, uint32_t n_steps, bool record) {
+template <typename NB, bool TABLE>
+int resident_steps_t(vegas_gpu* h, const NB& nb, uint32_t n_steps, bool record) {
     ResidentPlan rp{};
     rp.n_colours = h->n_colours;
     rp.n = (uint32_t)h->n;
+    rp.zmax = TABLE ? h->resident_cols : 0;
     uint32_t widest = 1;
     for (int c = 0; c < h->n_colours; ++c) {
         rp.sites[c] = h->g_sites[c];
@@ -901,30 +927,38 @@ int resident_steps(vegas_gpu* h, const NB& nb, uint32_t n_steps, bool record) {
         widest = std::max(widest, h->g_counts[c]);
     }
     const uint32_t threads = std::min<uint32_t>(1024, std::max<uint32_t>(128, (widest + 31) / 32 * 32));
+    const size_t smem = resident_smem_bytes(rp.n, rp.zmax, h->family == FAM_ISING_GEN ? 1 : 3 * real_bytes(h));
     const PhiloxKey pk = make_philox_key(h->md.seed);
     unsigned long long* rows = record ? h->obs : nullptr;
     unsigned long long* scratch = h->obs + OBS_CAP * OBS_W;
+    const double J = nb.J;
     if (h->family == FAM_ISING_GEN) {
         IsingGeneralParams p{};
         p.thr = h->g_thr; p.code = h->g_code;
         p.uniform = (h->csr_input && h->d_val) ? 0 : 1;
         p.h_o = ising_h_o(h); p.invT = 1.0 / h->T;
+        constexpr bool SYMM = std::is_same<NB, StructuredNb>::value;  // a user CSR may be asymmetric: full reduction per step
         if (h->md.proposal == VEGAS_PROPOSE_RANDOM)
-            return resident_launch(h, ising_resident_kernel<NB, true>, threads, h->g_s8, nb, rp, p, h->sweeps, n_steps, pk, rows, OBS_W, scratch);
-        return resident_launch(h, ising_resident_kernel<NB, false>, threads, h->g_s8, nb, rp, p, h->sweeps, n_steps, pk, rows, OBS_W, scratch);
+            return resident_launch(h, ising_resident_kernel<NB, true, TABLE, SYMM>, threads, smem, h->g_s8, nb, rp, p, J, h->sweeps, n_steps, pk, rows, OBS_W, scratch);
+        return resident_launch(h, ising_resident_kernel<NB, false, TABLE, SYMM>, threads, smem, h->g_s8, nb, rp, p, J, h->sweeps, n_steps, pk, rows, OBS_W, scratch);
     }
     const bool flip = h->md.proposal == VEGAS_PROPOSE_FLIP;
     const double ax = h->md.anisotropy_axis[0], ay = h->md.anisotropy_axis[1], az = h->md.anisotropy_axis[2];
     if (h->md.precision == VEGAS_F64) {
         const HeisParams<double> p = heis_params<double>(h);
         double *x = (double*)h->g_s[0], *y = (double*)h->g_s[1], *z = (double*)h->g_s[2];
-        if (flip) return resident_launch(h, heis_resident_kernel<NB, double, true>, threads, x, y, z, nb, rp, p, ax, ay, az, h->sweeps, n_steps, pk, (double*)rows, OBS_W, (double*)scratch);
-        return resident_launch(h, heis_resident_kernel<NB, double, false>, threads, x, y, z, nb, rp, p, ax, ay, az, h->sweeps, n_steps, pk, (double*)rows, OBS_W, (double*)scratch);
+        if (flip) return resident_launch(h, heis_resident_kernel<NB, double, true, TABLE>, threads, smem, x, y, z, nb, rp, p, J, ax, ay, az, h->sweeps, n_steps, pk, (double*)rows, OBS_W, (double*)scratch);
+        return resident_launch(h, heis_resident_kernel<NB, double, false, TABLE>, threads, smem, x, y, z, nb, rp, p, J, ax, ay, az, h->sweeps, n_steps, pk, (double*)rows, OBS_W, (double*)scratch);
     }
     const HeisParams<float> p = heis_params<float>(h);
     float *x = (float*)h->g_s[0], *y = (float*)h->g_s[1], *z = (float*)h->g_s[2];
-    if (flip) return resident_launch(h, heis_resident_kernel<NB, float, true>, threads, x, y, z, nb, rp, p, ax, ay, az, h->sweeps, n_steps, pk, (double*)rows, OBS_W, (double*)scratch);
-    return resident_launch(h, heis_resident_kernel<NB, float, false>, threads, x, y, z, nb, rp, p, ax, ay, az, h->sweeps, n_steps, pk, (double*)rows, OBS_W, (double*)scratch);
+    if (flip) return resident_launch(h, heis_resident_kernel<NB, float, true, TABLE>, threads, smem, x, y, z, nb, rp, p, J, ax, ay, az, h->sweeps, n_steps, pk, (double*)rows, OBS_W, (double*)scratch);
+    return resident_launch(h, heis_resident_kernel<NB, float, false, TABLE>, threads, smem, x, y, z, nb, rp, p, J, ax, ay, az, h->sweeps, n_steps, pk, (double*)rows, OBS_W, (double*)scratch);
+}
+
+template <typename NB>
+int resident_steps(vegas_gpu* h, const NB& nb, uint32_t n_steps, bool record) {
+    return h->resident_cols > 0 ? resident_steps_t<NB, true>(h, nb, n_steps, record) : resident_steps_t<NB, false>(h, nb, n_steps, record);
 }
 
 // One Monte Carlo step (= N attempts): every colour once.  obs_row != null records observables.
@@ -1964,7 +1998,7 @@ int vegas_gpu_set_tuning(vegas_gpu_t h, const char* key, long value) {
     else if (k == "heis_wave") h->wave_enable = (int)value;
     else if (k == "heis_wave_planes") h->wave_planes = (uint32_t)value;
     else if (k == "heis_wave_lag") h->wave_lag = (uint32_t)value;
-    else if (k == "resident_max") h->resident_max = (uint32_t)value;
+    else if (k == "resident_max") { h->resident_max = (uint32_t)value; h->resident_cols = -2; }
     else return fail(h, VEGAS_ERR_INVALID, "unknown tuning key: " + k);
     h->fused_ready = false;  // re-plan at the next step
     h->wave_ready = false;
