@@ -51,7 +51,8 @@ SMALL_WORKLOADS = {
                             dtype="int8 in shared memory"),
 }
 ALL_WORKLOADS = {**WORKLOADS, **SMALL_WORKLOADS}
-POLL_S = float(os.environ.get("VEGAS_BENCH_POLL_MS", "0")) * 1e-3  # pause between NVML polls of the clock sampler
+POLL_S = float(os.environ.get("VEGAS_BENCH_POLL_MS", "1")) * 1e-3  # pause between NVML polls of the clock sampler (back-to-back
+# polling cost the fcc workload 1.7 %: profiles/r01v_poll_probe.txt)
 METRIC = "spin-flip attempts/sec"
 UNIT = "attempts/s"
 
@@ -411,7 +412,8 @@ def main():
                 r = run_workload(other, min(args.steps, 10) if heavy else args.steps, args.warmup, rank, world, device, dist, torch,
                                  0 if heavy else args.e2e_steps, args.e2e_steps > 0)
                 also[other] = {"value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "roofline": r["roofline"],
-                               "e2e": r["e2e"], "e2e_machine": r["e2e_machine"], "family": r["family"],
+                               "e2e": r["e2e"], "e2e_machine": r["e2e_machine"], "family": r["family"], "clocks": r["clocks"],
+                               "gpu_launches": r["launches"],
                                "note": {"ising2d_8192": "8 MiB state is L2 resident: not an HBM measurement",
                                         "heis_fcc_384": "heis_basis kernel (scalar loads, one Philox call per site), 4 colours, single GPU"}.get(other, "")}
         if world == 1 and args.e2e_steps > 0:
