@@ -479,19 +479,48 @@ def test_heisenberg_wave_kernel_identical(built, precision):
     e1, m1 = ref.step(1)
     want = ref.download(); acc = ref.attempt_count()
     ref.close()
-    for planes, lag in ((1, 1), (2, 1), (3, 2), (4, 2), (5, 7)):
+    # (planes per chunk, lag in chunks, steps fused into one launch)
+    for planes, lag, k in ((1, 1, 1), (2, 1, 1), (3, 2, 1), (4, 2, 1), (5, 7, 1), (1, 3, 2), (2, 4, 2), (1, 3, 3), (3, 5, 4), (1, 4, 4),
+                           (6, 3, 2)):
         g = vg.GpuMetropolis(vg.HEISENBERG, **kw, **lat)
         g.set_tuning("heis_wave", 1); g.set_tuning("heis_wave_planes", planes); g.set_tuning("heis_wave_lag", lag)
+        g.set_tuning("heis_wave_steps", k)
         assert g.step_kernel == "heis_wave"
         g.randomize(); g.set_thermostat(0.8, (0, 0, 1.0), 0.4)
         e, m = g.step(3)
         g.step(2, observe=False)
         e2, m2 = g.step(1)
         g.synchronize()
-        assert np.array_equal(g.download(), want), (planes, lag)
+        assert np.array_equal(g.download(), want), (planes, lag, k)
         assert np.allclose(e, e0, rtol=1e-6) and np.allclose(e2, e1, rtol=1e-6) and np.allclose(m, m0, rtol=1e-5, atol=1e-3)
         assert g.attempt_count() == acc
         g.close()
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_heisenberg_wave_multi_step_launch_identical(built, k):
+    """Several steps fused into one persistent launch (2k colour-pass phases in rotated wave order, many tiles per
+    chunk, all CTAs waiting on each other's chunk counters): same trajectory and the same per-step E, M rows as single
+    steps; a batch that is not a multiple of k ends with a shorter launch."""
+    lat = dict(unitcell=vg.SC, size=(128, 64, 24))
+    kw = dict(precision=vg.F32, seed=33, anisotropy=((0, 0, 1.0), 0.1))
+    res = []
+    for steps_per_launch in (1, k):
+        g = vg.GpuMetropolis(vg.HEISENBERG, **kw, **lat)
+        g.set_tuning("heis_wave", 1); g.set_tuning("heis_wave_planes", 2); g.set_tuning("heis_wave_lag", 3)
+        g.set_tuning("heis_wave_steps", steps_per_launch)
+        assert g.step_kernel == "heis_wave"
+        g.randomize(); g.set_thermostat(1.2, (0, 0, 1.0), 0.5)
+        e, m = g.step(2 * k + 1)
+        g.step(k, observe=False)
+        g.synchronize()
+        res.append((g.download(), e, m, g.attempt_count(), g.launches))
+        g.close()
+    (s1, e1, m1, a1, l1), (sk, ek, mk, ak, lk) = res
+    assert np.array_equal(s1, sk)
+    assert np.allclose(e1, ek, rtol=1e-6) and np.allclose(m1, mk, rtol=1e-5, atol=1e-2)
+    assert a1 == ak
+    assert lk < l1                                            # fewer launches for the same steps
 
 
 def test_heisenberg_fused_flip_proposal_and_larger(built):

@@ -307,46 +307,67 @@ heis_stencil_kernel(HeisPtrs<real> P, HeisGeom g, int colour, uint32_t z_begin, 
 }
 
 // ---------------------------------------------------------------------------------------
-// K3w: the two colour passes of one step as ONE persistent launch in wave order, so that the second pass finds the
-// planes of the first in L2 (36 -> ~27 B/attempt of DRAM traffic).  Work items = (unit, tile); a unit is one colour
-// on a chunk of C planes; `units` lists them in an order in which colour 1 on chunk j comes `lag` chunks behind the
-// colour-0 front (colour-1 chunk 0 last: it needs colour 0 on the last chunk, and colour 0 on the last chunk reads the
-// OLD colour 1 of plane 0).  Items are dealt round-robin to the co-resident CTAs (static, in order: an item only waits
-// for lower-numbered items, so the lowest unfinished item can always run).  A colour-1 item waits until colour 0 is
-// complete on its own and the two adjacent chunks (per-chunk counters of finished tiles, release/acquire fences).
+// K3w: the colour passes of ONE OR SEVERAL steps as one persistent launch in wave order, so that every pass finds the
+// planes the previous pass wrote in L2 (two separate passes move 36 B/attempt through DRAM; one step in wave order
+// ~33 B measured; k steps per launch divide the compulsory 24 B by k).
+// A phase is one colour pass: phase = 2 * step + colour.  Work items = (unit, tile); a unit is one phase on a chunk of
+// C planes.  Phase p visits the chunks in the rotated order p, p+1, ..., n-1, 0, ..., p-1 (its chunk p-1 needs phase
+// p-1 on chunk p-2, which that phase visits last) and trails phase p-1 by `lag` >= 3 positions.  Unit (p, j) may run once
+// phase p-1 is complete on chunks j-1, j, j+1: that single rule covers the true dependencies (the neighbours' new
+// values) and the anti-dependencies (phase p-1 on j+-1 has read the old values (p, j) overwrites).  `units` lists the
+// units by time slot; items are dealt round-robin to the co-resident CTAs (static, in order: an item only waits for
+// lower-numbered items, so the lowest unfinished item can always run).  Completion is counted per (phase, chunk) with
+// release/acquire fences; the counters are monotone over the launches (each launch passes its own targets).
 // ---------------------------------------------------------------------------------------
+constexpr int WAVE_MAX_STEPS = 4;
 struct WaveSched {
-    const uint32_t* units;       // [n_units]: colour << 31 | chunk
-    uint32_t n_units, tiles, C, n_chunks;
-    unsigned long long* done;    // [n_chunks] colour-0 tiles finished on the chunk, monotone over the steps
-    unsigned long long target;   // value of done[] when colour 0 is complete on a chunk in THIS step
+    const uint32_t* units;       // [n_units]: phase << 24 | chunk
+    uint32_t n_units, tiles, C, n_chunks, n_phases;
+    unsigned long long* done;    // [2 * WAVE_MAX_STEPS][n_chunks] tiles finished, monotone over the launches
+    unsigned long long target[2 * WAVE_MAX_STEPS];  // value of done[p][.] once phase p is complete on a chunk in THIS launch
     unsigned int* error;         // != 0: a dependency wait timed out (results invalid)
 };
 
-template <typename real, bool FLIP, bool RECORD>
+// MULTI = false: one step per launch (phases 0 and 1 only; the step bookkeeping below folds away)
+template <typename real, bool FLIP, bool RECORD, bool MULTI>
 __global__ void __launch_bounds__(128, HEIS_MINB)
 heis_wave_kernel(HeisPtrs<real> P0, HeisPtrs<real> P1, HeisGeom g, WaveSched ws, HeisParams<real> p, uint64_t sweep,
-                 PhiloxKey pk, double* __restrict__ obs) {
-    __shared__ double s_acc[6];
-    if (threadIdx.x < 6) s_acc[threadIdx.x] = 0.0;
+                 PhiloxKey pk, double* __restrict__ obs, int obs_stride /* doubles between the rows of consecutive steps */) {
+    constexpr int KS = MULTI ? WAVE_MAX_STEPS : 1;
+    __shared__ double s_acc[KS][6];
+    if (threadIdx.x < KS * 6) (&s_acc[0][0])[threadIdx.x] = 0.0;
     __syncthreads();
     real facc[5] = {0, 0, 0, 0, 0};
     int accepted = 0;
     const uint32_t n_items = ws.n_units * ws.tiles;
-    uint32_t since_flush = 0;
+    uint32_t since_flush = 0, acc_step = 0;  // facc / accepted hold sums of step acc_step only
+    auto flush = [&]() {
+        if (RECORD) heis_flush(facc, s_acc[acc_step]);
+        const int a = __reduce_add_sync(0xffffffffu, accepted);
+        if ((threadIdx.x & 31u) == 0 && a != 0) atomicAdd(&s_acc[acc_step][5], (double)a);
+        accepted = 0;
+        since_flush = 0;
+    };
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const uint32_t u = item / ws.tiles, tile = item - u * ws.tiles;
         const uint32_t unit = ws.units[u];
-        const int colour = (int)(unit >> 31);
-        const uint32_t chunk = unit & 0x7FFFFFFFu;
+        const uint32_t phase = unit >> 24, chunk = unit & 0x00FFFFFFu;
+        const int colour = (int)(phase & 1u);
+        const uint32_t step = MULTI ? phase >> 1 : 0u;
         const uint32_t z0 = chunk * ws.C, z1 = min(z0 + ws.C, g.Lz);
-        if (colour == 1) {
+        if (MULTI && step != acc_step) { if (since_flush) flush(); acc_step = step; }
+        if (phase > 0) {
             if (threadIdx.x < 3) {
                 const uint32_t dep = threadIdx.x == 0 ? (chunk == 0 ? ws.n_chunks - 1 : chunk - 1)
                                    : threadIdx.x == 1 ? chunk : (chunk + 1 == ws.n_chunks ? 0u : chunk + 1);
-                const volatile unsigned long long* d = ws.done + dep;
+                const volatile unsigned long long* d = ws.done + (size_t)(phase - 1) * ws.n_chunks + dep;
+                unsigned long long target = ws.target[0];  // static indices only: a dynamic one would copy ws to local memory
+                if (MULTI) {
+#pragma unroll
+                    for (uint32_t q = 1; q + 1 < 2 * WAVE_MAX_STEPS; ++q) if (phase - 1 == q) target = ws.target[q];
+                }
                 uint32_t spins = 0;
-                while (*d < ws.target) {
+                while (*d < target) {
                     __nanosleep(256);
                     if (++spins > (1u << 22)) { atomicExch(ws.error, 1u); break; }  // never hang the GPU
                 }
@@ -356,22 +377,22 @@ heis_wave_kernel(HeisPtrs<real> P0, HeisPtrs<real> P1, HeisGeom g, WaveSched ws,
         }
         const uint32_t t2 = tile * blockDim.x + threadIdx.x;
         if (colour == 0)
-            heis_march<real, 3, FLIP, true, RECORD, false, false>(P0, g, 0, t2, z0, z1, false, p, sweep, pk, facc, accepted, [] {});
+            heis_march<real, 3, FLIP, true, RECORD, false, false>(P0, g, 0, t2, z0, z1, false, p, sweep + step, pk, facc, accepted, [] {});
         else
-            heis_march<real, 3, FLIP, true, RECORD, false, false>(P1, g, 1, t2, z0, z1, true, p, sweep, pk, facc, accepted, [] {});
-        if (colour == 0) {
+            heis_march<real, 3, FLIP, true, RECORD, false, false>(P1, g, 1, t2, z0, z1, true, p, sweep + step, pk, facc, accepted, [] {});
+        if (MULTI ? phase + 1 < ws.n_phases : phase == 0) {
             __syncthreads();  // every thread's stores of this tile are issued
-            if (threadIdx.x == 0) { __threadfence(); atomicAdd(ws.done + chunk, 1ull); }
+            if (threadIdx.x == 0) { __threadfence(); atomicAdd(ws.done + (size_t)phase * ws.n_chunks + chunk, 1ull); }
         }
-        if (RECORD && ++since_flush == 8) { heis_flush(facc, s_acc); since_flush = 0; }
+        if (++since_flush == 8) flush();
     }
-    if (RECORD) heis_flush(facc, s_acc);
-    {
-        const int a = __reduce_add_sync(0xffffffffu, accepted);
-        if ((threadIdx.x & 31u) == 0 && a != 0) atomicAdd(&s_acc[5], (double)a);
-    }
+    if (since_flush) flush();
     __syncthreads();
-    if (threadIdx.x < 6 && s_acc[threadIdx.x] != 0.0) atomicAdd(obs + threadIdx.x, s_acc[threadIdx.x]);
+    const uint32_t n_steps = MULTI ? ws.n_phases >> 1 : 1u;
+    if (threadIdx.x < 6 * n_steps) {
+        const uint32_t st = threadIdx.x / 6, k = threadIdx.x - st * 6;
+        if (s_acc[st][k] != 0.0) atomicAdd(obs + (size_t)st * obs_stride + k, s_acc[st][k]);
+    }
 }
 
 // ---------------------------------------------------------------------------------------

@@ -72,13 +72,16 @@ struct vegas_gpu {
     uint32_t wave_c = 0;                  // experiment: interleave the two colour passes in chunks of wave_c planes
     // --- persistent wave kernel (heis_wave_kernel): both colour passes in one launch, L2-friendly order
     int wave_enable = -1;                 // tuning key heis_wave: -1 auto (lattices with >= 32 planes), 0 never, 1 always
-    uint32_t wave_planes = 4, wave_lag = 4;
+    uint32_t wave_planes = 4, wave_lag = 5;
     bool wave_ready = false;
     WaveSched wave_sched{};
-    uint32_t* wave_units = nullptr;
+    uint32_t wave_k = 1;                  // tuning key heis_wave_steps: steps fused into one launch (<= WAVE_MAX_STEPS)
+    uint32_t wave_kmax = 1;               // planned value
+    uint32_t* wave_units[WAVE_MAX_STEPS] = {};      // unit order of a launch of k steps at index k - 1
+    uint32_t wave_n_units[WAVE_MAX_STEPS] = {};
     unsigned long long* wave_done = nullptr;
+    unsigned long long wave_phase_launches[2 * WAVE_MAX_STEPS] = {};  // launches that ran phase p so far
     unsigned int* wave_error = nullptr;
-    unsigned long long wave_steps = 0;
     int wave_grid = 0;
     bool fused_ready = false;
     FusedGeom fused_geom{};
@@ -798,41 +801,56 @@ int fused_step_t(vegas_gpu* h, double* obs_row, bool record) {
 }
 
 // ---- persistent wave step (heis_wave_kernel) ------------------------------------------------------
+// Unit order of a launch of `k` steps (2k phases) over n chunks: phase p visits chunk (p + pos) % n at time slot
+// pos + p * lag; slots ascending, phases ascending inside a slot (see heis.cuh, K3w).
+std::vector<uint32_t> wave_units_for(uint32_t n, uint32_t lag, uint32_t k) {
+    std::vector<uint32_t> units;
+    const uint32_t phases = 2 * k;
+    for (uint32_t t = 0; t < n + (phases - 1) * lag; ++t)
+        for (uint32_t p = 0; p < phases; ++p) {
+            if (t < p * lag || t - p * lag >= n) continue;
+            units.push_back((p << 24) | ((p + (t - p * lag)) % n));
+        }
+    return units;
+}
+
 bool wave_plan(vegas_gpu* h) {
     if (h->wave_ready) return true;
     if (h->family != FAM_HEIS_STENCIL || h->ndim != 3 || h->slab || h->wave_enable == 0) return false;
     if (h->wave_enable < 0 && (h->ld.nz < 32 || h->fused_enable == 1 || h->wave_c > 0)) return false;  // auto: big lattices only
     const uint32_t Lz = (uint32_t)h->ld.nz, C = std::max<uint32_t>(1, h->wave_planes);
     const uint32_t n = cdiv(Lz, C);
-    if (n < 2) return false;
-    const uint32_t D = std::max<uint32_t>(1, std::min(h->wave_lag, n - 1));
-    // colour 0 on chunk a, then colour 1 on chunk a - D (chunk 0 of colour 1 goes last)
-    std::vector<uint32_t> units;
-    for (uint32_t a = 0; a < n; ++a) {
-        units.push_back(a);
-        if (a >= D && a - D >= 1) units.push_back(0x80000000u | (a - D));
+    if (n < 2 || n >= (1u << 24)) return false;
+    const uint32_t D = std::max<uint32_t>(3, h->wave_lag);   // lag >= 3: dependencies precede their users (lag >= n: no overlap)
+    const uint32_t kmax = std::max<uint32_t>(1, std::min<uint32_t>(h->wave_k, WAVE_MAX_STEPS));
+    for (uint32_t k = 0; k < WAVE_MAX_STEPS; ++k) { cudaFree(h->wave_units[k]); h->wave_units[k] = nullptr; h->wave_n_units[k] = 0; }
+    cudaFree(h->wave_done); cudaFree(h->wave_error);
+    h->wave_done = nullptr; h->wave_error = nullptr;
+    for (uint32_t k = 1; k <= kmax; ++k) {
+        const std::vector<uint32_t> units = wave_units_for(n, D, k);
+        if (units.size() != (size_t)2 * k * n) return false;
+        if (cudaMalloc(&h->wave_units[k - 1], units.size() * 4) != cudaSuccess) { cudaGetLastError(); return false; }
+        cudaMemcpy(h->wave_units[k - 1], units.data(), units.size() * 4, cudaMemcpyHostToDevice);
+        h->wave_n_units[k - 1] = (uint32_t)units.size();
     }
-    for (uint32_t j = std::max<uint32_t>(1, n - D); j < n; ++j) units.push_back(0x80000000u | j);
-    units.push_back(0x80000000u);
-    if (units.size() != 2 * (size_t)n) return false;
-    cudaFree(h->wave_units); cudaFree(h->wave_done); cudaFree(h->wave_error);
-    h->wave_units = nullptr; h->wave_done = nullptr; h->wave_error = nullptr;
-    if (cudaMalloc(&h->wave_units, units.size() * 4) != cudaSuccess || cudaMalloc(&h->wave_done, (size_t)n * 8) != cudaSuccess ||
-        cudaMalloc(&h->wave_error, 4) != cudaSuccess) { cudaGetLastError(); return false; }
-    cudaMemcpy(h->wave_units, units.data(), units.size() * 4, cudaMemcpyHostToDevice);
-    cudaMemset(h->wave_done, 0, (size_t)n * 8);
+    const size_t done_bytes = (size_t)2 * WAVE_MAX_STEPS * n * sizeof(unsigned long long);
+    if (cudaMalloc(&h->wave_done, done_bytes) != cudaSuccess || cudaMalloc(&h->wave_error, 4) != cudaSuccess) {
+        cudaGetLastError(); return false;
+    }
+    cudaMemset(h->wave_done, 0, done_bytes);
+    for (auto& c : h->wave_phase_launches) c = 0;
     cudaMemset(h->wave_error, 0, 4);
-    h->wave_steps = 0;
     const HeisGeom g = heis_geom(h);
     WaveSched ws{};
-    ws.units = h->wave_units; ws.n_units = (uint32_t)units.size(); ws.tiles = cdiv((uint64_t)g.Ly * g.Gx, 128);
+    ws.tiles = cdiv((uint64_t)g.Ly * g.Gx, 128);
     ws.C = C; ws.n_chunks = n; ws.done = h->wave_done; ws.error = h->wave_error;
     h->wave_sched = ws;
+    h->wave_kmax = kmax;
     // every CTA of the grid must be resident at once (static round-robin over the items)
     int per_sm = 0, sms = 0;
     const bool f64 = h->md.precision == VEGAS_F64;
-    cudaError_t e = f64 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, heis_wave_kernel<double, false, true>, 128, 0)
-                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, heis_wave_kernel<float, false, true>, 128, 0);
+    cudaError_t e = f64 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, heis_wave_kernel<double, false, true, true>, 128, 0)
+                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, heis_wave_kernel<float, false, true, true>, 128, 0);
     if (e != cudaSuccess || per_sm < 1 || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) != cudaSuccess) return false;
     h->wave_grid = per_sm * sms;
     h->wave_ready = true;
@@ -851,19 +869,28 @@ void wave_ptrs(vegas_gpu* h, int colour, HeisPtrs<real>& P) {
     }
 }
 
+// k consecutive steps (1 <= k <= wave_kmax) in one launch; obs_row = row of the first step (rows OBS_W apart) when
+// recording, else the scratch row (all steps add into it)
 template <typename real>
-void wave_step_t(vegas_gpu* h, double* obs_row, bool record) {
+void wave_steps_t(vegas_gpu* h, uint32_t k, double* obs_row, bool record) {
     HeisPtrs<real> P0{}, P1{};
     wave_ptrs<real>(h, 0, P0); wave_ptrs<real>(h, 1, P1);
     WaveSched ws = h->wave_sched;
-    ws.target = (unsigned long long)ws.tiles * (++h->wave_steps);
+    ws.units = h->wave_units[k - 1]; ws.n_units = h->wave_n_units[k - 1]; ws.n_phases = 2 * k;
+    // the last phase of a launch has no dependants and is not counted (heis_wave_kernel)
+    for (uint32_t ph = 0; ph + 1 < 2 * k; ++ph) ws.target[ph] = (unsigned long long)ws.tiles * (++h->wave_phase_launches[ph]);
     const HeisGeom g = heis_geom(h);
     const HeisParams<real> p = heis_params<real>(h);
     const PhiloxKey pk = make_philox_key(h->md.seed);
     const bool flip = h->md.proposal == VEGAS_PROPOSE_FLIP;
     const int grid = (int)std::min<uint64_t>((uint64_t)h->wave_grid, (uint64_t)ws.n_units * ws.tiles);
+    const int stride = record ? OBS_W : 0;
     h->launches++;
-#define WL(FLIP, REC) heis_wave_kernel<real, FLIP, REC><<<grid, 128, 0, h->stream>>>(P0, P1, g, ws, p, h->sweeps, pk, obs_row)
+#define WL(FLIP, REC)                                                                                                         \
+    do {                                                                                                                      \
+        if (k > 1) heis_wave_kernel<real, FLIP, REC, true><<<grid, 128, 0, h->stream>>>(P0, P1, g, ws, p, h->sweeps, pk, obs_row, stride); \
+        else heis_wave_kernel<real, FLIP, REC, false><<<grid, 128, 0, h->stream>>>(P0, P1, g, ws, p, h->sweeps, pk, obs_row, stride);      \
+    } while (0)
     if (record) { if (flip) WL(true, true); else WL(false, true); }
     else { if (flip) WL(true, false); else WL(false, false); }
 #undef WL
@@ -968,7 +995,7 @@ void do_step(vegas_gpu* h, void* obs_row, void* scratch_row) {
         for (int b = 0; b < h->n_colours; ++b) basis_pass_any(h, rec ? 1 : 0, b, (double*)(rec ? obs_row : scratch_row));
     } else if (h->family == FAM_HEIS_STENCIL && wave_plan(h)) {
         double* row = (double*)(rec ? obs_row : scratch_row);
-        if (h->md.precision == VEGAS_F64) wave_step_t<double>(h, row, rec); else wave_step_t<float>(h, row, rec);
+        if (h->md.precision == VEGAS_F64) wave_steps_t<double>(h, 1, row, rec); else wave_steps_t<float>(h, 1, row, rec);
     } else if (h->family == FAM_HEIS_STENCIL && fused_plan(h)) {
         double* row = (double*)(rec ? obs_row : scratch_row);
         if (h->md.precision == VEGAS_F64) fused_step_t<double>(h, row, rec); else fused_step_t<float>(h, row, rec);
@@ -1327,7 +1354,8 @@ void vegas_gpu_destroy(vegas_gpu_t h) {
     cudaFree(h->d_row_ptr); cudaFree(h->d_col); cudaFree(h->d_val);
     cudaFree(h->g_thr); cudaFree(h->g_code);
     cudaFree(h->obs);
-    cudaFree(h->wave_units); cudaFree(h->wave_done); cudaFree(h->wave_error);
+    for (int k = 0; k < WAVE_MAX_STEPS; ++k) cudaFree(h->wave_units[k]);
+    cudaFree(h->wave_done); cudaFree(h->wave_error);
     if (h->stream_b) { cudaStreamSynchronize(h->stream_b); cudaStreamDestroy(h->stream_b); }
     if (h->ev_main) cudaEventDestroy(h->ev_main);
     if (h->ev_bnd) cudaEventDestroy(h->ev_bnd);
@@ -1674,7 +1702,20 @@ int vegas_gpu_step_async(vegas_gpu_t h, uint64_t n_steps, int record) {
         CU(cudaGetLastError());
         return VEGAS_OK;
     }
-    for (uint64_t s = 0; s < n_steps; ++s) do_step(h, record ? (void*)(h->obs + s * OBS_W) : nullptr, scratch);
+    for (uint64_t s = 0; s < n_steps;) {
+        if (h->family == FAM_HEIS_STENCIL && h->wave_k > 1 && wave_plan(h) && h->wave_kmax > 1 && n_steps - s > 1) {
+            // several steps per persistent launch: the later colour passes find the earlier ones' planes in L2
+            const uint32_t k = (uint32_t)std::min<uint64_t>(h->wave_kmax, n_steps - s);
+            double* row = (double*)(record ? h->obs + s * OBS_W : scratch);
+            if (h->md.precision == VEGAS_F64) wave_steps_t<double>(h, k, row, record != 0); else wave_steps_t<float>(h, k, row, record != 0);
+            h->sweeps += k;
+            h->attempts += h->n * k;
+            s += k;
+            continue;
+        }
+        do_step(h, record ? (void*)(h->obs + s * OBS_W) : nullptr, scratch);
+        ++s;
+    }
     CU(cudaGetLastError());
     return VEGAS_OK;
 }
@@ -1998,6 +2039,7 @@ int vegas_gpu_set_tuning(vegas_gpu_t h, const char* key, long value) {
     else if (k == "heis_wave") h->wave_enable = (int)value;
     else if (k == "heis_wave_planes") h->wave_planes = (uint32_t)value;
     else if (k == "heis_wave_lag") h->wave_lag = (uint32_t)value;
+    else if (k == "heis_wave_steps") h->wave_k = (uint32_t)std::max<long>(1, std::min<long>(value, WAVE_MAX_STEPS));
     else if (k == "resident_max") { h->resident_max = (uint32_t)value; h->resident_cols = -2; }
     else return fail(h, VEGAS_ERR_INVALID, "unknown tuning key: " + k);
     h->fused_ready = false;  // re-plan at the next step
