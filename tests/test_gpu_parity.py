@@ -30,6 +30,8 @@ LATTICES = [
     ("bcc_literal", dict(unitcell=vg.BCC, size=(3, 3, 3), literal=True)),
     ("fcc", dict(unitcell=vg.FCC, size=(3, 2, 4))),
     ("fcc_open", dict(unitcell=vg.FCC, size=(3, 3, 2), pbc=(True, False, False))),
+    ("bcc_vec", dict(unitcell=vg.BCC, size=(8, 3, 4))),      # nx % 4 == 0: the 16-byte variant of the basis kernel
+    ("fcc_vec", dict(unitcell=vg.FCC, size=(4, 3, 4))),
 ]
 
 
@@ -220,7 +222,7 @@ def test_heisenberg_sweep_replay(built, precision, general):
     g.close()
 
 
-@pytest.mark.parametrize("name", ["bcc", "fcc", "fcc_open", "bcc_literal"])
+@pytest.mark.parametrize("name", ["bcc", "fcc", "fcc_open", "bcc_literal", "bcc_vec", "fcc_vec"])
 @pytest.mark.parametrize("precision", [vg.F64, vg.F32], ids=["f64", "f32"])
 def test_heisenberg_basis_lattices_recorded_step(built, name, precision):
     """bcc / fcc: the recorded step reduces E and M inside the colour passes (each bond once, towards the lower colours);
@@ -229,7 +231,7 @@ def test_heisenberg_basis_lattices_recorded_step(built, name, precision):
     kw = dict(exchange=1.0, zeeman=True, anisotropy=((0.6, 0.0, 0.8), 0.25))
     g = vg.GpuMetropolis(vg.HEISENBERG, precision=precision, seed=12, **kw, **lat)
     # periodic bcc / fcc take the basis-split kernel with compile-time neighbour tables, the rest the general one
-    assert g.kernel_family == ("heis_basis" if name in ("bcc", "fcc") else "heis_general")
+    assert g.kernel_family == ("heis_basis" if name in ("bcc", "fcc", "bcc_vec", "fcc_vec") else "heis_general")
     H, _ = oracle_model(ob.HEISENBERG, **kw, **lat)
     n = n_sites(lat)
     s0 = random_state(ob.HEISENBERG, n, 3)
@@ -543,13 +545,37 @@ def test_heisenberg_fused_flip_proposal_and_larger(built):
         assert pair[0][3] == pair[1][3]
 
 
+@pytest.mark.parametrize("uc,size", [(vg.FCC, (16, 6, 5)), (vg.BCC, (8, 7, 6)), (vg.FCC, (4, 2, 2))], ids=["fcc", "bcc", "fcc_tiny"])
+@pytest.mark.parametrize("precision", [vg.F32, vg.F64], ids=["f32", "f64"])
+def test_heisenberg_basis_vector_kernel_identical(built, uc, size, precision):
+    """heis_basis_vec_kernel (16-byte loads, shifted rows with a scalar carry) walks the neighbour table in the order of
+    the scalar kernel: same sums, same random numbers, the same trajectory bit for bit; recorded E, M agree to rounding."""
+    res = []
+    for vec in (1, 0):
+        g = vg.GpuMetropolis(vg.HEISENBERG, unitcell=uc, size=size, precision=precision, seed=55, anisotropy=((0.6, 0, 0.8), 0.3))
+        assert g.kernel_family == "heis_basis"
+        g.set_tuning("basis_vec", vec)
+        g.randomize(); g.set_thermostat(2.0, (0, 0, 1.0), 0.4)
+        e, m = g.step(4)
+        g.step(3, observe=False)
+        res.append((g.download(), e, m, g.attempt_count(), g.total_energy()))
+        g.close()
+    (s1, e1, m1, a1, t1), (s0, e0, m0, a0, t0) = res
+    assert np.array_equal(s1, s0) and a1 == a0
+    tol = 1e-5 if precision == vg.F32 else 1e-12
+    assert np.allclose(e1, e0, rtol=tol, atol=tol * len(s0)) and np.allclose(m1, m0, rtol=tol, atol=tol * len(s0))
+    assert abs(t1 - t0) <= tol * len(s0) * 12
+
+
 # ------------------------------------------------------------------------------------------ slabs
 SLAB_KINDS = {
     # kind: (model, unitcell, (nx, ny, nz) in cells, sites per cell)
     "ising": (vg.ISING, vg.SC, (256, 4, 8), 1),
     "heisenberg": (vg.HEISENBERG, vg.SC, (16, 4, 8), 1),
     "heisenberg_bcc": (vg.HEISENBERG, vg.BCC, (5, 3, 8), 2),
-    "heisenberg_fcc": (vg.HEISENBERG, vg.FCC, (4, 3, 8), 4),
+    "heisenberg_fcc": (vg.HEISENBERG, vg.FCC, (4, 3, 8), 4),       # nx % 4 == 0: 16-byte variant (peer stores as vectors)
+    "heisenberg_fcc_scalar": (vg.HEISENBERG, vg.FCC, (6, 3, 8), 4),
+    "heisenberg_bcc_vec": (vg.HEISENBERG, vg.BCC, (12, 5, 8), 2),
 }
 
 

@@ -105,6 +105,7 @@ struct vegas_gpu {
     std::vector<uint64_t> h_row_ptr; std::vector<uint32_t> h_col; std::vector<double> h_val;  // csr input copy
     std::vector<uint8_t> h_colour;
     // --- shared-memory-resident batches of steps for small general-family lattices (resident.cuh)
+    int basis_vec = 1;                    // tuning key "basis_vec": 16-byte accesses in the bcc / fcc colour pass when nx allows
     uint32_t resident_max = 8192;         // tuning key "resident_max": largest site count that takes this path (0: never)
     int resident_cols = -2;               // cached resident_columns(): -2 not planned yet, -1 no, 0 direct, > 0 table columns
     // --- observables
@@ -474,6 +475,9 @@ void preload_basis_one() {
     preload(heis_basis_kernel<real, UC, B, false, 0, true>); preload(heis_basis_kernel<real, UC, B, false, 1, true>);
     preload(heis_basis_kernel<real, UC, B, true, 0, true>); preload(heis_basis_kernel<real, UC, B, true, 1, true>);
     preload(heis_basis_kernel<real, UC, B, false, 2, true>);
+    preload(heis_basis_vec_kernel<real, UC, B, false, 0, true>); preload(heis_basis_vec_kernel<real, UC, B, false, 1, true>);
+    preload(heis_basis_vec_kernel<real, UC, B, true, 0, true>); preload(heis_basis_vec_kernel<real, UC, B, true, 1, true>);
+    preload(heis_basis_vec_kernel<real, UC, B, false, 2, true>);
 }
 template <typename real>
 void preload_basis_slab() {
@@ -663,6 +667,24 @@ void basis_launch(vegas_gpu* h, int mode, double* obs, uint32_t zb, uint32_t zc,
     BasisPeers<real> peers{};
     if (slab && mode != 2) { peers.lo = (real*)h->peer_halo[0]; peers.hi = (real*)h->peer_halo[1]; }
     h->launches++;
+    constexpr uint32_t NV = (uint32_t)VecOf<real>::N;
+    if (h->basis_vec != 0 && g.nx % NV == 0) {
+        // K4v: 16-byte accesses; a thread walks `ipt` work items (NV cells each) of one plane: ~16 CTAs per SM, at most
+        // 64 cells per thread (the fp32 partial sums stay short)
+        const uint64_t items = (uint64_t)(g.nx / NV) * g.ny;
+        const uint32_t ipt = (uint32_t)std::min<uint64_t>(64 / NV, std::max<uint64_t>(1, items * zc / 128 / (148u * 16u)));
+        const dim3 vgrid(cdiv(items, 128 * ipt), 1, zc);
+#define BV(FLIP, MODE)                                                                                                          \
+    do {                                                                                                                        \
+        if (slab) heis_basis_vec_kernel<real, UC, B, FLIP, MODE, true><<<vgrid, 128, 0, st>>>(P, peers, g, ipt, zb, zstep, p, h->sweeps, pk, obs); \
+        else heis_basis_vec_kernel<real, UC, B, FLIP, MODE, false><<<vgrid, 128, 0, st>>>(P, peers, g, ipt, zb, zstep, p, h->sweeps, pk, obs);    \
+    } while (0)
+        if (mode == 2) BV(false, 2);
+        else if (mode == 1) { if (flip) BV(true, 1); else BV(false, 1); }
+        else { if (flip) BV(true, 0); else BV(false, 0); }
+#undef BV
+        return;
+    }
 #define BL(FLIP, MODE)                                                                                                          \
     do {                                                                                                                        \
         if (slab) heis_basis_kernel<real, UC, B, FLIP, MODE, true><<<grid, 128, 0, st>>>(P, peers, g, rows, zb, zstep, p, h->sweeps, pk, obs); \
@@ -2040,6 +2062,7 @@ int vegas_gpu_set_tuning(vegas_gpu_t h, const char* key, long value) {
     else if (k == "heis_wave_planes") h->wave_planes = (uint32_t)value;
     else if (k == "heis_wave_lag") h->wave_lag = (uint32_t)value;
     else if (k == "heis_wave_steps") h->wave_k = (uint32_t)std::max<long>(1, std::min<long>(value, WAVE_MAX_STEPS));
+    else if (k == "basis_vec") h->basis_vec = (int)value;
     else if (k == "resident_max") { h->resident_max = (uint32_t)value; h->resident_cols = -2; }
     else return fail(h, VEGAS_ERR_INVALID, "unknown tuning key: " + k);
     h->fused_ready = false;  // re-plan at the next step
