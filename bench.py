@@ -42,7 +42,7 @@ WORKLOADS = {
 NCU_TRAFFIC = {
     "ising3d_1024": (134.37e6 + 30.83e6, "profiles/r01o_ising_msc.metrics.txt (one colour pass)"),
     "heis3d_512": (2.887e9 + 1.562e9, "profiles/r01u_heis_wave.metrics.txt (one step = both colours)"),
-    "heis_fcc_384": (2.753e9 + 0.662e9, "profiles/r01s_heis_basis.metrics.txt (one colour pass)"),
+    "heis_fcc_384": (2.829e9 + 0.686e9, "profiles/r01z_heis_basis_vec.metrics.txt (one colour pass)"),
 }
 # cfg[0] (docs/metropolis.toml, the reference's own CPU-runnable case): 1000 sites, latency bound; runs on the
 # shared-memory-resident kernel (one launch per batch of steps), reported in "also" without a roofline
@@ -415,7 +415,7 @@ def main():
                                "e2e": r["e2e"], "e2e_machine": r["e2e_machine"], "family": r["family"], "clocks": r["clocks"],
                                "gpu_launches": r["launches"],
                                "note": {"ising2d_8192": "8 MiB state is L2 resident: not an HBM measurement",
-                                        "heis_fcc_384": "heis_basis kernel (scalar loads, one Philox call per site), 4 colours, single GPU"}.get(other, "")}
+                                        "heis_fcc_384": "heis_basis vector kernel (16-byte loads, one Philox call per site), 4 colour passes per step, single GPU"}.get(other, "")}
         if world == 1 and args.e2e_steps > 0:
             for small in SMALL_WORKLOADS:
                 also[small] = run_small_workload(small, device, torch, not args.no_cpu)
