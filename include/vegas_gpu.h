@@ -173,10 +173,19 @@ int vegas_gpu_slab_connect_local(vegas_gpu_t self, vegas_gpu_t lower, vegas_gpu_
  *     "heis_fused_ty" : interior rows per CTA tile (0 = auto), "heis_fused_cz": planes per z-chunk (0 = auto)
  *     "heis_wave"     : -1 auto (default: lattices with >= 32 planes), 0 never, 1 always -- both colour passes of a
  *                       Heisenberg step as ONE persistent launch in wave order (second pass finds the first in L2);
- *                       "heis_wave_planes" (planes per chunk, default 4), "heis_wave_lag" (chunks, default 4)
+ *                       "heis_wave_planes" (planes per chunk, default 4), "heis_wave_lag" (positions a colour pass
+ *                       trails the previous one by, >= 3, default 5), "heis_wave_steps" (steps fused into one launch,
+ *                       1..4, default 1: more was measured slower)
  *     "heis_wave_c"   : experiment: the two passes as separate launches interleaved in chunks of C planes
+ *     "basis_vec"     : 1 (default) 16-byte accesses in the bcc / fcc colour pass when nx % 4 == 0 (fp64: % 2), 0 scalar
+ *     "resident_max"  : largest site count of a general-family lattice that runs batches of steps in ONE launch with
+ *                       the State in shared memory (default 8192; 0 = always one launch per colour)
  * Results do not depend on these knobs (same Philox keys, same arithmetic). */
 int vegas_gpu_set_tuning(vegas_gpu_t, const char* key, long value);
+/* host-only: the unit order of a persistent wave launch of `steps` steps over `n_chunks` chunks with lag `lag`
+ * (units[i] = phase << 24 | chunk, phase = 2 * step + colour; 2 * steps * n_chunks entries).  Exposed so that the
+ * schedule's invariant -- every unit comes after the three units it waits for -- is tested without a GPU. */
+int vegas_gpu_wave_schedule(uint32_t n_chunks, uint32_t lag, uint32_t steps, uint32_t* units, uint64_t capacity, uint64_t* count);
 /* name of the kernel the NEXT step will launch: "heis_fused", "heis_stencil", "ising_msc", ... */
 const char* vegas_gpu_step_kernel(vegas_gpu_t);
 

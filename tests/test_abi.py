@@ -95,3 +95,32 @@ def test_bench_reference_arm_line(built):
     assert line["value"] > 1e5 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "attempts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["config"]["workload"] == "ising_sc10_cfg0"
+
+
+@pytest.mark.parametrize("n_chunks,lag,steps", [(2, 3, 1), (3, 3, 2), (4, 3, 4), (12, 3, 3), (12, 5, 1), (128, 5, 1), (128, 3, 2),
+                                                (64, 4, 4), (7, 9, 2), (5, 1, 3)])
+def test_wave_schedule_dependencies_precede_their_users(built, n_chunks, lag, steps):
+    """The persistent wave kernel deals its work units to co-resident CTAs in list order and a unit spins until the
+    previous colour-pass phase is complete on its chunk and the two neighbouring chunks (csrc/heis.cuh, K3w).  That can
+    only terminate if every one of those three units comes EARLIER in the list; each (phase, chunk) must appear once."""
+    from vegas_rs_b200 import _lib
+    lib = _lib.load()
+    count = C.c_uint64()
+    assert lib.vegas_gpu_wave_schedule(n_chunks, lag, steps, None, 0, C.byref(count)) == 0
+    assert count.value == 2 * steps * n_chunks
+    units = np.zeros(count.value, np.uint32)
+    assert lib.vegas_gpu_wave_schedule(n_chunks, lag, steps, units.ctypes.data_as(C.c_void_p), units.size, C.byref(count)) == 0
+    phase, chunk = units >> 24, units & 0xFFFFFF
+    position = {(int(p), int(c)): i for i, (p, c) in enumerate(zip(phase, chunk))}
+    assert len(position) == units.size and set(position) == {(p, c) for p in range(2 * steps) for c in range(n_chunks)}
+    for (p, c), i in position.items():
+        if p == 0:
+            continue
+        for dep in ((c - 1) % n_chunks, c, (c + 1) % n_chunks):
+            assert position[(p - 1, dep)] < i, (p, c, dep)
+    # phase p starts at chunk p (rotated order): the wrap-around chunk is the last one a phase visits
+    for p in range(2 * steps):
+        mine = [int(c) for q, c in zip(phase, chunk) if q == p]
+        assert mine == [(p + k) % n_chunks for k in range(n_chunks)]
+    assert lib.vegas_gpu_wave_schedule(0, 3, 1, None, 0, C.byref(count)) != 0
+    assert lib.vegas_gpu_wave_schedule(8, 3, 5, None, 0, C.byref(count)) != 0

@@ -2050,6 +2050,17 @@ int vegas_gpu_check_basis_tables(void) {
            check_basis_table<2, 2>() + check_basis_table<2, 3>();
 }
 
+int vegas_gpu_wave_schedule(uint32_t n_chunks, uint32_t lag, uint32_t steps, uint32_t* units, uint64_t capacity, uint64_t* count) {
+    if (n_chunks == 0 || n_chunks >= (1u << 24) || steps == 0 || steps > (uint32_t)WAVE_MAX_STEPS || !count) return VEGAS_ERR_INVALID;
+    const std::vector<uint32_t> u = wave_units_for(n_chunks, std::max<uint32_t>(3, lag), steps);
+    *count = u.size();
+    if (units) {
+        if (capacity < u.size()) return VEGAS_ERR_INVALID;
+        std::memcpy(units, u.data(), u.size() * sizeof(uint32_t));
+    }
+    return VEGAS_OK;
+}
+
 // ---- tuning knobs ---------------------------------------------------------------------------
 int vegas_gpu_set_tuning(vegas_gpu_t h, const char* key, long value) {
     if (!h || !key) return VEGAS_ERR_INVALID;
