@@ -124,3 +124,26 @@ def test_wave_schedule_dependencies_precede_their_users(built, n_chunks, lag, st
         assert mine == [(p + k) % n_chunks for k in range(n_chunks)]
     assert lib.vegas_gpu_wave_schedule(0, 3, 1, None, 0, C.byref(count)) != 0
     assert lib.vegas_gpu_wave_schedule(8, 3, 5, None, 0, C.byref(count)) != 0
+
+
+def test_rust_shim_struct_layout_matches_header():
+    """bindings/rust/gpu.rs cannot be compiled here; at least its #[repr(C)] structs must list the fields of
+    include/vegas_gpu.h in the same order, and every extern function it declares must exist in the headers."""
+    rs = open(os.path.join(ROOT, "bindings", "rust", "gpu.rs")).read()
+    hdr = open(os.path.join(ROOT, "include", "vegas_gpu.h")).read() + open(os.path.join(ROOT, "include", "vegas_host.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    for name in ("vegas_model_desc", "vegas_lattice_desc"):
+        end = hdr.index("} " + name + ";")
+        body = hdr[hdr.rindex("typedef struct {", 0, end) + len("typedef struct {"):end]
+        c_fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            names = decl.split(None, 1)[1] if " " in decl else decl
+            c_fields += [re.sub(r"\[.*\]", "", n).strip() for n in names.split(",")]
+        rs_body = re.search(r"pub struct " + name + r" \{(.*?)\n\}", rs, flags=re.S).group(1)
+        rs_fields = re.findall(r"pub (\w+):", rs_body)
+        assert rs_fields == c_fields, (name, rs_fields, c_fields)
+    for fn in re.findall(r"\bfn (vegas_\w+)\(", rs):
+        assert re.search(r"\b" + fn + r"\s*\(", hdr), fn
