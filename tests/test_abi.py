@@ -147,3 +147,27 @@ def test_rust_shim_struct_layout_matches_header():
         assert rs_fields == c_fields, (name, rs_fields, c_fields)
     for fn in re.findall(r"\bfn (vegas_\w+)\(", rs):
         assert re.search(r"\b" + fn + r"\s*\(", hdr), fn
+
+
+def test_create_rejects_bad_arguments_before_touching_the_device(built):
+    """Argument validation comes before the CUDA device check and never aborts: status VEGAS_ERR_INVALID (-1) with a
+    message (the reference returns Result everywhere, src/error.rs) -- testable without a GPU."""
+    import vegas_rs_b200 as vg
+
+    def code_of(**kw):
+        with pytest.raises(vg.VegasGpuError) as ei:
+            vg.GpuMetropolis(kw.pop("model", vg.ISING), **kw)
+        return ei.value.code, str(ei.value)
+
+    assert code_of(unitcell=vg.SC, size=(0, 4, 4)) == (-1, "vegas_gpu error -1: empty lattice")
+    assert code_of(unitcell=vg.SC, size=(4, 4, 0))[0] == -1
+    assert code_of(unitcell=7, size=(4, 4, 4)) == (-1, "vegas_gpu error -1: unknown unit cell")
+    assert code_of(model=5, unitcell=vg.SC, size=(4, 4, 4)) == (-1, "vegas_gpu error -1: unknown model")
+    assert code_of(unitcell=vg.SC, size=(4, 4, 4), proposal=9)[1].endswith("unknown proposal")
+    assert code_of(model=vg.HEISENBERG, unitcell=vg.SC, size=(4, 4, 4), precision=3)[1].endswith("unknown precision")
+    # Exchange::new(CsMat): malformed CSR
+    rp = np.array([0, 2, 3], np.uint64); ci = np.array([1, 5, 0], np.uint32)
+    assert code_of(csr=(rp, ci, None))[1].endswith("column index out of range")
+    assert code_of(csr=(np.array([0, 2, 1], np.uint64), np.array([1, 0], np.uint32), None))[1].endswith("row_ptr not monotone")
+    wide = np.array([0, 40, 40], np.uint64)
+    assert code_of(csr=(wide, np.ones(40, np.uint32), None))[1].endswith("rows longer than 32 are not supported")

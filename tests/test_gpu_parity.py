@@ -699,3 +699,34 @@ def test_full_size_heisenberg_fcc_384(built):
     a, acc = g.attempt_count()
     assert a == 2 * N and 0 < acc < a
     g.close()
+
+
+def test_runtime_error_paths_return_status_and_keep_the_handle_usable(built):
+    """Misuse returns a status with a message (never aborts, never touches the state) and the handle keeps working."""
+    g = vg.GpuMetropolis(vg.ISING, unitcell=vg.SC, size=(64, 4, 4), seed=9)
+    s = random_state(ob.ISING, 1024, 2)
+    g.upload(s)
+    for bad, text in ((lambda: g.upload(s[:100]), "wrong model or size"),
+                      (lambda: g._check(g._lib.vegas_gpu_upload_heisenberg(g._h, vg.gpu_metropolis._ptr(np.zeros((1024, 3))), 1024)),
+                       "upload_heisenberg: wrong model or size"),
+                      (lambda: g.set_thermostat(float("nan")), "temperature is NaN"),
+                      (lambda: g.step_async(5000, True), "at most 4096 steps"),
+                      (lambda: g.set_tuning("no_such_key", 1), "unknown tuning key"),
+                      (lambda: g.slab_export(), "not a slab")):
+        with pytest.raises(vg.VegasGpuError) as ei:
+            bad()
+        assert text in str(ei.value) and ei.value.code in (-1, -4)
+    assert np.array_equal(g.download(), s)                    # untouched by the failed calls
+    g.set_thermostat(0.0)                                     # Thermostat clamps T to f64::EPSILON (thermostat.rs:29-40)
+    e, m = g.step(2)
+    assert e[-1] <= e[0] and g.attempt_count()[0] == 2 * 1024
+    g.close()
+    h = vg.GpuMetropolis(vg.HEISENBERG, unitcell=vg.SC, size=(16, 4, 4), seed=9)
+    with pytest.raises(vg.VegasGpuError):                     # Ising state into a Heisenberg handle
+        h._check(h._lib.vegas_gpu_upload_ising(h._h, vg.gpu_metropolis._ptr(s[:256].copy()), 256))
+    with pytest.raises(vg.VegasGpuError):
+        h.ising_thresholds()
+    h.close()
+    with pytest.raises(vg.VegasGpuError) as ei:               # z-slab of a lattice the stencil path cannot take
+        vg.GpuMetropolis(vg.ISING, unitcell=vg.SC, size=(10, 10, 5), nz_global=10, z_offset=0)
+    assert "z-slab decomposition needs" in str(ei.value)
