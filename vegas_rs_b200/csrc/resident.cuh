@@ -160,6 +160,31 @@ __device__ __forceinline__ void resident_block_sum_int3(int (&v)[3], int* acc) {
     }
 }
 
+// One colour phase of the Ising table variant; Z = compile-time row width (0: run-time zmax).  The width is chosen once
+// per phase (uniform switch in the kernel), not once per attempt.
+template <int Z, bool RANDPROP, bool TRACK>
+__device__ __forceinline__ void ising_table_phase(int8_t* s, const ResidentSmem& m, uint32_t n, int zmax, uint32_t base,
+                                                  uint32_t count, uint64_t sweep, const PhiloxKey& pk, int& accepted, int& dS,
+                                                  int& dM) {
+    for (uint32_t t = threadIdx.x; t < count; t += blockDim.x) {
+        const uint32_t i = m.order[base + t];
+        const int si = s[i];
+        uint32_t r[4];
+        philox_at((uint64_t)i, sweep, 0u, pk, r);
+        const unsigned long long U = ((unsigned long long)r[0] << 32) | r[1];
+        bool proposed = true;
+        if (RANDPROP) proposed = ((r[2] & 1u) ? 1 : -1) != si;  // IsingSpin::rand src/state.rs:76-84
+        const int msum = res_msum_fixed<Z>(s, m.tab, n, i, zmax);
+        bool ok = ising_table_decision(si, msum, U, m.thr, m.code);
+        if (!proposed) ok = true;
+        if (ok && proposed) {
+            s[i] = (int8_t)-si;
+            if (TRACK) { dS -= 4 * si * msum; dM -= 2 * si; }
+        }
+        accepted += ok ? 1 : 0;
+    }
+}
+
 // SYMM: the adjacency is symmetric (every structured lattice: Exchange::from_lattice adds (s,t) and (t,s),
 // src/energy.rs:181-184), so a recorded batch reduces sum_i sum_j s_i s_j and sum s ONCE at launch and then follows
 // them exactly, in integers, through the accepted flips: flipping s_i changes the double sum by -4 s_i m_i.
@@ -177,11 +202,11 @@ ising_resident_kernel(int8_t* __restrict__ s_glob, NB nb, ResidentPlan rp, Ising
         resident_build(nb, rp, m);
         for (uint32_t i = threadIdx.x; i < RES_THR; i += blockDim.x) { m.thr[i] = p.thr[i]; m.code[i] = p.code[i]; }
     }
+    constexpr bool TRACK = TABLE && SYMM;
     int* iacc = reinterpret_cast<int*>(m.red);  // three ints of the integer block sums (the doubles use m.red + 2 up)
     if (threadIdx.x < 3) iacc[threadIdx.x] = 0;
     __syncthreads();
     const IsingSpins sp{s};
-    constexpr bool TRACK = TABLE && SYMM;
     long long S = 0, M = 0;  // thread 0: sum_i (s_i m_i + self entries), sum_i s_i of the current state
     if (TRACK && obs != nullptr) {
         int v[3] = {0, 0, 0};
@@ -201,23 +226,15 @@ ising_resident_kernel(int8_t* __restrict__ s_glob, NB nb, ResidentPlan rp, Ising
         for (int c = 0; c < rp.n_colours; ++c) {
             const uint32_t count = rp.counts[c];
             if (TABLE) {
-                for (uint32_t t = threadIdx.x; t < count; t += blockDim.x) {
-                    const uint32_t i = m.order[base + t];
-                    const int si = s[i];
-                    uint32_t r[4];
-                    philox_at((uint64_t)i, sweep0 + step, 0u, pk, r);
-                    const unsigned long long U = ((unsigned long long)r[0] << 32) | r[1];
-                    bool proposed = true;
-                    if (RANDPROP) proposed = ((r[2] & 1u) ? 1 : -1) != si;  // IsingSpin::rand src/state.rs:76-84
-                    const int msum = res_msum(s, m.tab, rp.n, i, rp.zmax);
-                    bool ok = ising_table_decision(si, msum, U, m.thr, m.code);
-                    if (!proposed) ok = true;
-                    if (ok && proposed) {
-                        s[i] = (int8_t)-si;
-                        if (TRACK) { dS -= 4 * si * msum; dM -= 2 * si; }
-                    }
-                    accepted += ok ? 1 : 0;
+#define VG_PHASE(Z) ising_table_phase<Z, RANDPROP, TRACK>(s, m, rp.n, rp.zmax, base, count, sweep0 + step, pk, accepted, dS, dM)
+                switch (rp.zmax) {
+                    case 4: VG_PHASE(4); break;
+                    case 6: VG_PHASE(6); break;
+                    case 8: VG_PHASE(8); break;
+                    case 12: VG_PHASE(12); break;
+                    default: VG_PHASE(0); break;
                 }
+#undef VG_PHASE
             } else {
                 const uint32_t* __restrict__ sites = rp.sites[c];
                 for (uint32_t t = threadIdx.x; t < count; t += blockDim.x)
