@@ -175,3 +175,49 @@ def test_oracle_heisenberg_single_spin_langevin():
         acc.append(s[:, 2].mean())
     exact = -(1 / np.tanh(1.5 / 0.8) - 0.8 / 1.5)
     assert abs(np.mean(acc) - exact) < 5e-3
+
+
+GPU_FIXTURES = ["ising_msc_3d_field", "ising_resident_sc10", "heis_stencil_f64", "heis_fcc_vec_f64"]
+
+
+@pytest.mark.parametrize("name", GPU_FIXTURES)
+def test_oracle_replays_committed_gpu_trajectories(built, name):
+    """tests/golden/gpu_replay_*.npz were recorded on a B200 (tests/golden/make_gpu_replay_fixtures.py): initial state,
+    per-sweep energies and final state of the CUDA kernels.  The oracle replays the same colour-ordered sweeps with the
+    same Philox numbers but its own restatement of Hamiltonian::energy and of the accept rule (src/integrator.rs:77-88,
+    :123-134): the trajectories must coincide -- bit for bit for Ising, to 1e-12 for fp64 Heisenberg -- and every recorded
+    energy must equal Hamiltonian::total_energy (the compound's trait default, src/energy.rs:55-59) of the replayed state.
+    This pins the GPU path against the CPU restatement in the CPU-only suite."""
+    import json
+    from helpers import oracle_model
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"gpu_replay_{name}.npz"))
+    meta = json.loads(str(z["meta"]))
+    size, seed = tuple(meta["size"]), meta["seed"]
+    model = ob.ISING if meta["model"] == "ising" else ob.HEISENBERG
+    kw = {}
+    if meta.get("anisotropy"):
+        kw["anisotropy"] = (tuple(meta["anisotropy"][0]), meta["anisotropy"][1])
+    H, _ = oracle_model(model, unitcell=meta["unitcell"], size=size, **kw)
+    th = H.thermostat(meta["T"], (0.0, 0.0, 1.0), meta["H"])
+    state = z["initial"].copy()
+    colours, nc = z["colours"], meta["n_colours"]
+    for sweep in range(meta["sweeps"]):
+        if meta["kernel_family"] == "ising_msc":
+            H.replay_ising_msc(th, ob.PROPOSE_FLIP, seed, sweep, size, state)
+        elif model == ob.ISING:
+            H.replay_ising_sites(th, ob.PROPOSE_FLIP, seed, sweep, colours, nc, state)
+        else:
+            H.replay_heisenberg(th, ob.PROPOSE_RANDOM, False, seed, sweep, colours, nc, state)
+        e_ref = H.total_energy(th, state)
+        if model == ob.ISING:
+            assert z["energy"][sweep] == e_ref
+            assert z["magnetization"][sweep, 2] == state.sum()
+        else:
+            assert abs(z["energy"][sweep] - e_ref) < 1e-9
+            assert np.max(np.abs(z["magnetization"][sweep] - state.sum(axis=0))) < 1e-9
+    if model == ob.ISING:
+        assert np.array_equal(z["final"], state)
+    else:
+        assert np.max(np.abs(z["final"] - state)) < 1e-12
+        assert np.max(np.abs(np.linalg.norm(z["final"], axis=1) - 1.0)) < 1e-12
+    assert not np.array_equal(z["final"], z["initial"])       # the sweeps did move spins
