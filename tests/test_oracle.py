@@ -177,6 +177,33 @@ def test_oracle_heisenberg_single_spin_langevin():
     assert abs(np.mean(acc) - exact) < 5e-3
 
 
+def test_oracle_heisenberg_open_chain_exact_energy():
+    """Exact layer (SURVEY section 4 ii): open classical Heisenberg chain, J = 1, no field.  The partition function
+    factorises over the bonds, so <s_i.s_{i+1}> = coth(J/T) - T/J and the physical energy per bond is its negative; the
+    restated MetropolisIntegrator (random site, Marsaglia proposal, src/integrator.rs:66-92) over the restated
+    Exchange (src/energy.rs:164-214) must reproduce it -- the reference itself has no Exchange or integrator test."""
+    n, T = 48, 0.7
+    lat = ob.Lattice(ob.SC, n, 1, 1, pbc=(False, False, False))
+    csr = ob.Csr.from_lattice(lat, 1.0, False)
+    H = ob.Hamiltonian(ob.HEISENBERG, [ob.TERM_EXCHANGE], csr)     # Exchange::total_energy alone: every bond once
+    rng = ob.OracleRng(7)
+    s = H.rand_state(rng, n)
+    mach = ob.Machine(H, ob.PROPOSE_RANDOM, rng, s, n_sensors=2)
+    mach.set_thermostat(H.thermostat(T))
+    mach.relax_for(3000)
+    means = []
+    for _ in range(20):
+        mach.m.obs_len = 0
+        mach.measure_for(4000)
+        e, _ = mach.observables()
+        means.append(e.mean() / (n - 1))
+    exact = -(1 / np.tanh(1 / T) - T)
+    se = np.std(means, ddof=1) / np.sqrt(len(means))
+    assert abs(np.mean(means) - exact) < 4 * se + 1e-3, (np.mean(means), exact, se)
+    # the nearest-neighbour correlation measured directly on the final state series agrees as well
+    assert abs((s[:-1] * s[1:]).sum(axis=1).mean() + exact) < 0.15
+
+
 GPU_FIXTURES = ["ising_msc_3d_field", "ising_resident_sc10", "heis_stencil_f64", "heis_fcc_vec_f64"]
 
 
