@@ -138,26 +138,31 @@ def test_accumulator_and_stat_line():
     assert m.hysteresis(1, 1, 1.0, 0.0, 0.1) == 5 and m.hysteresis(1, 1, 1.0, 1.0, 0.0) == 6
 
 
+@pytest.mark.parametrize("boundary", ["pbc", "open"])
 @pytest.mark.parametrize("T", [2.0, 2.269185314213022, 4.0])
-def test_oracle_metropolis_vs_exact_enumeration(T):
-    """The restated MetropolisFlipIntegrator samples the Boltzmann distribution of the 4x4 model."""
-    ex = [r for r in EXACT["pbc"]["rows"] if abs(r["T"] - T) < 1e-9][0]
-    H, m = oracle_model(ob.ISING, unitcell=ob.SC, size=(4, 4, 1), pbc=(True, True, False))
+def test_oracle_metropolis_vs_exact_enumeration(T, boundary):
+    """The restated MetropolisFlipIntegrator samples the Boltzmann distribution of the 4x4 model (periodic: 32 bonds;
+    open: 24 bonds, the adjacency the `drop_*` calls of src/input.rs:296-322 leave)."""
+    ex = [r for r in EXACT[boundary]["rows"] if abs(r["T"] - T) < 1e-9][0]
+    H, m = oracle_model(ob.ISING, unitcell=ob.SC, size=(4, 4, 1), pbc=(boundary == "pbc", boundary == "pbc", False))
     He = ob.Hamiltonian(ob.ISING, [ob.TERM_EXCHANGE], m)  # physical energy: Exchange::total_energy alone
     rng = ob.OracleRng(11)
     s = He.rand_state(rng, 16)
     mach = ob.Machine(He, ob.PROPOSE_FLIP, rng, s, n_sensors=2)
     mach.set_thermostat(He.thermostat(T))
     mach.relax_for(2000)
-    means_e, means_m = [], []
+    means_e, means_m, cvs, chis = [], [], [], []
     for _ in range(20):
         mach.m.obs_len = 0
         mach.measure_for(5000)
         e, mg = mach.observables()
         means_e.append(e.mean()); means_m.append(mg.mean())
-    se_e = np.std(means_e, ddof=1) / np.sqrt(20); se_m = np.std(means_m, ddof=1) / np.sqrt(20)
-    assert abs(np.mean(means_e) - ex["E"]) < 4 * se_e + 1e-3
-    assert abs(np.mean(means_m) - ex["M"]) < 4 * se_m + 1e-3
+        cvs.append(e.var() / (16 * T * T)); chis.append(mg.var() / (16 * T))   # StatSensor, src/instrument.rs:98-131
+    se = lambda x: np.std(x, ddof=1) / np.sqrt(len(x))
+    assert abs(np.mean(means_e) - ex["E"]) < 4 * se(means_e) + 1e-3
+    assert abs(np.mean(means_m) - ex["M"]) < 4 * se(means_m) + 1e-3
+    assert abs(np.mean(cvs) - ex["Cv"]) < 4 * se(cvs) + 5e-3       # block variances are biased low by O(tau / block)
+    assert abs(np.mean(chis) - ex["chi"]) < 4 * se(chis) + 5e-3
 
 
 def test_oracle_heisenberg_single_spin_langevin():
