@@ -224,3 +224,31 @@ observables = "{tmp_path / 'hyst.parquet'}"
     # reference sign (+|H| s.o, src/energy.rs:147-151): the spins turn AGAINST the field orientation
     mags = np.array(obs.column("magnetization").to_pylist())
     assert np.all(mags >= 0)
+
+
+def test_parquet_sinks_match_the_reference_schemas(tmp_path):
+    """ObservableParquetOutput / StateParquetOutput (src/output.rs:33-51, :122-141, :101-113): column names, types,
+    non-nullable fields, SNAPPY, written to `<stem>.parquet.tmp` and renamed on close.  No GPU involved."""
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    from vegas_rs_b200 import run
+    for schema, names, path in ((run.observable_schema(), ["relax", "stage", "step", "n", "temperature", "field", "energy", "magnetization"],
+                                 tmp_path / "obs.parquet"),
+                                (run.state_schema(), ["relax", "stage", "step", "temperature", "field", "id", "sx", "sy", "sz"],
+                                 tmp_path / "deep" / ".." / "state.out")):
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        assert schema.names == names and not any(f.nullable for f in schema)
+        assert [str(f.type) for f in schema][:3] == ["bool", "uint64", "uint64"] and all(str(f.type) == "double" or f.name in ("relax", "stage", "step", "n", "id") for f in schema)
+        sink = run.ParquetSink(str(path), schema)
+        stem = os.path.splitext(str(path))[0]
+        assert os.path.exists(stem + ".parquet.tmp") and not os.path.exists(str(path))   # Path::with_extension("parquet.tmp")
+        k = 5
+        cols = [pa.array(np.arange(k) % 2 == 0)] + [pa.array(np.arange(k, dtype=np.uint64) + i) if str(f.type) == "uint64"
+                                                    else pa.array(np.linspace(0, 1, k) + i) for i, f in enumerate(schema) if f.name != "relax"]
+        sink.write(cols); sink.write(cols)
+        sink.close(); sink.close()                                # idempotent, as Drop + explicit close in the reference
+        assert os.path.exists(str(path)) and not os.path.exists(stem + ".parquet.tmp")
+        t = pq.read_table(str(path))
+        assert t.num_rows == 2 * k and t.schema.names == names and not any(f.nullable for f in t.schema)
+        md = pq.ParquetFile(str(path)).metadata
+        assert all(md.row_group(0).column(c).compression == "SNAPPY" for c in range(md.num_columns))
