@@ -1,0 +1,204 @@
+"""CPU-only tests of the C++ host layer (vegas_rs_b200/csrc/vegas_host.cpp: Machine, StatSensor / ObservableSensor /
+StateSensor, Relax / CoolDown / HysteresisLoop) against the reference's semantics (src/machine.rs:91-125,
+src/instrument.rs:61-351, src/program.rs:97-336).  The host layer is compiled together with a SCRIPTED test double of the
+device handle (tests/mock/mock_vegas_gpu.cpp: step k reports fixed formulas, every call is logged) -- no GPU, no Monte
+Carlo, nothing from the product package is replaced."""
+import ctypes as C
+import os
+import subprocess
+import types
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MOCK_DIR = os.path.join(ROOT, "tests", "mock")
+EPS = np.finfo(float).eps
+
+
+@pytest.fixture(scope="module")
+def mock_lib():
+    so = os.path.join(MOCK_DIR, "libvegas_host_mock.so")
+    srcs = [os.path.join(MOCK_DIR, "mock_vegas_gpu.cpp"), os.path.join(ROOT, "vegas_rs_b200", "csrc", "vegas_host.cpp")]
+    deps = srcs + [os.path.join(ROOT, "vegas_rs_b200", "csrc", "vegas_host.hpp"), os.path.join(ROOT, "include", "vegas_host.h"),
+                   os.path.join(ROOT, "include", "vegas_gpu.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-o", so, *srcs], check=True)
+    lib = C.CDLL(so)
+    lib.mock_gpu_create.restype, lib.mock_gpu_create.argtypes = C.c_void_p, [C.c_uint64, C.c_int, C.c_uint64]
+    lib.mock_gpu_destroy.restype, lib.mock_gpu_destroy.argtypes = None, [C.c_void_p]
+    lib.mock_gpu_log.restype, lib.mock_gpu_log.argtypes = C.c_uint64, [C.c_void_p, C.c_void_p, C.c_uint64]
+    lib.mock_gpu_steps.restype, lib.mock_gpu_steps.argtypes = C.c_uint64, [C.c_void_p]
+    return lib
+
+
+class Rig:
+    """A Machine of the real host layer over the scripted device, with the three sensors recording what they receive."""
+
+    def __init__(self, lib, n=10, heisenberg=False, fail_at=2**64 - 1, state_frequency=None):
+        from vegas_rs_b200.machine import Machine
+        from vegas_rs_b200 import ISING, HEISENBERG
+        self.lib, self.n, self.heis = lib, n, heisenberg
+        self.h = C.c_void_p(lib.mock_gpu_create(n, int(heisenberg), fail_at))
+        self.m = Machine(types.SimpleNamespace(_h=self.h, model=HEISENBERG if heisenberg else ISING), lib=lib)
+        self.lines, self.batches, self.dumps = [], [], []
+        self.m.add_stat_sensor(lambda line, row: self.lines.append((line, row)))
+        self.m.add_observable_sensor(lambda *a: self.batches.append(a))
+        if state_frequency is not None:
+            self.m.add_state_sensor(state_frequency, lambda *a: self.dumps.append(a))
+
+    def log(self):
+        k = self.lib.mock_gpu_log(self.h, None, 0)
+        out = np.zeros(k)
+        self.lib.mock_gpu_log(self.h, out.ctypes.data_as(C.c_void_p), k)
+        return out.reshape(-1, 4)
+
+    def close(self):
+        self.m.close()
+        self.lib.mock_gpu_destroy(self.h)
+
+
+def energy(k, T):
+    return -0.5 * k + T
+
+
+def magnitude(k, heis):
+    if heis:
+        a = float(k % 5)
+        mag = np.sqrt((3 * a) ** 2 + (4 * a) ** 2)
+        return 0.0 if abs(mag) < EPS else abs(mag)            # HeisenbergSpin::from_projections, src/state.rs:150-160
+    return abs(float((k * 37) % 101) - 50.0)                  # IsingSpin::from_projections, src/state.rs:86-92
+
+
+def test_machine_default_thermostat_and_hook_order(mock_lib):
+    r = Rig(mock_lib)
+    assert r.m.thermostat() == (2.8, 0.0)                     # Thermostat::new(2.8, Field::zero()), src/input.rs:274
+    r.m.relax(5, 6.0)
+    r.m.set_thermostat(3.0, (0, 0, 1.0), 0.25)
+    r.m.measure_for(7)
+    assert r.m.steps_done == 12 and mock_lib.mock_gpu_steps(r.h) == 12
+    # ObservableSensor: one batch per stage, relax flag, stage counter over both kinds of stage (instrument.rs:229-252)
+    assert [(b[0], b[1], b[2], b[3], b[4], len(b[5])) for b in r.batches] == [(True, 0, 10, 6.0, 0.0, 5), (False, 1, 10, 3.0, 0.25, 7)]
+    assert np.array_equal(r.batches[0][5], [energy(k, 6.0) for k in range(1, 6)])
+    assert np.array_equal(r.batches[1][6], [magnitude(k, False) for k in range(6, 13)])
+    # StatSensor: measure stages only; population variance / (N T^2), / (N T); Binder cumulant of |M| (instrument.rs:98-131)
+    assert len(r.lines) == 1
+    e = np.array([energy(k, 3.0) for k in range(6, 13)]); m = np.array([magnitude(k, False) for k in range(6, 13)])
+    row = r.lines[0][1]
+    want = (3.0, 0.25, e.mean(), e.var() / (10 * 9.0), m.mean(), m.var() / (10 * 3.0), 1 - (m**4).mean() / (3 * (m**2).mean() ** 2))
+    assert np.allclose(row, want, rtol=1e-13, atol=1e-13)
+    assert r.lines[0][0] == " ".join(f"{v:.16f}" for v in row)                      # "{:.16} ..." line, instrument.rs:118-128
+    # the device saw: thermostats in order, one recorded batch per stage
+    log = r.log()
+    assert [tuple(x) for x in log[log[:, 0] == 1][:, 1:3]] == [(2.8, 0.0), (6.0, 0.0), (3.0, 0.25)]
+    assert [tuple(x) for x in log[log[:, 0] == 2][:, 1:]] == [(5, 1, 0), (7, 1, 5)]
+    r.close()
+
+
+def test_machine_chunks_long_stages_without_reordering_steps(mock_lib):
+    """Stages longer than the device's observable ring (4096 rows) run as several batches; the sensors still see every
+    step exactly once and in order (src/machine.rs:91-101)."""
+    r = Rig(mock_lib, heisenberg=True, n=24)
+    r.m.set_thermostat(1.5)
+    r.m.measure_for(10000)
+    steps = r.log()[r.log()[:, 0] == 2]
+    assert [int(x) for x in steps[:, 1]] == [4096, 4096, 1808] and [int(x) for x in steps[:, 3]] == [0, 4096, 8192]
+    (relax, stage, n, T, field, e, mag), = r.batches
+    assert (relax, stage, n, T, len(e)) == (False, 0, 24, 1.5, 10000)
+    assert np.array_equal(e, [energy(k, 1.5) for k in range(1, 10001)])
+    assert np.array_equal(mag, [magnitude(k, True) for k in range(1, 10001)])     # |M| = norm of the three projections
+    assert mag.min() == 0.0 and mag.max() == 20.0
+    r.close()
+
+
+@pytest.mark.parametrize("heis", [False, True], ids=["ising", "heisenberg"])
+def test_state_sensor_schedule_and_contents(mock_lib, heis):
+    """StateSensor (src/instrument.rs:265-351): a dump when step.is_multiple_of(frequency), the counter restarts every
+    stage, the stage index counts relax and measure stages, and the dumped State is the one AFTER that step -- the
+    Machine therefore cuts its device batches so that a due step is the last of its batch."""
+    r = Rig(mock_lib, n=6, heisenberg=heis, state_frequency=4)
+    r.m.relax(10, 2.0)
+    r.m.measure_for(6)
+    got = [(d[0], d[1], d[2]) for d in r.dumps]
+    assert got == [(True, 0, 0), (True, 0, 4), (True, 0, 8), (False, 1, 0), (False, 1, 4)]
+    # the device step count when each dump was taken: step index s of a stage = the state after s + 1 steps of it
+    device_steps = [1, 5, 9, 11, 15]
+    for d, k in zip(r.dumps, device_steps):
+        state = d[5]
+        want = np.array([1 if (k + i) & 1 else -1 for i in range(6)])
+        if heis:
+            assert state.shape == (6, 3) and np.array_equal(state[:, 2], want) and not state[:, :2].any()
+        else:
+            assert state.shape == (6,) and np.array_equal(state, want)
+    log = r.log()
+    assert [int(x) for x in log[log[:, 0] == 3][:, 1]] == device_steps
+    # batches end on the due steps: 1 | 4 | 4 | 1 (relax 10) and 1 | 4 | 1 (measure 6)
+    assert [int(x) for x in log[log[:, 0] == 2][:, 1]] == [1, 4, 4, 1, 1, 4, 1]
+    # every step still reaches the observable sensor once
+    assert [len(b[5]) for b in r.batches] == [10, 6]
+    assert np.array_equal(np.concatenate([b[5] for b in r.batches]), [energy(k, 2.0) for k in range(1, 17)])
+    r.close()
+
+
+def test_state_sensor_frequency_zero_dumps_only_step_zero(mock_lib):
+    r = Rig(mock_lib, n=4, state_frequency=0)
+    r.m.relax(5, 1.0)
+    r.m.relax(3, 1.0)
+    assert [(d[1], d[2]) for d in r.dumps] == [(0, 0), (1, 0)]
+    r.close()
+
+
+def test_cooldown_program_sequence(mock_lib):
+    """CoolDown::run (src/program.rs:182-214): T -= cool_rate in f64 until T < min; relax then measure at every point."""
+    r = Rig(mock_lib)
+    r.m.cooldown(3.0, 2.0, 0.1, 3, 5)
+    temps, t = [], 3.0
+    while True:
+        temps.append(t)
+        t -= 0.1
+        if t < 2.0:
+            break
+    assert len(temps) == 10 and temps[-1] != 2.0 + 0.1          # the 2.0 point is lost to rounding
+    assert [l[1][0] for l in r.lines] == temps
+    assert [(b[0], b[3], len(b[5])) for b in r.batches] == [x for T in temps for x in ((True, T, 3), (False, T, 5))]
+    assert r.m.steps_done == 10 * 8
+    log = r.log()
+    assert list(log[log[:, 0] == 1][:, 1]) == [2.8] + temps
+    r.close()
+
+
+def test_hysteresis_program_sequence(mock_lib):
+    """HysteresisLoop::run (src/program.rs:281-336): 0 -> +max (overshooting by one step), down to -max (overshooting),
+    back up; the thermostat receives the signed magnitude, the sensors report Field::magnitude() = |H|."""
+    r = Rig(mock_lib, heisenberg=True)
+    r.m.hysteresis(4, 2, 1.25, 1.0, 0.5)
+    signed = [0.0, 0.5, 1.0, 1.5, 1.0, 0.5, 0.0, -0.5, -1.0, -1.5, -1.0, -0.5, 0.0, 0.5, 1.0]
+    log = r.log()
+    th = log[log[:, 0] == 1]
+    assert list(th[2:, 2]) == signed and set(th[2:, 1]) == {1.25} and set(th[2:, 3]) == {1.0}   # Field::new(S::up(), magnitude)
+    assert [l[1][1] for l in r.lines] == [abs(x) for x in signed]
+    assert [b[4] for b in r.batches] == [abs(x) for x in signed for _ in (0, 1)]
+    assert r.m.steps_done == len(signed) * 6
+    r.close()
+
+
+def test_program_errors_and_device_failures_propagate(mock_lib):
+    from vegas_rs_b200.machine import ProgramError
+    from vegas_rs_b200 import VegasGpuError
+    r = Rig(mock_lib)
+    for call, name in ((lambda: r.m.relax(0, 1.0), "NoSteps"), (lambda: r.m.relax(5, 0.0), "ZeroTemperature"),
+                       (lambda: r.m.cooldown(1.0, 2.0, 0.1, 1, 1), "TemperatureMaxLessThanMin"),
+                       (lambda: r.m.cooldown(2.0, 1.0, 0.0, 1, 1), "ZeroCoolRate"), (lambda: r.m.cooldown(2.0, 0.0, 0.1, 1, 1), "ZeroTemperature"),
+                       (lambda: r.m.hysteresis(1, 1, 1.0, 0.0, 0.1), "ZeroField"), (lambda: r.m.hysteresis(1, 1, 1.0, 1.0, 0.0), "ZeroFieldStep"),
+                       (lambda: r.m.hysteresis(0, 1, 1.0, 1.0, 0.1), "NoSteps")):
+        with pytest.raises(ProgramError) as ei:
+            call()
+        assert name in str(ei.value)                           # ProgramError variants, src/error.rs:31-46
+    assert mock_lib.mock_gpu_steps(r.h) == 0 and not r.lines   # nothing ran
+    r.close()
+    bad = Rig(mock_lib, fail_at=9000)
+    with pytest.raises(VegasGpuError) as ei:
+        bad.m.relax(20000, 2.0)
+    assert "scripted device failure" in str(ei.value) and ei.value.code == -2
+    assert bad.m.steps_done == 8192                            # the two batches before the failing one were delivered
+    bad.close()

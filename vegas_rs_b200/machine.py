@@ -40,8 +40,9 @@ class ProgramError(VegasGpuError):
     pass
 
 
-def _load():
-    lib = _lib.load()
+def bind_host_symbols(lib):
+    """ctypes signatures of include/vegas_host.h on `lib` (the CUDA library, or the host layer linked against the scripted
+    test double of tests/mock/ in the CPU-only tests)."""
     if not getattr(lib, "_host_bound", False):
         for name, res, args in HOST_SYMBOLS:
             fn = getattr(lib, name)
@@ -50,12 +51,16 @@ def _load():
     return lib
 
 
+def _load():
+    return bind_host_symbols(_lib.load())
+
+
 class Machine:
     """Machine::new(Thermostat::new(2.8, Field::zero()), hamiltonian, integrator, instruments, state)
     (src/input.rs:273-279) with the GPU handle standing in for hamiltonian + integrator + state."""
 
-    def __init__(self, gpu: GpuMetropolis):
-        self._lib = _load()
+    def __init__(self, gpu: GpuMetropolis, lib=None):
+        self._lib = _load() if lib is None else bind_host_symbols(lib)   # lib: tests only (host layer over a test double)
         self.gpu = gpu
         self._m = C.c_void_p()
         rc = self._lib.vegas_machine_create(gpu._h, C.byref(self._m))
