@@ -35,13 +35,15 @@ def mock_lib():
 class Rig:
     """A Machine of the real host layer over the scripted device, with the three sensors recording what they receive."""
 
-    def __init__(self, lib, n=10, heisenberg=False, fail_at=2**64 - 1, state_frequency=None):
+    def __init__(self, lib, n=10, heisenberg=False, fail_at=2**64 - 1, state_frequency=None, sensors=True):
         from vegas_rs_b200.machine import Machine
         from vegas_rs_b200 import ISING, HEISENBERG
         self.lib, self.n, self.heis = lib, n, heisenberg
         self.h = C.c_void_p(lib.mock_gpu_create(n, int(heisenberg), fail_at))
         self.m = Machine(types.SimpleNamespace(_h=self.h, model=HEISENBERG if heisenberg else ISING), lib=lib)
         self.lines, self.batches, self.dumps = [], [], []
+        if not sensors:
+            return
         self.m.add_stat_sensor(lambda line, row: self.lines.append((line, row)))
         self.m.add_observable_sensor(lambda *a: self.batches.append(a))
         if state_frequency is not None:
@@ -202,3 +204,58 @@ def test_program_errors_and_device_failures_propagate(mock_lib):
     assert "scripted device failure" in str(ei.value) and ei.value.code == -2
     assert bad.m.steps_done == 8192                            # the two batches before the failing one were delivered
     bad.close()
+
+
+@pytest.mark.parametrize("heis", [False, True], ids=["ising", "heisenberg"])
+def test_toml_front_end_writes_reference_outputs(mock_lib, tmp_path, heis):
+    """`vegas run` wiring (src/input.rs:264-345) over the scripted device: the stdout lines of StatSensor, the observables
+    parquet (one row per step of every stage, relax flag, stage and step counters, n, T, |H|) and the state parquet (one
+    row per site and dump) -- docs/metropolis.toml's shape, shortened."""
+    import io
+    import pyarrow.parquet as pq
+    from vegas_rs_b200 import run
+    text = open(os.path.join(ROOT, "tests", "golden", "cfg0_ising_sc10.toml")).read()
+    text = text.replace("steps = 20000", "steps = 6").replace("relax = 1000", "relax = 3").replace("steps = 1000", "steps = 5")
+    text = text.replace("cool_rate = 0.05", "cool_rate = 2.5").replace("frequency = 1000", "frequency = 4")
+    text = text.replace("./output.parquet", str(tmp_path / "output.parquet")).replace("./state.parquet", str(tmp_path / "state.parquet"))
+    if heis:
+        text = text.replace('model = "Ising"', 'model = "Heisenberg"')
+    cfg = run.parse_input(text)
+    assert cfg["model"] == ("Heisenberg" if heis else "Ising") and cfg["size"] == (10, 10, 10)
+    r = Rig(mock_lib, n=1000, heisenberg=heis, sensors=False)
+    out = io.StringIO()
+    run.run_stages(cfg, r.m, out)
+    # stages: Relax(5 @ 6.0), CoolDown 6.0 -> 1.0 by 2.5 = points 6.0, 3.5, 1.0, each relax 3 + measure 6
+    lines = out.getvalue().strip().split("\n")
+    assert [l.split()[0] for l in lines] == ["6.0000000000000000", "3.5000000000000000", "1.0000000000000000"]
+    obs = pq.read_table(tmp_path / "output.parquet").to_pydict()
+    stages = [(True, 5, 6.0)] + [x for T in (6.0, 3.5, 1.0) for x in ((True, 3, T), (False, 6, T))]
+    assert obs["relax"] == [rx for rx, k, _ in stages for _ in range(k)]
+    assert obs["stage"] == [i for i, (_, k, _) in enumerate(stages) for _ in range(k)]
+    assert obs["step"] == [j for _, k, _ in stages for j in range(k)]
+    assert set(obs["n"]) == {1000} and set(obs["field"]) == {0.0}
+    assert obs["temperature"] == [T for _, k, T in stages for _ in range(k)]
+    device_step = np.arange(1, 33)
+    assert np.array_equal(obs["energy"], [energy(k, T) for k, T in zip(device_step, obs["temperature"])])
+    assert np.array_equal(obs["magnetization"], [magnitude(k, heis) for k in device_step])
+    st = pq.read_table(tmp_path / "state.parquet").to_pydict()
+    dumps = [(True, 0, 0, 6.0), (True, 0, 4, 6.0)] + [x for i, T in enumerate((6.0, 3.5, 1.0))
+                                                     for x in ((True, 1 + 2 * i, 0, T), (False, 2 + 2 * i, 0, T), (False, 2 + 2 * i, 4, T))]
+    assert len(st["id"]) == 1000 * len(dumps) and st["id"][:1000] == list(range(1000))
+    assert [(st["relax"][i], st["stage"][i], st["step"][i], st["temperature"][i]) for i in range(0, len(st["id"]), 1000)] == dumps
+    assert set(st["sz"]) == {1.0, -1.0} and set(st["sx"]) == {0.0} and set(st["sy"]) == {0.0}
+    assert not os.path.exists(tmp_path / "output.parquet.tmp") and not os.path.exists(tmp_path / "state.parquet.tmp")
+    r.close()
+
+
+def test_run_input_needs_the_cuda_device(built):
+    """`python -m vegas_rs_b200.run` has no CPU fallback: without a device the run fails with the library's message."""
+    import torch
+    from vegas_rs_b200 import run, VegasGpuError
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    cfg = run.parse_input(open(os.path.join(ROOT, "tests", "golden", "cfg0_ising_sc10.toml")).read())
+    cfg["output"] = None
+    with pytest.raises(VegasGpuError) as ei:
+        run.run_input(cfg, seed=1)
+    assert ei.value.code == -2 and "no CPU fallback" in str(ei.value)

@@ -97,21 +97,10 @@ def state_schema():
                       pa.field("sz", pa.float64(), False)])
 
 
-def run_input(cfg: dict, seed: int | None = None, out=sys.stdout, device: int = 0, literal: bool = False):
-    """Input::run (src/input.rs:347-367) -> run_with_spin (:264-294)."""
-    if cfg["algorithm"] == "Wolff":
-        raise NotImplementedError("the Wolff cluster integrator is outside the GPU sweep's scope (SURVEY section 2)")
-    model = ISING if cfg["model"] == "Ising" else HEISENBERG
-    if seed is None:
-        seed = int.from_bytes(os.urandom(8), "little")  # Pcg64::from_rng(&mut rand::rng()), src/main.rs:70-73
-    uc = {"sc": SC, "bcc": BCC, "fcc": FCC}[cfg["unitcell"]]
-    exchange = cfg["exchange"] if cfg["exchange"] is not None else 1.0  # src/input.rs:352
-    # hamiltonian!(Exchange::from_lattice(exchange, &lattice), Zeeman::new()), src/input.rs:271
-    g = GpuMetropolis(model, unitcell=uc, size=cfg["size"], pbc=cfg["pbc"], exchange=exchange, zeeman=True, seed=seed,
-                      device=device, literal=literal)
-    g.set_energy_convention(E_REFERENCE_COMPOUND)
-    g.randomize()  # State::rand_with_size, src/input.rs:278
-    m = Machine(g)
+def run_stages(cfg: dict, m, out=sys.stdout):
+    """run_with_spin's instrument wiring and stage loop (src/input.rs:273-292, :324-345) on a Machine: StatSensor ->
+    `out`, ObservableSensor -> observables parquet, StateSensor -> state parquet; then every stage in order.  Closes the
+    parquet sinks (tmp file renamed) whether or not a stage fails."""
     sinks = []
     # Input::instruments, src/input.rs:324-345: StatSensor(stdout) [+ ObservableSensor] [+ StateSensor]
     m.add_stat_sensor(lambda line, row: print(line, file=out, flush=True))
@@ -150,7 +139,29 @@ def run_input(cfg: dict, seed: int | None = None, out=sys.stdout, device: int = 
     finally:
         for s in sinks:
             s.close()
-        m.close()
+
+
+def run_input(cfg: dict, seed: int | None = None, out=sys.stdout, device: int = 0, literal: bool = False):
+    """Input::run (src/input.rs:347-367) -> run_with_spin (:264-294)."""
+    if cfg["algorithm"] == "Wolff":
+        raise NotImplementedError("the Wolff cluster integrator is outside the GPU sweep's scope (SURVEY section 2)")
+    model = ISING if cfg["model"] == "Ising" else HEISENBERG
+    if seed is None:
+        seed = int.from_bytes(os.urandom(8), "little")  # Pcg64::from_rng(&mut rand::rng()), src/main.rs:70-73
+    uc = {"sc": SC, "bcc": BCC, "fcc": FCC}[cfg["unitcell"]]
+    exchange = cfg["exchange"] if cfg["exchange"] is not None else 1.0  # src/input.rs:352
+    # hamiltonian!(Exchange::from_lattice(exchange, &lattice), Zeeman::new()), src/input.rs:271
+    g = GpuMetropolis(model, unitcell=uc, size=cfg["size"], pbc=cfg["pbc"], exchange=exchange, zeeman=True, seed=seed,
+                      device=device, literal=literal)
+    try:
+        g.set_energy_convention(E_REFERENCE_COMPOUND)
+        g.randomize()  # State::rand_with_size, src/input.rs:278
+        m = Machine(g)
+        try:
+            run_stages(cfg, m, out)
+        finally:
+            m.close()
+    finally:
         g.close()
 
 
