@@ -171,3 +171,14 @@ def test_create_rejects_bad_arguments_before_touching_the_device(built):
     assert code_of(csr=(np.array([0, 2, 1], np.uint64), np.array([1, 0], np.uint32), None))[1].endswith("row_ptr not monotone")
     wide = np.array([0, 40, 40], np.uint64)
     assert code_of(csr=(wide, np.ones(40, np.uint32), None))[1].endswith("rows longer than 32 are not supported")
+
+
+def test_documented_tuning_keys_exist_in_the_library_source():
+    """include/vegas_gpu.h documents the kernel-selection knobs; each must be handled by vegas_gpu_set_tuning and vice versa."""
+    hdr = open(os.path.join(ROOT, "include", "vegas_gpu.h")).read()
+    block = hdr[hdr.index("kernel selection knobs"):hdr.index("int vegas_gpu_set_tuning")]
+    documented = set(re.findall(r'"([a-z_]+)"', block))
+    src = open(os.path.join(ROOT, "vegas_rs_b200", "csrc", "vegas_gpu.cu")).read()
+    body = src[src.index("int vegas_gpu_set_tuning("):src.index("const char* vegas_gpu_step_kernel(")]
+    handled = set(re.findall(r'k == "([a-z_]+)"', body))
+    assert documented == handled, (sorted(documented - handled), sorted(handled - documented))
