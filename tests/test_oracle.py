@@ -72,6 +72,32 @@ def test_all_up_sc_known_answers(L, field):
     assert He.total_energy(th, s) == -3 * n
 
 
+@pytest.mark.parametrize("uc,z,nb", [(ob.BCC, 8, 2), (ob.FCC, 12, 4)], ids=["bcc", "fcc"])
+@pytest.mark.parametrize("model", [ob.ISING, ob.HEISENBERG], ids=["ising", "heisenberg"])
+def test_all_up_bcc_fcc_known_answers(uc, z, nb, model):
+    """Derived known answers on the other two unit cells of src/input.rs:296-322 (z = 8, 12): all spins up, J = 1,
+    hamiltonian!(Exchange, Zeeman): energy(i) = -z + |H|, compound total = N (-z + |H|) (exchange counted twice,
+    App. A Q3), Exchange::total_energy alone = -z N / 2, and flipping any spin costs 2 z - 2 |H|."""
+    size, field = (4, 3, 5), 0.75
+    H, m = oracle_model(model, unitcell=uc, size=size)
+    n = int(np.prod(size)) * nb
+    s = np.ones(n, np.int8) if model == ob.ISING else np.tile([0.0, 0.0, 1.0], (n, 1))
+    th = H.thermostat(2.0, (0, 0, 1.0), field)
+    assert np.all(H.site_energies(th, s) == -z + field)
+    assert H.total_energy(th, s) == n * (-z + field)
+    assert np.all(H.delta_energies(th, s) == 2 * z - 2 * field)
+    He = ob.Hamiltonian(model, [ob.TERM_EXCHANGE], m)
+    assert He.total_energy(th, s) == -z * n / 2
+    # one spin down: its own energy changes sign, each of its z neighbours loses two units of bond energy
+    if model == ob.ISING:
+        s[7] = -1
+    else:
+        s[7] = [0.0, 0.0, -1.0]
+    e = H.site_energies(th, s)
+    assert e[7] == z - field and sorted(set(e.tolist())) == sorted({z - field, -z + 2 + field, -z + field})
+    assert int(np.sum(e == -z + 2 + field)) == z
+
+
 def test_lattice_coordination_and_csr_shape():
     for uc, z, nb in ((ob.SC, 6, 1), (ob.BCC, 8, 2), (ob.FCC, 12, 4)):
         lat = ob.Lattice(uc, 4, 3, 5)
