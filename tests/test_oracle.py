@@ -279,3 +279,47 @@ def test_oracle_replays_committed_gpu_trajectories(built, name):
         assert np.max(np.abs(z["final"] - state)) < 1e-12
         assert np.max(np.abs(np.linalg.norm(z["final"], axis=1) - 1.0)) < 1e-12
     assert not np.array_equal(z["final"], z["initial"])       # the sweeps did move spins
+
+
+@pytest.mark.parametrize("model", [ob.ISING, ob.HEISENBERG], ids=["ising", "heisenberg"])
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_oracle_consistency_on_random_weighted_graphs(model, seed):
+    """Properties every Hamiltonian of src/energy.rs must satisfy, on random symmetric CSR graphs with per-bond values
+    (Exchange::new), anisotropy and gauge: the compound total is the sum of the per-site energies (trait default,
+    :55-59); delta_energies equals energy-after minus energy-before of an explicit move (integrator.rs:77-81); a sweep at
+    T -> infinity accepts every proposal; at T -> 0 (clamped to EPSILON, thermostat.rs:29-40) the energy never rises."""
+    rng = np.random.default_rng(seed)
+    n = 60
+    i = rng.integers(0, n, 150); j = rng.integers(0, n, 150)
+    keep = i != j
+    i, j = i[keep], j[keep]
+    w = rng.integers(-8, 9, len(i)) / 4.0                                   # dyadic couplings: sums are exact
+    m = ob.Csr.from_triplets(n, np.concatenate([i, j]), np.concatenate([j, i]), np.concatenate([w, w]))
+    terms = [ob.TERM_EXCHANGE, ob.TERM_ZEEMAN, ob.TERM_ANISOTROPY, ob.TERM_GAUGE]
+    H = ob.Hamiltonian(model, terms, m, gauge=0.5, aniso_k=0.25, aniso_axis=(0.0, 0.0, 1.0))
+    orng = ob.OracleRng(seed)
+    s = H.rand_state(orng, n)
+    th = H.thermostat(1.5, (0, 0, 1.0), 0.75)
+    e_sites = H.site_energies(th, s)
+    assert abs(H.total_energy(th, s) - e_sites.sum()) < 1e-9
+    assert all(H.energy(th, s, k) == e_sites[k] for k in (0, 17, n - 1))
+    d = H.delta_energies(th, s)                                              # flip of every site, one at a time
+    for k in (3, 29, 58):
+        t = s.copy()
+        t[k] = -t[k]
+        assert abs((H.energy(th, t, k) - H.energy(th, s, k)) - d[k]) < 1e-12
+    # T -> infinity: every attempt of a step is accepted
+    hot = H.thermostat(1e300)
+    proposal = ob.PROPOSE_FLIP if model == ob.ISING else ob.PROPOSE_RANDOM
+    assert H.step(hot, proposal, orng, s) == n
+    # T -> 0: only moves with e_new - e_old <= 0 pass, so the energy whose single-site differences the integrator uses
+    # (every bond ONCE: the compound total counts the exchange twice, App. A Q3, so subtract it once) never rises
+    He = ob.Hamiltonian(model, [ob.TERM_EXCHANGE], m)
+    cold = H.thermostat(0.0, (0, 0, 1.0), 0.75)
+    physical = lambda: H.total_energy(cold, s) - He.total_energy(cold, s)
+    e_prev = physical()
+    for _ in range(8):
+        H.step(cold, proposal, orng, s)
+        e_now = physical()
+        assert e_now <= e_prev + 1e-9
+        e_prev = e_now
