@@ -8,7 +8,12 @@ per-step energy / magnetisation observers fused in (src/instrument.rs:133-141). 
   ising3d_1024  cfg[2]  Ising sc 1024^3 pbc, T=4.5 (default: > L2, and the z-slab config; weak scaling: 1024^3 per GPU)
   ising2d_8192  cfg[1]  Ising sc 8192^2 pbc, T=2.269 (8 MiB bit-packed: L2 resident, reported in "also")
   heis3d_512    cfg[3]  Heisenberg sc 512^3 pbc, Exchange+Anisotropy+Zeeman, T=1.0, |H|=1, fp32
-Prints ONE JSON line on rank 0.
+  heis_fcc_384  cfg[4]  Heisenberg fcc 384^3 cells (226 M sites, z = 12), T=3.2, fp32 (z-slabs of 384 cell planes per GPU)
+  ising_sc10_cfg0 cfg[0] docs/metropolis.toml's 10^3 lattice on the shared-memory-resident kernel (inside "also"; main
+                        workload of --impl reference only)
+Prints ONE JSON line on rank 0: the bench contract's keys plus roofline, cpu_baseline, e2e (Integrator::step's own
+signature: host State in / out every step), e2e_machine (Machine::measure_for with the State resident), clocks,
+gpu_launches, and "also" = the other workloads with their own roofline / e2e / clocks.
 """
 from __future__ import annotations
 
