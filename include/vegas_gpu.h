@@ -171,6 +171,11 @@ int vegas_gpu_slab_connect_local(vegas_gpu_t self, vegas_gpu_t lower, vegas_gpu_
  * key "heis_fused"    : -1 auto (default), 0 never, 1 whenever the lattice fits  -- the one-launch-per-step
  *                       two-colour Heisenberg kernel (heis_fused.cuh) instead of two colour passes
  *     "heis_fused_ty" : interior rows per CTA tile (0 = auto), "heis_fused_cz": planes per z-chunk (0 = auto)
+ *     "heis_pipe"     : -1 auto (default: 3-D lattices with >= 32 planes whose rows fit), 0 never, 1 whenever the lattice
+ *                       fits -- both colour passes of a Heisenberg step as ONE cooperative, phase-pipelined launch whose
+ *                       plane tiles are staged by TMA into mbarrier-guarded shared-memory rings (heis_pipe.cu);
+ *                       "heis_pipe_stages" / "heis_pipe_own" (ring depths of the other / own colour, 0 = auto),
+ *                       "heis_pipe_tiles" (bands of rows per colour, 0 = auto: half the SM count)
  *     "heis_wave"     : -1 auto (default: lattices with >= 32 planes), 0 never, 1 always -- both colour passes of a
  *                       Heisenberg step as ONE persistent launch in wave order (second pass finds the first in L2);
  *                       "heis_wave_planes" (planes per chunk, default 4), "heis_wave_lag" (positions a colour pass

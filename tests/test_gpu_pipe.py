@@ -1,0 +1,116 @@
+"""K3p, the phase-pipelined TMA Heisenberg kernel (vegas_rs_b200/csrc/heis_pipe.cu): same trajectories as the two colour
+passes it replaces (src/integrator.rs:66-92, :109-138), decision-by-decision equal to the oracle replay, all through the
+C ABI.  GPU only."""
+import numpy as np
+import pytest
+
+import vegas_rs_b200 as vg
+from oracle import binding as ob
+from helpers import oracle_model, random_state
+
+pytestmark = pytest.mark.gpu
+
+
+def _two_pass(**kw):
+    g = vg.GpuMetropolis(vg.HEISENBERG, **kw)
+    g.set_tuning("heis_pipe", 0); g.set_tuning("heis_wave", 0)
+    assert g.step_kernel == "heis_stencil"
+    return g
+
+
+def _pipe(tiles=0, stages=0, own=0, **kw):
+    g = vg.GpuMetropolis(vg.HEISENBERG, **kw)
+    g.set_tuning("heis_pipe", 1)
+    if tiles:
+        g.set_tuning("heis_pipe_tiles", tiles)
+    if stages:
+        g.set_tuning("heis_pipe_stages", stages); g.set_tuning("heis_pipe_own", own)
+    assert g.step_kernel == "heis_pipe"
+    return g
+
+
+# (size, precision, band count, other-ring stages, own-ring stages): even and uneven bands (14 rows over 4 bands = 4+4+3+3),
+# one-row bands, a single band (its own y-neighbour), minimal and deep rings, more planes than ring slots
+CASES = [
+    ((64, 14, 12), vg.F32, 4, 0, 0),
+    ((64, 14, 12), vg.F32, 4, 4, 1),
+    ((64, 12, 9 + 1), vg.F32, 12, 5, 2),
+    ((64, 8, 8), vg.F32, 1, 4, 2),
+    ((128, 30, 16), vg.F32, 0, 0, 0),
+    ((128, 230, 8), vg.F32, 0, 6, 3),
+    ((32, 14, 12), vg.F64, 4, 0, 0),
+    ((64, 10, 20), vg.F64, 3, 4, 1),
+]
+
+
+@pytest.mark.parametrize("size,precision,tiles,stages,own", CASES)
+@pytest.mark.parametrize("proposal", [vg.PROPOSE_RANDOM, vg.PROPOSE_FLIP], ids=["random", "flip"])
+def test_pipe_kernel_identical_to_two_passes(built, size, precision, tiles, stages, own, proposal):
+    kw = dict(unitcell=vg.SC, size=size, precision=precision, seed=21, anisotropy=((0, 0.6, 0.8), 0.2), proposal=proposal)
+    ref = _two_pass(**kw)
+    ref.randomize(); ref.set_thermostat(0.8, (0, 0, 1.0), 0.4)
+    e0, m0 = ref.step(3)
+    ref.step(2, observe=False)
+    e1, m1 = ref.step(1)
+    want = ref.download(); acc = ref.attempt_count()
+    ref.close()
+    g = _pipe(tiles, stages, own, **kw)
+    g.randomize(); g.set_thermostat(0.8, (0, 0, 1.0), 0.4)
+    e, m = g.step(3)
+    g.step(2, observe=False)
+    e2, m2 = g.step(1)
+    g.synchronize()
+    assert np.array_equal(g.download(), want)
+    n = size[0] * size[1] * size[2]
+    tol = 1e-12 if precision == vg.F64 else 1e-6
+    assert np.allclose(e, e0, rtol=tol, atol=tol * n) and np.allclose(e2, e1, rtol=tol, atol=tol * n)
+    assert np.allclose(m, m0, rtol=10 * tol, atol=10 * tol * n) and np.allclose(m2, m1, rtol=10 * tol, atol=10 * tol * n)
+    assert g.attempt_count() == acc
+    g.close()
+
+
+@pytest.mark.parametrize("precision", [vg.F64, vg.F32], ids=["f64", "f32"])
+def test_pipe_kernel_replays_the_reference_rule(built, precision):
+    """Every decision of the pipelined step against the oracle: dE from its restatement of Hamiltonian::energy
+    (src/energy.rs:63-214), accept rule of src/integrator.rs:82-88, same Philox numbers; fused E and M equal
+    total_energy / magnetization of the replayed state."""
+    size = (32, 6, 10) if precision == vg.F64 else (64, 6, 10)
+    lat = dict(unitcell=vg.SC, size=size)
+    kw = dict(exchange=1.0, zeeman=True, anisotropy=((0.0, 0.0, 1.0), -0.3))
+    seed = 77
+    g = _pipe(3, precision=precision, seed=seed, **kw, **lat)
+    H, _ = oracle_model(ob.HEISENBERG, **kw, **lat)
+    n = size[0] * size[1] * size[2]
+    g.upload(random_state(ob.HEISENBERG, n, 51))
+    cpu = g.download(); col = g.colours()
+    g.set_thermostat(1.2, (0, 0, 1.0), 0.5)
+    th = H.thermostat(1.2, (0, 0, 1.0), 0.5)
+    for _ in range(3):
+        sweep = g.sweeps
+        e, m = g.step(1)
+        H.replay_heisenberg(th, ob.PROPOSE_RANDOM, precision == vg.F32, seed, sweep, col, 2, cpu)
+        dev = g.download()
+        diff = np.max(np.abs(dev - cpu), axis=1)
+        if precision == vg.F64:
+            assert np.max(diff) < 1e-12
+            assert abs(e[0] - H.total_energy(th, cpu)) < 1e-12 * n * 10
+            assert np.max(np.abs(m[0] - cpu.sum(axis=0))) < 1e-12 * n
+        else:
+            assert np.sum(diff > 1e-5) <= max(2, n // 200)
+            assert abs(e[0] - H.total_energy(th, dev)) < 1e-5 * n * 6
+            cpu = dev.copy()
+    g.close()
+
+
+def test_pipe_kernel_is_the_default_for_big_lattices(built):
+    g = vg.GpuMetropolis(vg.HEISENBERG, unitcell=vg.SC, size=(128, 64, 32), seed=5)
+    assert g.step_kernel == "heis_pipe"
+    g.randomize(); g.set_thermostat(1.0, (0, 0, 1.0), 0.3)
+    e, m = g.step(4)
+    assert abs(g.total_energy() - e[-1]) < 1e-5 * abs(e[-1]) + 1e-5 * g.n_sites
+    assert np.max(np.abs(g.magnetization() - m[-1])) < 1e-5 * g.n_sites
+    g.close()
+    # lattices the kernel cannot take (row of 48 bytes) keep the older kernels
+    g = vg.GpuMetropolis(vg.HEISENBERG, unitcell=vg.SC, size=(24, 64, 32), seed=5)
+    assert g.step_kernel in ("heis_wave", "heis_stencil")
+    g.close()

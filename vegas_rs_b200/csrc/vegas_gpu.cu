@@ -17,6 +17,7 @@
 #include "heis.cuh"
 #include "heis_basis.cuh"
 #include "heis_fused.cuh"
+#include "heis_pipe.hpp"
 #include "ising_msc.cuh"
 #include "lattice.hpp"
 #include "resident.cuh"
@@ -83,6 +84,12 @@ struct vegas_gpu {
     unsigned long long wave_phase_launches[2 * WAVE_MAX_STEPS] = {};  // launches that ran phase p so far
     unsigned int* wave_error = nullptr;
     int wave_grid = 0;
+    // --- phase-pipelined TMA kernel (heis_pipe.cu): the default step of big 3-D sc Heisenberg lattices
+    int pipe_enable = -1;                 // tuning key heis_pipe: -1 auto (>= 32 planes), 0 never, 1 whenever the lattice fits
+    uint32_t pipe_stages_other = 0, pipe_stages_own = 0, pipe_tiles = 0;   // tuning keys heis_pipe_stages / _own / _tiles (0 = auto)
+    bool pipe_planned = false;
+    HeisPipeState* pipe = nullptr;
+    std::string pipe_why;
     bool fused_ready = false;
     FusedGeom fused_geom{};
     size_t fused_smem = 0;
@@ -918,6 +925,54 @@ void wave_steps_t(vegas_gpu* h, uint32_t k, double* obs_row, bool record) {
 #undef WL
 }
 
+// ---- phase-pipelined TMA step (heis_pipe.cu) ---------------------------------------------------------
+// Both colour passes of a step in ONE cooperative launch: dedicated CTAs per colour march the planes in lock step, the
+// second colour a few planes behind the first (per-plane progress counters), tiles staged by TMA into mbarrier rings.
+bool pipe_plan(vegas_gpu* h) {
+    if (h->pipe_planned) return h->pipe != nullptr;
+    if (h->family != FAM_HEIS_STENCIL || h->ndim != 3 || h->pipe_enable == 0) return false;
+    if (h->pipe_enable < 0 && (h->ld.nz < 32 || h->fused_enable == 1 || h->wave_c > 0 || h->wave_enable == 1 || h->wave_k > 1)) return false;
+    if (h->slab) return false;   // slabs: see pipe_plan_slab (connected, one process per GPU)
+    h->pipe_planned = true;
+    HeisPipeDesc d;
+    d.device = h->device; d.f64 = h->md.precision == VEGAS_F64;
+    d.Lx = (uint32_t)h->ld.nx; d.Ly = (uint32_t)h->ld.ny; d.Lz = (uint32_t)h->ld.nz; d.z_offset = (uint32_t)h->z_offset;
+    for (int col = 0; col < 2; ++col) for (int c = 0; c < 3; ++c) d.arr[col][c] = h->hs[col][c];
+    d.stages_other = h->pipe_stages_other; d.stages_own = h->pipe_stages_own; d.tiles = h->pipe_tiles;
+    h->pipe = heis_pipe_create(d, h->pipe_why);
+    return h->pipe != nullptr;
+}
+
+int pipe_step(vegas_gpu* h, double* obs_row, bool record) {
+    const PhiloxKey pk = make_philox_key(h->md.seed);
+    const bool flip = h->md.proposal == VEGAS_PROPOSE_FLIP;
+    h->launches++;
+    std::string err;
+    const int rc = h->md.precision == VEGAS_F64 ? heis_pipe_step<double>(h->pipe, heis_params<double>(h), flip, record, h->sweeps, pk, obs_row, h->stream, err)
+                                               : heis_pipe_step<float>(h->pipe, heis_params<float>(h), flip, record, h->sweeps, pk, obs_row, h->stream, err);
+    if (rc) h->err = err;
+    return rc;
+}
+
+// Persistent kernels report a dependency wait that timed out through a device flag; every entry point that hands
+// results to the caller checks it after synchronising (a stale-plane sweep must never look like a valid one).
+int check_async_errors(vegas_gpu* h) {
+    if (h->wave_error) {
+        unsigned int werr = 0;
+        CU(cudaMemcpy(&werr, h->wave_error, 4, cudaMemcpyDeviceToHost));
+        if (werr) {
+            cudaMemset(h->wave_error, 0, 4);
+            h->wave_ready = false; h->wave_enable = 0;   // co-residency cannot be relied on here: two-pass kernels from now on
+            return fail(h, VEGAS_ERR_CUDA, "heis_wave_kernel: a dependency wait timed out (results invalid)");
+        }
+    }
+    if (h->pipe) {
+        std::string e;
+        if (heis_pipe_check(h->pipe, e)) return fail(h, VEGAS_ERR_CUDA, e);
+    }
+    return VEGAS_OK;
+}
+
 // ---- K2r: a batch of steps of a small general-family lattice in ONE launch (state resident in shared memory) ----
 constexpr size_t RES_SMEM_LIMIT = 226 * 1024;  // of the 227 KB a CTA may opt in to
 constexpr uint32_t RES_DIRECT_MAX = 2048;      // the direct variant (per-bond values) only pays off on tiny lattices
@@ -1015,6 +1070,8 @@ void do_step(vegas_gpu* h, void* obs_row, void* scratch_row) {
     const bool rec = obs_row != nullptr;
     if (h->family == FAM_HEIS_BASIS) {
         for (int b = 0; b < h->n_colours; ++b) basis_pass_any(h, rec ? 1 : 0, b, (double*)(rec ? obs_row : scratch_row));
+    } else if (h->family == FAM_HEIS_STENCIL && pipe_plan(h)) {
+        pipe_step(h, (double*)(rec ? obs_row : scratch_row), rec);   // a failed launch surfaces through cudaGetLastError / h->err
     } else if (h->family == FAM_HEIS_STENCIL && wave_plan(h)) {
         double* row = (double*)(rec ? obs_row : scratch_row);
         if (h->md.precision == VEGAS_F64) wave_steps_t<double>(h, 1, row, rec); else wave_steps_t<float>(h, 1, row, rec);
@@ -1119,6 +1176,7 @@ int measure_now(vegas_gpu* h, Canon& out) {
     CU(cudaMemcpyAsync(host, row, sizeof host, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
+    { const int rc = check_async_errors(h); if (rc) return rc; }
     out = canon_of(h, host);
     return VEGAS_OK;
 }
@@ -1378,6 +1436,7 @@ void vegas_gpu_destroy(vegas_gpu_t h) {
     cudaFree(h->obs);
     for (int k = 0; k < WAVE_MAX_STEPS; ++k) cudaFree(h->wave_units[k]);
     cudaFree(h->wave_done); cudaFree(h->wave_error);
+    heis_pipe_destroy(h->pipe);
     if (h->stream_b) { cudaStreamSynchronize(h->stream_b); cudaStreamDestroy(h->stream_b); }
     if (h->ev_main) cudaEventDestroy(h->ev_main);
     if (h->ev_bnd) cudaEventDestroy(h->ev_bnd);
@@ -1646,7 +1705,7 @@ int vegas_gpu_download_heisenberg(vegas_gpu_t h, double* sxyz, uint64_t n) {
     CU(cudaFreeAsync(tmp, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
-    return VEGAS_OK;
+    return check_async_errors(h);
 }
 
 int vegas_gpu_randomize(vegas_gpu_t h) {
@@ -1725,7 +1784,7 @@ int vegas_gpu_step_async(vegas_gpu_t h, uint64_t n_steps, int record) {
         return VEGAS_OK;
     }
     for (uint64_t s = 0; s < n_steps;) {
-        if (h->family == FAM_HEIS_STENCIL && h->wave_k > 1 && wave_plan(h) && h->wave_kmax > 1 && n_steps - s > 1) {
+        if (h->family == FAM_HEIS_STENCIL && h->wave_k > 1 && !pipe_plan(h) && wave_plan(h) && h->wave_kmax > 1 && n_steps - s > 1) {
             // several steps per persistent launch: the later colour passes find the earlier ones' planes in L2
             const uint32_t k = (uint32_t)std::min<uint64_t>(h->wave_kmax, n_steps - s);
             double* row = (double*)(record ? h->obs + s * OBS_W : scratch);
@@ -1749,6 +1808,7 @@ int vegas_gpu_read_observables(vegas_gpu_t h, uint64_t n_steps, double* energy, 
     CU(cudaMemcpyAsync(host.data(), h->obs, host.size() * 8, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
+    { const int rc = check_async_errors(h); if (rc) return rc; }
     for (uint64_t s = 0; s < n_steps; ++s) {
         const Canon c = canon_of(h, host.data() + s * OBS_W);
         h->accepted += c.accepted;
@@ -1774,7 +1834,7 @@ int vegas_gpu_step(vegas_gpu_t h, uint64_t n_steps, double* energy, double* mag_
     }
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
-    return VEGAS_OK;
+    return check_async_errors(h);
 }
 
 int vegas_gpu_synchronize(vegas_gpu_t h) {
@@ -1782,12 +1842,7 @@ int vegas_gpu_synchronize(vegas_gpu_t h) {
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
-    if (h->wave_error) {
-        unsigned int werr = 0;
-        CU(cudaMemcpy(&werr, h->wave_error, 4, cudaMemcpyDeviceToHost));
-        if (werr) return fail(h, VEGAS_ERR_CUDA, "heis_wave_kernel: a dependency wait timed out");
-    }
-    return VEGAS_OK;
+    return check_async_errors(h);
 }
 
 int vegas_gpu_step_host_ising(vegas_gpu_t h, int8_t* state, uint64_t n, double* energy, double* mag_xyz) {
@@ -2073,16 +2128,22 @@ int vegas_gpu_set_tuning(vegas_gpu_t h, const char* key, long value) {
     else if (k == "heis_wave_planes") h->wave_planes = (uint32_t)value;
     else if (k == "heis_wave_lag") h->wave_lag = (uint32_t)value;
     else if (k == "heis_wave_steps") h->wave_k = (uint32_t)std::max<long>(1, std::min<long>(value, WAVE_MAX_STEPS));
+    else if (k == "heis_pipe") h->pipe_enable = (int)value;
+    else if (k == "heis_pipe_stages") h->pipe_stages_other = (uint32_t)value;
+    else if (k == "heis_pipe_own") h->pipe_stages_own = (uint32_t)value;
+    else if (k == "heis_pipe_tiles") h->pipe_tiles = (uint32_t)value;
     else if (k == "basis_vec") h->basis_vec = (int)value;
     else if (k == "resident_max") { h->resident_max = (uint32_t)value; h->resident_cols = -2; }
     else return fail(h, VEGAS_ERR_INVALID, "unknown tuning key: " + k);
     h->fused_ready = false;  // re-plan at the next step
     h->wave_ready = false;
+    if (h->pipe_planned) { cudaStreamSynchronize(h->stream); heis_pipe_destroy(h->pipe); h->pipe = nullptr; h->pipe_planned = false; }
     return VEGAS_OK;
 }
 
 const char* vegas_gpu_step_kernel(vegas_gpu_t h) {
     if (!h) return "";
+    if (h->family == FAM_HEIS_STENCIL && cudaSetDevice(h->device) == cudaSuccess && pipe_plan(h)) return "heis_pipe";
     if (h->family == FAM_HEIS_STENCIL && cudaSetDevice(h->device) == cudaSuccess && wave_plan(h)) return "heis_wave";
     if (h->family == FAM_HEIS_STENCIL && cudaSetDevice(h->device) == cudaSuccess && fused_plan(h)) return "heis_fused";
     if (resident_plan(h)) return h->family == FAM_ISING_GEN ? "ising_resident" : "heis_resident";
