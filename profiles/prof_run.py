@@ -5,7 +5,7 @@ import bench
 
 name = sys.argv[1]
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-g, w = bench.make_handle(name, 0, 1, 0)
+g, w = bench.make_handle(name, 0, 1, 0)  # honours VEGAS_TUNE
 g.randomize()
 g.set_thermostat(w["T"], (0.0, 0.0, 1.0), w["H"])
 g.step_async(steps, True)

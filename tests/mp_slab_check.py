@@ -32,7 +32,11 @@ def main():
     g = vg.GpuMetropolis(model, unitcell=uc, size=(Lx, Ly, nz), nz_global=Lz, z_offset=zoff, seed=11, device=dev)
     g.upload(full[zoff * plane:(zoff + nz) * plane])
     g.set_thermostat(2.0 if model == vg.HEISENBERG else 4.0, (0, 0, 1.0), 0.25)
+    for kv in filter(None, os.environ.get("VEGAS_TUNE", "").split(",")):   # e.g. heis_pipe=1: force a kernel on the SLAB handles only
+        k, v = kv.split("=")
+        g.set_tuning(k, int(v))
     vd.connect_slabs(g, dist)
+    slab_kernel = g.step_kernel
     steps = 6
     g.step_async(steps, True)
     e, m = g.read_observables(steps)
@@ -51,7 +55,7 @@ def main():
         ok = np.array_equal(ref, got)
         tol = 0 if model == vg.ISING else 1e-6 * abs(e_ref[-1]) + 1e-6
         ok = ok and abs(e[-1] - e_ref[-1]) <= tol
-        print(f"mp_slab_check model={kind} family={whole.kernel_family} world={world} identical_state={np.array_equal(ref, got)} "
+        print(f"mp_slab_check model={kind} family={whole.kernel_family} slab_kernel={slab_kernel} world={world} identical_state={np.array_equal(ref, got)} "
               f"E_slabs={e[-1]:.6f} E_single={e_ref[-1]:.6f} -> {'OK' if ok else 'FAIL'}", flush=True)
     dist.barrier()
     g.close()

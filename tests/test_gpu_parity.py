@@ -533,8 +533,8 @@ def test_heisenberg_fused_flip_proposal_and_larger(built):
         for fused in (1, 0):
             g = vg.GpuMetropolis(vg.HEISENBERG, precision=vg.F32, seed=9, proposal=proposal, anisotropy=((0, 0, 1.0), 0.1), **lat)
             g.set_tuning("heis_fused", fused)
-            # 32 planes: without the fused kernel the auto choice is the persistent wave kernel (same trajectory)
-            assert g.step_kernel == ("heis_fused" if fused else "heis_wave")
+            # 32 planes: without the fused kernel the auto choice is the pipelined TMA kernel (same trajectory)
+            assert g.step_kernel == ("heis_fused" if fused else "heis_pipe")
             g.randomize()
             g.set_thermostat(1.0, (0, 0, 1.0), 1.0)
             e, m = g.step(4)

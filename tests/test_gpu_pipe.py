@@ -18,9 +18,11 @@ def _two_pass(**kw):
     return g
 
 
-def _pipe(tiles=0, stages=0, own=0, **kw):
+def _pipe(tiles=0, stages=0, own=0, vec=0, **kw):
     g = vg.GpuMetropolis(vg.HEISENBERG, **kw)
     g.set_tuning("heis_pipe", 1)
+    if vec:
+        g.set_tuning("heis_pipe_vec", vec)
     if tiles:
         g.set_tuning("heis_pipe_tiles", tiles)
     if stages:
@@ -29,23 +31,26 @@ def _pipe(tiles=0, stages=0, own=0, **kw):
     return g
 
 
-# (size, precision, band count, other-ring stages, own-ring stages): even and uneven bands (14 rows over 4 bands = 4+4+3+3),
-# one-row bands, a single band (its own y-neighbour), minimal and deep rings, more planes than ring slots
+# (size, precision, band count, other-ring stages, own-ring stages, sites per thread): even and uneven bands (14 rows over
+# 4 bands = 4+4+3+3), one-row bands, a single band (its own y-neighbour), minimal and deep rings, more planes than ring
+# slots, whole and half 16-byte vectors per thread
 CASES = [
-    ((64, 14, 12), vg.F32, 4, 0, 0),
-    ((64, 14, 12), vg.F32, 4, 4, 1),
-    ((64, 12, 9 + 1), vg.F32, 12, 5, 2),
-    ((64, 8, 8), vg.F32, 1, 4, 2),
-    ((128, 30, 16), vg.F32, 0, 0, 0),
-    ((128, 230, 8), vg.F32, 0, 6, 3),
-    ((32, 14, 12), vg.F64, 4, 0, 0),
-    ((64, 10, 20), vg.F64, 3, 4, 1),
+    ((64, 14, 12), vg.F32, 4, 0, 0, 0),
+    ((64, 14, 12), vg.F32, 4, 4, 1, 4),
+    ((64, 12, 9 + 1), vg.F32, 12, 5, 2, 2),
+    ((64, 8, 8), vg.F32, 1, 4, 2, 4),
+    ((128, 30, 16), vg.F32, 0, 0, 0, 4),
+    ((128, 230, 8), vg.F32, 0, 6, 3, 2),
+    ((256, 36, 40), vg.F32, 3, 5, 4, 2),
+    ((32, 14, 12), vg.F64, 4, 0, 0, 0),
+    ((64, 10, 20), vg.F64, 3, 4, 1, 2),
+    ((64, 10, 20), vg.F64, 5, 6, 3, 1),
 ]
 
 
-@pytest.mark.parametrize("size,precision,tiles,stages,own", CASES)
+@pytest.mark.parametrize("size,precision,tiles,stages,own,vec", CASES)
 @pytest.mark.parametrize("proposal", [vg.PROPOSE_RANDOM, vg.PROPOSE_FLIP], ids=["random", "flip"])
-def test_pipe_kernel_identical_to_two_passes(built, size, precision, tiles, stages, own, proposal):
+def test_pipe_kernel_identical_to_two_passes(built, size, precision, tiles, stages, own, vec, proposal):
     kw = dict(unitcell=vg.SC, size=size, precision=precision, seed=21, anisotropy=((0, 0.6, 0.8), 0.2), proposal=proposal)
     ref = _two_pass(**kw)
     ref.randomize(); ref.set_thermostat(0.8, (0, 0, 1.0), 0.4)
@@ -54,7 +59,7 @@ def test_pipe_kernel_identical_to_two_passes(built, size, precision, tiles, stag
     e1, m1 = ref.step(1)
     want = ref.download(); acc = ref.attempt_count()
     ref.close()
-    g = _pipe(tiles, stages, own, **kw)
+    g = _pipe(tiles, stages, own, vec, **kw)
     g.randomize(); g.set_thermostat(0.8, (0, 0, 1.0), 0.4)
     e, m = g.step(3)
     g.step(2, observe=False)

@@ -28,7 +28,7 @@ struct HeisParams {
 //   z = 1 - 2 u0 with u0 = (f0 + 1/2) 2^-21 in (0,1);   azimuth = 2 pi (f1 2^-21 - 1/2)
 __device__ __forceinline__ void sphere_point(float f0, float f1, float& x, float& y, float& z) {
     z = fmaf(f0, -0x1.0p-20f, 1.0f - 0x1.0p-21f);
-    const float t = (1.0f - z) * (1.0f + z);      // = 4 u0 (1 - u0) > 0, both factors exact
+    const float t = fmaf(-z, z, 1.0f);            // = 4 u0 (1 - u0) > 0; one rounding of the exact 1 - z^2, as (1 - z)(1 + z) with its two exact factors gave
     const float rxy = t * rsqrtf(t);
     const float ang = fmaf(f1, 6.283185307179586f * 0x1.0p-21f, -3.141592653589793f);
     x = rxy * __cosf(ang); y = rxy * __sinf(ang);
@@ -87,7 +87,8 @@ __device__ __forceinline__ void heis_rand(uint64_t site, uint64_t sweep, const P
 // numbers are known:  -dE = (s' - s).f - k[(s'.a)^2 - (s.a)^2]   (reference signs).
 // src/integrator.rs:82-88 accepts if dE < 0, else if u < exp(-dE/T); since u < 1 both cases are
 // u < exp(-dE/T), evaluated as 2^(-dE log2(e)/T).  Returns true when accepted.
-template <typename real, bool FLIP>
+// AXZ: the caller guarantees a = (0, 0, a_z); s.a = s_z a_z is then bit-identical to the general dot product.
+template <typename real, bool FLIP, bool AXZ = false>
 __device__ __forceinline__ bool heis_attempt(real& sx, real& sy, real& sz, real fx, real fy, real fz,
                                              const HeisParams<real>& p, const HeisRand<real>& rnd) {
     real px, py, pz;
@@ -97,8 +98,8 @@ __device__ __forceinline__ bool heis_attempt(real& sx, real& sy, real& sz, real 
     real mdE = dx * fx + dy * fy + dz * fz;
     if (!FLIP) {  // (s.a)^2 is invariant under a flip.  Kept branch-free: a uniform "k == 0" / "axis = z" shortcut was
         // measured SLOWER on the wave kernel (1.42e11 vs 1.47e11): the branches stop the interleaving of the 4 sites
-        const real da_new = px * p.a[0] + py * p.a[1] + pz * p.a[2];
-        const real da_old = sx * p.a[0] + sy * p.a[1] + sz * p.a[2];
+        const real da_new = AXZ ? pz * p.a[2] : px * p.a[0] + py * p.a[1] + pz * p.a[2];
+        const real da_old = AXZ ? sz * p.a[2] : sx * p.a[0] + sy * p.a[1] + sz * p.a[2];
         mdE -= p.k * ((da_new - da_old) * (da_new + da_old));
     }
     const bool acc = rnd.ua < fast_exp2(mdE * p.invTl + HeisAcceptShift<real>::value);

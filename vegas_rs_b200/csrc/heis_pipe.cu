@@ -55,11 +55,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(b)), "r"(parity)
+        : "r"(smem_u32(b)), "r"(parity), "r"(2000u)   // suspend-time hint (ns): sleep in hardware instead of re-polling
         : "memory");
     return ok != 0;
 }
@@ -72,6 +72,17 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
         ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+
+// TMA store of a box from shared memory (bulk async-group completion)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, uint32_t c0, uint32_t c1, uint32_t c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"((uint64_t)map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
     unsigned long long v;
@@ -107,15 +118,16 @@ __device__ __forceinline__ bool wait_bar(uint64_t* b, uint32_t parity, volatile 
     return true;
 }
 
-// Spins until *p >= target (SYS: the word is written by another GPU).
+// Spins until *p >= target (SYS: the word is written by another GPU); `seen` receives the last value read.
 template <bool SYS>
-__device__ __forceinline__ bool wait_counter(const unsigned long long* p, unsigned long long target, volatile uint32_t* abort_flag,
-                                             unsigned int* gerr, unsigned int code) {
-    if ((SYS ? ld_acquire_sys(p) : ld_acquire_gpu(p)) >= target) return true;
+__device__ __forceinline__ bool wait_counter(const unsigned long long* p, unsigned long long target, unsigned long long& seen,
+                                             volatile uint32_t* abort_flag, unsigned int* gerr, unsigned int code) {
+    seen = SYS ? ld_acquire_sys(p) : ld_acquire_gpu(p);
+    if (seen >= target) return true;
     const unsigned long long t0 = global_timer();
     uint32_t n = 0;
-    while ((SYS ? ld_acquire_sys(p) : ld_acquire_gpu(p)) < target) {
-        __nanosleep(32);
+    while ((seen = (SYS ? ld_acquire_sys(p) : ld_acquire_gpu(p))) < target) {
+        __nanosleep(200);     // the helper warps outrank the consumers in the issue arbiter: do not burn their slots
         if ((++n & 63u) == 0) {
             if (*abort_flag) return false;
             if (global_timer() - t0 > PIPE_TIMEOUT_NS) { *abort_flag = 1u; atomicExch(gerr, code); return false; }
@@ -137,8 +149,8 @@ struct PipeArgs {
     real* peer[2][2][3];                 // [colour][to lower / to upper][component] (HALO)
     const CUtensorMap* maps;
     HeisGeom g;
-    uint32_t tiles, rows, tiles_long, S, SO, n_cw;
-    unsigned long long* prog;            // [2][tiles] planes x consumer warps finished, monotone over the launches
+    uint32_t tiles, rows, tiles_long, S, SO, n_cw, lead, pub_every;
+    unsigned long long* prog;            // [2][tiles] planes finished (published), monotone over the launches
     unsigned long long base;             // value of every progress counter when this launch starts
     const unsigned long long* flags;     // HALO: [lower, upper][colour] boundary-plane CTAs that have stored into my halos
     unsigned long long* peer_flags[2];   // HALO: the word block of the lower / upper neighbour I add to
@@ -150,18 +162,20 @@ struct PipeArgs {
     double* obs;
 };
 
-struct PlaneRef { uint32_t array, z; };   // tensor-map array index and plane coordinate inside it
+// A position in a ring of `n` mbarrier-guarded slots: slot index and the parity of its current use.
+struct RingPos {
+    uint32_t slot = 0, parity = 0;
+    __device__ __forceinline__ void advance(uint32_t n) { if (++slot == n) { slot = 0; parity ^= 1u; } }
+};
 
 // March bookkeeping shared by the producer and the consumers of a CTA.
 //   planes of the `other` sequence q = 0, 1, ...: step i consumes q = qbase(i), +1, +2 (z-1, z, z+1)
 template <bool HALO>
 struct March {
     uint32_t Lz, phase;
-    __device__ __forceinline__ uint32_t steps() const { return Lz; }
     __device__ __forceinline__ uint32_t z_of(uint32_t i) const { const uint32_t z = phase + i; return z >= Lz ? z - Lz : z; }
     // HALO colour 1: planes 1 .. Lz-1 use q = i .. i+2 over [0 .. Lz-1, HI]; the last step (plane 0) uses [LO, 0, 1] = q Lz+1 ..
     __device__ __forceinline__ uint32_t qbase(uint32_t i) const { return (HALO && phase == 1 && i + 1 == Lz) ? Lz + 1 : i; }
-    __device__ __forceinline__ uint32_t n_q() const { return (HALO && phase == 1) ? Lz + 4 : Lz + 2; }
     // plane of sequence entry q: local z, or -1 (lower halo) / Lz (upper halo) for a slab
     __device__ __forceinline__ int plane_of(uint32_t q) const {
         if (!HALO) { const uint32_t z = phase + Lz - 1 + q; return (int)(z % Lz); }
@@ -170,9 +184,38 @@ struct March {
     }
 };
 
-template <typename real, bool FLIP, bool RECORD, bool HALO, int MAXT>
+template <typename real, int V> struct PackOf;
+template <> struct PackOf<float, 4> { typedef float4 type; };
+template <> struct PackOf<float, 2> { typedef float2 type; };
+template <> struct PackOf<double, 2> { typedef double2 type; };
+template <> struct PackOf<double, 1> { typedef double type; };
+template <typename real, int V>
+__device__ __forceinline__ void pack_load(const real* p, real (&v)[V]) {
+    typedef typename PackOf<real, V>::type T;
+    const T q = *reinterpret_cast<const T*>(p);
+    const real* e = reinterpret_cast<const real*>(&q);
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[i] = e[i];
+}
+template <typename real, int V>
+__device__ __forceinline__ void pack_store(real* p, const real (&v)[V]) {
+    typedef typename PackOf<real, V>::type T;
+    T q;
+    real* e = reinterpret_cast<real*>(&q);
+#pragma unroll
+    for (int i = 0; i < V; ++i) e[i] = v[i];
+    *reinterpret_cast<T*>(p) = q;
+}
+
+constexpr uint32_t PIPE_DONE_SLOTS = 8;   // > own-ring depth (<= 4): the consumers are never that far ahead of the publisher, which
+                                          // co-owns the own-ring slots (it arrives on empty_w after publishing the plane)
+
+// V = sites per consumer thread (one 16-byte vector, or half of one for twice the warps per band)
+// The consumers write the new spins back into the own-ring slot and the publisher stores the tile with TMA (no generic
+// global stores in flight, so the release that publishes a plane has nothing to drain).
+// AXZ: the anisotropy axis is (0, 0, a_z): s.a = s_z a_z (bit-identical to the general dot product, 7 instructions fewer per site)
+template <typename real, int V, bool FLIP, bool RECORD, bool HALO, bool AXZ, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) heis_pipe_kernel(const __grid_constant__ PipeArgs<real> A) {
-    constexpr int N = VecOf<real>::N;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const HeisGeom& g = A.g;
     const uint32_t phase = blockIdx.x / A.tiles, tile = blockIdx.x - phase * A.tiles;
@@ -190,13 +233,18 @@ __global__ void __launch_bounds__(MAXT, 1) heis_pipe_kernel(const __grid_constan
     uint64_t* empty_o = full_o + S;
     uint64_t* full_w = empty_o + S;
     uint64_t* empty_w = full_w + SO;
-    double* s_acc = reinterpret_cast<double*>(empty_w + SO);              // 6 doubles
+    uint64_t* done = empty_w + SO;                                        // PIPE_DONE_SLOTS: plane stored by every consumer warp
+    double* s_acc = reinterpret_cast<double*>(done + PIPE_DONE_SLOTS);    // 6 doubles
     volatile uint32_t* abort_flag = reinterpret_cast<volatile uint32_t*>(s_acc + 6);
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t n_phases = gridDim.x / A.tiles;
+    const bool publish = true;     // every phase: the next one waits for it, and the first one may not run too far ahead of the last
+    const bool has_publisher = publish || HALO;
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < S; ++s) { mbar_init(full_o + s, 1u); mbar_init(empty_o + s, n_cw); }
-        for (uint32_t s = 0; s < SO; ++s) { mbar_init(full_w + s, 1u); mbar_init(empty_w + s, n_cw); }
+        for (uint32_t s = 0; s < SO; ++s) { mbar_init(full_w + s, 1u); mbar_init(empty_w + s, 1u); }
+        for (uint32_t s = 0; s < PIPE_DONE_SLOTS; ++s) mbar_init(done + s, n_cw);
         *abort_flag = 0u;
         fence_barrier_init();
         fence_proxy_async();
@@ -205,135 +253,211 @@ __global__ void __launch_bounds__(MAXT, 1) heis_pipe_kernel(const __grid_constan
     __syncthreads();
 
     March<HALO> mz{Lz, phase};
-    const uint32_t n_phases = gridDim.x / A.tiles;
 
     if (warp == n_cw) {
-        // ===================== producer: one thread issues every TMA load of this CTA =====================
-        if (lane == 0) {
-            const uint32_t oc = (uint32_t)(1 - colour);
-            const uint32_t kind = nr == rows ? 0u : 1u;
-            const uint32_t ym = y0 == 0 ? Ly - 1 : y0 - 1, yp = y0 + nr == Ly ? 0u : y0 + nr;
-            const uint32_t bytes_o = 3u * (nr + 2u) * Hx * (uint32_t)sizeof(real), bytes_w = 3u * nr * Hx * (uint32_t)sizeof(real);
-            const uint32_t tm = tile == 0 ? A.tiles - 1 : tile - 1, tp = tile + 1 == A.tiles ? 0u : tile + 1;
-            const unsigned long long* dep = phase > 0 ? A.prog + (size_t)(phase - 1) * A.tiles : nullptr;
-            bool ok = true;
-            auto load_other = [&](uint32_t q) {
-                const uint32_t slot = q % S, use = q / S;
-                if (use > 0 && !wait_bar(empty_o + slot, (use - 1u) & 1u, abort_flag, A.error, PIPE_ERR_EMPTY)) { ok = false; return; }
-                const int pl = mz.plane_of(q);
-                uint32_t array = oc, zc = (uint32_t)pl;
-                if (HALO && (pl < 0 || pl >= (int)Lz)) {
+        // ===================== producer warp: lane 0 waits (ring slots, phase dependencies), the lanes issue the TMA loads =====
+        // (one thread issuing the 12 loads of a plane one after the other took longer than the consumers need per plane)
+        const uint32_t oc = (uint32_t)(1 - colour);
+        const uint32_t kind = nr == rows ? 0u : 1u;
+        const uint32_t ym = y0 == 0 ? Ly - 1 : y0 - 1, yp = y0 + nr == Ly ? 0u : y0 + nr;
+        const uint32_t bytes_o = 3u * (nr + 2u) * Hx * (uint32_t)sizeof(real);
+        const uint32_t tm = tile == 0 ? A.tiles - 1 : tile - 1, tp = tile + 1 == A.tiles ? 0u : tile + 1;
+        const unsigned long long* dep = phase > 0 ? A.prog + (size_t)(phase - 1) * A.tiles : nullptr;
+        // lane l < 9 loads part l % 3 (halo row below, band rows, halo row above) of component l / 3 of an `other` plane;
+        // lane l < 3 loads component l of an own plane
+        const uint32_t my_c = lane / 3u, my_part = lane - my_c * 3u;
+        const uint32_t my_y = my_part == 0 ? ym : (my_part == 1 ? y0 : yp);
+        const uint32_t my_row = my_part == 0 ? 0u : (my_part == 1 ? 1u : 1u + nr);
+        const uint32_t my_kind = my_part == 1 ? kind : 2u;
+        bool ok = true;
+        RingPos po;              // next `other` slot to fill; parity = of the fill being made
+        unsigned long long seen[3] = {0, 0, 0};   // lane 0: last progress values read (monotone counters)
+        uint32_t q_next = 0, z_next = (phase + Lz - 1) % Lz;     // non-slab: plane of entry q_next (advances with wrap)
+        auto load_other = [&]() {
+            const uint32_t q = q_next++;
+            const uint32_t slot = po.slot, parity = po.parity;
+            po.advance(S);
+            int pl;
+            if (HALO) pl = mz.plane_of(q);
+            else { pl = (int)z_next; z_next = z_next + 1 == Lz ? 0u : z_next + 1; }
+            uint32_t array = oc, zc = (uint32_t)pl;
+            const bool is_halo = HALO && (pl < 0 || pl >= (int)Lz);
+            if (is_halo) { array = 2u + oc * 2u + (pl < 0 ? 0u : 1u); zc = 0u; }
+            uint32_t good = 1u, fenced = 0u;
+            if (lane == 0) {
+                if (q >= S && !wait_bar(empty_o + slot, parity ^ 1u, abort_flag, A.error, PIPE_ERR_EMPTY)) good = 0u;
+                if (good && is_halo) {
                     // a neighbour's boundary plane: wait until all its CTAs have stored it.  Other colour = phase - 1's
                     // output of THIS step for colour 1, the previous step's colour 1 for colour 0.
-                    const uint32_t hi = pl < 0 ? 0u : 1u;
                     const unsigned long long target = A.flag_base + (colour == 1 ? (unsigned long long)A.tiles : 0ull);
-                    if (!wait_counter<true>(A.flags + hi * 2u + oc, target, abort_flag, A.error, PIPE_ERR_PEER)) { ok = false; return; }
-                    array = 2u + oc * 2u + hi; zc = 0u;
-                    fence_proxy_async();
-                } else if (phase > 0) {
+                    unsigned long long seen_peer = 0;
+                    if (!wait_counter<true>(A.flags + (pl < 0 ? 0u : 2u) + oc, target, seen_peer, abort_flag, A.error, PIPE_ERR_PEER)) good = 0u;
+                    fenced = 1u;
+                } else if (good && phase > 0) {
                     // position of this plane in the previous phase's march (it starts at plane phase - 1; slabs at 0)
                     const uint32_t first = HALO ? 0u : (phase - 1u) % Lz;
                     const uint32_t j = zc >= first ? zc - first : zc + Lz - first;
-                    const unsigned long long target = A.base + (unsigned long long)(j + 1u) * n_cw;
-                    if (!wait_counter<false>(dep + tm, target, abort_flag, A.error, PIPE_ERR_GATE) ||
-                        !wait_counter<false>(dep + tile, target, abort_flag, A.error, PIPE_ERR_GATE) ||
-                        !wait_counter<false>(dep + tp, target, abort_flag, A.error, PIPE_ERR_GATE)) { ok = false; return; }
-                    fence_proxy_async();
+                    const unsigned long long target = A.base + (unsigned long long)(j + 1u);
+                    // progress is published in groups of planes: most of the time the last values seen already cover the target
+                    if (seen[0] < target || seen[1] < target || seen[2] < target) {
+                        if (!wait_counter<false>(dep + tm, target, seen[0], abort_flag, A.error, PIPE_ERR_GATE) ||
+                            !wait_counter<false>(dep + tile, target, seen[1], abort_flag, A.error, PIPE_ERR_GATE) ||
+                            !wait_counter<false>(dep + tp, target, seen[2], abort_flag, A.error, PIPE_ERR_GATE)) good = 0u;
+                        fenced = 1u;
+                    }
                 }
-                mbar_expect_tx(full_o + slot, bytes_o);
-                real* dst = ring_o + (size_t)slot * stage_o;
-                const CUtensorMap* m = A.maps + (size_t)array * 9;
-#pragma unroll
-                for (uint32_t c = 0; c < 3; ++c) {
-                    tma_load_3d(dst + (c * orow) * Hx, m + c * 3 + 2, full_o + slot, 0u, ym, zc);
-                    tma_load_3d(dst + (c * orow + 1u) * Hx, m + c * 3 + kind, full_o + slot, 0u, y0, zc);
-                    tma_load_3d(dst + (c * orow + 1u + nr) * Hx, m + c * 3 + 2, full_o + slot, 0u, yp, zc);
+                if (good) mbar_expect_tx(full_o + slot, bytes_o);
+            }
+            const uint32_t both = __shfl_sync(0xffffffffu, good | (fenced << 1), 0);
+            if (!(both & 1u)) { ok = false; return; }
+            if (lane < 9) {
+                if (both & 2u) fence_proxy_async();   // data written through the generic proxy by other SMs, read by TMA
+                real* dst = ring_o + (size_t)slot * stage_o + (my_c * orow + my_row) * Hx;
+                tma_load_3d(dst, A.maps + (size_t)array * 9 + my_c * 3 + my_kind, full_o + slot, 0u, my_y, zc);
+            }
+        };
+        // sequence entries in the order the consumers need them: q <= qbase(i) + 2 before step i
+        for (uint32_t i = 0; ok && i < Lz; ++i) {
+            const uint32_t q_need = mz.qbase(i) + 2u;
+            while (ok && q_next <= q_need) load_other();
+        }
+    } else if (warp == n_cw + 2) {
+        // ===================== own-ring producer warp (independent of the other ring: neither holds the other up) =========
+        const uint32_t kind = nr == rows ? 0u : 1u;
+        const uint32_t bytes_w = 3u * nr * Hx * (uint32_t)sizeof(real);
+        // the first phase may lead the last one by at most `lead` planes: everything in between stays in L2
+        const unsigned long long* const tail = A.prog + (size_t)(n_phases - 1) * A.tiles + tile;
+        unsigned long long seen_tail = 0;
+        RingPos pw;
+        for (uint32_t i = 0; i < Lz; ++i) {
+            const uint32_t slot = pw.slot, parity = pw.parity;
+            pw.advance(SO);
+            uint32_t good = 1u;
+            if (lane == 0) {
+                if (phase == 0 && i >= A.lead && seen_tail < A.base + (unsigned long long)(i - A.lead) + 1ull &&
+                    !wait_counter<false>(tail, A.base + (unsigned long long)(i - A.lead) + 1ull, seen_tail, abort_flag, A.error, PIPE_ERR_GATE)) good = 0u;
+                if (good && i >= SO && !wait_bar(empty_w + slot, parity ^ 1u, abort_flag, A.error, PIPE_ERR_EMPTY)) good = 0u;
+                if (good) mbar_expect_tx(full_w + slot, bytes_w);
+            }
+            good = __shfl_sync(0xffffffffu, good, 0);
+            if (!good) break;
+            if (lane < 3) {
+                real* dst = ring_w + (size_t)slot * stage_w + (lane * rows) * Hx;
+                tma_load_3d(dst, A.maps + (size_t)colour * 9 + lane * 3 + kind, full_w + slot, 0u, y0, mz.z_of(i));
+            }
+        }
+    } else if (warp == n_cw + 1) {
+        // ===================== publisher: makes finished planes visible to the next phase / the neighbour slabs ==========
+        // (keeps the gpu-scope fence off the consumers' critical path; the consumers' stores are ordered before it by
+        // their arrive on the `done` barrier)
+        if (lane == 0 && has_publisher) {
+            unsigned long long* const my_prog = A.prog + (size_t)phase * A.tiles + tile;
+            RingPos pd, pown;
+            uint32_t since_pub = 0;
+            const uint32_t kind = nr == rows ? 0u : 1u;
+            auto signal_peers = [&](uint32_t z) {
+                if (z == 0 || z + 1 == Lz) {
+                    __threadfence_system();
+                    // plane 0 feeds the lower neighbour's UPPER halo: its "from upper" words [2 + colour]; plane Lz-1 the upper
+                    // neighbour's "from lower" words [colour]
+                    if (z == 0) atomicAdd_system(A.peer_flags[0] + 2 + colour, 1ull);
+                    if (z + 1 == Lz) atomicAdd_system(A.peer_flags[1] + colour, 1ull);
                 }
             };
-            auto load_own = [&](uint32_t i) {
-                const uint32_t slot = i % SO, use = i / SO;
-                if (use > 0 && !wait_bar(empty_w + slot, (use - 1u) & 1u, abort_flag, A.error, PIPE_ERR_EMPTY)) { ok = false; return; }
-                mbar_expect_tx(full_w + slot, bytes_w);
-                real* dst = ring_w + (size_t)slot * stage_w;
+            for (uint32_t i = 0; i < Lz; ++i) {
+                if (!wait_bar(done + pd.slot, pd.parity, abort_flag, A.error, PIPE_ERR_FULL)) break;
+                pd.advance(PIPE_DONE_SLOTS);
+                // plane i sits updated in its own-ring slot: store it; then retire plane i - 1 (slot readable again once the
+                // store has read it, progress published once its writes are complete)
+                const real* src = ring_w + (size_t)pown.slot * stage_w;
                 const CUtensorMap* m = A.maps + (size_t)colour * 9;
                 const uint32_t z = mz.z_of(i);
 #pragma unroll
-                for (uint32_t c = 0; c < 3; ++c) tma_load_3d(dst + (c * rows) * Hx, m + c * 3 + kind, full_w + slot, 0u, y0, z);
-            };
-            // sequence entries in the order the consumers need them: q <= qbase(i) + 2 and own(i) before step i
-            uint32_t q_next = 0;
-            for (uint32_t i = 0; ok && i < Lz; ++i) {
-                const uint32_t q_need = mz.qbase(i) + 2u;
-                while (ok && q_next <= q_need) load_other(q_next++);
-                if (ok) load_own(i);
+                for (uint32_t c = 0; c < 3; ++c) tma_store_3d(m + c * 3 + kind, src + (c * rows) * Hx, 0u, y0, z);
+                tma_store_commit();
+                tma_store_wait_read<0>();               // the store has read the slot: the producer may refill it
+                mbar_arrive(empty_w + pown.slot);
+                pown.advance(SO);
+                if (i > 0 && ++since_pub == A.pub_every) {   // planes < i are complete once at most this store is pending
+                    since_pub = 0;
+                    tma_store_wait<1>();
+                    fence_proxy_async();
+                    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(my_prog), "l"(A.base + (unsigned long long)i) : "memory");
+                }
+                if (HALO) signal_peers(z);
+            }
+            {
+                tma_store_wait<0>();
+                fence_proxy_async();
+                asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(my_prog), "l"(A.base + (unsigned long long)Lz) : "memory");
             }
         }
     } else {
-        // ===================== consumers: one thread per 16-byte vector of the band =====================
-        const uint32_t r = threadIdx.x / g.Gx, gx = threadIdx.x - r * g.Gx;
+        // ===================== consumers: one thread per V sites of the band =====================
+        const uint32_t Tx = Hx / V;                                   // threads per row
+        const uint32_t r = threadIdx.x / Tx, gx = threadIdx.x - r * Tx;
         const bool active = r < nr;
         const uint32_t y = y0 + (active ? r : 0u);
-        const uint32_t plane = Ly * Hx;
-        const uint32_t el = y * Hx + gx * N;                    // offset inside a plane
-        const uint32_t so_row = ((active ? r : 0u) + 1u) * Hx + gx * N;   // my row inside a component block of an `other` stage
-        const uint32_t sw_row = (active ? r : 0u) * Hx + gx * N;
-        const uint32_t cx_right = (gx + 1 == g.Gx) ? 0u : (gx + 1) * N, cx_left = (gx == 0 ? g.Gx : gx) * N - 1;
-        real* const own0 = colour ? A.arr[1][0] : A.arr[0][0];
-        real* const own1 = colour ? A.arr[1][1] : A.arr[0][1];
-        real* const own2 = colour ? A.arr[1][2] : A.arr[0][2];
-        unsigned long long* const my_prog = A.prog + (size_t)phase * A.tiles + tile;
-        const bool publish = phase + 1 < n_phases;
+        const uint32_t el = y * Hx + gx * V;                          // offset inside a plane
+        const uint32_t so_row = ((active ? r : 0u) + 1u) * Hx + gx * V;   // my row inside a component block of an `other` stage
+        const uint32_t sw_row = (active ? r : 0u) * Hx + gx * V;
+        const uint32_t cx_right = (gx + 1 == Tx) ? 0u : (gx + 1) * V, cx_left = (gx == 0 ? Tx : gx) * V - 1;
         const bool energy = colour == 1;
         real facc[5] = {0, 0, 0, 0, 0};
         int accepted = 0;
         bool ok = true;
-        uint32_t q_waited = 0;                                  // `other` entries < q_waited have landed
+        RingPos p_lo, p_wait, p_own, p_done;    // q = qbase(i); next `other` entry to wait for; own ring; done ring
+        uint32_t q_waited = 0;                  // `other` entries < q_waited have landed
         for (uint32_t i = 0; i < Lz; ++i) {
             const uint32_t qb = mz.qbase(i);
-            for (; q_waited <= qb + 2u; ++q_waited)
-                ok = ok && wait_bar(full_o + q_waited % S, (q_waited / S) & 1u, abort_flag, A.error, PIPE_ERR_FULL);
-            const uint32_t slot_w = i % SO;
-            ok = ok && wait_bar(full_w + slot_w, (i / SO) & 1u, abort_flag, A.error, PIPE_ERR_FULL);
+            for (; q_waited <= qb + 2u; ++q_waited) {
+                ok = ok && wait_bar(full_o + p_wait.slot, p_wait.parity, abort_flag, A.error, PIPE_ERR_FULL);
+                p_wait.advance(S);
+            }
+            ok = ok && wait_bar(full_w + p_own.slot, p_own.parity, abort_flag, A.error, PIPE_ERR_FULL);
             if (!__all_sync(0xffffffffu, ok)) break;
             const uint32_t z = mz.z_of(i);
+            const uint32_t slot_lo = p_lo.slot, slot_n0 = slot_lo + 1 == S ? 0u : slot_lo + 1, slot_hi = slot_n0 + 1 == S ? 0u : slot_n0 + 1;
             if (active) {
                 const uint32_t zg = z + g.z_offset;
                 const uint32_t rp = (y + zg + (uint32_t)colour) & 1u;
-                const real* pl = ring_o + (size_t)(qb % S) * stage_o + so_row;
-                const real* pn = ring_o + (size_t)((qb + 1u) % S) * stage_o + so_row;
-                const real* ph = ring_o + (size_t)((qb + 2u) % S) * stage_o + so_row;
-                const real* pc = ring_o + (size_t)((qb + 1u) % S) * stage_o + (so_row - gx * N) + (rp ? cx_right : cx_left);
-                const real* pw = ring_w + (size_t)slot_w * stage_w + sw_row;
-                real s[3][N], nsum[3][N];
+                const real* pl = ring_o + slot_lo * stage_o + so_row;
+                const real* pn = ring_o + slot_n0 * stage_o + so_row;
+                const real* ph = ring_o + slot_hi * stage_o + so_row;
+                const real* pc = ring_o + slot_n0 * stage_o + (so_row - gx * V) + (rp ? cx_right : cx_left);
+                const real* pw = ring_w + p_own.slot * stage_w + sw_row;
+                real s[3][V], nsum[3][V];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    real n0[N], a[N], b[N], lo[N], hi[N];
+                    real n0[V], a[V], b[V], lo[V], hi[V];
                     const uint32_t co = (uint32_t)c * orow * Hx;
-                    vec_load(pw + (uint32_t)c * rows * Hx, s[c]);
-                    vec_load(pn + co, n0);
-                    vec_load(pn + co - Hx, a);
-                    vec_load(pn + co + Hx, b);
+                    pack_load<real, V>(pw + (uint32_t)c * rows * Hx, s[c]);
+                    pack_load<real, V>(pn + co, n0);
+                    pack_load<real, V>(pn + co - Hx, a);
+                    pack_load<real, V>(pn + co + Hx, b);
                     const real carry = pc[co];
-                    vec_load(pl + co, lo);
-                    vec_load(ph + co, hi);
+                    pack_load<real, V>(pl + co, lo);
+                    pack_load<real, V>(ph + co, hi);
                     // same association order as heis_march (heis.cuh): bit-identical neighbour sums
 #pragma unroll
-                    for (int e = 0; e < N; ++e) nsum[c][e] = n0[e] + (a[e] + b[e]);
-                    if (rp) {
+                    for (int e = 0; e < V; ++e) nsum[c][e] = n0[e] + (a[e] + b[e]);
+                    if (rp) {   // warp-uniform (a warp lies inside one row); the empty asm keeps the arms from being if-converted into selects
+                        asm volatile("");
 #pragma unroll
-                        for (int e = 0; e < N; ++e) nsum[c][e] += e + 1 < N ? n0[(e + 1) % N] : carry;
+                        for (int e = 0; e < V; ++e) nsum[c][e] += e + 1 < V ? n0[(e + 1) % V] : carry;
                     } else {
+                        asm volatile("");
 #pragma unroll
-                        for (int e = 0; e < N; ++e) nsum[c][e] += e > 0 ? n0[(e + N - 1) % N] : carry;
+                        for (int e = 0; e < V; ++e) nsum[c][e] += e > 0 ? n0[(e + V - 1) % V] : carry;
                     }
 #pragma unroll
-                    for (int e = 0; e < N; ++e) nsum[c][e] += lo[e] + hi[e];
+                    for (int e = 0; e < V; ++e) nsum[c][e] += lo[e] + hi[e];
                 }
-                HeisRand<real> rnd[N];
-                const uint64_t site0 = (uint64_t)(zg * Ly + y) * g.Lx + 2u * (gx * N) + rp;  // element e: site0 + 2e
+                HeisRand<real> rnd[V];
+                const uint64_t site0 = (uint64_t)(zg * Ly + y) * g.Lx + 2u * (gx * V) + rp;  // element e: site0 + 2e
                 if (sizeof(real) == 4) {
 #pragma unroll
-                    for (int e = 0; e < N; e += 2) {
+                    for (int e = 0; e < V; e += 2) {   // bit 1 of site0 is clear: elements e, e + 1 share a Philox call
                         uint32_t rr[4];
                         philox_at(site0 + 2u * e, A.sweep, 0u, A.pk, rr);
                         reinterpret_cast<HeisRand<float>&>(rnd[e]) = heis_rand_words(rr[0], rr[1]);
@@ -341,52 +465,47 @@ __global__ void __launch_bounds__(MAXT, 1) heis_pipe_kernel(const __grid_constan
                     }
                 } else {
 #pragma unroll
-                    for (int e = 0; e < N; ++e) heis_rand(site0 + 2u * e, A.sweep, A.pk, rnd[e]);
+                    for (int e = 0; e < V; ++e) heis_rand(site0 + 2u * e, A.sweep, A.pk, rnd[e]);
                 }
 #pragma unroll
-                for (int e = 0; e < N; ++e) {
-                    const bool acc = heis_attempt<real, FLIP>(s[0][e], s[1][e], s[2][e], A.p.J * nsum[0][e] - A.p.h[0],
+                for (int e = 0; e < V; ++e) {
+                    const bool acc = heis_attempt<real, FLIP, AXZ>(s[0][e], s[1][e], s[2][e], A.p.J * nsum[0][e] - A.p.h[0],
                                                               A.p.J * nsum[1][e] - A.p.h[1], A.p.J * nsum[2][e] - A.p.h[2], A.p, rnd[e]);
                     accepted += acc ? 1 : 0;
                     if (RECORD) {
                         if (energy) facc[0] -= A.p.J * (s[0][e] * nsum[0][e] + s[1][e] * nsum[1][e] + s[2][e] * nsum[2][e]);
                         facc[1] += s[0][e]; facc[2] += s[1][e]; facc[3] += s[2][e];
-                        const real d1 = s[0][e] * A.p.a[0] + s[1][e] * A.p.a[1] + s[2][e] * A.p.a[2];
+                        const real d1 = AXZ ? s[2][e] * A.p.a[2] : s[0][e] * A.p.a[0] + s[1][e] * A.p.a[1] + s[2][e] * A.p.a[2];
                         facc[4] += d1 * d1;
                     }
                 }
-                const uint32_t e0 = z * plane + el;
-                vec_store(own0 + e0, s[0]); vec_store(own1 + e0, s[1]); vec_store(own2 + e0, s[2]);
+                real* pws = ring_w + p_own.slot * stage_w + sw_row;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) pack_store<real, V>(pws + (uint32_t)c * rows * Hx, s[c]);
+                fence_proxy_async_smem();     // my shared-memory writes before the publisher's TMA store reads them
                 if (HALO) {
                     if (z == 0) {
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) vec_store(A.peer[colour][0][c] + el, s[c]);
+                        for (int c = 0; c < 3; ++c) pack_store<real, V>(A.peer[colour][0][c] + el, s[c]);
                     }
                     if (z + 1 == Lz) {
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) vec_store(A.peer[colour][1][c] + el, s[c]);
+                        for (int c = 0; c < 3; ++c) pack_store<real, V>(A.peer[colour][1][c] + el, s[c]);
                     }
                 }
             }
             __syncwarp();
+            // the `other` entries the next step no longer needs, my own-ring slot, and "this warp has stored plane i"
+            const uint32_t n_rel = i + 1 < Lz ? mz.qbase(i + 1) - qb : 1u;
+            for (uint32_t k = 0; k < n_rel; ++k) {
+                if (lane == 0) mbar_arrive(empty_o + p_lo.slot);
+                p_lo.advance(S);
+            }
             if (lane == 0) {
-                // the `other` entries the next step no longer needs, and my own-ring slot
-                const uint32_t q_rel_end = i + 1 < Lz ? mz.qbase(i + 1) : qb + 1u;
-                for (uint32_t q = qb; q < q_rel_end; ++q) mbar_arrive(empty_o + q % S);
-                mbar_arrive(empty_w + slot_w);
-                if (publish) { __threadfence(); atomicAdd(my_prog, 1ull); }
+                if (has_publisher) mbar_arrive(done + p_done.slot);
             }
-            if (HALO && (z == 0 || z + 1 == Lz)) {
-                // every consumer warp has stored its part of a boundary plane into the neighbour's halo: one signal per CTA
-                asm volatile("bar.sync 1, %0;" ::"r"(n_cw * 32u) : "memory");
-                if (threadIdx.x == 0) {
-                    __threadfence_system();
-                    // plane 0 feeds the lower neighbour's UPPER halo: its "from upper" words [2 + colour]; plane Lz-1 the upper
-                    // neighbour's "from lower" words [colour]
-                    if (z == 0) atomicAdd_system(A.peer_flags[0] + 2 + colour, 1ull);
-                    if (z + 1 == Lz) atomicAdd_system(A.peer_flags[1] + colour, 1ull);
-                }
-            }
+            p_own.advance(SO);
+            p_done.advance(PIPE_DONE_SLOTS);
             if (RECORD && (i & 15u) == 15u) heis_flush(facc, s_acc);
         }
         if (RECORD) heis_flush(facc, s_acc);
@@ -421,7 +540,7 @@ EncodeTiledFn encode_tiled_fn() {
 
 struct HeisPipeState {
     HeisPipeDesc d;
-    uint32_t Hx = 0, Gx = 0, tiles = 0, rows = 0, tiles_long = 0, S = 0, SO = 0, n_cw = 0, threads = 0;
+    uint32_t Hx = 0, V = 0, tiles = 0, rows = 0, tiles_long = 0, S = 0, SO = 0, n_cw = 0, threads = 0;
     size_t smem = 0;
     CUtensorMap* d_maps = nullptr;
     unsigned long long* d_prog = nullptr;
@@ -432,18 +551,25 @@ struct HeisPipeState {
 
 namespace {
 
-template <typename real, bool HALO, int MAXT>
+template <typename real, int V, bool HALO, bool AXZ, int MAXT>
 const void* pipe_kernel_ptr(bool flip, bool record) {
-    if (flip) return record ? (const void*)heis_pipe_kernel<real, true, true, HALO, MAXT> : (const void*)heis_pipe_kernel<real, true, false, HALO, MAXT>;
-    return record ? (const void*)heis_pipe_kernel<real, false, true, HALO, MAXT> : (const void*)heis_pipe_kernel<real, false, false, HALO, MAXT>;
+    if (flip) return record ? (const void*)heis_pipe_kernel<real, V, true, true, HALO, AXZ, MAXT> : (const void*)heis_pipe_kernel<real, V, true, false, HALO, AXZ, MAXT>;
+    return record ? (const void*)heis_pipe_kernel<real, V, false, true, HALO, AXZ, MAXT> : (const void*)heis_pipe_kernel<real, V, false, false, HALO, AXZ, MAXT>;
 }
+template <typename real, int V, int MAXT>
+const void* pipe_kernel_v(bool axz, bool flip, bool record, bool halo) {
+    if (axz) return halo ? pipe_kernel_ptr<real, V, true, true, MAXT>(flip, record) : pipe_kernel_ptr<real, V, false, true, MAXT>(flip, record);
+    return halo ? pipe_kernel_ptr<real, V, true, false, MAXT>(flip, record) : pipe_kernel_ptr<real, V, false, false, MAXT>(flip, record);
+}
+// variants: a whole 16-byte vector per thread with up to 576 or 1024 threads, or half a vector (always 1024)
 template <typename real>
-const void* pipe_kernel(bool flip, bool record, bool halo, uint32_t threads) {
-    if (threads <= 512) return halo ? pipe_kernel_ptr<real, true, 512>(flip, record) : pipe_kernel_ptr<real, false, 512>(flip, record);
-    return halo ? pipe_kernel_ptr<real, true, 1024>(flip, record) : pipe_kernel_ptr<real, false, 1024>(flip, record);
+const void* pipe_kernel(uint32_t V, bool axz, bool flip, bool record, bool halo, uint32_t threads) {
+    constexpr int N = VecOf<real>::N;
+    if (V != (uint32_t)N) return pipe_kernel_v<real, N / 2, 1024>(axz, flip, record, halo);
+    return threads <= 576 ? pipe_kernel_v<real, N, 576>(axz, flip, record, halo) : pipe_kernel_v<real, N, 1024>(axz, flip, record, halo);
 }
-const void* pipe_kernel_any(bool f64, bool flip, bool record, bool halo, uint32_t threads) {
-    return f64 ? pipe_kernel<double>(flip, record, halo, threads) : pipe_kernel<float>(flip, record, halo, threads);
+const void* pipe_kernel_any(bool f64, uint32_t V, bool axz, bool flip, bool record, bool halo, uint32_t threads) {
+    return f64 ? pipe_kernel<double>(V, axz, flip, record, halo, threads) : pipe_kernel<float>(V, axz, flip, record, halo, threads);
 }
 
 }  // namespace
@@ -466,7 +592,7 @@ HeisPipeState* heis_pipe_create(const HeisPipeDesc& d, std::string& why) {
     if (!encode) { why = "cuTensorMapEncodeTiled is not available from this driver"; return nullptr; }
     HeisPipeState* st = new HeisPipeState();
     st->d = d;
-    st->Hx = Hx; st->Gx = Hx / N;
+    st->Hx = Hx;
     // bands: one CTA per SM, half of them per colour
     uint32_t tiles = d.tiles ? d.tiles : (uint32_t)(sms / 2);
     tiles = std::max(1u, std::min(tiles, d.Ly));
@@ -475,21 +601,29 @@ HeisPipeState* heis_pipe_create(const HeisPipeDesc& d, std::string& why) {
     tiles = (d.Ly + rows - 1) / rows;                       // no empty bands
     st->tiles = tiles; st->rows = rows;
     st->tiles_long = d.Ly - tiles * (rows - 1);             // bands of `rows` rows; the others have rows - 1
-    const uint32_t cthreads = (rows * st->Gx + 31u) / 32u * 32u;
-    st->n_cw = cthreads / 32; st->threads = cthreads + 32;
+    // sites per consumer thread: half a 16-byte vector (twice the warps to hide the Philox / MUFU chains) when the band
+    // then still fits one CTA, else a whole vector
+    auto threads_for = [&](uint32_t V) { return (rows * (Hx / V) + 31u) / 32u * 32u + 96u; };   // + the two producer warps and the publisher warp
+    uint32_t V = d.vec ? d.vec : N / 2;
+    if (V != N && V != N / 2) { why = "sites per thread must be a whole or half 16-byte vector"; delete st; return nullptr; }
+    if (!d.vec && threads_for(V) > 1024) V = N;
+    st->V = V;
+    st->threads = threads_for(V);
+    st->n_cw = st->threads / 32 - 3;
     if (st->threads > 1024) { why = "band needs more than 1024 threads"; delete st; return nullptr; }
     const size_t stage_o = (size_t)3 * (rows + 2) * Hx * sz, stage_w = (size_t)3 * rows * Hx * sz;
-    const uint32_t choices[][2] = {{6, 3}, {5, 3}, {5, 2}, {4, 2}, {4, 1}};
-    auto smem_for = [&](uint32_t S, uint32_t SO) { return S * stage_o + SO * stage_w + (size_t)(2 * S + 2 * SO) * 8 + 6 * 8 + 16; };
-    if (d.stages_other >= 4 && d.stages_own >= 1) { st->S = d.stages_other; st->SO = d.stages_own; }
+    // ring depths: an own plane holds its slot from the load until the TMA store has read the updated tile
+    const uint32_t choices[][2] = {{6, 3}, {5, 3}, {4, 3}, {4, 2}, {4, 1}};   // measured on 512^3 fp32: 0.862 / 0.878 ms per step for the first two
+    auto smem_for = [&](uint32_t S, uint32_t SO) { return S * stage_o + SO * stage_w + (size_t)(2 * S + 2 * SO + PIPE_DONE_SLOTS) * 8 + 6 * 8 + 16; };
+    if (d.stages_other >= 4 && d.stages_own >= 1) { st->S = d.stages_other; st->SO = std::min(4u, d.stages_own); }
     else
         for (auto& c : choices)
             if (smem_for(c[0], c[1]) <= (size_t)smem_max) { st->S = c[0]; st->SO = c[1]; break; }
     if (st->S == 0 || smem_for(st->S, st->SO) > (size_t)smem_max) { why = "band does not fit in shared memory"; delete st; return nullptr; }
     st->smem = smem_for(st->S, st->SO);
     // every variant must be able to hold one CTA per SM with this configuration, and the grid must be co-resident
-    for (int v = 0; v < 8; ++v) {
-        const void* k = pipe_kernel_any(d.f64, v & 1, v & 2, v & 4, st->threads);
+    for (int v = 0; v < 16; ++v) {
+        const void* k = pipe_kernel_any(d.f64, st->V, v & 8, v & 1, v & 2, v & 4, st->threads);
         int per_sm = 0;
         if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem) != cudaSuccess ||
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, (int)st->threads, st->smem) != cudaSuccess || per_sm < 1 ||
@@ -533,8 +667,8 @@ HeisPipeState* heis_pipe_create(const HeisPipeDesc& d, std::string& why) {
     cudaMemset(st->d_prog, 0, (size_t)2 * tiles * 8);
     cudaMemset(st->d_error, 0, 4);
     char buf[256];
-    snprintf(buf, sizeof buf, "heis_pipe: %u bands x 2 colours, %u rows/band, %u threads, other ring %u, own ring %u, %zu B smem%s",
-             tiles, rows, st->threads, st->S, st->SO, st->smem, d.slab ? ", slab" : "");
+    snprintf(buf, sizeof buf, "heis_pipe: %u bands x 2 colours, %u rows/band, %u sites/thread, %u threads, other ring %u, own ring %u, %zu B smem%s",
+             tiles, rows, st->V, st->threads, st->S, st->SO, st->smem, d.slab ? ", slab" : "");
     st->text = buf;
     return st;
 }
@@ -546,10 +680,11 @@ void heis_pipe_destroy(HeisPipeState* st) {
 }
 
 const char* heis_pipe_describe(const HeisPipeState* st) { return st ? st->text.c_str() : ""; }
+uint32_t heis_pipe_tiles(const HeisPipeState* st) { return st ? st->tiles : 0u; }
 
 template <typename real>
 int heis_pipe_step(HeisPipeState* st, const HeisParams<real>& p, bool flip, bool record, uint64_t sweep, const PhiloxKey& pk,
-                   double* obs_row, cudaStream_t stream, std::string& err) {
+                   double* obs_row, uint64_t slab_steps, cudaStream_t stream, std::string& err) {
     const HeisPipeDesc& d = st->d;
     PipeArgs<real> A;
     memset(&A, 0, sizeof A);
@@ -560,16 +695,21 @@ int heis_pipe_step(HeisPipeState* st, const HeisParams<real>& p, bool flip, bool
             A.peer[col][1][c] = (real*)d.peer[col][1][c];
         }
     A.maps = st->d_maps;
-    A.g.Hx = st->Hx; A.g.Gx = st->Gx; A.g.Ly = d.Ly; A.g.Lz = d.Lz; A.g.z_offset = d.z_offset; A.g.Lx = d.Lx;
+    A.g.Hx = st->Hx; A.g.Gx = st->Hx / st->V; A.g.Ly = d.Ly; A.g.Lz = d.Lz; A.g.z_offset = d.z_offset; A.g.Lx = d.Lx;
     A.tiles = st->tiles; A.rows = st->rows; A.tiles_long = st->tiles_long; A.S = st->S; A.SO = st->SO; A.n_cw = st->n_cw;
+    A.pub_every = std::max(1u, d.pub_every ? d.pub_every : 4u);
+    // smaller leads than 2 pub_every + 2 can deadlock (see the publisher); 32 planes of 512^2 fp32 spins are ~100 MB, most of which
+    // is never live at once (measured: pub 4 / lead 32 0.882 ms, lead 24 0.889, pub 2 / lead 16 0.934)
+    A.lead = std::max(2u * A.pub_every + 2u, d.lead ? d.lead : 8u * A.pub_every);
     A.prog = st->d_prog;
-    A.base = st->launches * (unsigned long long)d.Lz * st->n_cw;
+    A.base = st->launches * (unsigned long long)d.Lz;
     A.flags = d.flags;
     A.peer_flags[0] = d.peer_flags[0]; A.peer_flags[1] = d.peer_flags[1];
-    A.flag_base = st->launches * (unsigned long long)st->tiles;
+    A.flag_base = slab_steps * (unsigned long long)st->tiles;
     A.error = st->d_error;
     A.p = p; A.sweep = sweep; A.pk = pk; A.obs = obs_row;
-    const void* k = pipe_kernel<real>(flip, record, d.slab, st->threads);
+    const bool axz = p.a[0] == (real)0 && p.a[1] == (real)0;
+    const void* k = pipe_kernel<real>(st->V, axz, flip, record, d.slab, st->threads);
     void* args[] = {&A};
     const cudaError_t e = cudaLaunchCooperativeKernel(k, dim3(2 * st->tiles), dim3(st->threads), args, st->smem, stream);
     if (e != cudaSuccess) {
@@ -580,8 +720,8 @@ int heis_pipe_step(HeisPipeState* st, const HeisParams<real>& p, bool flip, bool
     st->launches++;
     return 0;
 }
-template int heis_pipe_step<float>(HeisPipeState*, const HeisParams<float>&, bool, bool, uint64_t, const PhiloxKey&, double*, cudaStream_t, std::string&);
-template int heis_pipe_step<double>(HeisPipeState*, const HeisParams<double>&, bool, bool, uint64_t, const PhiloxKey&, double*, cudaStream_t, std::string&);
+template int heis_pipe_step<float>(HeisPipeState*, const HeisParams<float>&, bool, bool, uint64_t, const PhiloxKey&, double*, uint64_t, cudaStream_t, std::string&);
+template int heis_pipe_step<double>(HeisPipeState*, const HeisParams<double>&, bool, bool, uint64_t, const PhiloxKey&, double*, uint64_t, cudaStream_t, std::string&);
 
 int heis_pipe_check(HeisPipeState* st, std::string& err) {
     if (!st) return 0;

@@ -23,7 +23,9 @@ struct HeisPipeDesc {
     unsigned long long* peer_flags[2] = {};    // the neighbours' flag words I add to (lower neighbour: its [1], upper: its [0])
     bool slab = false;
     // tuning (0 = automatic)
-    uint32_t stages_other = 0, stages_own = 0, tiles = 0;
+    uint32_t stages_other = 0, stages_own = 0, tiles = 0, vec = 0;   // vec: sites per consumer thread
+    uint32_t lead = 0;      // planes the first colour may run ahead of the last (>= 2 pub_every + 2; bounds the L2 working set)
+    uint32_t pub_every = 0; // planes per published progress update (one gpu-scope release fence each)
 };
 
 struct HeisPipeState;
@@ -32,11 +34,13 @@ struct HeisPipeState;
 HeisPipeState* heis_pipe_create(const HeisPipeDesc& d, std::string& why_not);
 void heis_pipe_destroy(HeisPipeState*);
 const char* heis_pipe_describe(const HeisPipeState*);
+uint32_t heis_pipe_tiles(const HeisPipeState*);   // bands per colour (= CTAs that signal a boundary plane)
 
-// one Monte Carlo step (both colour passes) on stream `st`; obs_row as heis_stencil_kernel (6 doubles, added to)
+// one Monte Carlo step (both colour passes) on stream `st`; obs_row as heis_stencil_kernel (6 doubles, added to).
+// slab_steps: pipelined steps this slab and its neighbours have done since they were connected (all ranks step together)
 template <typename real>
 int heis_pipe_step(HeisPipeState*, const HeisParams<real>& p, bool flip, bool record, uint64_t sweep, const PhiloxKey& pk,
-                   double* obs_row, cudaStream_t st, std::string& err);
+                   double* obs_row, uint64_t slab_steps, cudaStream_t st, std::string& err);
 // after the stream has been synchronised: != 0 (and a message) when a wait inside the kernel timed out
 int heis_pipe_check(HeisPipeState*, std::string& err);
 

@@ -31,6 +31,7 @@ const char* const FAMILY_NAME[5] = {"ising_msc", "heis_stencil", "ising_general"
 
 constexpr uint64_t OBS_CAP = 4096;  // steps of observables kept on the device per batch
 constexpr int OBS_W = 8;            // 8 x 8-byte slots per step
+constexpr int PIPE_FLAG_WORD = 8;   // words 8..11 of a slab's flag block: boundary-plane counters of the pipelined kernel (heis_pipe.cu)
 
 std::string g_create_error;
 
@@ -86,8 +87,9 @@ struct vegas_gpu {
     int wave_grid = 0;
     // --- phase-pipelined TMA kernel (heis_pipe.cu): the default step of big 3-D sc Heisenberg lattices
     int pipe_enable = -1;                 // tuning key heis_pipe: -1 auto (>= 32 planes), 0 never, 1 whenever the lattice fits
-    uint32_t pipe_stages_other = 0, pipe_stages_own = 0, pipe_tiles = 0;   // tuning keys heis_pipe_stages / _own / _tiles (0 = auto)
+    uint32_t pipe_stages_other = 0, pipe_stages_own = 0, pipe_tiles = 0, pipe_vec = 0, pipe_lead = 0, pipe_pub = 0;   // tuning keys heis_pipe_stages / _own / _tiles / _vec (0 = auto)
     bool pipe_planned = false;
+    uint64_t pipe_slab_steps = 0;         // pipelined steps since the slab was connected (the neighbours' boundary counters are relative to it)
     HeisPipeState* pipe = nullptr;
     std::string pipe_why;
     bool fused_ready = false;
@@ -101,6 +103,7 @@ struct vegas_gpu {
     void* peer_halo[2] = {nullptr, nullptr};            // lower / upper neighbour's halo allocation
     unsigned long long* peer_flags[2] = {nullptr, nullptr};
     bool slab = false, connected = false, peer_is_ipc = false;
+    bool peers_remote = false;            // both z-neighbours sweep on other devices (other processes, or other GPUs of this one)
     uint64_t pass_counter = 0;
     // --- general family
     int8_t* g_s8 = nullptr;               // Ising natural order
@@ -932,13 +935,28 @@ bool pipe_plan(vegas_gpu* h) {
     if (h->pipe_planned) return h->pipe != nullptr;
     if (h->family != FAM_HEIS_STENCIL || h->ndim != 3 || h->pipe_enable == 0) return false;
     if (h->pipe_enable < 0 && (h->ld.nz < 32 || h->fused_enable == 1 || h->wave_c > 0 || h->wave_enable == 1 || h->wave_k > 1)) return false;
-    if (h->slab) return false;   // slabs: see pipe_plan_slab (connected, one process per GPU)
+    // a slab runs it once it is connected to neighbours that sweep on OTHER devices: the kernel occupies every SM of its
+    // device and waits for the neighbours' boundary planes inside the launch (slabs sharing a device would deadlock)
+    if (h->slab && !(h->connected && h->peers_remote)) return false;
     h->pipe_planned = true;
     HeisPipeDesc d;
     d.device = h->device; d.f64 = h->md.precision == VEGAS_F64;
     d.Lx = (uint32_t)h->ld.nx; d.Ly = (uint32_t)h->ld.ny; d.Lz = (uint32_t)h->ld.nz; d.z_offset = (uint32_t)h->z_offset;
     for (int col = 0; col < 2; ++col) for (int c = 0; c < 3; ++c) d.arr[col][c] = h->hs[col][c];
-    d.stages_other = h->pipe_stages_other; d.stages_own = h->pipe_stages_own; d.tiles = h->pipe_tiles;
+    if (h->slab) {
+        d.slab = true;
+        for (int col = 0; col < 2; ++col)
+            for (int c = 0; c < 3; ++c) {
+                d.halo[col][0][c] = (char*)h->halo + halo_offset(h, col, 0, c);
+                d.halo[col][1][c] = (char*)h->halo + halo_offset(h, col, 1, c);
+                // my plane 0 goes to the lower neighbour's UPPER halo of my colour, my plane Lz-1 to the upper neighbour's LOWER halo
+                d.peer[col][0][c] = (char*)h->peer_halo[0] + halo_offset(h, col, 1, c);
+                d.peer[col][1][c] = (char*)h->peer_halo[1] + halo_offset(h, col, 0, c);
+            }
+        d.flags = h->flags + PIPE_FLAG_WORD;
+        d.peer_flags[0] = h->peer_flags[0] + PIPE_FLAG_WORD; d.peer_flags[1] = h->peer_flags[1] + PIPE_FLAG_WORD;
+    }
+    d.stages_other = h->pipe_stages_other; d.stages_own = h->pipe_stages_own; d.tiles = h->pipe_tiles; d.vec = h->pipe_vec; d.lead = h->pipe_lead; d.pub_every = h->pipe_pub;
     h->pipe = heis_pipe_create(d, h->pipe_why);
     return h->pipe != nullptr;
 }
@@ -948,9 +966,10 @@ int pipe_step(vegas_gpu* h, double* obs_row, bool record) {
     const bool flip = h->md.proposal == VEGAS_PROPOSE_FLIP;
     h->launches++;
     std::string err;
-    const int rc = h->md.precision == VEGAS_F64 ? heis_pipe_step<double>(h->pipe, heis_params<double>(h), flip, record, h->sweeps, pk, obs_row, h->stream, err)
-                                               : heis_pipe_step<float>(h->pipe, heis_params<float>(h), flip, record, h->sweeps, pk, obs_row, h->stream, err);
+    const int rc = h->md.precision == VEGAS_F64 ? heis_pipe_step<double>(h->pipe, heis_params<double>(h), flip, record, h->sweeps, pk, obs_row, h->pipe_slab_steps, h->stream, err)
+                                               : heis_pipe_step<float>(h->pipe, heis_params<float>(h), flip, record, h->sweeps, pk, obs_row, h->pipe_slab_steps, h->stream, err);
     if (rc) h->err = err;
+    else h->pipe_slab_steps++;
     return rc;
 }
 
@@ -1165,9 +1184,27 @@ double energy_of(const vegas_gpu* h, const Canon& c) {
     }
 }
 
+// Before anything reads the halos of a slab that steps with the pipelined kernel: the neighbours' boundary planes of the
+// last step may still be on their way (the kernel only waits for what it needs itself).  Bounded spin, never hangs.
+__global__ void pipe_halo_wait_kernel(const unsigned long long* flags, unsigned long long target) {
+    if (threadIdx.x < 4) {
+        unsigned long long v;
+        for (uint32_t spins = 0; spins < (1u << 22); ++spins) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory");
+            if (v >= target) break;
+            __nanosleep(256);
+        }
+    }
+    __threadfence_system();
+}
+
 int measure_now(vegas_gpu* h, Canon& out) {
     unsigned long long* row = h->obs + (OBS_CAP + 1) * OBS_W;
     CU(cudaMemsetAsync(row, 0, OBS_W * 8, h->stream));
+    if (h->slab && h->pipe && h->pipe_slab_steps > 0) {
+        pipe_halo_wait_kernel<<<1, 32, 0, h->stream>>>(h->flags + PIPE_FLAG_WORD, h->pipe_slab_steps * (unsigned long long)heis_pipe_tiles(h->pipe));
+        h->launches++;
+    }
     if (h->family == FAM_ISING_MSC || h->family == FAM_HEIS_STENCIL) stencil_colour_pass(h, 2, 1, row);
     else if (h->family == FAM_HEIS_BASIS) { for (int b = 0; b < h->n_colours; ++b) basis_pass_any(h, 2, b, (double*)row); }
     else if (h->csr_input) general_reduce(h, csr_nb(h), (double*)row);
@@ -2071,7 +2108,10 @@ int vegas_gpu_slab_connect(vegas_gpu_t h, const void* lower, const void* upper) 
             return fail(h, VEGAS_ERR_CUDA, "CUDA IPC mapping of the neighbour's halo buffer is not where expected");
     }
     h->peer_is_ipc = true;
+    h->peers_remote = true;     // one process per GPU (SlabBlob::device is the neighbour's ordinal in ITS process: not comparable)
     h->connected = true;
+    h->pipe_slab_steps = 0;
+    if (h->pipe_planned) { heis_pipe_destroy(h->pipe); h->pipe = nullptr; h->pipe_planned = false; }
     preload_slab_kernels(h);
     return push_boundaries(h);
 }
@@ -2095,7 +2135,10 @@ int vegas_gpu_slab_connect_local(vegas_gpu_t h, vegas_gpu_t lower, vegas_gpu_t u
         h->peer_flags[d] = nbr[d]->flags;
     }
     h->peer_is_ipc = false;
+    h->peers_remote = lower->device != h->device && upper->device != h->device;
     h->connected = true;
+    h->pipe_slab_steps = 0;
+    if (h->pipe_planned) { heis_pipe_destroy(h->pipe); h->pipe = nullptr; h->pipe_planned = false; }
     preload_slab_kernels(h);
     return push_boundaries(h);
 }
@@ -2132,6 +2175,9 @@ int vegas_gpu_set_tuning(vegas_gpu_t h, const char* key, long value) {
     else if (k == "heis_pipe_stages") h->pipe_stages_other = (uint32_t)value;
     else if (k == "heis_pipe_own") h->pipe_stages_own = (uint32_t)value;
     else if (k == "heis_pipe_tiles") h->pipe_tiles = (uint32_t)value;
+    else if (k == "heis_pipe_vec") h->pipe_vec = (uint32_t)value;
+    else if (k == "heis_pipe_lead") h->pipe_lead = (uint32_t)value;
+    else if (k == "heis_pipe_pub") h->pipe_pub = (uint32_t)value;
     else if (k == "basis_vec") h->basis_vec = (int)value;
     else if (k == "resident_max") { h->resident_max = (uint32_t)value; h->resident_cols = -2; }
     else return fail(h, VEGAS_ERR_INVALID, "unknown tuning key: " + k);
