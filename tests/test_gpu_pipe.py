@@ -119,3 +119,74 @@ def test_pipe_kernel_is_the_default_for_big_lattices(built):
     g = vg.GpuMetropolis(vg.HEISENBERG, unitcell=vg.SC, size=(24, 64, 32), seed=5)
     assert g.step_kernel in ("heis_wave", "heis_stencil")
     g.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K4p: all colour passes of a periodic bcc / fcc step in one phase-pipelined launch (vegas_rs_b200/csrc/basis_pipe.cu)
+# ---------------------------------------------------------------------------------------------------------------------
+BASIS_CASES = [
+    (vg.FCC, (16, 6, 9), vg.F32, 0, 0, 0),
+    (vg.FCC, (16, 14, 12), vg.F32, 4, 6, 1),        # uneven bands (4 + 4 + 3 + 3 rows), minimal lead
+    (vg.FCC, (8, 9, 8), vg.F64, 9, 0, 2),           # one-row bands, progress published every second plane
+    (vg.FCC, (4, 2, 8), vg.F32, 1, 0, 0),           # a single band: its own y-neighbour
+    (vg.BCC, (8, 7, 10), vg.F32, 0, 0, 0),
+    (vg.BCC, (6, 10, 16), vg.F64, 3, 0, 0),
+    (vg.FCC, (384, 40, 8), vg.F32, 0, 0, 0),        # config[4] rows: two rounds of items per thread
+]
+
+
+@pytest.mark.parametrize("uc,size,precision,tiles,lead,pub", BASIS_CASES)
+@pytest.mark.parametrize("proposal", [vg.PROPOSE_RANDOM, vg.PROPOSE_FLIP], ids=["random", "flip"])
+def test_basis_pipe_identical_to_colour_passes(built, uc, size, precision, tiles, lead, pub, proposal):
+    kw = dict(unitcell=uc, size=size, precision=precision, seed=31, anisotropy=((0.6, 0, 0.8), 0.15), proposal=proposal)
+    ref = vg.GpuMetropolis(vg.HEISENBERG, **kw)
+    ref.set_tuning("basis_pipe", 0)
+    assert ref.step_kernel == "heis_basis"
+    ref.randomize(); ref.set_thermostat(1.4, (0, 0, 1.0), 0.4)
+    e0, m0 = ref.step(3)
+    ref.step(2, observe=False)
+    e1, m1 = ref.step(1)
+    want = ref.download(); acc = ref.attempt_count()
+    ref.close()
+    g = vg.GpuMetropolis(vg.HEISENBERG, **kw)
+    g.set_tuning("basis_pipe", 1)
+    for k, v in (("basis_pipe_tiles", tiles), ("basis_pipe_lead", lead), ("basis_pipe_pub", pub)):
+        if v:
+            g.set_tuning(k, v)
+    assert g.step_kernel == "basis_pipe"
+    g.randomize(); g.set_thermostat(1.4, (0, 0, 1.0), 0.4)
+    e, m = g.step(3)
+    g.step(2, observe=False)
+    e2, m2 = g.step(1)
+    g.synchronize()
+    assert np.array_equal(g.download(), want)
+    n = g.n_sites
+    tol = 1e-12 if precision == vg.F64 else 1e-6
+    assert np.allclose(e, e0, rtol=tol, atol=tol * n) and np.allclose(e2, e1, rtol=tol, atol=tol * n)
+    assert np.allclose(m, m0, rtol=10 * tol, atol=10 * tol * n) and np.allclose(m2, m1, rtol=10 * tol, atol=10 * tol * n)
+    assert g.attempt_count() == acc
+    g.close()
+
+
+def test_basis_pipe_replays_the_reference_rule(built):
+    """fcc, fp64: every decision of the pipelined step against the oracle replay (Hamiltonian::energy of src/energy.rs,
+    accept rule of src/integrator.rs:82-88); the fused E and M equal total_energy / magnetization of the replayed state."""
+    lat = dict(unitcell=vg.FCC, size=(8, 6, 8))
+    kw = dict(exchange=1.0, zeeman=True, anisotropy=((0.6, 0.0, 0.8), 0.25))
+    g = vg.GpuMetropolis(vg.HEISENBERG, precision=vg.F64, seed=12, **kw, **lat)
+    g.set_tuning("basis_pipe", 1)
+    assert g.step_kernel == "basis_pipe"
+    H, _ = oracle_model(ob.HEISENBERG, **kw, **lat)
+    n = g.n_sites
+    g.upload(random_state(ob.HEISENBERG, n, 3))
+    cpu = g.download(); col = g.colours()
+    g.set_thermostat(1.5, (0, 0, 1.0), 0.7)
+    th = H.thermostat(1.5, (0, 0, 1.0), 0.7)
+    for _ in range(3):
+        sweep = g.sweeps
+        e, m = g.step(1)
+        H.replay_heisenberg(th, ob.PROPOSE_RANDOM, False, 12, sweep, col, g.n_colours, cpu)
+        assert np.max(np.abs(g.download() - cpu)) < 1e-12
+        assert abs(e[0] - H.total_energy(th, cpu)) < 1e-12 * n * 10
+        assert np.max(np.abs(m[0] - cpu.sum(axis=0))) < 1e-12 * n
+    g.close()

@@ -21,8 +21,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 # headers a translation unit includes (directly or not); anything not listed depends on every header
 _DEPS = {
-    "heis_pipe.cu": ["heis_pipe.hpp", "heis.cuh", "common.cuh"],
-    "basis_pipe.cu": ["basis_pipe.hpp", "heis_basis.cuh", "heis.cuh", "common.cuh"],
+    "heis_pipe.cu": ["heis_pipe.hpp", "pipe_ptx.cuh", "heis.cuh", "common.cuh"],
+    "basis_pipe.cu": ["basis_pipe.hpp", "pipe_ptx.cuh", "heis_basis.cuh", "heis.cuh", "common.cuh"],
     "vegas_host.cpp": ["vegas_host.hpp"],
 }
 

@@ -31,110 +31,11 @@
 #include <vector>
 
 #include "heis_pipe.hpp"
+#include "pipe_ptx.cuh"
 
 namespace vg {
 
 namespace {
-
-// ---------------------------------------------------------------------------------------
-// PTX wrappers: mbarrier, TMA, fences, scoped loads
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(b)), "r"(parity), "r"(2000u)   // suspend-time hint (ns): sleep in hardware instead of re-polling
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, uint32_t c0, uint32_t c1, uint32_t c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-
-// TMA store of a box from shared memory (bulk async-group completion)
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, uint32_t c0, uint32_t c1, uint32_t c2) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                 ::"l"((uint64_t)map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-template <int N> __device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long global_timer() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-
-constexpr unsigned long long PIPE_TIMEOUT_NS = 4000000000ull;   // a wait that long means a broken dependency: give up, never hang
-
-enum PipeError : unsigned int { PIPE_ERR_FULL = 1, PIPE_ERR_EMPTY = 2, PIPE_ERR_GATE = 3, PIPE_ERR_PEER = 4 };
-
-// Waits for phase `parity` of an mbarrier.  False when the launch is being abandoned (abort flag) or on time-out.
-__device__ __forceinline__ bool wait_bar(uint64_t* b, uint32_t parity, volatile uint32_t* abort_flag, unsigned int* gerr, unsigned int code) {
-    if (mbar_try_wait(b, parity)) return true;
-    const unsigned long long t0 = global_timer();
-    uint32_t n = 0;
-    while (!mbar_try_wait(b, parity)) {
-        if ((++n & 63u) == 0) {
-            if (*abort_flag) return false;
-            if (global_timer() - t0 > PIPE_TIMEOUT_NS) { *abort_flag = 1u; atomicExch(gerr, code); return false; }
-        }
-    }
-    return true;
-}
-
-// Spins until *p >= target (SYS: the word is written by another GPU); `seen` receives the last value read.
-template <bool SYS>
-__device__ __forceinline__ bool wait_counter(const unsigned long long* p, unsigned long long target, unsigned long long& seen,
-                                             volatile uint32_t* abort_flag, unsigned int* gerr, unsigned int code) {
-    seen = SYS ? ld_acquire_sys(p) : ld_acquire_gpu(p);
-    if (seen >= target) return true;
-    const unsigned long long t0 = global_timer();
-    uint32_t n = 0;
-    while ((seen = (SYS ? ld_acquire_sys(p) : ld_acquire_gpu(p))) < target) {
-        __nanosleep(200);     // the helper warps outrank the consumers in the issue arbiter: do not burn their slots
-        if ((++n & 63u) == 0) {
-            if (*abort_flag) return false;
-            if (global_timer() - t0 > PIPE_TIMEOUT_NS) { *abort_flag = 1u; atomicExch(gerr, code); return false; }
-        }
-    }
-    return true;
-}
 
 // ---------------------------------------------------------------------------------------
 // kernel arguments
@@ -160,12 +61,6 @@ struct PipeArgs {
     uint64_t sweep;
     PhiloxKey pk;
     double* obs;
-};
-
-// A position in a ring of `n` mbarrier-guarded slots: slot index and the parity of its current use.
-struct RingPos {
-    uint32_t slot = 0, parity = 0;
-    __device__ __forceinline__ void advance(uint32_t n) { if (++slot == n) { slot = 0; parity ^= 1u; } }
 };
 
 // March bookkeeping shared by the producer and the consumers of a CTA.
@@ -601,12 +496,11 @@ HeisPipeState* heis_pipe_create(const HeisPipeDesc& d, std::string& why) {
     tiles = (d.Ly + rows - 1) / rows;                       // no empty bands
     st->tiles = tiles; st->rows = rows;
     st->tiles_long = d.Ly - tiles * (rows - 1);             // bands of `rows` rows; the others have rows - 1
-    // sites per consumer thread: half a 16-byte vector (twice the warps to hide the Philox / MUFU chains) when the band
-    // then still fits one CTA, else a whole vector
+    // sites per consumer thread: a whole 16-byte vector, or half of one (tuning key: twice the warps, more instructions per site)
     auto threads_for = [&](uint32_t V) { return (rows * (Hx / V) + 31u) / 32u * 32u + 96u; };   // + the two producer warps and the publisher warp
-    uint32_t V = d.vec ? d.vec : N / 2;
+    uint32_t V = d.vec ? d.vec : N;   // measured on 512^3 fp32: whole vectors 0.88 ms per step, half vectors (twice the warps) 1.04
     if (V != N && V != N / 2) { why = "sites per thread must be a whole or half 16-byte vector"; delete st; return nullptr; }
-    if (!d.vec && threads_for(V) > 1024) V = N;
+    if (!d.vec && threads_for(V) > 1024) { why = "band needs more than 1024 threads"; delete st; return nullptr; }
     st->V = V;
     st->threads = threads_for(V);
     st->n_cw = st->threads / 32 - 3;

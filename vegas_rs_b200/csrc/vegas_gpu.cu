@@ -18,6 +18,7 @@
 #include "heis_basis.cuh"
 #include "heis_fused.cuh"
 #include "heis_pipe.hpp"
+#include "basis_pipe.hpp"
 #include "ising_msc.cuh"
 #include "lattice.hpp"
 #include "resident.cuh"
@@ -92,6 +93,11 @@ struct vegas_gpu {
     uint64_t pipe_slab_steps = 0;         // pipelined steps since the slab was connected (the neighbours' boundary counters are relative to it)
     HeisPipeState* pipe = nullptr;
     std::string pipe_why;
+    // --- phase-pipelined bcc / fcc step (basis_pipe.cu): all colour passes in one cooperative launch
+    int bpipe_enable = -1;                // tuning key basis_pipe: -1 auto (>= 32 cell planes, single handle), 0 never, 1 whenever it fits
+    uint32_t bpipe_lead = 0, bpipe_pub = 0, bpipe_tiles = 0;
+    bool bpipe_planned = false;
+    BasisPipeState* bpipe = nullptr;
     bool fused_ready = false;
     FusedGeom fused_geom{};
     size_t fused_smem = 0;
@@ -961,6 +967,32 @@ bool pipe_plan(vegas_gpu* h) {
     return h->pipe != nullptr;
 }
 
+bool bpipe_plan(vegas_gpu* h) {
+    if (h->bpipe_planned) return h->bpipe != nullptr;
+    if (h->family != FAM_HEIS_BASIS || h->slab || h->bpipe_enable == 0) return false;
+    if (h->bpipe_enable < 0 && h->ld.nz < 32) return false;
+    h->bpipe_planned = true;
+    BasisPipeDesc d;
+    d.device = h->device; d.f64 = h->md.precision == VEGAS_F64;
+    d.unitcell = h->ld.unitcell == VEGAS_BCC ? 1 : 2;
+    d.nx = (uint32_t)h->ld.nx; d.ny = (uint32_t)h->ld.ny; d.nz = (uint32_t)h->ld.nz;
+    for (int b = 0; b < 4; ++b) for (int c = 0; c < 3; ++c) d.arr[b][c] = h->hb[b][c];
+    d.tiles = h->bpipe_tiles; d.lead = h->bpipe_lead; d.pub_every = h->bpipe_pub;
+    h->bpipe = basis_pipe_create(d, h->pipe_why);
+    return h->bpipe != nullptr;
+}
+
+int bpipe_step(vegas_gpu* h, double* obs_row, bool record) {
+    const PhiloxKey pk = make_philox_key(h->md.seed);
+    const bool flip = h->md.proposal == VEGAS_PROPOSE_FLIP;
+    h->launches++;
+    std::string err;
+    const int rc = h->md.precision == VEGAS_F64 ? basis_pipe_step<double>(h->bpipe, heis_params<double>(h), flip, record, h->sweeps, pk, obs_row, h->stream, err)
+                                               : basis_pipe_step<float>(h->bpipe, heis_params<float>(h), flip, record, h->sweeps, pk, obs_row, h->stream, err);
+    if (rc) h->err = err;
+    return rc;
+}
+
 int pipe_step(vegas_gpu* h, double* obs_row, bool record) {
     const PhiloxKey pk = make_philox_key(h->md.seed);
     const bool flip = h->md.proposal == VEGAS_PROPOSE_FLIP;
@@ -988,6 +1020,10 @@ int check_async_errors(vegas_gpu* h) {
     if (h->pipe) {
         std::string e;
         if (heis_pipe_check(h->pipe, e)) return fail(h, VEGAS_ERR_CUDA, e);
+    }
+    if (h->bpipe) {
+        std::string e;
+        if (basis_pipe_check(h->bpipe, e)) return fail(h, VEGAS_ERR_CUDA, e);
     }
     return VEGAS_OK;
 }
@@ -1087,7 +1123,9 @@ int resident_steps(vegas_gpu* h, const NB& nb, uint32_t n_steps, bool record) {
 // One Monte Carlo step (= N attempts): every colour once.  obs_row != null records observables.
 void do_step(vegas_gpu* h, void* obs_row, void* scratch_row) {
     const bool rec = obs_row != nullptr;
-    if (h->family == FAM_HEIS_BASIS) {
+    if (h->family == FAM_HEIS_BASIS && bpipe_plan(h)) {
+        bpipe_step(h, (double*)(rec ? obs_row : scratch_row), rec);
+    } else if (h->family == FAM_HEIS_BASIS) {
         for (int b = 0; b < h->n_colours; ++b) basis_pass_any(h, rec ? 1 : 0, b, (double*)(rec ? obs_row : scratch_row));
     } else if (h->family == FAM_HEIS_STENCIL && pipe_plan(h)) {
         pipe_step(h, (double*)(rec ? obs_row : scratch_row), rec);   // a failed launch surfaces through cudaGetLastError / h->err
@@ -1474,6 +1512,7 @@ void vegas_gpu_destroy(vegas_gpu_t h) {
     for (int k = 0; k < WAVE_MAX_STEPS; ++k) cudaFree(h->wave_units[k]);
     cudaFree(h->wave_done); cudaFree(h->wave_error);
     heis_pipe_destroy(h->pipe);
+    basis_pipe_destroy(h->bpipe);
     if (h->stream_b) { cudaStreamSynchronize(h->stream_b); cudaStreamDestroy(h->stream_b); }
     if (h->ev_main) cudaEventDestroy(h->ev_main);
     if (h->ev_bnd) cudaEventDestroy(h->ev_bnd);
@@ -2178,18 +2217,24 @@ int vegas_gpu_set_tuning(vegas_gpu_t h, const char* key, long value) {
     else if (k == "heis_pipe_vec") h->pipe_vec = (uint32_t)value;
     else if (k == "heis_pipe_lead") h->pipe_lead = (uint32_t)value;
     else if (k == "heis_pipe_pub") h->pipe_pub = (uint32_t)value;
+    else if (k == "basis_pipe") h->bpipe_enable = (int)value;
+    else if (k == "basis_pipe_lead") h->bpipe_lead = (uint32_t)value;
+    else if (k == "basis_pipe_pub") h->bpipe_pub = (uint32_t)value;
+    else if (k == "basis_pipe_tiles") h->bpipe_tiles = (uint32_t)value;
     else if (k == "basis_vec") h->basis_vec = (int)value;
     else if (k == "resident_max") { h->resident_max = (uint32_t)value; h->resident_cols = -2; }
     else return fail(h, VEGAS_ERR_INVALID, "unknown tuning key: " + k);
     h->fused_ready = false;  // re-plan at the next step
     h->wave_ready = false;
     if (h->pipe_planned) { cudaStreamSynchronize(h->stream); heis_pipe_destroy(h->pipe); h->pipe = nullptr; h->pipe_planned = false; }
+    if (h->bpipe_planned) { cudaStreamSynchronize(h->stream); basis_pipe_destroy(h->bpipe); h->bpipe = nullptr; h->bpipe_planned = false; }
     return VEGAS_OK;
 }
 
 const char* vegas_gpu_step_kernel(vegas_gpu_t h) {
     if (!h) return "";
     if (h->family == FAM_HEIS_STENCIL && cudaSetDevice(h->device) == cudaSuccess && pipe_plan(h)) return "heis_pipe";
+    if (h->family == FAM_HEIS_BASIS && cudaSetDevice(h->device) == cudaSuccess && bpipe_plan(h)) return "basis_pipe";
     if (h->family == FAM_HEIS_STENCIL && cudaSetDevice(h->device) == cudaSuccess && wave_plan(h)) return "heis_wave";
     if (h->family == FAM_HEIS_STENCIL && cudaSetDevice(h->device) == cudaSuccess && fused_plan(h)) return "heis_fused";
     if (resident_plan(h)) return h->family == FAM_ISING_GEN ? "ising_resident" : "heis_resident";
