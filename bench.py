@@ -45,10 +45,18 @@ WORKLOADS = {
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from the committed `ncu --set full`
 # captures (cold cache): (bytes, source)
 NCU_TRAFFIC = {
-    "ising3d_1024": (134.37e6 + 30.83e6, "profiles/r01o_ising_msc.metrics.txt (one colour pass)"),
-    "heis3d_512": (2.887e9 + 1.562e9, "profiles/r01u_heis_wave.metrics.txt (one step = both colours)"),
-    "heis_fcc_384": (2.829e9 + 0.686e9, "profiles/r01z_heis_basis_vec.metrics.txt (one colour pass)"),
+    "ising3d_1024": {"ising_msc": (134.37e6 + 30.83e6, "profiles/r01o_ising_msc.metrics.txt (one colour pass)")},
+    "heis3d_512": {"heis_pipe": (1.674e9 + 1.555e9, "profiles/r02_heis_pipe.metrics.txt (one step = both colours, one launch)"),
+                   "heis_wave": (2.887e9 + 1.562e9, "profiles/r01u_heis_wave.metrics.txt (one step = both colours)"),
+                   "heis_stencil": (2.42e9, "profiles/r01o_heis_stencil.metrics.txt (one colour pass)")},
+    "heis_fcc_384": {"heis_basis": (2.829e9 + 0.686e9, "profiles/r01z_heis_basis_vec.metrics.txt (one colour pass)"),
+                     "basis_pipe": (2.981e9 + 2.667e9, "profiles/r02_basis_pipe.metrics.txt (one step = four colours, one launch)")},
 }
+# step kernels that do every colour of a step in ONE launch
+ONE_LAUNCH_KERNELS = ("heis_pipe", "basis_pipe", "heis_wave", "heis_fused")
+# the CPU arm always runs this many single-threaded replicas (or every core of a smaller host), so that the driver's
+# GPU / reference ratio means the same thing on every box
+REFERENCE_REPLICAS = 16
 # cfg[0] (docs/metropolis.toml, the reference's own CPU-runnable case): 1000 sites, latency bound; runs on the
 # shared-memory-resident kernel (one launch per batch of steps), reported in "also" without a roofline
 SMALL_WORKLOADS = {
@@ -173,7 +181,7 @@ def reference_arm(args):
     if rank != 0:
         return
     name = args.workload
-    cores = min(os.cpu_count() or 1, 32)
+    cores = min(os.cpu_count() or 1, REFERENCE_REPLICAS)
     # every timed "step" is a bounded sample of the workload; the whole --steps/--warmup run stays within ~3 minutes
     budget = max(0.25, min(6.0, 150.0 / max(1, args.warmup + args.steps)))
     per_step = cpu_steps_for(name, budget)
@@ -187,7 +195,10 @@ def reference_arm(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": float(np.mean([wl for _, wl in vals]) * 1e3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": name, "lattice": list(w["cpu_L"]), "note": "CPU oracle port of vegas-rs 0.9.0 Metropolis (Rust toolchain absent)"},
+            "config": {"workload": name, "lattice": list(w["cpu_L"]), "cores": cores, "host_cores": os.cpu_count(),
+                       "note": "CPU oracle port of vegas-rs 0.9.0 Metropolis (Rust toolchain absent); the reference is single-threaded: "
+                               f"{cores} independent replicas (fixed at {REFERENCE_REPLICAS} so that the ratio does not depend on the host), "
+                               "per-core rate = value / cores"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -320,15 +331,18 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, world: int, devi
     peak, peak_src = peaks()
     # sweep launches per step: one per colour, or ONE for the persistent wave kernel (both colours); a connected slab
     # adds wait / signal / boundary launches, so count colours there
-    passes = g.n_colours if slab else max(1, round(launches / steps))
+    passes = 1 if step_kernel in ONE_LAUNCH_KERNELS else (g.n_colours if slab else max(1, round(launches / steps)))
     per_launch_s = ms * 1e-3 / (passes * steps)
     alg_bytes_per_launch = w["bytes_per_attempt"] * n_local / passes
     achieved = alg_bytes_per_launch / per_launch_s / 1e9
+    traffic, traffic_src = NCU_TRAFFIC.get(name, {}).get(step_kernel, (None, None))
+    if traffic is not None and slab:
+        traffic_src += "; single-GPU capture of the same kernel (halo planes add " + ("1/%d" % w["size"][2]) + " of it per neighbour)"
     res = {"value": value, "ms_per_step": ms / steps, "launches": launches, "clocks": clocks, "e2e": e2e, "e2e_machine": e2e_machine,
            "family": step_kernel, "n_local": n_local,
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": NCU_TRAFFIC.get(name, (None, None))[0], "traffic_source": NCU_TRAFFIC.get(name, (None, None))[1],
-                        "algorithmic_bytes_per_launch": alg_bytes_per_launch, "peak_source": peak_src, "kernel": f"{step_kernel} " + ("step (both colours, one launch)" if passes == 1 else "colour pass"),
+                        "traffic": traffic, "traffic_source": traffic_src,
+                        "algorithmic_bytes_per_launch": alg_bytes_per_launch, "peak_source": peak_src, "kernel": f"{step_kernel} " + ("step (all colours, one launch)" if passes == 1 else "colour pass"),
                         "algorithmic_bytes_per_attempt": w["bytes_per_attempt"]},
            "energy_per_site_last": float(e_series[-1] / (n_local * (world if slab else 1)))}
     g.close()
@@ -413,7 +427,7 @@ def main():
     also = {}
     if not args.no_also:
         for other in WORKLOADS:
-            if other != args.workload and not (world > 1 and "unitcell" in WORKLOADS[other]):
+            if other != args.workload:
                 heavy = "unitcell" in WORKLOADS[other]   # 226 M sites: fewer steps, no 5 GB host round trip
                 try:
                     r = run_workload(other, min(args.steps, 10) if heavy else args.steps, args.warmup, rank, world, device, dist, torch,
@@ -426,8 +440,10 @@ def main():
                 also[other] = {"value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "roofline": r["roofline"],
                                "e2e": r["e2e"], "e2e_machine": r["e2e_machine"], "family": r["family"], "clocks": r["clocks"],
                                "gpu_launches": r["launches"],
-                               "note": {"ising2d_8192": "8 MiB state is L2 resident: not an HBM measurement",
-                                        "heis_fcc_384": "heis_basis vector kernel (16-byte loads, one Philox call per site), 4 colour passes per step, single GPU"}.get(other, "")}
+                               "note": {"ising2d_8192": "8 MiB state is L2 resident: not an HBM measurement" + ("; independent replicas, one per GPU" if world > 1 else ""),
+                                        "heis3d_512": "z-slabs of 512 planes per GPU" if world > 1 else "",
+                                        "heis_fcc_384": "heis_basis vector kernel (16-byte loads, one Philox call per site), 4 colour passes per step" +
+                                                        ("; z-slabs of 384 cell planes per GPU" if world > 1 else "")}.get(other, "")}
         if world == 1 and args.e2e_steps > 0:
             for small in SMALL_WORKLOADS:
                 try:

@@ -118,7 +118,8 @@ uint64_t vo_replay_heisenberg(const vo_hamiltonian* h, const vo_thermostat_t* th
                     p[1] = (double)(rxy * (float)sin((double)ang));
                     p[2] = (double)z;
                 }
-                u = (double)((float)(((w0 & 0x7FFu) << 11) | (w1 & 0x7FFu)) * 0x1.0p-22f);
+                /* the centre of the 2^-22 cell (heis.cuh heis_rand_words): never 0, so a vanishing Boltzmann factor is never accepted */
+                u = (double)(((float)(((w0 & 0x7FFu) << 11) | (w1 & 0x7FFu)) + 0.5f) * 0x1.0p-22f);
             } else {
                 philox_at(i, sweep, 0u, seed, r);
                 if (proposal != VO_PROPOSE_FLIP) {

@@ -108,8 +108,8 @@ __device__ __forceinline__ void basis_item(const BasisPipeArgs<real>& A, uint32_
     for (int e = 0; e < N; ++e) {
         HeisRand<real> rnd;
         heis_rand((gcell + e) * NB + B, A.sweep, A.pk, rnd);
-        const bool ok = heis_attempt<real, FLIP>(sx[e], sy[e], sz[e], A.p.J * n[0][e] - A.p.h[0], A.p.J * n[1][e] - A.p.h[1],
-                                                 A.p.J * n[2][e] - A.p.h[2], A.p, rnd);
+        const bool ok = heis_attempt<real, FLIP>(sx[e], sy[e], sz[e], heis_field(A.p.J, n[0][e], A.p.h[0]), heis_field(A.p.J, n[1][e], A.p.h[1]),
+                                                 heis_field(A.p.J, n[2][e], A.p.h[2]), A.p, rnd);
         accepted += ok ? 1 : 0;
     }
     vec_store(out + out_off, sx); vec_store(out + out_comp + out_off, sy); vec_store(out + 2 * out_comp + out_off, sz);

@@ -21,18 +21,45 @@ struct HeisParams {
     real invTl;    // log2(e) / T: the Boltzmann factor is evaluated as 2^(-dE * invTl)
 };
 
+// ---------------------------------------------------------------------------------------
+// fp32 lane arithmetic.  The attempt is written ONCE over a lane type L: float (one site per instruction) or float2 (two
+// sites per instruction: Blackwell's packed FADD2 / FMUL2 / FFMA2, half the issue slots).  Every operation is an explicit
+// round-to-nearest intrinsic -- never contracted, never reassociated -- so the scalar kernels and the packed one produce
+// the same bits per site.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float l_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float l_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float l_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ float l_neg(float a) { return -a; }
+__device__ __forceinline__ float2 l_add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 l_mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 l_fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 l_neg(float2 a) { return make_float2(-a.x, -a.y); }   // folds into the operand modifiers
+template <typename L> __device__ __forceinline__ L l_bc(float x);
+template <> __device__ __forceinline__ float l_bc<float>(float x) { return x; }
+template <> __device__ __forceinline__ float2 l_bc<float2>(float x) { return make_float2(x, x); }
+// per-lane special functions (MUFU): hardware rsqrt / cos / sin / ex2
+__device__ __forceinline__ float l_rsqrt(float a) { return rsqrtf(a); }
+__device__ __forceinline__ float l_cos(float a) { return __cosf(a); }
+__device__ __forceinline__ float l_sin(float a) { return __sinf(a); }
+__device__ __forceinline__ float2 l_rsqrt(float2 a) { return make_float2(rsqrtf(a.x), rsqrtf(a.y)); }
+__device__ __forceinline__ float2 l_cos(float2 a) { return make_float2(__cosf(a.x), __cosf(a.y)); }
+__device__ __forceinline__ float2 l_sin(float2 a) { return make_float2(__sinf(a.x), __sinf(a.y)); }
+
 // Uniform point on the sphere from two uniforms (Archimedes' hat-box); same distribution as
 // util.rs:21-34 (Marsaglia) without a rejection loop.
 // fp32: the uniforms arrive as integer-valued floats f0, f1 in [0, 2^21) so that the scalings fold into
 // the multiply-adds; hardware sin/cos/rsqrt (abs. error ~2^-21, spin norm 1 +- 1e-6, inside the fp32 bar).
 //   z = 1 - 2 u0 with u0 = (f0 + 1/2) 2^-21 in (0,1);   azimuth = 2 pi (f1 2^-21 - 1/2)
-__device__ __forceinline__ void sphere_point(float f0, float f1, float& x, float& y, float& z) {
-    z = fmaf(f0, -0x1.0p-20f, 1.0f - 0x1.0p-21f);
-    const float t = fmaf(-z, z, 1.0f);            // = 4 u0 (1 - u0) > 0; one rounding of the exact 1 - z^2, as (1 - z)(1 + z) with its two exact factors gave
-    const float rxy = t * rsqrtf(t);
-    const float ang = fmaf(f1, 6.283185307179586f * 0x1.0p-21f, -3.141592653589793f);
-    x = rxy * __cosf(ang); y = rxy * __sinf(ang);
+template <typename L>
+__device__ __forceinline__ void sphere_point_f32(L f0, L f1, L& x, L& y, L& z) {
+    z = l_fma(f0, l_bc<L>(-0x1.0p-20f), l_bc<L>(1.0f - 0x1.0p-21f));
+    const L t = l_fma(l_neg(z), z, l_bc<L>(1.0f));   // = 4 u0 (1 - u0) > 0: one rounding of the exact 1 - z^2
+    const L rxy = l_mul(t, l_rsqrt(t));
+    const L ang = l_fma(f1, l_bc<L>(6.283185307179586f * 0x1.0p-21f), l_bc<L>(-3.141592653589793f));
+    x = l_mul(rxy, l_cos(ang)); y = l_mul(rxy, l_sin(ang));
 }
+__device__ __forceinline__ void sphere_point(float f0, float f1, float& x, float& y, float& z) { sphere_point_f32<float>(f0, f1, x, y, z); }
 // fp64: u0 in [0,1), u1 in [0,1)
 __device__ __forceinline__ void sphere_point(double u0, double u1, double& x, double& y, double& z) {
     z = 1.0 - 2.0 * u0;
@@ -51,19 +78,21 @@ __device__ __forceinline__ float fast_exp2(float x) {
 __device__ __forceinline__ double fast_exp2(double x) { return exp2(x); }
 
 // The three random numbers of one attempt: direction (u0, u1) and acceptance (ua).
-// fp32: integer-valued floats, u0, u1 in [0, 2^21), ua in [0, 2^22)  (64 random bits per attempt);
+// fp32: u0, u1 integer-valued floats in [0, 2^21); ua = k + 1/2 with k in [0, 2^22), i.e. the acceptance uniform is the
+//       CENTRE (k + 1/2) 2^-22 of its cell (64 random bits per attempt).  With the cell's lower edge instead, k = 0 would
+//       accept any move whose Boltzmann factor is merely positive: a floor of 2^-22 per attempt that breaks balance at low T;
 // fp64: uniforms in [0, 1) with 53 bits.
 template <typename real>
 struct HeisRand { real u0, u1, ua; };
 template <typename real> struct HeisAcceptShift;
-template <> struct HeisAcceptShift<float> { static constexpr float value = 22.0f; };   // ua < 2^22 * exp(-dE/T)
+template <> struct HeisAcceptShift<float> { static constexpr float value = 22.0f; };   // (k + 1/2) < 2^22 * exp(-dE/T)
 template <> struct HeisAcceptShift<double> { static constexpr double value = 0.0; };
 
 __device__ __forceinline__ HeisRand<float> heis_rand_words(uint32_t w0, uint32_t w1) {
     HeisRand<float> o;
     o.u0 = (float)(w0 >> 11);
     o.u1 = (float)(w1 >> 11);
-    o.ua = (float)(((w0 & 0x7FFu) << 11) | (w1 & 0x7FFu));
+    o.ua = (float)(((w0 & 0x7FFu) << 11) | (w1 & 0x7FFu)) + 0.5f;   // exact: 23 significant bits
     return o;
 }
 
@@ -83,28 +112,70 @@ __device__ __forceinline__ void heis_rand(uint64_t site, uint64_t sweep, const P
     o.u0 = u53(r[0], r[1]); o.u1 = u53(r[2], r[3]); o.ua = u53(q[0], q[1]);
 }
 
+// Effective field of a site from its neighbour sum: f = J n - h, one fused multiply-add (all stencil / basis kernels
+// go through here so that they agree bit for bit).
+__device__ __forceinline__ float heis_field(float J, float n, float h) { return __fmaf_rn(J, n, -h); }
+__device__ __forceinline__ float2 heis_field(float J, float2 n, float h) { return __ffma2_rn(make_float2(J, J), n, make_float2(-h, -h)); }
+__device__ __forceinline__ double heis_field(double J, double n, double h) { return __fma_rn(J, n, -h); }
+
 // One Metropolis attempt on a site whose effective field f = sum_j J_ij s_j - |H| o (energy units) and random
 // numbers are known:  -dE = (s' - s).f - k[(s'.a)^2 - (s.a)^2]   (reference signs).
 // src/integrator.rs:82-88 accepts if dE < 0, else if u < exp(-dE/T); since u < 1 both cases are
-// u < exp(-dE/T), evaluated as 2^(-dE log2(e)/T).  Returns true when accepted.
+// u < exp(-dE/T), evaluated as 2^(-dE log2(e)/T).
 // AXZ: the caller guarantees a = (0, 0, a_z); s.a = s_z a_z is then bit-identical to the general dot product.
+//
+// fp32, any lane type: the proposal (px, py, pz) and the exponent x = -dE log2(e)/T + 22 of the acceptance bound 2^x
+template <typename L, bool FLIP, bool AXZ>
+__device__ __forceinline__ L heis_propose_f32(L sx, L sy, L sz, L fx, L fy, L fz, const HeisParams<float>& p, L u0, L u1, L& px, L& py, L& pz) {
+    if (FLIP) { px = l_neg(sx); py = l_neg(sy); pz = l_neg(sz); }
+    else sphere_point_f32<L>(u0, u1, px, py, pz);
+    const L dx = l_add(px, l_neg(sx)), dy = l_add(py, l_neg(sy)), dz = l_add(pz, l_neg(sz));
+    L mdE = l_fma(dz, fz, l_fma(dy, fy, l_mul(dx, fx)));
+    if (!FLIP) {  // (s.a)^2 is invariant under a flip
+        const L da_new = AXZ ? l_mul(pz, l_bc<L>(p.a[2])) : l_fma(pz, l_bc<L>(p.a[2]), l_fma(py, l_bc<L>(p.a[1]), l_mul(px, l_bc<L>(p.a[0]))));
+        const L da_old = AXZ ? l_mul(sz, l_bc<L>(p.a[2])) : l_fma(sz, l_bc<L>(p.a[2]), l_fma(sy, l_bc<L>(p.a[1]), l_mul(sx, l_bc<L>(p.a[0]))));
+        mdE = l_fma(l_bc<L>(-p.k), l_mul(l_add(da_new, l_neg(da_old)), l_add(da_new, da_old)), mdE);
+    }
+    return l_fma(mdE, l_bc<L>(p.invTl), l_bc<L>(HeisAcceptShift<float>::value));
+}
+
+// Returns true when accepted (the spin is then replaced by the proposal).
 template <typename real, bool FLIP, bool AXZ = false>
 __device__ __forceinline__ bool heis_attempt(real& sx, real& sy, real& sz, real fx, real fy, real fz,
                                              const HeisParams<real>& p, const HeisRand<real>& rnd) {
-    real px, py, pz;
-    if (FLIP) { px = -sx; py = -sy; pz = -sz; }
-    else sphere_point(rnd.u0, rnd.u1, px, py, pz);
-    const real dx = px - sx, dy = py - sy, dz = pz - sz;
-    real mdE = dx * fx + dy * fy + dz * fz;
-    if (!FLIP) {  // (s.a)^2 is invariant under a flip.  Kept branch-free: a uniform "k == 0" / "axis = z" shortcut was
-        // measured SLOWER on the wave kernel (1.42e11 vs 1.47e11): the branches stop the interleaving of the 4 sites
-        const real da_new = AXZ ? pz * p.a[2] : px * p.a[0] + py * p.a[1] + pz * p.a[2];
-        const real da_old = AXZ ? sz * p.a[2] : sx * p.a[0] + sy * p.a[1] + sz * p.a[2];
-        mdE -= p.k * ((da_new - da_old) * (da_new + da_old));
+    if constexpr (sizeof(real) == 4) {
+        float px, py, pz;
+        const float x = heis_propose_f32<float, FLIP, AXZ>(sx, sy, sz, fx, fy, fz, p, rnd.u0, rnd.u1, px, py, pz);
+        const bool acc = rnd.ua < fast_exp2(x);
+        if (acc) { sx = px; sy = py; sz = pz; }
+        return acc;
+    } else {
+        real px, py, pz;
+        if (FLIP) { px = -sx; py = -sy; pz = -sz; }
+        else sphere_point(rnd.u0, rnd.u1, px, py, pz);
+        const real dx = px - sx, dy = py - sy, dz = pz - sz;
+        real mdE = dx * fx + dy * fy + dz * fz;
+        if (!FLIP) {
+            const real da_new = AXZ ? pz * p.a[2] : px * p.a[0] + py * p.a[1] + pz * p.a[2];
+            const real da_old = AXZ ? sz * p.a[2] : sx * p.a[0] + sy * p.a[1] + sz * p.a[2];
+            mdE -= p.k * ((da_new - da_old) * (da_new + da_old));
+        }
+        const bool acc = rnd.ua < fast_exp2(mdE * p.invTl + HeisAcceptShift<real>::value);
+        if (acc) { sx = px; sy = py; sz = pz; }
+        return acc;
     }
-    const bool acc = rnd.ua < fast_exp2(mdE * p.invTl + HeisAcceptShift<real>::value);
-    if (acc) { sx = px; sy = py; sz = pz; }
-    return acc;
+}
+
+// Two sites per instruction (fp32): lanes .x / .y with their own random numbers; a0 / a1 = accepted.
+template <bool FLIP, bool AXZ>
+__device__ __forceinline__ void heis_attempt2(float2& sx, float2& sy, float2& sz, float2 fx, float2 fy, float2 fz, const HeisParams<float>& p,
+                                              const HeisRand<float>& r0, const HeisRand<float>& r1, bool& a0, bool& a1) {
+    float2 px, py, pz;
+    const float2 x = heis_propose_f32<float2, FLIP, AXZ>(sx, sy, sz, fx, fy, fz, p, make_float2(r0.u0, r1.u0), make_float2(r0.u1, r1.u1), px, py, pz);
+    a0 = r0.ua < fast_exp2(x.x);
+    a1 = r1.ua < fast_exp2(x.y);
+    if (a0) { sx.x = px.x; sy.x = py.x; sz.x = pz.x; }
+    if (a1) { sx.y = px.y; sy.y = py.y; sz.y = pz.y; }
 }
 
 struct HeisGeom {
@@ -240,8 +311,8 @@ __device__ __forceinline__ void heis_march(const HeisPtrs<real>& P, const HeisGe
 #pragma unroll
             for (int e = 0; e < N; ++e) {
                 if (UPDATE) {
-                    const bool ok = heis_attempt<real, FLIP>(s[0][e], s[1][e], s[2][e], p.J * nsum[0][e] - p.h[0],
-                                                             p.J * nsum[1][e] - p.h[1], p.J * nsum[2][e] - p.h[2], p, rnd[e]);
+                    const bool ok = heis_attempt<real, FLIP>(s[0][e], s[1][e], s[2][e], heis_field(p.J, nsum[0][e], p.h[0]),
+                                                             heis_field(p.J, nsum[1][e], p.h[1]), heis_field(p.J, nsum[2][e], p.h[2]), p, rnd[e]);
                     accepted += ok ? 1 : 0;
                 }
                 if (OBS) {

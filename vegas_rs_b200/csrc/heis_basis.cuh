@@ -115,7 +115,7 @@ heis_basis_kernel(BasisPtrs<real> P, BasisPeers<real> peers, BasisGeom g, uint32
                 HeisRand<real> rnd;
                 const uint64_t gcell = ((uint64_t)(iz + g.z_offset) * g.ny + iy) * g.nx + ix;  // global cell: slab-independent keys
                 heis_rand(gcell * NB + B, sweep, pk, rnd);
-                const bool ok = heis_attempt<real, FLIP>(x, y, z, p.J * nx - p.h[0], p.J * ny - p.h[1], p.J * nz - p.h[2], p, rnd);
+                const bool ok = heis_attempt<real, FLIP>(x, y, z, heis_field(p.J, nx, p.h[0]), heis_field(p.J, ny, p.h[1]), heis_field(p.J, nz, p.h[2]), p, rnd);
                 if (ok) { P.s[B][0][cell] = x; P.s[B][1][cell] = y; P.s[B][2][cell] = z; }
                 if (SLAB) {  // boundary planes also go straight into the neighbours' halo planes (peer memory over NVLink)
                     const size_t in_plane = (size_t)iy * g.nx + ix, pl = (size_t)g.ny * g.nx;
@@ -227,8 +227,8 @@ heis_basis_vec_kernel(BasisPtrs<real> P, BasisPeers<real> peers, BasisGeom g, ui
             for (int e = 0; e < N; ++e) {
                 HeisRand<real> rnd;
                 heis_rand((gcell + e) * NB + B, sweep, pk, rnd);
-                const bool ok = heis_attempt<real, FLIP>(sx[e], sy[e], sz[e], p.J * n[0][e] - p.h[0], p.J * n[1][e] - p.h[1],
-                                                         p.J * n[2][e] - p.h[2], p, rnd);
+                const bool ok = heis_attempt<real, FLIP>(sx[e], sy[e], sz[e], heis_field(p.J, n[0][e], p.h[0]), heis_field(p.J, n[1][e], p.h[1]),
+                                                         heis_field(p.J, n[2][e], p.h[2]), p, rnd);
                 accepted += ok ? 1 : 0;
             }
             vec_store(P.s[B][0] + cell, sx); vec_store(P.s[B][1] + cell, sy); vec_store(P.s[B][2] + cell, sz);

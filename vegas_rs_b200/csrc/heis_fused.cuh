@@ -150,8 +150,8 @@ heis_fused_kernel(FusedPtrs<real> P, FusedGeom g, HeisParams<real> p, uint64_t s
                     HeisRand<real> rnd;
                     reinterpret_cast<HeisRand<float>&>(rnd) = heis_rand_words(w[2 * h2], w[2 * h2 + 1]);
                     const bool ok = heis_attempt<real, FLIP>(s[0][e + h2], s[1][e + h2], s[2][e + h2],
-                                                             p.J * nsum[0][e + h2] - p.h[0], p.J * nsum[1][e + h2] - p.h[1],
-                                                             p.J * nsum[2][e + h2] - p.h[2], p, rnd);
+                                                             heis_field(p.J, nsum[0][e + h2], p.h[0]), heis_field(p.J, nsum[1][e + h2], p.h[1]),
+                                                             heis_field(p.J, nsum[2][e + h2], p.h[2]), p, rnd);
                     accepted += (ok && count) ? 1 : 0;
                 }
             }
@@ -160,8 +160,8 @@ heis_fused_kernel(FusedPtrs<real> P, FusedGeom g, HeisParams<real> p, uint64_t s
             for (int e = 0; e < N; ++e) {
                 HeisRand<real> rnd;
                 heis_rand(site0 + 2u * e, sweep, pk, rnd);
-                const bool ok = heis_attempt<real, FLIP>(s[0][e], s[1][e], s[2][e], p.J * nsum[0][e] - p.h[0],
-                                                         p.J * nsum[1][e] - p.h[1], p.J * nsum[2][e] - p.h[2], p, rnd);
+                const bool ok = heis_attempt<real, FLIP>(s[0][e], s[1][e], s[2][e], heis_field(p.J, nsum[0][e], p.h[0]),
+                                                         heis_field(p.J, nsum[1][e], p.h[1]), heis_field(p.J, nsum[2][e], p.h[2]), p, rnd);
                 accepted += (ok && count) ? 1 : 0;
             }
         }

@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(MAXT, 1) heis_pipe_kernel(const __grid_constan
     uint64_t* done = empty_w + SO;                                        // PIPE_DONE_SLOTS: plane stored by every consumer warp
     double* s_acc = reinterpret_cast<double*>(done + PIPE_DONE_SLOTS);    // 6 doubles
     volatile uint32_t* abort_flag = reinterpret_cast<volatile uint32_t*>(s_acc + 6);
+    uint32_t* ready = const_cast<uint32_t*>(abort_flag) + 1;   // planes whose TMA stores are complete (publisher -> releaser)
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t n_phases = gridDim.x / A.tiles;
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(MAXT, 1) heis_pipe_kernel(const __grid_constan
         for (uint32_t s = 0; s < SO; ++s) { mbar_init(full_w + s, 1u); mbar_init(empty_w + s, 1u); }
         for (uint32_t s = 0; s < PIPE_DONE_SLOTS; ++s) mbar_init(done + s, n_cw);
         *abort_flag = 0u;
+        *ready = 0u;
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -216,6 +218,25 @@ __global__ void __launch_bounds__(MAXT, 1) heis_pipe_kernel(const __grid_constan
             const uint32_t q_need = mz.qbase(i) + 2u;
             while (ok && q_next <= q_need) load_other();
         }
+    } else if (warp == n_cw + 3) {
+        // ===================== releaser: publishes the band's progress (planes whose stores are complete) at gpu scope ==========
+        // Runs at its own pace: when a release takes longer than a plane, the next one simply covers several planes.
+        if (lane == 0) {
+            unsigned long long* const my_prog = A.prog + (size_t)phase * A.tiles + tile;
+            uint32_t last = 0;
+            const unsigned long long t0 = global_timer();
+            while (last < Lz) {
+                uint32_t now;
+                asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(now) : "r"(smem_u32(ready)) : "memory");
+                if (now == last) {
+                    __nanosleep(100);
+                    if (*abort_flag || global_timer() - t0 > 8 * PIPE_TIMEOUT_NS) break;
+                    continue;
+                }
+                last = now;
+                asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(my_prog), "l"(A.base + (unsigned long long)now) : "memory");
+            }
+        }
     } else if (warp == n_cw + 2) {
         // ===================== own-ring producer warp (independent of the other ring: neither holds the other up) =========
         const uint32_t kind = nr == rows ? 0u : 1u;
@@ -246,7 +267,6 @@ __global__ void __launch_bounds__(MAXT, 1) heis_pipe_kernel(const __grid_constan
         // (keeps the gpu-scope fence off the consumers' critical path; the consumers' stores are ordered before it by
         // their arrive on the `done` barrier)
         if (lane == 0 && has_publisher) {
-            unsigned long long* const my_prog = A.prog + (size_t)phase * A.tiles + tile;
             RingPos pd, pown;
             uint32_t since_pub = 0;
             const uint32_t kind = nr == rows ? 0u : 1u;
@@ -273,19 +293,19 @@ __global__ void __launch_bounds__(MAXT, 1) heis_pipe_kernel(const __grid_constan
                 tma_store_wait_read<0>();               // the store has read the slot: the producer may refill it
                 mbar_arrive(empty_w + pown.slot);
                 pown.advance(SO);
-                if (i > 0 && ++since_pub == A.pub_every) {   // planes < i are complete once at most this store is pending
+                // planes <= i - PUB_LAG are complete once at most PUB_LAG stores are pending: waiting for older stores only
+                // keeps the publisher (which also frees the own-ring slots) from ever blocking on a store's completion latency
+                constexpr uint32_t PUB_LAG = 2;
+                if (i >= PUB_LAG && ++since_pub == A.pub_every) {
                     since_pub = 0;
-                    tma_store_wait<1>();
-                    fence_proxy_async();
-                    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(my_prog), "l"(A.base + (unsigned long long)i) : "memory");
+                    tma_store_wait<PUB_LAG>();
+                    // hand the count to the releaser warp: the gpu-scope release costs about a plane's time and must not sit here
+                    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(ready)), "r"(i + 1u - PUB_LAG) : "memory");
                 }
                 if (HALO) signal_peers(z);
             }
-            {
-                tma_store_wait<0>();
-                fence_proxy_async();
-                asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(my_prog), "l"(A.base + (unsigned long long)Lz) : "memory");
-            }
+            tma_store_wait<0>();
+            asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(ready)), "r"(Lz) : "memory");
         }
     } else {
         // ===================== consumers: one thread per V sites of the band =====================
@@ -299,6 +319,15 @@ __global__ void __launch_bounds__(MAXT, 1) heis_pipe_kernel(const __grid_constan
         const uint32_t cx_right = (gx + 1 == Tx) ? 0u : (gx + 1) * V, cx_left = (gx == 0 ? Tx : gx) * V - 1;
         const bool energy = colour == 1;
         real facc[5] = {0, 0, 0, 0, 0};
+        float2 facc2[5];   // fp32: per-lane partial sums of the packed path, folded into facc at every flush
+#pragma unroll
+        for (int k = 0; k < 5; ++k) facc2[k] = make_float2(0.0f, 0.0f);
+        auto fold = [&]() {
+            if constexpr (sizeof(real) == 4) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) { facc[k] += facc2[k].x + facc2[k].y; facc2[k] = make_float2(0.0f, 0.0f); }
+            }
+        };
         int accepted = 0;
         bool ok = true;
         RingPos p_lo, p_wait, p_own, p_done;    // q = qbase(i); next `other` entry to wait for; own ring; done ring
@@ -321,57 +350,115 @@ __global__ void __launch_bounds__(MAXT, 1) heis_pipe_kernel(const __grid_constan
                 const real* ph = ring_o + slot_hi * stage_o + so_row;
                 const real* pc = ring_o + slot_n0 * stage_o + (so_row - gx * V) + (rp ? cx_right : cx_left);
                 const real* pw = ring_w + p_own.slot * stage_w + sw_row;
-                real s[3][V], nsum[3][V];
+                real s[3][V];
+                if constexpr (sizeof(real) == 4) {
+                    // fp32: two sites per instruction (FADD2 / FMUL2 / FFMA2); lane arithmetic identical to the scalar kernels
+                    constexpr int NP = V / 2;
+                    float2 s2[3][NP], n2[3][NP];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    real n0[V], a[V], b[V], lo[V], hi[V];
-                    const uint32_t co = (uint32_t)c * orow * Hx;
-                    pack_load<real, V>(pw + (uint32_t)c * rows * Hx, s[c]);
-                    pack_load<real, V>(pn + co, n0);
-                    pack_load<real, V>(pn + co - Hx, a);
-                    pack_load<real, V>(pn + co + Hx, b);
-                    const real carry = pc[co];
-                    pack_load<real, V>(pl + co, lo);
-                    pack_load<real, V>(ph + co, hi);
-                    // same association order as heis_march (heis.cuh): bit-identical neighbour sums
+                    for (int c = 0; c < 3; ++c) {
+                        float n0[V], a[V], b[V], lo[V], hi[V], sv[V];
+                        const uint32_t co = (uint32_t)c * orow * Hx;
+                        pack_load<float, V>(pw + (uint32_t)c * rows * Hx, sv);
+                        pack_load<float, V>(pn + co, n0);
+                        pack_load<float, V>(pn + co - Hx, a);
+                        pack_load<float, V>(pn + co + Hx, b);
+                        const float carry = pc[co];
+                        pack_load<float, V>(pl + co, lo);
+                        pack_load<float, V>(ph + co, hi);
+                        // same association order as heis_march (heis.cuh): ((n0 + (a + b)) + x-shifted) + (lo + hi)
 #pragma unroll
-                    for (int e = 0; e < V; ++e) nsum[c][e] = n0[e] + (a[e] + b[e]);
-                    if (rp) {   // warp-uniform (a warp lies inside one row); the empty asm keeps the arms from being if-converted into selects
-                        asm volatile("");
-#pragma unroll
-                        for (int e = 0; e < V; ++e) nsum[c][e] += e + 1 < V ? n0[(e + 1) % V] : carry;
-                    } else {
-                        asm volatile("");
-#pragma unroll
-                        for (int e = 0; e < V; ++e) nsum[c][e] += e > 0 ? n0[(e + V - 1) % V] : carry;
+                        for (int q = 0; q < NP; ++q) {
+                            const int e = 2 * q;
+                            float2 t = l_add(make_float2(n0[e], n0[e + 1]), l_add(make_float2(a[e], a[e + 1]), make_float2(b[e], b[e + 1])));
+                            float2 sh;
+                            if (rp) {   // warp-uniform: a warp lies inside one row
+                                asm volatile("");
+                                sh = make_float2(n0[e + 1], e + 2 < V ? n0[(e + 2) % V] : carry);
+                            } else {
+                                asm volatile("");
+                                sh = make_float2(e > 0 ? n0[(e + V - 1) % V] : carry, n0[e]);
+                            }
+                            t = l_add(t, sh);
+                            n2[c][q] = l_add(t, l_add(make_float2(lo[e], lo[e + 1]), make_float2(hi[e], hi[e + 1])));
+                            s2[c][q] = make_float2(sv[e], sv[e + 1]);
+                        }
                     }
+                    const uint64_t site0 = (uint64_t)(zg * Ly + y) * g.Lx + 2u * (gx * V) + rp;  // element e: site0 + 2e
 #pragma unroll
-                    for (int e = 0; e < V; ++e) nsum[c][e] += lo[e] + hi[e];
-                }
-                HeisRand<real> rnd[V];
-                const uint64_t site0 = (uint64_t)(zg * Ly + y) * g.Lx + 2u * (gx * V) + rp;  // element e: site0 + 2e
-                if (sizeof(real) == 4) {
-#pragma unroll
-                    for (int e = 0; e < V; e += 2) {   // bit 1 of site0 is clear: elements e, e + 1 share a Philox call
+                    for (int q = 0; q < NP; ++q) {   // bit 1 of site0 is clear: elements 2q, 2q + 1 share a Philox call
                         uint32_t rr[4];
-                        philox_at(site0 + 2u * e, A.sweep, 0u, A.pk, rr);
-                        reinterpret_cast<HeisRand<float>&>(rnd[e]) = heis_rand_words(rr[0], rr[1]);
-                        reinterpret_cast<HeisRand<float>&>(rnd[e + 1]) = heis_rand_words(rr[2], rr[3]);
+                        philox_at(site0 + 4u * q, A.sweep, 0u, A.pk, rr);
+                        const HeisRand<float> r0 = heis_rand_words(rr[0], rr[1]), r1 = heis_rand_words(rr[2], rr[3]);
+                        bool a0, a1;
+                        heis_attempt2<FLIP, AXZ>(s2[0][q], s2[1][q], s2[2][q], heis_field(A.p.J, n2[0][q], A.p.h[0]),
+                                                 heis_field(A.p.J, n2[1][q], A.p.h[1]), heis_field(A.p.J, n2[2][q], A.p.h[2]), A.p, r0, r1, a0, a1);
+                        accepted += (a0 ? 1 : 0) + (a1 ? 1 : 0);
+                        if (RECORD) {
+                            if (energy) facc2[0] = l_fma(l_bc<float2>(-A.p.J), l_fma(s2[2][q], n2[2][q], l_fma(s2[1][q], n2[1][q], l_mul(s2[0][q], n2[0][q]))), facc2[0]);
+                            facc2[1] = l_add(facc2[1], s2[0][q]); facc2[2] = l_add(facc2[2], s2[1][q]); facc2[3] = l_add(facc2[3], s2[2][q]);
+                            const float2 d1 = AXZ ? l_mul(s2[2][q], l_bc<float2>(A.p.a[2]))
+                                                  : l_fma(s2[2][q], l_bc<float2>(A.p.a[2]), l_fma(s2[1][q], l_bc<float2>(A.p.a[1]), l_mul(s2[0][q], l_bc<float2>(A.p.a[0]))));
+                            facc2[4] = l_fma(d1, d1, facc2[4]);
+                        }
                     }
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+#pragma unroll
+                        for (int q = 0; q < NP; ++q) { s[c][2 * q] = s2[c][q].x; s[c][2 * q + 1] = s2[c][q].y; }
                 } else {
-#pragma unroll
-                    for (int e = 0; e < V; ++e) heis_rand(site0 + 2u * e, A.sweep, A.pk, rnd[e]);
-                }
-#pragma unroll
-                for (int e = 0; e < V; ++e) {
-                    const bool acc = heis_attempt<real, FLIP, AXZ>(s[0][e], s[1][e], s[2][e], A.p.J * nsum[0][e] - A.p.h[0],
-                                                              A.p.J * nsum[1][e] - A.p.h[1], A.p.J * nsum[2][e] - A.p.h[2], A.p, rnd[e]);
-                    accepted += acc ? 1 : 0;
-                    if (RECORD) {
-                        if (energy) facc[0] -= A.p.J * (s[0][e] * nsum[0][e] + s[1][e] * nsum[1][e] + s[2][e] * nsum[2][e]);
-                        facc[1] += s[0][e]; facc[2] += s[1][e]; facc[3] += s[2][e];
-                        const real d1 = AXZ ? s[2][e] * A.p.a[2] : s[0][e] * A.p.a[0] + s[1][e] * A.p.a[1] + s[2][e] * A.p.a[2];
-                        facc[4] += d1 * d1;
+                    real nsum[3][V];
+    #pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        real n0[V], a[V], b[V], lo[V], hi[V];
+                        const uint32_t co = (uint32_t)c * orow * Hx;
+                        pack_load<real, V>(pw + (uint32_t)c * rows * Hx, s[c]);
+                        pack_load<real, V>(pn + co, n0);
+                        pack_load<real, V>(pn + co - Hx, a);
+                        pack_load<real, V>(pn + co + Hx, b);
+                        const real carry = pc[co];
+                        pack_load<real, V>(pl + co, lo);
+                        pack_load<real, V>(ph + co, hi);
+                        // same association order as heis_march (heis.cuh): bit-identical neighbour sums
+    #pragma unroll
+                        for (int e = 0; e < V; ++e) nsum[c][e] = n0[e] + (a[e] + b[e]);
+                        if (rp) {   // warp-uniform (a warp lies inside one row); the empty asm keeps the arms from being if-converted into selects
+                            asm volatile("");
+    #pragma unroll
+                            for (int e = 0; e < V; ++e) nsum[c][e] += e + 1 < V ? n0[(e + 1) % V] : carry;
+                        } else {
+                            asm volatile("");
+    #pragma unroll
+                            for (int e = 0; e < V; ++e) nsum[c][e] += e > 0 ? n0[(e + V - 1) % V] : carry;
+                        }
+    #pragma unroll
+                        for (int e = 0; e < V; ++e) nsum[c][e] += lo[e] + hi[e];
+                    }
+                    HeisRand<real> rnd[V];
+                    const uint64_t site0 = (uint64_t)(zg * Ly + y) * g.Lx + 2u * (gx * V) + rp;  // element e: site0 + 2e
+                    if (sizeof(real) == 4) {
+    #pragma unroll
+                        for (int e = 0; e < V; e += 2) {   // bit 1 of site0 is clear: elements e, e + 1 share a Philox call
+                            uint32_t rr[4];
+                            philox_at(site0 + 2u * e, A.sweep, 0u, A.pk, rr);
+                            reinterpret_cast<HeisRand<float>&>(rnd[e]) = heis_rand_words(rr[0], rr[1]);
+                            reinterpret_cast<HeisRand<float>&>(rnd[e + 1]) = heis_rand_words(rr[2], rr[3]);
+                        }
+                    } else {
+    #pragma unroll
+                        for (int e = 0; e < V; ++e) heis_rand(site0 + 2u * e, A.sweep, A.pk, rnd[e]);
+                    }
+    #pragma unroll
+                    for (int e = 0; e < V; ++e) {
+                        const bool acc = heis_attempt<real, FLIP, AXZ>(s[0][e], s[1][e], s[2][e], heis_field(A.p.J, nsum[0][e], A.p.h[0]),
+                                                                  heis_field(A.p.J, nsum[1][e], A.p.h[1]), heis_field(A.p.J, nsum[2][e], A.p.h[2]), A.p, rnd[e]);
+                        accepted += acc ? 1 : 0;
+                        if (RECORD) {
+                            if (energy) facc[0] -= A.p.J * (s[0][e] * nsum[0][e] + s[1][e] * nsum[1][e] + s[2][e] * nsum[2][e]);
+                            facc[1] += s[0][e]; facc[2] += s[1][e]; facc[3] += s[2][e];
+                            const real d1 = AXZ ? s[2][e] * A.p.a[2] : s[0][e] * A.p.a[0] + s[1][e] * A.p.a[1] + s[2][e] * A.p.a[2];
+                            facc[4] += d1 * d1;
+                        }
                     }
                 }
                 real* pws = ring_w + p_own.slot * stage_w + sw_row;
@@ -401,9 +488,9 @@ __global__ void __launch_bounds__(MAXT, 1) heis_pipe_kernel(const __grid_constan
             }
             p_own.advance(SO);
             p_done.advance(PIPE_DONE_SLOTS);
-            if (RECORD && (i & 15u) == 15u) heis_flush(facc, s_acc);
+            if (RECORD && (i & 15u) == 15u) { fold(); heis_flush(facc, s_acc); }
         }
-        if (RECORD) heis_flush(facc, s_acc);
+        if (RECORD) { fold(); heis_flush(facc, s_acc); }
         const int a = __reduce_add_sync(0xffffffffu, accepted);
         if (lane == 0 && a != 0) atomicAdd(&s_acc[5], (double)a);
     }
@@ -497,18 +584,18 @@ HeisPipeState* heis_pipe_create(const HeisPipeDesc& d, std::string& why) {
     st->tiles = tiles; st->rows = rows;
     st->tiles_long = d.Ly - tiles * (rows - 1);             // bands of `rows` rows; the others have rows - 1
     // sites per consumer thread: a whole 16-byte vector, or half of one (tuning key: twice the warps, more instructions per site)
-    auto threads_for = [&](uint32_t V) { return (rows * (Hx / V) + 31u) / 32u * 32u + 96u; };   // + the two producer warps and the publisher warp
+    auto threads_for = [&](uint32_t V) { return (rows * (Hx / V) + 31u) / 32u * 32u + 128u; };   // + two producer warps, the publisher and the releaser
     uint32_t V = d.vec ? d.vec : N;   // measured on 512^3 fp32: whole vectors 0.88 ms per step, half vectors (twice the warps) 1.04
     if (V != N && V != N / 2) { why = "sites per thread must be a whole or half 16-byte vector"; delete st; return nullptr; }
     if (!d.vec && threads_for(V) > 1024) { why = "band needs more than 1024 threads"; delete st; return nullptr; }
     st->V = V;
     st->threads = threads_for(V);
-    st->n_cw = st->threads / 32 - 3;
+    st->n_cw = st->threads / 32 - 4;
     if (st->threads > 1024) { why = "band needs more than 1024 threads"; delete st; return nullptr; }
     const size_t stage_o = (size_t)3 * (rows + 2) * Hx * sz, stage_w = (size_t)3 * rows * Hx * sz;
     // ring depths: an own plane holds its slot from the load until the TMA store has read the updated tile
     const uint32_t choices[][2] = {{6, 3}, {5, 3}, {4, 3}, {4, 2}, {4, 1}};   // measured on 512^3 fp32: 0.862 / 0.878 ms per step for the first two
-    auto smem_for = [&](uint32_t S, uint32_t SO) { return S * stage_o + SO * stage_w + (size_t)(2 * S + 2 * SO + PIPE_DONE_SLOTS) * 8 + 6 * 8 + 16; };
+    auto smem_for = [&](uint32_t S, uint32_t SO) { return S * stage_o + SO * stage_w + (size_t)(2 * S + 2 * SO + PIPE_DONE_SLOTS) * 8 + 6 * 8 + 32; };
     if (d.stages_other >= 4 && d.stages_own >= 1) { st->S = d.stages_other; st->SO = std::min(4u, d.stages_own); }
     else
         for (auto& c : choices)
@@ -591,10 +678,11 @@ int heis_pipe_step(HeisPipeState* st, const HeisParams<real>& p, bool flip, bool
     A.maps = st->d_maps;
     A.g.Hx = st->Hx; A.g.Gx = st->Hx / st->V; A.g.Ly = d.Ly; A.g.Lz = d.Lz; A.g.z_offset = d.z_offset; A.g.Lx = d.Lx;
     A.tiles = st->tiles; A.rows = st->rows; A.tiles_long = st->tiles_long; A.S = st->S; A.SO = st->SO; A.n_cw = st->n_cw;
+    // Defaults measured on 512^3 fp32 (profiles/r02/README.md): publishing every plane makes the fronts wait on each other's
+    // release latency (pub 1 / lead 32: 0.95 ms per step), every 4th with a lead of 32 planes 0.85 ms; leads below
+    // 2 pub + 8 can deadlock (publication lags the update by the store's completion and the releaser's turn-around)
     A.pub_every = std::max(1u, d.pub_every ? d.pub_every : 4u);
-    // smaller leads than 2 pub_every + 2 can deadlock (see the publisher); 32 planes of 512^2 fp32 spins are ~100 MB, most of which
-    // is never live at once (measured: pub 4 / lead 32 0.882 ms, lead 24 0.889, pub 2 / lead 16 0.934)
-    A.lead = std::max(2u * A.pub_every + 2u, d.lead ? d.lead : 8u * A.pub_every);
+    A.lead = std::max(2u * A.pub_every + 8u, d.lead ? d.lead : 8u * A.pub_every);
     A.prog = st->d_prog;
     A.base = st->launches * (unsigned long long)d.Lz;
     A.flags = d.flags;
