@@ -309,9 +309,12 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, world: int, devi
     # ---- the same steps through the host layer: Machine::measure_for with StatSensor + ObservableSensor fed from the
     # device-reduced per-step (E, M); the State stays in HBM (it only crosses PCIe for a StateSensor dump)
     e2e_machine = None
-    if machine_e2e and not slab:
+    if machine_e2e:
         from vegas_rs_b200.machine import Machine
         m = Machine(g)
+        if slab:   # slab group: one Machine per rank, the per-step (E, M) partial sums all-reduced before the sensors see them
+            from vegas_rs_b200 import run as vrun
+            m.set_group(vrun.group_reduce(dist, device), n_local * world)
         m.add_stat_sensor(lambda line, row: None)
         m.add_observable_sensor(lambda *a: None)
         m.set_thermostat(w["T"], (0.0, 0.0, 1.0), w["H"])
@@ -327,7 +330,8 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, world: int, devi
             dt = float(t.item())
         e2e_machine = {"value": n_local * world * steps / dt, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 64,
                        "steps": steps, "api": "vegas_machine_measure_for (Machine::measure_for, src/machine.rs:116-125) with "
-                                              "StatSensor + ObservableSensor; host wall clock"}
+                                              "StatSensor + ObservableSensor; host wall clock" +
+                                              ("; slab group (vegas_machine_set_group): per-step partial sums all-reduced over the ranks" if slab else "")}
     peak, peak_src = peaks()
     # sweep launches per step: one per colour, or ONE for the persistent wave kernel (both colours); a connected slab
     # adds wait / signal / boundary launches, so count colours there

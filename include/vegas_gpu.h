@@ -185,11 +185,12 @@ int vegas_gpu_slab_connect_local(vegas_gpu_t self, vegas_gpu_t lower, vegas_gpu_
  *                       trails the previous one by, >= 3, default 5), "heis_wave_steps" (steps fused into one launch,
  *                       1..4, default 1: more was measured slower)
  *     "heis_wave_c"   : experiment: the two passes as separate launches interleaved in chunks of C planes
- *     "basis_pipe"    : -1 auto (default: single handle with >= 32 cell planes), 0 never, 1 whenever the lattice fits -- all 2 / 4
+ *     "basis_pipe"    : 1 whenever the lattice fits (single handle); default -1 / 0: one launch per colour -- all 2 / 4
  *                       colour passes of a periodic bcc / fcc Heisenberg step as ONE cooperative, phase-pipelined launch
  *                       (basis_pipe.cu): colour b trails colour b-1 by a few planes so that the partner sublattices are read
  *                       from L2; "basis_pipe_lead" (planes the first colour may lead the last, 0 = auto), "basis_pipe_pub"
- *                       (planes per published progress update, 0 = auto: 1), "basis_pipe_tiles" (bands per colour, 0 = auto)
+ *                       (planes per published progress update, 0 = auto: 1), "basis_pipe_tiles" (bands per colour, 0 = auto).
+ *                       Opt-in: compulsory DRAM traffic only, but latency bound and slower than the colour launches so far
  *     "basis_vec"     : 1 (default) 16-byte accesses in the bcc / fcc colour pass when nx % 4 == 0 (fp64: % 2), 0 scalar
  *     "resident_max"  : largest site count of a general-family lattice that runs batches of steps in ONE launch with
  *                       the State in shared memory (default 8192; 0 = always one launch per colour)

@@ -33,6 +33,9 @@ typedef void (*vegas_observable_cb)(void* user, int relax, uint64_t stage, uint6
 typedef void (*vegas_state_cb)(void* user, int relax, uint64_t stage, uint64_t step, double temperature, double field,
                                const void* state, uint64_t n);
 
+/* Slab group (multi-GPU, no reference counterpart): sums `len` doubles in place over the ranks of the group; 0 = ok */
+typedef int (*vegas_reduce_cb)(void* user, double* values, uint64_t len);
+
 /* Machine::new(Thermostat::new(2.8, Field::zero()), ..) as src/input.rs:273-279 builds it.  The machine
  * borrows the handle; the caller keeps ownership of it. */
 int vegas_machine_create(vegas_gpu_t gpu, vegas_machine_t* out);
@@ -47,6 +50,13 @@ int vegas_machine_thermostat(vegas_machine_t, double* temperature, double* field
 int vegas_machine_relax_for(vegas_machine_t, uint64_t steps);    /* src/machine.rs:104-113 */
 int vegas_machine_measure_for(vegas_machine_t, uint64_t steps);  /* src/machine.rs:116-125 */
 uint64_t vegas_machine_steps_done(vegas_machine_t);
+/* One Machine per rank, each over its own connected z-slab of ONE lattice (vegas_gpu_slab_connect): the per-step
+ * energy and magnetisation projections of a batch -- sums over the rank's sites -- are added up over the group with
+ * `reduce` (4 * len doubles at once) before any instrument sees them, and the instruments are told
+ * State::len = n_sites_global.  Every rank runs the same program and replays the same hooks, so Relax / CoolDown /
+ * HysteresisLoop and StatSensor / ObservableSensor behave as on one GPU (src/machine.rs:91-125); a front end normally
+ * lets rank 0 own the output.  A StateSensor receives the rank's OWN slab (local sites).  reduce == NULL: back to one GPU. */
+int vegas_machine_set_group(vegas_machine_t, vegas_reduce_cb reduce, void* user, uint64_t n_sites_global);
 
 /* Programs (src/program.rs:97-115, :182-214, :281-336).  Return VEGAS_ERR_NO_STEPS ... as ProgramError. */
 int vegas_program_relax(vegas_machine_t, uint64_t steps, double temperature);

@@ -97,3 +97,51 @@ def test_sharded_cooldown_points_world2():
     assert [r[1] for r in res] == [3, 2]
     temps = [float(ln.split()[0]) for ln in res[0][2]]
     assert temps == [3.0, 2.75, 2.5, 2.25, 2.0] and res[0][2] == res[1][2]
+
+
+def _group_machine_worker(rank, world, port, q):
+    """One Machine per rank over the scripted test double of the device (tests/mock), grouped with the real
+    torch.distributed reduction the TOML front end uses (run.group_reduce) on gloo."""
+    import ctypes as C
+    import subprocess
+    import types
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = os.path.join(root, "tests", "mock", "libvegas_host_mock.so")
+    if rank == 0 and not os.path.exists(so):
+        subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-I", os.path.join(root, "include"), "-o", so,
+                        os.path.join(root, "tests", "mock", "mock_vegas_gpu.cpp"), os.path.join(root, "vegas_rs_b200", "csrc", "vegas_host.cpp")], check=True)
+    dist.barrier()
+    lib = C.CDLL(so)
+    lib.mock_gpu_create.restype, lib.mock_gpu_create.argtypes = C.c_void_p, [C.c_uint64, C.c_int, C.c_uint64]
+    lib.mock_gpu_destroy.restype, lib.mock_gpu_destroy.argtypes = None, [C.c_void_p]
+    from vegas_rs_b200 import ISING, run
+    from vegas_rs_b200.machine import Machine
+    h = C.c_void_p(lib.mock_gpu_create(10, 0, 2**64 - 1))
+    m = Machine(types.SimpleNamespace(_h=h, model=ISING), lib=lib)
+    lines, batches = [], []
+    m.add_stat_sensor(lambda line, row: lines.append(row))
+    m.add_observable_sensor(lambda *a: batches.append(a))
+    m.set_group(run.group_reduce(dist, 0), 10 * world)
+    m.set_thermostat(2.0)
+    m.measure_for(6)
+    q.put((rank, lines[0][2], batches[0][2], batches[0][5].tolist()))
+    m.close(); lib.mock_gpu_destroy(h)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_slab_group_machine_world2():
+    """Both ranks' sensors see the SUM of the two slabs' per-step energies and State::len = the global site count."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29400 + os.getpid() % 150
+    procs = [ctx.Process(target=_group_machine_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs: p.start()
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs: p.join(60)
+    assert all(p.exitcode == 0 for p in procs)
+    want = [2 * (-0.5 * k + 2.0) for k in range(1, 7)]      # the scripted device: E(step k) = -k/2 + T on each rank
+    for rank, mean_e, n, e in res:
+        assert n == 20 and e == want and abs(mean_e - np.mean(want)) < 1e-12

@@ -113,6 +113,66 @@ def test_machine_chunks_long_stages_without_reordering_steps(mock_lib):
     r.close()
 
 
+def test_hooks_of_a_batch_are_replayed_while_the_next_batch_sweeps(mock_lib):
+    """Without a StateSensor the machine launches batch k + 1 before it replays the hooks of batch k (the device sweeps
+    while the host accumulates); the device call order shows it, and the sensors' view is unchanged."""
+    r = Rig(mock_lib, n=16)
+    r.m.set_thermostat(2.0)
+    r.m.measure_for(9000)
+    calls = [int(c) for c in r.log()[:, 0] if c in (2, 4)]           # 2 = step_async, 4 = read_observables
+    assert calls == [2, 4, 2, 4, 2, 4]                                # launches and reads alternate (one device ring)
+    (relax, stage, n, T, field, e, mag), = r.batches
+    assert len(e) == 9000 and np.array_equal(e, [energy(k, 2.0) for k in range(1, 9001)])
+    (line, row), = r.lines
+    assert row[2] == np.mean([energy(k, 2.0) for k in range(1, 9001)]) or abs(row[2] - np.mean(e)) < 1e-9
+    r.close()
+
+
+def test_slab_group_machine_sums_the_partials_before_the_instruments(mock_lib):
+    """vegas_machine_set_group: the per-step (E, Mx, My, Mz) of a batch are summed over the ranks (here: a scripted
+    reduction that adds a second rank's partials) before StatSensor / ObservableSensor see them, and State::len is the
+    global site count (src/instrument.rs:98-131 divides the variances by it)."""
+    r = Rig(mock_lib, n=10)
+    seen = []
+
+    def reduce_sum(values):
+        seen.append(len(values))
+        k = len(values) // 4
+        values[:k] += 100.0                      # the other slab's energy partial
+        values[k:] *= 2.0                        # ... and a mirror-image magnetisation
+    r.m.set_group(reduce_sum, 20)
+    r.m.set_thermostat(3.0)
+    r.m.relax_for(3)                             # nothing records during relax here? the ObservableSensor does
+    r.m.measure_for(5000)
+    assert seen == [4 * 3, 4 * 4096, 4 * 904]
+    (_, _, n0, _, _, e0, m0), (relax, stage, n, T, field, e, mag) = r.batches
+    assert n0 == n == 20
+    assert np.array_equal(e, [energy(k, 3.0) + 100.0 for k in range(4, 5004)])
+    assert np.array_equal(mag, [2.0 * magnitude(k, False) for k in range(4, 5004)])
+    (line, row), = r.lines
+    assert abs(row[3] - np.var(e) / (20 * 9.0)) < 1e-9 * abs(row[3])       # Cv = Var(E) / (N_global T^2)
+    # a failing reduction surfaces as an error, with the Python exception that caused it
+    r2 = Rig(mock_lib, n=10)
+
+    def broken(values):
+        raise RuntimeError("rank 1 went away")
+    r2.m.set_group(broken, 20)
+    with pytest.raises(RuntimeError, match="rank 1 went away"):
+        r2.m.measure_for(2)
+    r.close(); r2.close()
+
+
+def test_python_exceptions_inside_sensor_callbacks_are_not_swallowed(mock_lib):
+    r = Rig(mock_lib, n=8, sensors=False)
+
+    def on_batch(*a):
+        raise OSError("disk full")
+    r.m.add_observable_sensor(on_batch)
+    with pytest.raises(OSError, match="disk full"):
+        r.m.measure_for(3)
+    r.close()
+
+
 @pytest.mark.parametrize("heis", [False, True], ids=["ising", "heisenberg"])
 def test_state_sensor_schedule_and_contents(mock_lib, heis):
     """StateSensor (src/instrument.rs:265-351): a dump when step.is_multiple_of(frequency), the counter restarts every

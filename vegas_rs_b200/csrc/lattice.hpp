@@ -125,14 +125,30 @@ struct Colouring {
     }
 };
 
-// first-fit greedy colouring of a CSR graph (diagonal ignored); returns number of colours, -1 if > 64
+// first-fit greedy colouring of a CSR graph (diagonal ignored); returns number of colours, -1 if > 64.
+// Exchange::new accepts any CsMat (src/energy.rs:171-173), also one whose pattern is not symmetric: a colour class must
+// be an independent set of the SYMMETRISED pattern (if j lists i but i does not list j, a pass that updates i while j
+// reads it would race), so the transpose's entries count as neighbours too.
 inline int greedy_colour(uint64_t n, const uint64_t* row_ptr, const uint32_t* col, std::vector<uint8_t>& colour) {
+    std::vector<uint64_t> tptr(n + 1, 0);
+    for (uint64_t p = 0; p < row_ptr[n]; ++p) tptr[col[p] + 1]++;
+    for (uint64_t i = 0; i < n; ++i) tptr[i + 1] += tptr[i];
+    std::vector<uint32_t> tcol(row_ptr[n]);
+    {
+        std::vector<uint64_t> fill(tptr.begin(), tptr.end() - 1);
+        for (uint64_t i = 0; i < n; ++i)
+            for (uint64_t p = row_ptr[i]; p < row_ptr[i + 1]; ++p) tcol[fill[col[p]]++] = (uint32_t)i;
+    }
     colour.assign(n, 0xFF);
     int ncol = 0;
     for (uint64_t i = 0; i < n; ++i) {
         uint64_t used = 0;
         for (uint64_t p = row_ptr[i]; p < row_ptr[i + 1]; ++p) {
             const uint32_t j = col[p];
+            if (j != i && colour[j] != 0xFF) used |= 1ull << colour[j];
+        }
+        for (uint64_t p = tptr[i]; p < tptr[i + 1]; ++p) {
+            const uint32_t j = tcol[p];
             if (j != i && colour[j] != 0xFF) used |= 1ull << colour[j];
         }
         int c = 0;

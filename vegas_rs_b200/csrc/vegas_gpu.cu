@@ -94,7 +94,7 @@ struct vegas_gpu {
     HeisPipeState* pipe = nullptr;
     std::string pipe_why;
     // --- phase-pipelined bcc / fcc step (basis_pipe.cu): all colour passes in one cooperative launch
-    int bpipe_enable = -1;                // tuning key basis_pipe: -1 auto (>= 32 cell planes, single handle), 0 never, 1 whenever it fits
+    int bpipe_enable = -1;                // tuning key basis_pipe: 1 = whenever the lattice fits (single handle); -1 / 0: colour launches
     uint32_t bpipe_lead = 0, bpipe_pub = 0, bpipe_tiles = 0;
     bool bpipe_planned = false;
     BasisPipeState* bpipe = nullptr;
@@ -109,6 +109,7 @@ struct vegas_gpu {
     void* peer_halo[2] = {nullptr, nullptr};            // lower / upper neighbour's halo allocation
     unsigned long long* peer_flags[2] = {nullptr, nullptr};
     bool slab = false, connected = false, peer_is_ipc = false;
+    unsigned int* slab_error = nullptr;   // set by a slab wait that timed out (neighbour missing)
     bool peers_remote = false;            // both z-neighbours sweep on other devices (other processes, or other GPUs of this one)
     uint64_t pass_counter = 0;
     // --- general family
@@ -128,6 +129,7 @@ struct vegas_gpu {
     unsigned long long* obs = nullptr;    // [OBS_CAP + 2][OBS_W]; row OBS_CAP = scratch, OBS_CAP+1 = query
     // --- counters
     uint64_t sweeps = 0, attempts = 0, accepted = 0, launches = 0;
+    uint64_t obs_unread = 0;              // rows of the last recorded batch whose accepted counts are not in `accepted` yet
     bool tables_dirty = true;
     std::string err;
 };
@@ -458,12 +460,18 @@ __global__ void signal_kernel(unsigned long long* lower_flag, unsigned long long
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(upper_flag + 0), "l"(value) : "memory");
     }
 }
-__global__ void wait_kernel(const unsigned long long* flags, unsigned long long value) {
+// Bounded: a neighbour that died or ran a different number of passes must not hang this GPU for ever (the sweep then
+// continues on stale halos and `*error` tells every entry point that hands out results).
+__global__ void wait_kernel(const unsigned long long* flags, unsigned long long value, unsigned int* error) {
     if (threadIdx.x < 2) {
         unsigned long long v;
-        do {
+        uint32_t spins = 0;
+        for (;;) {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory");
-        } while (v < value);
+            if (v >= value) break;
+            if (++spins > (1u << 24)) { atomicExch(error, 1u); break; }   // ~10 s
+            if (spins > 1024u) __nanosleep(512);
+        }
     }
     __threadfence_system();
 }
@@ -508,7 +516,7 @@ void preload_msc_slab() {
     preload(ising_msc_kernel<3, false, 3, RP, 0, false, true>); preload(ising_msc_kernel<3, false, 3, RP, 1, false, true>);
 }
 __global__ void signal_kernel(unsigned long long*, unsigned long long*, unsigned long long);
-__global__ void wait_kernel(const unsigned long long*, unsigned long long);
+__global__ void wait_kernel(const unsigned long long*, unsigned long long, unsigned int*);
 __global__ void copy_plane_kernel(uint32_t*, const uint32_t*, size_t);
 void preload_slab_kernels(vegas_gpu* h) {
     preload(signal_kernel); preload(wait_kernel); preload(copy_plane_kernel);
@@ -533,7 +541,7 @@ void stencil_colour_pass(vegas_gpu* h, int mode, int colour, void* obs_row) {
         // all slabs in one process (tests, or one process driving several GPUs): one stream, boundary planes first.
         // (A second stream per handle could alias hardware queues with another handle's spinning wait kernel.)
         h->pass_counter++;
-        if (h->pass_counter > 1) { wait_kernel<<<1, 32, 0, h->stream>>>(h->flags, h->pass_counter - 1); h->launches++; }
+        if (h->pass_counter > 1) { wait_kernel<<<1, 32, 0, h->stream>>>(h->flags, h->pass_counter - 1, h->slab_error); h->launches++; }
         if (Lz >= 2) run(0, 2, Lz - 1, h->stream); else run(0, 1, 1, h->stream);
         signal_kernel<<<1, 32, 0, h->stream>>>(h->peer_flags[0], h->peer_flags[1], h->pass_counter);
         h->launches++;
@@ -546,7 +554,7 @@ void stencil_colour_pass(vegas_gpu* h, int mode, int colour, void* obs_row) {
         cudaEventRecord(h->ev_main, h->stream);
         cudaStreamWaitEvent(h->stream_b, h->ev_main, 0);
         cudaStreamWaitEvent(h->stream, h->ev_bnd, 0);
-        if (h->pass_counter > 1) { wait_kernel<<<1, 32, 0, h->stream_b>>>(h->flags, h->pass_counter - 1); h->launches++; }
+        if (h->pass_counter > 1) { wait_kernel<<<1, 32, 0, h->stream_b>>>(h->flags, h->pass_counter - 1, h->slab_error); h->launches++; }
         if (Lz >= 2) run(0, 2, Lz - 1, h->stream_b); else run(0, 1, 1, h->stream_b);
         signal_kernel<<<1, 32, 0, h->stream_b>>>(h->peer_flags[0], h->peer_flags[1], h->pass_counter);
         h->launches++;
@@ -728,7 +736,7 @@ void basis_pass(vegas_gpu* h, int mode, int b, double* obs, uint32_t zb, uint32_
     }
 }
 __global__ void signal_kernel(unsigned long long*, unsigned long long*, unsigned long long);
-__global__ void wait_kernel(const unsigned long long*, unsigned long long);
+__global__ void wait_kernel(const unsigned long long*, unsigned long long, unsigned int*);
 void basis_pass_any(vegas_gpu* h, int mode, int b, double* obs) {
     const uint32_t nz = (uint32_t)h->ld.nz;
     auto run = [&](uint32_t zb, uint32_t zc, uint32_t zstep, cudaStream_t st) {
@@ -741,7 +749,7 @@ void basis_pass_any(vegas_gpu* h, int mode, int b, double* obs) {
     if (!exchange) { run(0, nz, 1, h->stream); return; }
     h->pass_counter++;
     if (!h->peer_is_ipc) {  // all slabs in one process: one stream (see stencil_colour_pass)
-        if (h->pass_counter > 1) { wait_kernel<<<1, 32, 0, h->stream>>>(h->flags, h->pass_counter - 1); h->launches++; }
+        if (h->pass_counter > 1) { wait_kernel<<<1, 32, 0, h->stream>>>(h->flags, h->pass_counter - 1, h->slab_error); h->launches++; }
         if (nz >= 2) run(0, 2, nz - 1, h->stream); else run(0, 1, 1, h->stream);
         signal_kernel<<<1, 32, 0, h->stream>>>(h->peer_flags[0], h->peer_flags[1], h->pass_counter);
         h->launches++;
@@ -752,7 +760,7 @@ void basis_pass_any(vegas_gpu* h, int mode, int b, double* obs) {
     cudaEventRecord(h->ev_main, h->stream);
     cudaStreamWaitEvent(h->stream_b, h->ev_main, 0);
     cudaStreamWaitEvent(h->stream, h->ev_bnd, 0);
-    if (h->pass_counter > 1) { wait_kernel<<<1, 32, 0, h->stream_b>>>(h->flags, h->pass_counter - 1); h->launches++; }
+    if (h->pass_counter > 1) { wait_kernel<<<1, 32, 0, h->stream_b>>>(h->flags, h->pass_counter - 1, h->slab_error); h->launches++; }
     if (nz >= 2) run(0, 2, nz - 1, h->stream_b); else run(0, 1, 1, h->stream_b);
     signal_kernel<<<1, 32, 0, h->stream_b>>>(h->peer_flags[0], h->peer_flags[1], h->pass_counter);
     h->launches++;
@@ -969,8 +977,9 @@ bool pipe_plan(vegas_gpu* h) {
 
 bool bpipe_plan(vegas_gpu* h) {
     if (h->bpipe_planned) return h->bpipe != nullptr;
-    if (h->family != FAM_HEIS_BASIS || h->slab || h->bpipe_enable == 0) return false;
-    if (h->bpipe_enable < 0 && h->ld.nz < 32) return false;
+    // opt-in (tuning key basis_pipe=1): it moves the compulsory 24 B/attempt through DRAM (5.6 GB per fcc 384^3 step against
+    // 14 GB for four colour launches) but is latency bound at 17 warps per SM: 3.3 ms per step against 2.5 (profiles/r02/README.md)
+    if (h->family != FAM_HEIS_BASIS || h->slab || h->bpipe_enable != 1) return false;
     h->bpipe_planned = true;
     BasisPipeDesc d;
     d.device = h->device; d.f64 = h->md.precision == VEGAS_F64;
@@ -1008,6 +1017,14 @@ int pipe_step(vegas_gpu* h, double* obs_row, bool record) {
 // Persistent kernels report a dependency wait that timed out through a device flag; every entry point that hands
 // results to the caller checks it after synchronising (a stale-plane sweep must never look like a valid one).
 int check_async_errors(vegas_gpu* h) {
+    if (h->slab && h->connected && h->slab_error) {
+        unsigned int serr = 0;
+        CU(cudaMemcpy(&serr, h->slab_error, 4, cudaMemcpyDeviceToHost));
+        if (serr) {
+            cudaMemset(h->slab_error, 0, 4);
+            return fail(h, VEGAS_ERR_CUDA, "slab halo exchange: a z-neighbour never signalled its pass (results invalid)");
+        }
+    }
     if (h->wave_error) {
         unsigned int werr = 0;
         CU(cudaMemcpy(&werr, h->wave_error, 4, cudaMemcpyDeviceToHost));
@@ -1283,6 +1300,8 @@ int common_init(vegas_gpu* h) {
         unsigned long long keep = ~0ull;
         CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     }
+    CU(cudaMalloc(&h->slab_error, 4));
+    CU(cudaMemsetAsync(h->slab_error, 0, 4, h->stream));
     CU(cudaMalloc(&h->obs, (OBS_CAP + 2) * OBS_W * 8));
     CU(cudaMemsetAsync(h->obs, 0, (OBS_CAP + 2) * OBS_W * 8, h->stream));
     return VEGAS_OK;
@@ -1508,7 +1527,7 @@ void vegas_gpu_destroy(vegas_gpu_t h) {
     for (uint32_t* p : h->g_sites) cudaFree(p);
     cudaFree(h->d_row_ptr); cudaFree(h->d_col); cudaFree(h->d_val);
     cudaFree(h->g_thr); cudaFree(h->g_code);
-    cudaFree(h->obs);
+    cudaFree(h->obs); cudaFree(h->slab_error);
     for (int k = 0; k < WAVE_MAX_STEPS; ++k) cudaFree(h->wave_units[k]);
     cudaFree(h->wave_done); cudaFree(h->wave_error);
     heis_pipe_destroy(h->pipe);
@@ -1841,11 +1860,12 @@ int vegas_gpu_set_energy_convention(vegas_gpu_t h, int conv) {
 int vegas_gpu_step_async(vegas_gpu_t h, uint64_t n_steps, int record) {
     if (!h) return VEGAS_ERR_INVALID;
     if (record && n_steps > OBS_CAP) return fail(h, VEGAS_ERR_INVALID, "step_async records at most 4096 steps per call");
+    if (h->slab && !h->connected) return fail(h, VEGAS_ERR_STATE, "slab handle is not connected to its z-neighbours (vegas_gpu_slab_connect)");
     CU(cudaSetDevice(h->device));
     int rc = update_tables(h);
     if (rc) return rc;
     unsigned long long* scratch = h->obs + OBS_CAP * OBS_W;
-    if (record) CU(cudaMemsetAsync(h->obs, 0, n_steps * OBS_W * 8, h->stream));
+    if (record) { CU(cudaMemsetAsync(h->obs, 0, n_steps * OBS_W * 8, h->stream)); h->obs_unread = n_steps; }
     if (resident_plan(h)) {  // small lattice: the whole batch is one launch with the State in shared memory
         uint64_t done = 0;
         while (done < n_steps) {
@@ -1887,10 +1907,11 @@ int vegas_gpu_read_observables(vegas_gpu_t h, uint64_t n_steps, double* energy, 
     { const int rc = check_async_errors(h); if (rc) return rc; }
     for (uint64_t s = 0; s < n_steps; ++s) {
         const Canon c = canon_of(h, host.data() + s * OBS_W);
-        h->accepted += c.accepted;
+        if (s < h->obs_unread) h->accepted += c.accepted;   // each recorded batch is folded into the counter once
         if (energy) energy[s] = energy_of(h, c);
         if (mag_xyz) { mag_xyz[3 * s] = c.m[0]; mag_xyz[3 * s + 1] = c.m[1]; mag_xyz[3 * s + 2] = c.m[2]; }
     }
+    h->obs_unread = 0;
     return VEGAS_OK;
 }
 

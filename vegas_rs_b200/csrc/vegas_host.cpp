@@ -17,17 +17,47 @@ int Machine::set_thermostat(const Thermostat& th) {
     return 0;
 }
 
+// The hooks of one finished batch, in the reference's order (src/machine.rs:96-98): per step every instrument's
+// after_step with the recorded (E, |M|); the StateSensor dump of the batch's last step just before its after_step.
+int Machine::replay_hooks(uint64_t chunk, const std::vector<double>& e, const std::vector<double>& m, bool heis, bool dump,
+                          const std::vector<char>& state, uint64_t n_local) {
+    for (uint64_t s = 0; s < chunk; ++s) {
+        StepView v;
+        v.energy = e[s];
+        const double mx = m[3 * s], my = m[3 * s + 1], mz = m[3 * s + 2];
+        if (heis) {  // HeisenbergSpin::from_projections src/state.rs:150-160
+            const double mag = std::sqrt(mx * mx + my * my + mz * mz);
+            v.magnetization = std::fabs(mag) < DBL_EPSILON ? 0.0 : std::fabs(mag);
+        } else {     // IsingSpin::from_projections src/state.rs:86-92
+            v.magnetization = std::fabs(mz);
+        }
+        for (auto& i : instruments_) {
+            if (s + 1 == chunk && dump && i->next_state_dump(1) == 0) {
+                const int rc = i->state_dump(state.data(), n_local);
+                if (rc) return fail(rc, "state sensor failed");
+            }
+            const int rc = i->after_step(v);
+            if (rc) return fail(rc, "instrument failed");
+        }
+    }
+    return 0;
+}
+
 // Machine::run, src/machine.rs:91-101: steps x { state = integrator.step(..); every instrument.after_step(&state) }.
 // The steps of a batch run back to back on the device with the observers fused into the sweep; the hooks
-// are then replayed in the reference's order with the recorded per-step (E, |M|).
+// are then replayed in the reference's order with the recorded per-step (E, |M|).  Without a StateSensor (whose step
+// counter decides where a batch must end) the hooks of batch k are replayed on the host WHILE batch k + 1 sweeps.
+// In a slab group the per-step partial sums are first summed over the ranks (every rank replays the same hooks).
 int Machine::run(uint64_t steps) {
-    const uint64_t n = n_sites();
+    const uint64_t n_local = vegas_gpu_n_sites(gpu_);
     // every Heisenberg family (heis_stencil, heis_general, heis_basis) reports |M| from three projections and dumps
     // 24-byte spins
     const bool heis = std::strncmp(vegas_gpu_kernel_family(gpu_), "heis", 4) == 0;
-    std::vector<double> e, m;
+    bool overlap = true;
+    for (auto& i : instruments_) overlap = overlap && !i->dumps_states();
+    std::vector<double> e, m, pe, pm, buf;     // current batch; previous batch (hooks pending)
     std::vector<char> state;
-    uint64_t remaining = steps;
+    uint64_t remaining = steps, pending = 0;
     while (remaining > 0) {
         uint64_t chunk = std::min(remaining, CHUNK);
         bool record = false;
@@ -38,42 +68,44 @@ int Machine::run(uint64_t steps) {
         }
         int rc = vegas_gpu_step_async(gpu_, chunk, record ? 1 : 0);
         if (rc) return fail(rc, vegas_gpu_last_error(gpu_));
+        if (pending) {   // the device is busy with this batch: replay the previous one's hooks now
+            rc = replay_hooks(pending, pe, pm, heis, false, state, n_local);
+            if (rc) return rc;
+            pending = 0;
+        }
         e.assign(chunk, 0.0); m.assign(3 * chunk, 0.0);
         if (record) {
             rc = vegas_gpu_read_observables(gpu_, chunk, e.data(), m.data());
             if (rc) return fail(rc, vegas_gpu_last_error(gpu_));
+            if (reduce_) {   // E and the three projections are sums over sites: add the slabs' partials
+                buf.resize(4 * chunk);
+                std::copy(e.begin(), e.end(), buf.begin());
+                std::copy(m.begin(), m.end(), buf.begin() + chunk);
+                if (reduce_(reduce_user_, buf.data(), 4 * chunk)) return fail(VEGAS_ERR_STATE, "slab group reduction failed");
+                std::copy(buf.begin(), buf.begin() + chunk, e.begin());
+                std::copy(buf.begin() + chunk, buf.end(), m.begin());
+            }
         }
         bool dump = false;
         for (auto& i : instruments_) dump = dump || i->next_state_dump(chunk) == (int64_t)chunk - 1;
         if (dump) {  // the only place a host State exists (src/instrument.rs:340-350 needs it)
-            state.resize(heis ? n * 24 : n);
-            rc = heis ? vegas_gpu_download_heisenberg(gpu_, (double*)state.data(), n)
-                      : vegas_gpu_download_ising(gpu_, (int8_t*)state.data(), n);
+            state.resize(heis ? n_local * 24 : n_local);
+            rc = heis ? vegas_gpu_download_heisenberg(gpu_, (double*)state.data(), n_local)
+                      : vegas_gpu_download_ising(gpu_, (int8_t*)state.data(), n_local);
             if (rc) return fail(rc, vegas_gpu_last_error(gpu_));
-        }
-        for (uint64_t s = 0; s < chunk; ++s) {
-            StepView v;
-            v.energy = e[s];
-            const double mx = m[3 * s], my = m[3 * s + 1], mz = m[3 * s + 2];
-            if (heis) {  // HeisenbergSpin::from_projections src/state.rs:150-160
-                const double mag = std::sqrt(mx * mx + my * my + mz * mz);
-                v.magnetization = std::fabs(mag) < DBL_EPSILON ? 0.0 : std::fabs(mag);
-            } else {     // IsingSpin::from_projections src/state.rs:86-92
-                v.magnetization = std::fabs(mz);
-            }
-            for (auto& i : instruments_) {
-                if (s + 1 == chunk && dump && i->next_state_dump(1) == 0) {
-                    rc = i->state_dump(state.data(), n);
-                    if (rc) return fail(rc, "state sensor failed");
-                }
-                rc = i->after_step(v);
-                if (rc) return fail(rc, "instrument failed");
-            }
         }
         remaining -= chunk;
         steps_done_ += chunk;
+        if (overlap && remaining > 0) {
+            pe.swap(e); pm.swap(m); pending = chunk;
+        } else {
+            rc = replay_hooks(chunk, e, m, heis, dump, state, n_local);
+            if (rc) return rc;
+        }
     }
-    return vegas_gpu_synchronize(gpu_);
+    if (pending) { const int rc = replay_hooks(pending, pe, pm, heis, false, state, n_local); if (rc) return rc; }
+    const int rc = vegas_gpu_synchronize(gpu_);
+    return rc ? fail(rc, vegas_gpu_last_error(gpu_)) : 0;
 }
 
 int Machine::relax_for(uint64_t steps) {  // src/machine.rs:104-113
@@ -191,6 +223,11 @@ int vegas_machine_thermostat(vegas_machine_t m, double* temperature, double* fie
 int vegas_machine_relax_for(vegas_machine_t m, uint64_t steps) { return m ? m->m.relax_for(steps) : VEGAS_ERR_INVALID; }
 int vegas_machine_measure_for(vegas_machine_t m, uint64_t steps) { return m ? m->m.measure_for(steps) : VEGAS_ERR_INVALID; }
 uint64_t vegas_machine_steps_done(vegas_machine_t m) { return m ? m->m.steps_done() : 0; }
+int vegas_machine_set_group(vegas_machine_t m, vegas_reduce_cb reduce, void* user, uint64_t n_sites_global) {
+    if (!m || (reduce && n_sites_global == 0)) return VEGAS_ERR_INVALID;
+    m->m.set_group(reduce, user, n_sites_global);
+    return VEGAS_OK;
+}
 
 int vegas_program_relax(vegas_machine_t m, uint64_t steps, double temperature) {
     if (!m) return VEGAS_ERR_INVALID;

@@ -67,6 +67,7 @@ class Instrument {
     virtual int after_step(const StepView&) { return 0; }
     virtual bool wants_observables() const { return false; }  // needs (E, M) of the coming steps
     virtual int64_t next_state_dump(uint64_t /*steps_ahead*/) const { return -1; }  // steps until a host State is needed
+    virtual bool dumps_states() const { return false; }   // true: batch sizes depend on this instrument's step counter
     virtual int state_dump(const void* /*state*/, uint64_t /*n*/) { return 0; }
 };
 
@@ -146,6 +147,7 @@ class StateSensor : public Instrument {
         if (cb_ && relax_ >= 0) cb_(user_, relax_, stage_, step_, th_.temperature, th_.field_magnitude(), state, n);
         return 0;
     }
+    bool dumps_states() const override { return true; }
 };
 
 // src/machine.rs:44-125
@@ -155,16 +157,21 @@ class Machine {
     std::vector<std::unique_ptr<Instrument>> instruments_;
     uint64_t steps_done_ = 0;
     std::string err_;
+    // slab group (one Machine per rank, each over its own z-slab): sums the per-step partials over the ranks
+    vegas_reduce_cb reduce_ = nullptr; void* reduce_user_ = nullptr; uint64_t n_global_ = 0;
     int run(uint64_t steps);
+    int replay_hooks(uint64_t chunk, const std::vector<double>& e, const std::vector<double>& m, bool heis, bool dump,
+                     const std::vector<char>& state, uint64_t n_local);
   public:
     explicit Machine(vegas_gpu_t gpu) : gpu_(gpu) {}
+    void set_group(vegas_reduce_cb reduce, void* user, uint64_t n_sites_global) { reduce_ = reduce; reduce_user_ = user; n_global_ = n_sites_global; }
     const Thermostat& thermostat() const { return th_; }
     int set_thermostat(const Thermostat& th);
     void add(std::unique_ptr<Instrument> i) { instruments_.push_back(std::move(i)); }
     int relax_for(uint64_t steps);
     int measure_for(uint64_t steps);
     uint64_t steps_done() const { return steps_done_; }
-    uint64_t n_sites() const { return vegas_gpu_n_sites(gpu_); }
+    uint64_t n_sites() const { return reduce_ ? n_global_ : vegas_gpu_n_sites(gpu_); }   // State::len as the instruments see it
     const std::string& error() const { return err_; }
     int fail(int code, const std::string& msg) { err_ = msg; return code; }
 };

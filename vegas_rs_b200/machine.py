@@ -13,6 +13,7 @@ STAT_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p, C.c_double, C.c_double, C.c_
 OBS_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_double, C.c_double, C.POINTER(C.c_double),
                      C.POINTER(C.c_double), C.c_uint64)
 STATE_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_double, C.c_double, C.c_void_p, C.c_uint64)
+REDUCE_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_uint64)
 
 HOST_SYMBOLS = [
     ("vegas_machine_create", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
@@ -26,6 +27,7 @@ HOST_SYMBOLS = [
     ("vegas_machine_relax_for", C.c_int, [C.c_void_p, C.c_uint64]),
     ("vegas_machine_measure_for", C.c_int, [C.c_void_p, C.c_uint64]),
     ("vegas_machine_steps_done", C.c_uint64, [C.c_void_p]),
+    ("vegas_machine_set_group", C.c_int, [C.c_void_p, REDUCE_CB, C.c_void_p, C.c_uint64]),
     ("vegas_program_relax", C.c_int, [C.c_void_p, C.c_uint64, C.c_double]),
     ("vegas_program_cooldown", C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint64]),
     ("vegas_program_hysteresis", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_double, C.c_double, C.c_double]),
@@ -67,8 +69,22 @@ class Machine:
         if rc:
             raise VegasGpuError(rc, "vegas_machine_create failed")
         self._keep = []
+        self._cb_error = None
+
+    def _guard(self, fn):
+        """ctypes swallows exceptions raised inside a callback: keep the first one and re-raise it when the C call returns"""
+        def wrapped(*a):
+            if self._cb_error is None:
+                try:
+                    return fn(*a)
+                except Exception as e:
+                    self._cb_error = e
+        return wrapped
 
     def _check(self, rc):
+        err, self._cb_error = self._cb_error, None
+        if err is not None:
+            raise err
         if rc:
             msg = (self._lib.vegas_machine_last_error(self._m) or b"").decode()
             if rc in PROGRAM_ERRORS:
@@ -89,7 +105,7 @@ class Machine:
     # ---- instruments (called in the order added, src/machine.rs:96-98)
     def add_stat_sensor(self, on_line):
         """on_line(line: str, row: tuple of the 7 numbers) -- StatSensor, src/instrument.rs:61-142"""
-        cb = STAT_CB(lambda u, line, *row: on_line(line.decode(), row))
+        cb = STAT_CB(self._guard(lambda u, line, *row: on_line(line.decode(), row)))
         self._keep.append(cb)
         self._check(self._lib.vegas_machine_add_stat_sensor(self._m, cb, None))
 
@@ -99,7 +115,7 @@ class Machine:
             ea = np.ctypeslib.as_array(e, (ln,)).copy() if ln else np.zeros(0)
             ma = np.ctypeslib.as_array(m, (ln,)).copy() if ln else np.zeros(0)
             on_batch(bool(relax), stage, n, T, field, ea, ma)
-        cb = OBS_CB(tramp)
+        cb = OBS_CB(self._guard(tramp))
         self._keep.append(cb)
         self._check(self._lib.vegas_machine_add_observable_sensor(self._m, cb, None))
 
@@ -112,9 +128,24 @@ class Machine:
             else:
                 a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), (n, 3)).copy()
             on_state(bool(relax), stage, step, T, field, a)
-        cb = STATE_CB(tramp)
+        cb = STATE_CB(self._guard(tramp))
         self._keep.append(cb)
         self._check(self._lib.vegas_machine_add_state_sensor(self._m, frequency, cb, None))
+
+    # ---- slab group (multi-GPU): one Machine per rank over its own z-slab of one lattice
+    def set_group(self, reduce_sum, n_sites_global: int):
+        """reduce_sum(values: np.ndarray) sums the array IN PLACE over the ranks (e.g. an all-reduce); every rank must run
+        the same program.  The instruments then see the whole lattice's E, |M| and State::len = n_sites_global."""
+        def tramp(u, ptr, ln):
+            try:
+                reduce_sum(np.ctypeslib.as_array(ptr, (ln,)))
+                return 0
+            except Exception as e:  # ctypes would swallow it: report a failed reduction instead
+                self._cb_error = e
+                return 1
+        cb = REDUCE_CB(tramp)
+        self._keep.append(cb)
+        self._check(self._lib.vegas_machine_set_group(self._m, cb, None, n_sites_global))
 
     # ---- machine (src/machine.rs:104-125)
     def set_thermostat(self, temperature, field_dir=(0.0, 0.0, 1.0), field_mag=0.0):
