@@ -48,6 +48,7 @@ pub struct vegas_lattice_desc {
 type vegas_gpu_t = *mut c_void;
 type vegas_machine_t = *mut c_void;
 type stat_cb = extern "C" fn(*mut c_void, *const c_char, f64, f64, f64, f64, f64, f64, f64);
+type reduce_cb = extern "C" fn(*mut c_void, *mut f64, u64) -> c_int;   // in-place sum over the ranks of a slab group
 
 unsafe extern "C" {
     fn vegas_gpu_create_lattice(md: *const vegas_model_desc, ld: *const vegas_lattice_desc, out: *mut vegas_gpu_t) -> c_int;
@@ -66,6 +67,7 @@ unsafe extern "C" {
     fn vegas_machine_destroy(m: vegas_machine_t);
     fn vegas_machine_last_error(m: vegas_machine_t) -> *const c_char;
     fn vegas_machine_add_stat_sensor(m: vegas_machine_t, cb: stat_cb, user: *mut c_void) -> c_int;
+    fn vegas_machine_set_group(m: vegas_machine_t, reduce: reduce_cb, user: *mut c_void, n_sites_global: u64) -> c_int;
     fn vegas_program_relax(m: vegas_machine_t, steps: u64, temperature: f64) -> c_int;
     fn vegas_program_cooldown(m: vegas_machine_t, tmax: f64, tmin: f64, rate: f64, relax: u64, steps: u64) -> c_int;
     fn vegas_program_hysteresis(m: vegas_machine_t, steps: u64, relax: u64, t: f64, max_field: f64, step: f64) -> c_int;
