@@ -53,7 +53,7 @@ NCU_TRAFFIC = {
                      "basis_pipe": (2.981e9 + 2.667e9, "profiles/r02_basis_pipe.metrics.txt (one step = four colours, one launch)")},
 }
 # step kernels that do every colour of a step in ONE launch
-ONE_LAUNCH_KERNELS = ("heis_pipe", "basis_pipe", "heis_wave", "heis_fused")
+ONE_LAUNCH_KERNELS = ("heis_pipe", "basis_pipe", "basis_wave", "heis_wave", "heis_fused")
 # the CPU arm always runs this many single-threaded replicas (or every core of a smaller host), so that the driver's
 # GPU / reference ratio means the same thing on every box
 REFERENCE_REPLICAS = 16

@@ -191,6 +191,14 @@ int vegas_gpu_slab_connect_local(vegas_gpu_t self, vegas_gpu_t lower, vegas_gpu_
  *                       from L2; "basis_pipe_lead" (planes the first colour may lead the last, 0 = auto), "basis_pipe_pub"
  *                       (planes per published progress update, 0 = auto: 1), "basis_pipe_tiles" (bands per colour, 0 = auto).
  *                       Opt-in: compulsory DRAM traffic only, but latency bound and slower than the colour launches so far
+ *     "basis_wave"    : 1 whenever the lattice has enough planes; default -1 / 0: one launch per colour -- all 2 / 4 colour
+ *                       passes of a periodic bcc / fcc Heisenberg step as ONE persistent cooperative launch whose work items
+ *                       (those of the colour launches) are drawn in wave order, colour b a few planes behind colour b-1, so
+ *                       that a pass finds its partner sublattices in L2 (basis_wave.cu; also on connected z-slabs with
+ *                       neighbours on other devices); "basis_wave_lag" (time slots between consecutive colours, 0 = auto: 2),
+ *                       "basis_wave_ipt" (16-byte work items per thread and tile, 0 = auto), "basis_wave_grid" (cap on the
+ *                       number of CTAs, 0 = as many as are co-resident).  Opt-in: a third less DRAM traffic, but slower than
+ *                       the colour launches so far (per-item synchronisation, no L1 reuse between rows)
  *     "basis_vec"     : 1 (default) 16-byte accesses in the bcc / fcc colour pass when nx % 4 == 0 (fp64: % 2), 0 scalar
  *     "resident_max"  : largest site count of a general-family lattice that runs batches of steps in ONE launch with
  *                       the State in shared memory (default 8192; 0 = always one launch per colour)
@@ -200,6 +208,10 @@ int vegas_gpu_set_tuning(vegas_gpu_t, const char* key, long value);
  * (units[i] = phase << 24 | chunk, phase = 2 * step + colour; 2 * steps * n_chunks entries).  Exposed so that the
  * schedule's invariant -- every unit comes after the three units it waits for -- is tested without a GPU. */
 int vegas_gpu_wave_schedule(uint32_t n_chunks, uint32_t lag, uint32_t steps, uint32_t* units, uint64_t capacity, uint64_t* count);
+/* host-only: the unit order of one wave-ordered bcc / fcc step (basis_wave.cu) over `nz` cell planes with `lag` time slots
+ * between consecutive colours: units[i] = colour << 24 | plane, n_basis * nz entries (count = 0: too few planes for the
+ * scheme); need[b] bit 2a + r = colour b on plane z waits for colour a on plane (z + r) % nz.  unitcell: VEGAS_BCC / VEGAS_FCC. */
+int vegas_gpu_basis_wave_schedule(int unitcell, uint32_t nz, uint32_t lag, uint32_t* units, uint64_t capacity, uint64_t* count, uint32_t need[4]);
 /* name of the kernel the NEXT step will launch: "heis_fused", "heis_stencil", "ising_msc", ... */
 const char* vegas_gpu_step_kernel(vegas_gpu_t);
 

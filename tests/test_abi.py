@@ -126,6 +126,56 @@ def test_wave_schedule_dependencies_precede_their_users(built, n_chunks, lag, st
     assert lib.vegas_gpu_wave_schedule(8, 3, 5, None, 0, C.byref(count)) != 0
 
 
+@pytest.mark.parametrize("uc,nb", [(1, 2), (2, 4)], ids=["bcc", "fcc"])
+@pytest.mark.parametrize("nz,lag", [(384, 3), (32, 1), (12, 3), (7, 1), (40, 5)])
+def test_basis_wave_schedule_dependencies_precede_their_users(built, uc, nb, nz, lag):
+    """basis_wave.cu deals (colour, plane) units to co-resident CTAs in list order; a unit spins until every bonded LOWER
+    colour is complete on the planes its bonds reach.  Checked against the adjacency itself (vegas_gpu_lattice_adjacency):
+    every neighbour of a site of colour b on plane z that belongs to a lower colour lies on plane z or z + 1, the schedule
+    waits for exactly those (need mask), and the unit it waits for comes EARLIER in the list."""
+    from vegas_rs_b200 import _lib
+    lib = _lib.load()
+    count = C.c_uint64()
+    need = np.zeros(4, np.uint32)
+    assert lib.vegas_gpu_basis_wave_schedule(uc, nz, lag, None, 0, C.byref(count), need.ctypes.data_as(C.c_void_p)) == 0
+    assert count.value == nb * nz
+    units = np.zeros(count.value, np.uint32)
+    assert lib.vegas_gpu_basis_wave_schedule(uc, nz, lag, units.ctypes.data_as(C.c_void_p), units.size, C.byref(count), need.ctypes.data_as(C.c_void_p)) == 0
+    colour, plane = units >> 24, units & 0xFFFFFF
+    position = {(int(b), int(z)): i for i, (b, z) in enumerate(zip(colour, plane))}
+    assert len(position) == units.size and set(position) == {(b, z) for b in range(nb) for z in range(nz)}
+    # what the bonds really reach: a 4 x 4 x 6 lattice of the same unit cell (site = cell * nb + basis)
+    d = _lib.LatticeDesc(uc, 4, 4, 6, 1, 1, 1, 0, 0, 0)
+    n, nnz = C.c_uint64(), C.c_uint64()
+    assert lib.vegas_gpu_lattice_adjacency(C.byref(d), 1.0, C.byref(n), C.byref(nnz), None, None, None) == 0
+    rp = np.zeros(n.value + 1, np.uint64); col = np.zeros(nnz.value, np.uint32)
+    assert lib.vegas_gpu_lattice_adjacency(C.byref(d), 1.0, C.byref(n), C.byref(nnz), rp.ctypes.data_as(C.c_void_p), col.ctypes.data_as(C.c_void_p), None) == 0
+    reach = {}
+    for i in range(n.value):
+        b, zi = i % nb, (i // nb) // 16
+        for j in col[int(rp[i]):int(rp[i + 1])]:
+            a, zj = int(j) % nb, (int(j) // nb) // 16
+            reach.setdefault((b, a), set()).add((zj - zi + 3) % 6 - 3)
+    for b in range(nb):
+        want = 0
+        for a in range(b):
+            dzs = reach.get((b, a), set())
+            assert dzs <= {0, 1}, (b, a, dzs)          # lower colours only at dz >= 0: the structure the scheme relies on
+            for r in dzs:
+                want |= 1 << (2 * a + r)
+        assert int(need[b]) == want, (b, hex(int(need[b])), hex(want))
+    for (b, z), i in position.items():
+        for a in range(b):
+            for r in range(2):
+                if (int(need[b]) >> (2 * a + r)) & 1:
+                    assert position[(a, (z + r) % nz)] < i, (b, z, a, r)
+    # each colour walks the planes in order
+    for b in range(nb):
+        assert [int(z) for q, z in zip(colour, plane) if q == b] == list(range(nz))
+    assert lib.vegas_gpu_basis_wave_schedule(0, nz, lag, None, 0, C.byref(count), need.ctypes.data_as(C.c_void_p)) != 0
+    assert lib.vegas_gpu_basis_wave_schedule(uc, 3, 3, None, 0, C.byref(count), need.ctypes.data_as(C.c_void_p)) == 0 and count.value == 0
+
+
 def test_rust_shim_struct_layout_matches_header():
     """bindings/rust/gpu.rs cannot be compiled here; at least its #[repr(C)] structs must list the fields of
     include/vegas_gpu.h in the same order, and every extern function it declares must exist in the headers."""

@@ -140,7 +140,7 @@ BASIS_CASES = [
 def test_basis_pipe_identical_to_colour_passes(built, uc, size, precision, tiles, lead, pub, proposal):
     kw = dict(unitcell=uc, size=size, precision=precision, seed=31, anisotropy=((0.6, 0, 0.8), 0.15), proposal=proposal)
     ref = vg.GpuMetropolis(vg.HEISENBERG, **kw)
-    ref.set_tuning("basis_pipe", 0)
+    ref.set_tuning("basis_pipe", 0); ref.set_tuning("basis_wave", 0)
     assert ref.step_kernel == "heis_basis"
     ref.randomize(); ref.set_thermostat(1.4, (0, 0, 1.0), 0.4)
     e0, m0 = ref.step(3)
@@ -189,4 +189,95 @@ def test_basis_pipe_replays_the_reference_rule(built):
         assert np.max(np.abs(g.download() - cpu)) < 1e-12
         assert abs(e[0] - H.total_energy(th, cpu)) < 1e-12 * n * 10
         assert np.max(np.abs(m[0] - cpu.sum(axis=0))) < 1e-12 * n
+    g.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K4w: the colour passes of a periodic bcc / fcc step as one persistent launch in wave order (vegas_rs_b200/csrc/basis_wave.cu)
+# ---------------------------------------------------------------------------------------------------------------------
+# (unit cell, size, precision, slots between colours, items per thread, CTA cap): many tiles per unit, one tile per unit, fewer
+# CTAs than items of a slot (every CTA walks several units, the waits are real), minimal and wide lags, ragged last tile
+WAVE_CASES = [
+    (vg.FCC, (16, 6, 14), vg.F32, 0, 0, 0),
+    (vg.FCC, (64, 40, 12), vg.F32, 1, 1, 0),
+    (vg.FCC, (64, 40, 16), vg.F32, 2, 1, 3),
+    (vg.FCC, (64, 40, 16), vg.F32, 1, 2, 1),         # a single CTA: pure item order
+    (vg.FCC, (8, 9, 20), vg.F64, 3, 1, 5),
+    (vg.FCC, (4, 2, 8), vg.F32, 1, 0, 0),
+    (vg.BCC, (8, 7, 10), vg.F32, 0, 0, 0),
+    (vg.BCC, (36, 10, 16), vg.F64, 2, 1, 7),
+    (vg.FCC, (384, 40, 12), vg.F32, 0, 0, 0),        # config[4] rows
+]
+
+
+@pytest.mark.parametrize("uc,size,precision,lag,ipt,grid", WAVE_CASES)
+@pytest.mark.parametrize("proposal", [vg.PROPOSE_RANDOM, vg.PROPOSE_FLIP], ids=["random", "flip"])
+def test_basis_wave_identical_to_colour_passes(built, uc, size, precision, lag, ipt, grid, proposal):
+    kw = dict(unitcell=uc, size=size, precision=precision, seed=33, anisotropy=((0.6, 0, 0.8), 0.15), proposal=proposal)
+    ref = vg.GpuMetropolis(vg.HEISENBERG, **kw)
+    ref.set_tuning("basis_wave", 0)
+    assert ref.step_kernel == "heis_basis"
+    ref.randomize(); ref.set_thermostat(1.4, (0, 0, 1.0), 0.4)
+    e0, m0 = ref.step(3)
+    ref.step(2, observe=False)
+    e1, m1 = ref.step(1)
+    want = ref.download(); acc = ref.attempt_count()
+    ref.close()
+    g = vg.GpuMetropolis(vg.HEISENBERG, **kw)
+    g.set_tuning("basis_wave", 1)
+    for k, v in (("basis_wave_lag", lag), ("basis_wave_ipt", ipt), ("basis_wave_grid", grid)):
+        if v:
+            g.set_tuning(k, v)
+    assert g.step_kernel == "basis_wave"
+    g.randomize(); g.set_thermostat(1.4, (0, 0, 1.0), 0.4)
+    e, m = g.step(3)
+    g.step(2, observe=False)
+    e2, m2 = g.step(1)
+    g.synchronize()
+    assert np.array_equal(g.download(), want)
+    n = g.n_sites
+    tol = 1e-12 if precision == vg.F64 else 1e-6
+    assert np.allclose(e, e0, rtol=tol, atol=tol * n) and np.allclose(e2, e1, rtol=tol, atol=tol * n)
+    assert np.allclose(m, m0, rtol=10 * tol, atol=10 * tol * n) and np.allclose(m2, m1, rtol=10 * tol, atol=10 * tol * n)
+    assert g.attempt_count() == acc
+    g.close()
+
+
+def test_basis_wave_replays_the_reference_rule(built):
+    """fcc, fp64: every decision of the wave-ordered step against the oracle replay (Hamiltonian::energy of src/energy.rs,
+    accept rule of src/integrator.rs:82-88); the fused E and M equal total_energy / magnetization of the replayed state."""
+    lat = dict(unitcell=vg.FCC, size=(8, 6, 12))
+    kw = dict(exchange=1.0, zeeman=True, anisotropy=((0.6, 0.0, 0.8), 0.25))
+    g = vg.GpuMetropolis(vg.HEISENBERG, precision=vg.F64, seed=12, **kw, **lat)
+    g.set_tuning("basis_wave", 1); g.set_tuning("basis_wave_grid", 9)
+    assert g.step_kernel == "basis_wave"
+    H, _ = oracle_model(ob.HEISENBERG, **kw, **lat)
+    n = g.n_sites
+    g.upload(random_state(ob.HEISENBERG, n, 3))
+    cpu = g.download(); col = g.colours()
+    g.set_thermostat(1.5, (0, 0, 1.0), 0.7)
+    th = H.thermostat(1.5, (0, 0, 1.0), 0.7)
+    for _ in range(3):
+        sweep = g.sweeps
+        e, m = g.step(1)
+        H.replay_heisenberg(th, ob.PROPOSE_RANDOM, False, 12, sweep, col, g.n_colours, cpu)
+        assert np.max(np.abs(g.download() - cpu)) < 1e-12
+        assert abs(e[0] - H.total_energy(th, cpu)) < 1e-12 * n * 10
+        assert np.max(np.abs(m[0] - cpu.sum(axis=0))) < 1e-12 * n
+    g.close()
+
+
+def test_basis_wave_is_opt_in(built):
+    g = vg.GpuMetropolis(vg.HEISENBERG, unitcell=vg.FCC, size=(64, 32, 32), seed=5)
+    assert g.step_kernel == "heis_basis"          # measured slower than the colour launches so far: not a default
+    g.set_tuning("basis_wave", 1)
+    assert g.step_kernel == "basis_wave"
+    g.randomize(); g.set_thermostat(1.0, (0, 0, 1.0), 0.3)
+    e, m = g.step(4)
+    assert abs(g.total_energy() - e[-1]) < 1e-5 * abs(e[-1]) + 1e-5 * g.n_sites
+    assert np.max(np.abs(g.magnetization() - m[-1])) < 1e-5 * g.n_sites
+    g.close()
+    g = vg.GpuMetropolis(vg.HEISENBERG, unitcell=vg.FCC, size=(64, 32, 4), seed=5)     # too few planes for the wave order
+    g.set_tuning("basis_wave", 1)
+    assert g.step_kernel == "heis_basis"
     g.close()

@@ -15,7 +15,7 @@ def test_host_symbols_exported(built):
     lib = machine._load()
     text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "vegas_host.h")).read(), flags=re.S)
     names = sorted(set(re.findall(r"\b(vegas_(?:machine|program)_[a-z_]+)\s*\(", text)))
-    assert len(names) == 14
+    assert len(names) == 15 and "vegas_machine_set_group" in names
     bound = {s[0] for s in machine.HOST_SYMBOLS}
     for n in names:
         assert hasattr(lib, n) and n in bound, n

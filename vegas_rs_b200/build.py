@@ -23,6 +23,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 _DEPS = {
     "heis_pipe.cu": ["heis_pipe.hpp", "pipe_ptx.cuh", "heis.cuh", "common.cuh"],
     "basis_pipe.cu": ["basis_pipe.hpp", "pipe_ptx.cuh", "heis_basis.cuh", "heis.cuh", "common.cuh"],
+    "basis_wave.cu": ["basis_wave.hpp", "pipe_ptx.cuh", "heis_basis.cuh", "heis.cuh", "common.cuh"],
     "vegas_host.cpp": ["vegas_host.hpp"],
 }
 

@@ -34,7 +34,7 @@ template <typename real>
 struct BasisPipeArgs {
     BasisPtrs<real> P;
     uint32_t nx, ny, nz;
-    uint32_t tiles, rows, tiles_long, n_cw, lead, pub_every;
+    uint32_t tiles, items_per_band, lead, pub_every;   // bands per colour; work items (16-byte vectors) of a plane per band
     unsigned long long* prog;      // [NB][tiles] planes finished, monotone over the launches
     unsigned long long base;
     unsigned int* error;
@@ -55,11 +55,13 @@ constexpr __host__ __device__ int basis_reach() {
     return m;   // -1: no bond
 }
 
-constexpr uint32_t BP_STAGES = 2;   // output tiles in flight: one being filled, one being stored
+constexpr uint32_t BP_STAGES = 2;   // output tiles per warp: one being filled, one being stored
+constexpr uint32_t BP_CNT = 8;      // per-plane completion counters in flight; a warp may be at most BP_AHEAD planes ahead of the slowest
+constexpr uint32_t BP_AHEAD = 4;
 
 // One work item: NV consecutive cells of row iy of plane iz.  Neighbour walk copied from heis_basis_vec_kernel (heis_basis.cuh).
 template <typename real, int UC, int B, bool FLIP, bool RECORD>
-__device__ __forceinline__ void basis_item(const BasisPipeArgs<real>& A, uint32_t iz, uint32_t iy, uint32_t x0, real* out /* [3][rows * nx] */,
+__device__ __forceinline__ void basis_item(const BasisPipeArgs<real>& A, uint32_t iz, uint32_t iy, uint32_t x0, real* out /* [3][out_comp] */,
                                            uint32_t out_off, uint32_t out_comp, real (&fs)[5], int& accepted) {
     constexpr int NB = BasisCell<UC>::NB, Z = BasisCell<UC>::Z, N = VecOf<real>::N;
     const uint32_t nx = A.nx, ny = A.ny, nz = A.nz;
@@ -124,123 +126,151 @@ __device__ __forceinline__ void basis_item(const BasisPipeArgs<real>& A, uint32_
     }
 }
 
-struct BandCtx {
-    uint32_t tile, y0, nr, n_ct;            // band, first row, rows, consumer threads
-    uint64_t *done, *freed;                 // per output stage: filled by every consumer warp / read by the bulk store
-    volatile uint32_t* abort_flag;
-    double* s_acc;
+// shared control words of a CTA
+struct BandShared {
+    uint32_t gate_open;          // planes z < gate_open may be updated (dependencies on the other colours' bands known to hold)
+    uint32_t gate_lock;          // one warp at a time polls the progress counters
+    uint32_t cta_done;           // planes every warp of this CTA has stored completely
+    uint32_t abort_flag;
+    uint32_t plane_cnt[BP_CNT];  // warps whose stores of plane (z % BP_CNT) are complete
 };
 
-// The march of the consumers of CTA (B, band) over the planes.
-template <typename real, int UC, int B, bool FLIP, bool RECORD>
-__device__ __forceinline__ void basis_march(const BasisPipeArgs<real>& A, const BandCtx& cx, real* out_ring, uint32_t stage_elems) {
-    constexpr int NB = BasisCell<UC>::NB, N = VecOf<real>::N;
-    const uint32_t nz = A.nz, VX = A.nx / N, items = cx.nr * VX;
-    const uint32_t tm = cx.tile == 0 ? A.tiles - 1 : cx.tile - 1, tp = cx.tile + 1 == A.tiles ? 0u : cx.tile + 1;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t out_comp = A.rows * A.nx;
-    unsigned long long seen = 0;   // warp 0: last value read of the progress counter this lane watches
-    real fs[5] = {0, 0, 0, 0, 0};
-    int accepted = 0;
-    RingPos ps;     // output stage of plane z; parity of its use
-    for (uint32_t z = 0; z < nz; ++z) {
-        if (threadIdx.x < 32) {
-            // warp 0 does the waiting, one lane per counter, so that the (up to eleven) round trips to L2 overlap:
-            //   lanes 3a .. 3a+2: lower colour a on the bands t-1, t, t+1 (its planes my bonds reach must be final);
-            //   lane 9: the last colour (the first one stays within `lead` planes of it: L2 working set);
-            //   lane 10: my output stage (the store of plane z - BP_STAGES has read it)
-            constexpr int R0 = basis_reach<UC, B, 0>(), R1 = basis_reach<UC, B, (NB > 1 ? 1 : 0)>(), R2 = basis_reach<UC, B, (NB > 2 ? 2 : 0)>();
-            const uint32_t a = lane / 3u, which = lane - a * 3u;
-            const int reach = a == 0 ? R0 : (a == 1 ? R1 : R2);
-            if (lane < 9u && (int)a < B && reach >= 0) {
-                const unsigned long long target = A.base + (unsigned long long)min(z + (uint32_t)reach + 1u, nz);
-                if (seen < target)
-                    wait_counter<false>(A.prog + (size_t)a * A.tiles + (which == 0 ? tm : (which == 1 ? cx.tile : tp)), target, seen, cx.abort_flag, A.error, PIPE_ERR_GATE);
-            } else if (lane == 9u && B == 0 && NB > 1 && z >= A.lead) {
-                const unsigned long long target = A.base + (unsigned long long)(z - A.lead) + 1ull;
-                if (seen < target) wait_counter<false>(A.prog + (size_t)(NB - 1) * A.tiles + cx.tile, target, seen, cx.abort_flag, A.error, PIPE_ERR_GATE);
-            } else if (lane == 10u && z >= BP_STAGES) {
-                wait_bar(cx.freed + ps.slot, ps.parity ^ 1u, cx.abort_flag, A.error, PIPE_ERR_EMPTY);
-            }
-            __syncwarp();
-        }
-        asm volatile("bar.sync 1, %0;" ::"r"(cx.n_ct) : "memory");
-        if (*cx.abort_flag) break;
-        real* out = out_ring + (size_t)ps.slot * stage_elems;
-        for (uint32_t item = threadIdx.x; item < items; item += cx.n_ct) {
-            const uint32_t r = item / VX, x0 = (item - r * VX) * N;
-            basis_item<real, UC, B, FLIP, RECORD>(A, z, cx.y0 + r, x0, out, r * A.nx + x0, out_comp, fs, accepted);
-        }
-        fence_proxy_async_smem();     // my shared-memory writes before the publisher's bulk store reads them
-        __syncwarp();
-        if (lane == 0) mbar_arrive(cx.done + ps.slot);
-        ps.advance(BP_STAGES);
-        if (RECORD && (z & 15u) == 15u) heis_flush(fs, cx.s_acc);
-    }
-    if (RECORD) heis_flush(fs, cx.s_acc);
-    const int a = __reduce_add_sync(0xffffffffu, accepted);
-    if (lane == 0 && a != 0) atomicAdd(&cx.s_acc[5], (double)a);
+__device__ __forceinline__ bool st_abort(const BandShared* sh) {   // warp-uniform view of the abort flag
+    return __any_sync(0xffffffffu, *(volatile const uint32_t*)&sh->abort_flag != 0u);
 }
 
-template <typename real, int UC, bool FLIP, bool RECORD, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) basis_pipe_kernel(const __grid_constant__ BasisPipeArgs<real> A) {
-    constexpr int NB = BasisCell<UC>::NB;
+// The march of one warp of CTA (B, band): every thread owns ONE item (N cells) of the band in every plane.  No CTA-wide
+// barrier, no helper warp: a warp stores its own 32 items with bulk async copies, counts its finished planes in shared
+// memory, and whoever completes a plane's count publishes the band's progress.
+template <typename real, int UC, int B, bool FLIP, bool RECORD>
+__device__ __forceinline__ void basis_march(const BasisPipeArgs<real>& A, uint32_t band, uint32_t item0, uint32_t n_items, real* out_ring,
+                                            uint32_t out_comp, BandShared* sh, double* s_acc) {
+    constexpr int NB = BasisCell<UC>::NB, N = VecOf<real>::N;
+    const uint32_t nz = A.nz, VX = A.nx / N;
+    const uint32_t tm = band == 0 ? A.tiles - 1 : band - 1, tp = band + 1 == A.tiles ? 0u : band + 1;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const bool active = threadIdx.x < n_items;
+    const uint32_t item = item0 + (active ? threadIdx.x : 0u);
+    const uint32_t iy = item / VX, x0 = (item - iy * VX) * N;
+    // my warp's 32 items are contiguous in the band, hence in every component array
+    const uint32_t w_first = warp * 32u, w_count = w_first < n_items ? min(32u, n_items - w_first) : 0u;
+    const uint32_t w_bytes = w_count * N * (uint32_t)sizeof(real);
+    const size_t w_goff = (size_t)(item0 + w_first) * N;          // offset of my warp's first cell inside a plane
+    const size_t plane_elems = (size_t)A.ny * A.nx;
+    unsigned long long* const my_prog = A.prog + (size_t)B * A.tiles + band;
+    volatile uint32_t* const v_gate = &sh->gate_open;
+    volatile uint32_t* const v_done = &sh->cta_done;
+    volatile uint32_t* const v_abort = &sh->abort_flag;
+    constexpr int R0 = basis_reach<UC, B, 0>(), R1 = basis_reach<UC, B, (NB > 1 ? 1 : 0)>(), R2 = basis_reach<UC, B, (NB > 2 ? 2 : 0)>();
+    real fs[5] = {0, 0, 0, 0, 0};
+    int accepted = 0;
+    auto count_plane = [&](uint32_t zdone) {   // lane 0: my warp's stores of plane zdone are complete
+        __threadfence_block();   // my completed stores before my count, the other warps' counts before what follows
+        const uint32_t c = atomicAdd(&sh->plane_cnt[zdone % BP_CNT], 1u) + 1u;
+        __threadfence_block();
+        if (c == n_warps) {
+            sh->plane_cnt[zdone % BP_CNT] = 0u;
+            atomicMax(&sh->cta_done, zdone + 1u);
+            if ((zdone + 1u) % A.pub_every == 0u || zdone + 1u == nz) {
+                __threadfence();
+                atomicMax(my_prog, A.base + (unsigned long long)(zdone + 1u));
+            }
+        }
+    };
+    for (uint32_t z = 0; z < nz; ++z) {
+        // ---- may plane z be updated?  (other colours' progress, and not too far ahead of this CTA's slowest warp)
+        // lane 0 reads the shared control words and decides for the warp: 1 go, 2 poll (it took the lock), 3 abandon, 0 wait
+        {
+            unsigned long long t0 = 0;
+            uint32_t spins = 0;
+            for (;;) {
+                uint32_t st = 0;
+                if (lane == 0) {
+                    const uint32_t gate = *v_gate, done = *v_done;
+                    if (*v_abort) st = 3u;
+                    else if (z < gate && z <= done + BP_AHEAD) st = 1u;
+                    else if (z >= gate && atomicCAS(&sh->gate_lock, 0u, 1u) == 0u) st = 2u;
+                }
+                st = __shfl_sync(0xffffffffu, st, 0);
+                if (st == 1u || st == 3u) break;
+                if (st == 2u) {
+                    // lanes 3a .. 3a+2: lower colour a on the bands t-1, t, t+1; lane 9: the last colour (lead bound)
+                    const uint32_t a = lane / 3u, which = lane - a * 3u;
+                    const int reach = a == 0 ? R0 : (a == 1 ? R1 : R2);
+                    uint32_t open = nz;
+                    if (lane < 9u && (int)a < B && reach >= 0) {
+                        const unsigned long long v = ld_acquire_gpu(A.prog + (size_t)a * A.tiles + (which == 0 ? tm : (which == 1 ? band : tp)));
+                        const uint32_t pl = v > A.base ? (uint32_t)min(v - A.base, (unsigned long long)nz) : 0u;   // planes published
+                        open = pl >= nz ? nz : (pl > (uint32_t)reach ? pl - (uint32_t)reach : 0u);
+                    } else if (lane == 9u && B == 0 && NB > 1) {
+                        const unsigned long long v = ld_acquire_gpu(A.prog + (size_t)(NB - 1) * A.tiles + band);
+                        const uint32_t pl = v > A.base ? (uint32_t)min(v - A.base, (unsigned long long)nz) : 0u;
+                        open = min(nz, pl + A.lead);
+                    }
+                    open = __reduce_min_sync(0xffffffffu, open);
+                    if (lane == 0) {
+                        if (open > *v_gate) *v_gate = open;
+                        __threadfence_block();
+                        atomicExch(&sh->gate_lock, 0u);
+                    }
+                    __syncwarp();
+                    if (open > z) continue;          // decided at the top of the loop (the run-ahead bound may still hold the warp)
+                }
+                __nanosleep(200);
+                if (lane == 0 && (++spins & 63u) == 0) {
+                    if (t0 == 0) t0 = global_timer();
+                    else if (global_timer() - t0 > PIPE_TIMEOUT_NS) { sh->abort_flag = 1u; atomicExch(A.error, (unsigned int)PIPE_ERR_GATE); }
+                }
+            }
+            if (st_abort(sh)) break;
+        }
+        // ---- my warp's output stage: the store of plane z - 2 has read it
+        if (lane == 0 && z >= BP_STAGES) tma_store_wait_read<BP_STAGES - 1>();
+        __syncwarp();
+        real* out = out_ring + (size_t)(z % BP_STAGES) * 3 * out_comp;
+        if (active) basis_item<real, UC, B, FLIP, RECORD>(A, z, iy, x0, out, threadIdx.x * N, out_comp, fs, accepted);
+        fence_proxy_async_smem();     // my shared-memory writes before the bulk store reads them
+        __syncwarp();
+        if (lane == 0) {
+            if (w_count) {
+                const size_t goff = (size_t)z * plane_elems + w_goff;
+#pragma unroll
+                for (uint32_t c = 0; c < 3; ++c) bulk_store_1d(A.P.s[B][c] + goff, out + (size_t)c * out_comp + (size_t)w_first * N, w_bytes);
+            }
+            tma_store_commit();
+            if (z > 0) { tma_store_wait<1>(); count_plane(z - 1); }   // plane z - 1 of my warp is in global memory
+        }
+        if (RECORD && (z & 15u) == 15u) heis_flush(fs, s_acc);
+    }
+    if (!st_abort(sh) && lane == 0) { tma_store_wait<0>(); count_plane(nz - 1); }
+    if (RECORD) heis_flush(fs, s_acc);
+    const int a = __reduce_add_sync(0xffffffffu, accepted);
+    if (lane == 0 && a != 0) atomicAdd(&s_acc[5], (double)a);
+}
+
+template <typename real, int UC, bool FLIP, bool RECORD>
+__global__ void __launch_bounds__(1024, 1) basis_pipe_kernel(const __grid_constant__ BasisPipeArgs<real> A) {
+    constexpr int NB = BasisCell<UC>::NB, N = VecOf<real>::N;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const uint32_t b = blockIdx.x / A.tiles, tile = blockIdx.x - b * A.tiles;
-    const uint32_t rows = A.rows;
-    const uint32_t nr = tile < A.tiles_long ? rows : rows - 1;
-    const uint32_t y0 = tile < A.tiles_long ? tile * rows : A.tiles_long * rows + (tile - A.tiles_long) * (rows - 1);
-    const uint32_t stage_elems = 3 * rows * A.nx;
+    const uint32_t b = blockIdx.x / A.tiles, band = blockIdx.x - b * A.tiles;
+    const uint32_t total = A.ny * (A.nx / N);                         // items of a plane
+    const uint32_t item0 = band * A.items_per_band, n_items = min(A.items_per_band, total - item0);
+    const uint32_t out_comp = blockDim.x * N;                         // elements per component of an output stage
     real* out_ring = reinterpret_cast<real*>(smem_raw);
-    uint64_t* done = reinterpret_cast<uint64_t*>(out_ring + (size_t)BP_STAGES * stage_elems);
-    uint64_t* freed = done + BP_STAGES;
-    double* s_acc = reinterpret_cast<double*>(freed + BP_STAGES);
-    volatile uint32_t* abort_flag = reinterpret_cast<volatile uint32_t*>(s_acc + 6);
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, n_cw = A.n_cw;
+    double* s_acc = reinterpret_cast<double*>(out_ring + (size_t)BP_STAGES * 3 * out_comp);
+    BandShared* sh = reinterpret_cast<BandShared*>(s_acc + 6);
     if (threadIdx.x == 0) {
-        for (uint32_t s = 0; s < BP_STAGES; ++s) { mbar_init(done + s, n_cw); mbar_init(freed + s, 1u); }
-        *abort_flag = 0u;
-        fence_barrier_init();
-        fence_proxy_async();
+        sh->gate_open = (b == 0 && NB > 1) ? min(A.nz, A.lead) : (b == 0 ? A.nz : 0u);
+        sh->gate_lock = 0u; sh->cta_done = 0u; sh->abort_flag = 0u;
+        for (uint32_t k = 0; k < BP_CNT; ++k) sh->plane_cnt[k] = 0u;
     }
     if (threadIdx.x < 6) s_acc[threadIdx.x] = 0.0;
     __syncthreads();
-
-    if (warp == n_cw) {
-        // ===================== publisher: bulk-stores the finished tiles and releases the band's progress =====================
-        if (lane == 0) {
-            unsigned long long* const my_prog = A.prog + (size_t)b * A.tiles + tile;
-            const uint32_t bytes = nr * A.nx * (uint32_t)sizeof(real);
-            RingPos pd;
-            uint32_t since_pub = 0;
-            for (uint32_t z = 0; z < A.nz; ++z) {
-                if (!wait_bar(done + pd.slot, pd.parity, abort_flag, A.error, PIPE_ERR_FULL)) break;
-                const real* src = out_ring + (size_t)pd.slot * stage_elems;
-                const size_t goff = ((size_t)z * A.ny + y0) * A.nx;     // the band's rows of a plane are contiguous
-#pragma unroll
-                for (uint32_t c = 0; c < 3; ++c) bulk_store_1d(A.P.s[b][c] + goff, src + (size_t)c * rows * A.nx, bytes);
-                tma_store_commit();
-                tma_store_wait_read<0>();
-                mbar_arrive(freed + pd.slot);
-                pd.advance(BP_STAGES);
-                // a plane takes far longer than its store: publishing it at once keeps the colour fronts (and with them the
-                // working set that has to survive in L2) as close together as the dependencies allow
-                if (++since_pub == A.pub_every || z + 1 == A.nz) {
-                    since_pub = 0;
-                    tma_store_wait<0>();
-                    fence_proxy_async();
-                    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(my_prog), "l"(A.base + (unsigned long long)(z + 1u)) : "memory");
-                }
-            }
-        }
-    } else {
-        BandCtx cx{tile, y0, nr, n_cw * 32u, done, freed, abort_flag, s_acc};
-        switch (b) {
-            case 0: basis_march<real, UC, 0, FLIP, RECORD>(A, cx, out_ring, stage_elems); break;
-            case 1: basis_march<real, UC, 1, FLIP, RECORD>(A, cx, out_ring, stage_elems); break;
-            case 2: if (NB > 2) basis_march<real, UC, (NB > 2 ? 2 : 0), FLIP, RECORD>(A, cx, out_ring, stage_elems); break;
-            default: if (NB > 3) basis_march<real, UC, (NB > 3 ? 3 : 0), FLIP, RECORD>(A, cx, out_ring, stage_elems); break;
-        }
+    switch (b) {
+        case 0: basis_march<real, UC, 0, FLIP, RECORD>(A, band, item0, n_items, out_ring, out_comp, sh, s_acc); break;
+        case 1: basis_march<real, UC, 1, FLIP, RECORD>(A, band, item0, n_items, out_ring, out_comp, sh, s_acc); break;
+        case 2: if (NB > 2) basis_march<real, UC, (NB > 2 ? 2 : 0), FLIP, RECORD>(A, band, item0, n_items, out_ring, out_comp, sh, s_acc); break;
+        default: if (NB > 3) basis_march<real, UC, (NB > 3 ? 3 : 0), FLIP, RECORD>(A, band, item0, n_items, out_ring, out_comp, sh, s_acc); break;
     }
     __syncthreads();
     // layout of the basis kernels' observable row: [0] = sum_i sum_j J s_i.s_j with every bond twice (here: twice the bonds
@@ -253,7 +283,7 @@ __global__ void __launch_bounds__(MAXT, 1) basis_pipe_kernel(const __grid_consta
 
 struct BasisPipeState {
     BasisPipeDesc d;
-    uint32_t NB = 0, tiles = 0, rows = 0, tiles_long = 0, n_cw = 0, threads = 0, lead = 0, pub_every = 0;
+    uint32_t NB = 0, tiles = 0, items_per_band = 0, threads = 0, lead = 0, pub_every = 0;
     size_t smem = 0;
     unsigned long long* d_prog = nullptr;
     unsigned int* d_error = nullptr;
@@ -263,18 +293,17 @@ struct BasisPipeState {
 
 namespace {
 
-template <typename real, int UC, int MAXT>
+template <typename real, int UC>
 const void* bp_kernel_ptr(bool flip, bool record) {
-    if (flip) return record ? (const void*)basis_pipe_kernel<real, UC, true, true, MAXT> : (const void*)basis_pipe_kernel<real, UC, true, false, MAXT>;
-    return record ? (const void*)basis_pipe_kernel<real, UC, false, true, MAXT> : (const void*)basis_pipe_kernel<real, UC, false, false, MAXT>;
+    if (flip) return record ? (const void*)basis_pipe_kernel<real, UC, true, true> : (const void*)basis_pipe_kernel<real, UC, true, false>;
+    return record ? (const void*)basis_pipe_kernel<real, UC, false, true> : (const void*)basis_pipe_kernel<real, UC, false, false>;
 }
 template <typename real>
-const void* bp_kernel(int uc, bool flip, bool record, uint32_t threads) {
-    if (threads <= 576) return uc == 1 ? bp_kernel_ptr<real, 1, 576>(flip, record) : bp_kernel_ptr<real, 2, 576>(flip, record);
-    return uc == 1 ? bp_kernel_ptr<real, 1, 1024>(flip, record) : bp_kernel_ptr<real, 2, 1024>(flip, record);
+const void* bp_kernel(int uc, bool flip, bool record) {
+    return uc == 1 ? bp_kernel_ptr<real, 1>(flip, record) : bp_kernel_ptr<real, 2>(flip, record);
 }
-const void* bp_kernel_any(bool f64, int uc, bool flip, bool record, uint32_t threads) {
-    return f64 ? bp_kernel<double>(uc, flip, record, threads) : bp_kernel<float>(uc, flip, record, threads);
+const void* bp_kernel_any(bool f64, int uc, bool flip, bool record) {
+    return f64 ? bp_kernel<double>(uc, flip, record) : bp_kernel<float>(uc, flip, record);
 }
 
 }  // namespace
@@ -295,20 +324,19 @@ BasisPipeState* basis_pipe_create(const BasisPipeDesc& d, std::string& why) {
     }
     BasisPipeState* st = new BasisPipeState();
     st->d = d; st->NB = NB;
+    // bands of consecutive work items (16-byte vectors, row-major inside a plane): one per thread, at least one row each
+    const uint32_t VX = d.nx / N, total = d.ny * VX;
     uint32_t tiles = d.tiles ? d.tiles : (uint32_t)sms / NB;
     tiles = std::max(1u, std::min(std::min(tiles, d.ny), (uint32_t)sms / NB));
-    const uint32_t rows = (d.ny + tiles - 1) / tiles;
-    tiles = (d.ny + rows - 1) / rows;
-    st->tiles = tiles; st->rows = rows; st->tiles_long = d.ny - tiles * (rows - 1);
-    // consumer threads: the band's items (16-byte vectors of a plane) in as few equal rounds as 992 threads allow
-    const uint32_t items = rows * (d.nx / N);
-    const uint32_t rounds = (items + 991u) / 992u;
-    const uint32_t cthreads = std::max(32u, ((items + rounds - 1) / rounds + 31u) / 32u * 32u);
-    st->n_cw = cthreads / 32; st->threads = cthreads + 32;
-    st->smem = (size_t)BP_STAGES * 3 * rows * d.nx * sz + 2 * BP_STAGES * 8 + 6 * 8 + 16;
+    uint32_t ipb = std::max(VX, (total + tiles - 1) / tiles);
+    tiles = (total + ipb - 1) / ipb;
+    if (ipb > 1024) { why = "a band has more than 1024 work items per plane (lattice plane too large for one CTA per SM and colour)"; delete st; return nullptr; }
+    st->tiles = tiles; st->items_per_band = ipb;
+    st->threads = std::max(64u, (ipb + 31u) / 32u * 32u);
+    st->smem = (size_t)BP_STAGES * 3 * st->threads * 16 + 6 * 8 + sizeof(BandShared) + 16;
     if (st->smem > (size_t)smem_max) { why = "band does not fit in shared memory"; delete st; return nullptr; }
     for (int v = 0; v < 4; ++v) {
-        const void* k = bp_kernel_any(d.f64, d.unitcell, v & 1, v & 2, st->threads);
+        const void* k = bp_kernel_any(d.f64, d.unitcell, v & 1, v & 2);
         int per_sm = 0;
         if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem) != cudaSuccess ||
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, (int)st->threads, st->smem) != cudaSuccess || per_sm < 1 ||
@@ -330,8 +358,8 @@ BasisPipeState* basis_pipe_create(const BasisPipeDesc& d, std::string& why) {
     cudaMemset(st->d_prog, 0, (size_t)NB * tiles * 8);
     cudaMemset(st->d_error, 0, 4);
     char buf[256];
-    snprintf(buf, sizeof buf, "basis_pipe: %u colours x %u bands, %u rows/band, %u threads, lead %u planes, publish every %u, %zu B smem",
-             NB, tiles, rows, st->threads, st->lead, st->pub_every, st->smem);
+    snprintf(buf, sizeof buf, "basis_pipe: %u colours x %u bands, %u items/band, %u threads, lead %u planes, publish every %u, %zu B smem",
+             NB, tiles, ipb, st->threads, st->lead, st->pub_every, st->smem);
     st->text = buf;
     return st;
 }
@@ -352,12 +380,12 @@ int basis_pipe_step(BasisPipeState* st, const HeisParams<real>& p, bool flip, bo
     memset(&A, 0, sizeof A);
     for (int b = 0; b < 4; ++b) for (int c = 0; c < 3; ++c) A.P.s[b][c] = (real*)d.arr[b][c];
     A.nx = d.nx; A.ny = d.ny; A.nz = d.nz;
-    A.tiles = st->tiles; A.rows = st->rows; A.tiles_long = st->tiles_long; A.n_cw = st->n_cw; A.lead = st->lead; A.pub_every = st->pub_every;
+    A.tiles = st->tiles; A.items_per_band = st->items_per_band; A.lead = st->lead; A.pub_every = st->pub_every;
     A.prog = st->d_prog;
     A.base = st->launches * (unsigned long long)d.nz;
     A.error = st->d_error;
     A.p = p; A.sweep = sweep; A.pk = pk; A.obs = obs_row;
-    const void* k = bp_kernel<real>(d.unitcell, flip, record, st->threads);
+    const void* k = bp_kernel<real>(d.unitcell, flip, record);
     void* args[] = {&A};
     const cudaError_t e = cudaLaunchCooperativeKernel(k, dim3(st->NB * st->tiles), dim3(st->threads), args, st->smem, stream);
     if (e != cudaSuccess) {

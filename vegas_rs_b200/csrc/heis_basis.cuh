@@ -165,11 +165,93 @@ heis_basis_kernel(BasisPtrs<real> P, BasisPeers<real> peers, BasisGeom g, uint32
 #define BASIS_VEC_MINB 8   // 64 registers.  Uncapped the compiler hoists all 39 loads of an item (200 registers, 2 CTAs per
 #endif                     // SM); measured ms per fcc 384^3 step by cap 1/3/4/5/6/8: 2.79 / 2.85 / 2.69 / 2.84 / 2.56 / 2.51
                            // (profiles/r01y_fcc_vec_probe.txt)
+// One work item of K4v: the N cells x0 .. x0+N-1 of row iy of plane iz (w = iy * VX + x0 / N).  Shared by the per-colour
+// launches (heis_basis_vec_kernel) and the wave-ordered persistent step (basis_wave.cu): same loads, same summation
+// order, same random numbers.
+template <typename real, int UC, int B, bool FLIP, int MODE, bool SLAB>
+__device__ __forceinline__ void basis_vec_item(const BasisPtrs<real>& P, const BasisPeers<real>& peers, const BasisGeom& g, uint32_t iz,
+                                               const int (&zs)[3], uint32_t w, uint32_t VX, const HeisParams<real>& p, uint64_t sweep,
+                                               const PhiloxKey& pk, real (&fs)[5], int& accepted) {
+    constexpr int NB = BasisCell<UC>::NB, Z = BasisCell<UC>::Z, N = VecOf<real>::N;
+    const uint32_t iy = w / VX, x0 = (w - iy * VX) * N;
+    const uint32_t ys[3] = {iy == 0 ? g.ny - 1 : iy - 1, iy, iy + 1 == g.ny ? 0u : iy + 1};
+    const uint32_t xl = x0 == 0 ? g.nx - 1 : x0 - 1, xr = x0 + N == g.nx ? 0u : x0 + N;   // carries (periodic in x)
+    const int cell = ((int)iz * (int)g.ny + (int)iy) * (int)g.nx + (int)x0;
+    real n[3][N], l[3][N];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int e = 0; e < N; ++e) { n[c][e] = 0; l[c][e] = 0; }
+    auto gather = [&](auto qtag) {
+        constexpr int Q = decltype(qtag)::value;
+        constexpr BasisNb nb = basis_neighbour<UC, B>(Q);
+        const int row = (zs[nb.dz + 1] * (int)g.ny + (int)ys[nb.dy + 1]) * (int)g.nx;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            real v[N];
+            vec_load(P.s[nb.tb][c] + (row + (int)x0), v);   // identical address for the two x offsets of a row: loaded once
+            real u[N];
+            if (nb.dx == 0) {
+#pragma unroll
+                for (int e = 0; e < N; ++e) u[e] = v[e];
+            } else if (nb.dx < 0) {
+                u[0] = P.s[nb.tb][c][row + (int)xl];
+#pragma unroll
+                for (int e = 1; e < N; ++e) u[e] = v[e - 1];
+            } else {
+#pragma unroll
+                for (int e = 0; e + 1 < N; ++e) u[e] = v[e + 1];
+                u[N - 1] = P.s[nb.tb][c][row + (int)xr];
+            }
+#pragma unroll
+            for (int e = 0; e < N; ++e) {
+                n[c][e] += u[e];
+                if (MODE != 0 && nb.tb < B) l[c][e] += u[e];
+            }
+        }
+    };
+    basis_for_each(gather, std::make_index_sequence<Z>{});
+    real sx[N], sy[N], sz[N];
+    vec_load(P.s[B][0] + cell, sx); vec_load(P.s[B][1] + cell, sy); vec_load(P.s[B][2] + cell, sz);
+    if (MODE != 2) {
+        const uint64_t gcell = ((uint64_t)(iz + g.z_offset) * g.ny + iy) * g.nx + x0;  // global cell: slab-independent keys
+#pragma unroll
+        for (int e = 0; e < N; ++e) {
+            HeisRand<real> rnd;
+            heis_rand((gcell + e) * NB + B, sweep, pk, rnd);
+            const bool ok = heis_attempt<real, FLIP>(sx[e], sy[e], sz[e], heis_field(p.J, n[0][e], p.h[0]), heis_field(p.J, n[1][e], p.h[1]),
+                                                     heis_field(p.J, n[2][e], p.h[2]), p, rnd);
+            accepted += ok ? 1 : 0;
+        }
+        vec_store(P.s[B][0] + cell, sx); vec_store(P.s[B][1] + cell, sy); vec_store(P.s[B][2] + cell, sz);
+        if (SLAB) {  // boundary planes also go straight into the neighbours' halo planes (peer memory over NVLink)
+            const size_t in_plane = (size_t)iy * g.nx + x0, pl = (size_t)g.ny * g.nx;
+            if (iz == 0 && peers.lo != nullptr) {
+                real* q = peers.lo + (size_t)(B * 3) * g.ext + (size_t)(g.nz + 1) * pl + in_plane;  // their plane "nz"
+                vec_store(q, sx); vec_store(q + g.ext, sy); vec_store(q + 2 * g.ext, sz);
+            }
+            if (iz + 1 == g.nz && peers.hi != nullptr) {
+                real* q = peers.hi + (size_t)(B * 3) * g.ext + in_plane;                            // their plane "-1"
+                vec_store(q, sx); vec_store(q + g.ext, sy); vec_store(q + 2 * g.ext, sz);
+            }
+        }
+    }
+    if (MODE != 0) {
+#pragma unroll
+        for (int e = 0; e < N; ++e) {
+            fs[0] += sx[e] * l[0][e] + sy[e] * l[1][e] + sz[e] * l[2][e];
+            fs[1] += sx[e]; fs[2] += sy[e]; fs[3] += sz[e];
+            const real d = sx[e] * p.a[0] + sy[e] * p.a[1] + sz[e] * p.a[2];
+            fs[4] += d * d;
+        }
+    }
+}
+
 template <typename real, int UC, int B, bool FLIP, int MODE, bool SLAB = false>
 __global__ void __launch_bounds__(128, BASIS_VEC_MINB)
 heis_basis_vec_kernel(BasisPtrs<real> P, BasisPeers<real> peers, BasisGeom g, uint32_t items_per_thread, uint32_t z_begin,
                       uint32_t z_step, HeisParams<real> p, uint64_t sweep, PhiloxKey pk, double* __restrict__ obs) {
-    constexpr int NB = BasisCell<UC>::NB, Z = BasisCell<UC>::Z, N = VecOf<real>::N;
+    constexpr int N = VecOf<real>::N;
     __shared__ double s_red[6 * 32];
     const uint32_t iz = z_begin + blockIdx.z * z_step;
     const uint32_t VX = g.nx / N, items = VX * g.ny;
@@ -181,78 +263,7 @@ heis_basis_vec_kernel(BasisPtrs<real> P, BasisPeers<real> peers, BasisGeom g, ui
     for (uint32_t it = 0; it < items_per_thread; ++it) {
         const uint32_t w = w0 + it * blockDim.x;
         if (w >= items) break;
-        const uint32_t iy = w / VX, x0 = (w - iy * VX) * N;
-        const uint32_t ys[3] = {iy == 0 ? g.ny - 1 : iy - 1, iy, iy + 1 == g.ny ? 0u : iy + 1};
-        const uint32_t xl = x0 == 0 ? g.nx - 1 : x0 - 1, xr = x0 + N == g.nx ? 0u : x0 + N;   // carries (periodic in x)
-        const int cell = ((int)iz * (int)g.ny + (int)iy) * (int)g.nx + (int)x0;
-        real n[3][N], l[3][N];
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int e = 0; e < N; ++e) { n[c][e] = 0; l[c][e] = 0; }
-        auto gather = [&](auto qtag) {
-            constexpr int Q = decltype(qtag)::value;
-            constexpr BasisNb nb = basis_neighbour<UC, B>(Q);
-            const int row = (zs[nb.dz + 1] * (int)g.ny + (int)ys[nb.dy + 1]) * (int)g.nx;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                real v[N];
-                vec_load(P.s[nb.tb][c] + (row + (int)x0), v);   // identical address for the two x offsets of a row: loaded once
-                real u[N];
-                if (nb.dx == 0) {
-#pragma unroll
-                    for (int e = 0; e < N; ++e) u[e] = v[e];
-                } else if (nb.dx < 0) {
-                    u[0] = P.s[nb.tb][c][row + (int)xl];
-#pragma unroll
-                    for (int e = 1; e < N; ++e) u[e] = v[e - 1];
-                } else {
-#pragma unroll
-                    for (int e = 0; e + 1 < N; ++e) u[e] = v[e + 1];
-                    u[N - 1] = P.s[nb.tb][c][row + (int)xr];
-                }
-#pragma unroll
-                for (int e = 0; e < N; ++e) {
-                    n[c][e] += u[e];
-                    if (MODE != 0 && nb.tb < B) l[c][e] += u[e];
-                }
-            }
-        };
-        basis_for_each(gather, std::make_index_sequence<Z>{});
-        real sx[N], sy[N], sz[N];
-        vec_load(P.s[B][0] + cell, sx); vec_load(P.s[B][1] + cell, sy); vec_load(P.s[B][2] + cell, sz);
-        if (MODE != 2) {
-            const uint64_t gcell = ((uint64_t)(iz + g.z_offset) * g.ny + iy) * g.nx + x0;  // global cell: slab-independent keys
-#pragma unroll
-            for (int e = 0; e < N; ++e) {
-                HeisRand<real> rnd;
-                heis_rand((gcell + e) * NB + B, sweep, pk, rnd);
-                const bool ok = heis_attempt<real, FLIP>(sx[e], sy[e], sz[e], heis_field(p.J, n[0][e], p.h[0]), heis_field(p.J, n[1][e], p.h[1]),
-                                                         heis_field(p.J, n[2][e], p.h[2]), p, rnd);
-                accepted += ok ? 1 : 0;
-            }
-            vec_store(P.s[B][0] + cell, sx); vec_store(P.s[B][1] + cell, sy); vec_store(P.s[B][2] + cell, sz);
-            if (SLAB) {  // boundary planes also go straight into the neighbours' halo planes (peer memory over NVLink)
-                const size_t in_plane = (size_t)iy * g.nx + x0, pl = (size_t)g.ny * g.nx;
-                if (iz == 0 && peers.lo != nullptr) {
-                    real* q = peers.lo + (size_t)(B * 3) * g.ext + (size_t)(g.nz + 1) * pl + in_plane;  // their plane "nz"
-                    vec_store(q, sx); vec_store(q + g.ext, sy); vec_store(q + 2 * g.ext, sz);
-                }
-                if (iz + 1 == g.nz && peers.hi != nullptr) {
-                    real* q = peers.hi + (size_t)(B * 3) * g.ext + in_plane;                            // their plane "-1"
-                    vec_store(q, sx); vec_store(q + g.ext, sy); vec_store(q + 2 * g.ext, sz);
-                }
-            }
-        }
-        if (MODE != 0) {
-#pragma unroll
-            for (int e = 0; e < N; ++e) {
-                fs[0] += sx[e] * l[0][e] + sy[e] * l[1][e] + sz[e] * l[2][e];
-                fs[1] += sx[e]; fs[2] += sy[e]; fs[3] += sz[e];
-                const real d = sx[e] * p.a[0] + sy[e] * p.a[1] + sz[e] * p.a[2];
-                fs[4] += d * d;
-            }
-        }
+        basis_vec_item<real, UC, B, FLIP, MODE, SLAB>(P, peers, g, iz, zs, w, VX, p, sweep, pk, fs, accepted);
     }
     double acc[6] = {0, 0, 0, 0, 0, 0};
     if (MODE != 0) {

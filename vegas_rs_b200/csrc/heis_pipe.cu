@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(MAXT, 1) heis_pipe_kernel(const __grid_constan
     double* s_acc = reinterpret_cast<double*>(done + PIPE_DONE_SLOTS);    // 6 doubles
     volatile uint32_t* abort_flag = reinterpret_cast<volatile uint32_t*>(s_acc + 6);
     uint32_t* ready = const_cast<uint32_t*>(abort_flag) + 1;   // planes whose TMA stores are complete (publisher -> releaser)
+    uint32_t* bnd = ready + 1;   // HALO: [0] boundary planes the consumers have stored into the neighbours' halos so far, [1], [2] their z
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t n_phases = gridDim.x / A.tiles;
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(MAXT, 1) heis_pipe_kernel(const __grid_constan
         for (uint32_t s = 0; s < SO; ++s) { mbar_init(full_w + s, 1u); mbar_init(empty_w + s, 1u); }
         for (uint32_t s = 0; s < PIPE_DONE_SLOTS; ++s) mbar_init(done + s, n_cw);
         *abort_flag = 0u;
-        *ready = 0u;
+        *ready = 0u; bnd[0] = 0u;
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -223,10 +224,24 @@ __global__ void __launch_bounds__(MAXT, 1) heis_pipe_kernel(const __grid_constan
         // Runs at its own pace: when a release takes longer than a plane, the next one simply covers several planes.
         if (lane == 0) {
             unsigned long long* const my_prog = A.prog + (size_t)phase * A.tiles + tile;
-            uint32_t last = 0;
+            uint32_t last = 0, bnd_seen = 0;
             const unsigned long long t0 = global_timer();
-            while (last < Lz) {
+            while (last < Lz || (HALO && bnd_seen < 2u)) {
                 uint32_t now;
+                if (HALO) {
+                    uint32_t nb;
+                    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(nb) : "r"(smem_u32(bnd)) : "memory");
+                    if (nb != bnd_seen) {
+                        __threadfence_system();
+                        for (; bnd_seen < nb; ++bnd_seen) {
+                            // plane 0 feeds the lower neighbour's UPPER halo: its "from upper" words [2 + colour]; plane Lz-1 the
+                            // upper neighbour's "from lower" words [colour]
+                            const uint32_t z = ((volatile uint32_t*)bnd)[1 + bnd_seen];
+                            if (z == 0) atomicAdd_system(A.peer_flags[0] + 2 + colour, 1ull);
+                            else atomicAdd_system(A.peer_flags[1] + colour, 1ull);
+                        }
+                    }
+                }
                 asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(now) : "r"(smem_u32(ready)) : "memory");
                 if (now == last) {
                     __nanosleep(100);
@@ -270,13 +285,14 @@ __global__ void __launch_bounds__(MAXT, 1) heis_pipe_kernel(const __grid_constan
             RingPos pd, pown;
             uint32_t since_pub = 0;
             const uint32_t kind = nr == rows ? 0u : 1u;
+            uint32_t n_bnd = 0;
+            // a boundary plane sits in the neighbour's halo once every consumer warp has arrived: the releaser signals it (the
+            // system-scope fence waits for the NVLink stores and must not hold up the own-ring slots)
             auto signal_peers = [&](uint32_t z) {
                 if (z == 0 || z + 1 == Lz) {
-                    __threadfence_system();
-                    // plane 0 feeds the lower neighbour's UPPER halo: its "from upper" words [2 + colour]; plane Lz-1 the upper
-                    // neighbour's "from lower" words [colour]
-                    if (z == 0) atomicAdd_system(A.peer_flags[0] + 2 + colour, 1ull);
-                    if (z + 1 == Lz) atomicAdd_system(A.peer_flags[1] + colour, 1ull);
+                    bnd[1 + n_bnd] = z;
+                    ++n_bnd;
+                    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(bnd)), "r"(n_bnd) : "memory");
                 }
             };
             for (uint32_t i = 0; i < Lz; ++i) {
@@ -595,7 +611,7 @@ HeisPipeState* heis_pipe_create(const HeisPipeDesc& d, std::string& why) {
     const size_t stage_o = (size_t)3 * (rows + 2) * Hx * sz, stage_w = (size_t)3 * rows * Hx * sz;
     // ring depths: an own plane holds its slot from the load until the TMA store has read the updated tile
     const uint32_t choices[][2] = {{6, 3}, {5, 3}, {4, 3}, {4, 2}, {4, 1}};   // measured on 512^3 fp32: 0.862 / 0.878 ms per step for the first two
-    auto smem_for = [&](uint32_t S, uint32_t SO) { return S * stage_o + SO * stage_w + (size_t)(2 * S + 2 * SO + PIPE_DONE_SLOTS) * 8 + 6 * 8 + 32; };
+    auto smem_for = [&](uint32_t S, uint32_t SO) { return S * stage_o + SO * stage_w + (size_t)(2 * S + 2 * SO + PIPE_DONE_SLOTS) * 8 + 6 * 8 + 48; };
     if (d.stages_other >= 4 && d.stages_own >= 1) { st->S = d.stages_other; st->SO = std::min(4u, d.stages_own); }
     else
         for (auto& c : choices)

@@ -19,6 +19,7 @@
 #include "heis_fused.cuh"
 #include "heis_pipe.hpp"
 #include "basis_pipe.hpp"
+#include "basis_wave.hpp"
 #include "ising_msc.cuh"
 #include "lattice.hpp"
 #include "resident.cuh"
@@ -32,6 +33,7 @@ const char* const FAMILY_NAME[5] = {"ising_msc", "heis_stencil", "ising_general"
 
 constexpr uint64_t OBS_CAP = 4096;  // steps of observables kept on the device per batch
 constexpr int OBS_W = 8;            // 8 x 8-byte slots per step
+constexpr int BWAVE_FLAG_WORD = 16;  // words 16..23: boundary-plane step counters of the wave-ordered bcc / fcc step (basis_wave.cu)
 constexpr int PIPE_FLAG_WORD = 8;   // words 8..11 of a slab's flag block: boundary-plane counters of the pipelined kernel (heis_pipe.cu)
 
 std::string g_create_error;
@@ -98,6 +100,11 @@ struct vegas_gpu {
     uint32_t bpipe_lead = 0, bpipe_pub = 0, bpipe_tiles = 0;
     bool bpipe_planned = false;
     BasisPipeState* bpipe = nullptr;
+    // --- wave-ordered bcc / fcc step (basis_wave.cu): the colour passes of a step as one persistent launch, L2-friendly order
+    int bwave_enable = -1;                // tuning key basis_wave: 1 whenever possible; -1 / 0: colour launches
+    uint32_t bwave_lag = 0, bwave_ipt = 0, bwave_grid = 0;   // tuning keys basis_wave_lag / _ipt / _grid (0 = auto)
+    bool bwave_planned = false;
+    BasisWaveState* bwave = nullptr;
     bool fused_ready = false;
     FusedGeom fused_geom{};
     size_t fused_smem = 0;
@@ -991,6 +998,44 @@ bool bpipe_plan(vegas_gpu* h) {
     return h->bpipe != nullptr;
 }
 
+bool bwave_plan(vegas_gpu* h) {
+    if (h->bwave_planned) return basis_wave_usable(h->bwave);
+    // opt-in (tuning key basis_wave=1): 9.2 GB of DRAM traffic per fcc 384^3 step against 14 GB for four colour launches, but
+    // every item pays a dependency poll, two fences and two barriers and tiles of 128 items lose the L1 reuse between rows:
+    // 2.98 ms per step against 2.51 (profiles/r02/README.md section 2)
+    if (h->family != FAM_HEIS_BASIS || h->bwave_enable != 1 || h->basis_vec == 0) return false;
+    // a slab runs it once it is connected to neighbours that sweep on OTHER devices: the kernel occupies every SM of its
+    // device and waits for the neighbours' boundary planes inside the launch (slabs sharing a device would deadlock)
+    if (h->slab && !(h->connected && h->peers_remote)) return false;
+    h->bwave_planned = true;
+    BasisWaveDesc d;
+    d.device = h->device; d.f64 = h->md.precision == VEGAS_F64;
+    d.unitcell = h->ld.unitcell == VEGAS_BCC ? 1 : 2;
+    d.nx = (uint32_t)h->ld.nx; d.ny = (uint32_t)h->ld.ny; d.nz = (uint32_t)h->ld.nz;
+    d.z_offset = (uint32_t)h->z_offset; d.nz_global = (uint32_t)h->nz_global;
+    for (int b = 0; b < 4; ++b) for (int c = 0; c < 3; ++c) d.arr[b][c] = h->hb[b][c];
+    d.lag = h->bwave_lag; d.ipt = h->bwave_ipt; d.grid = h->bwave_grid;
+    if (h->slab) {
+        d.slab = true;
+        d.peer_lo = h->peer_halo[0]; d.peer_hi = h->peer_halo[1];
+        d.flags = h->flags + BWAVE_FLAG_WORD;
+        d.peer_flags[0] = h->peer_flags[0] + BWAVE_FLAG_WORD; d.peer_flags[1] = h->peer_flags[1] + BWAVE_FLAG_WORD;
+    }
+    h->bwave = basis_wave_create(d, h->pipe_why);
+    return h->bwave != nullptr;
+}
+
+int bwave_step(vegas_gpu* h, double* obs_row, bool record) {
+    const PhiloxKey pk = make_philox_key(h->md.seed);
+    const bool flip = h->md.proposal == VEGAS_PROPOSE_FLIP;
+    h->launches++;
+    std::string err;
+    const int rc = h->md.precision == VEGAS_F64 ? basis_wave_step<double>(h->bwave, heis_params<double>(h), flip, record, h->sweeps, pk, obs_row, h->stream, err)
+                                               : basis_wave_step<float>(h->bwave, heis_params<float>(h), flip, record, h->sweeps, pk, obs_row, h->stream, err);
+    if (rc) h->err = err;
+    return rc;
+}
+
 int bpipe_step(vegas_gpu* h, double* obs_row, bool record) {
     const PhiloxKey pk = make_philox_key(h->md.seed);
     const bool flip = h->md.proposal == VEGAS_PROPOSE_FLIP;
@@ -1041,6 +1086,10 @@ int check_async_errors(vegas_gpu* h) {
     if (h->bpipe) {
         std::string e;
         if (basis_pipe_check(h->bpipe, e)) return fail(h, VEGAS_ERR_CUDA, e);
+    }
+    if (h->bwave) {
+        std::string e;
+        if (basis_wave_check(h->bwave, e)) return fail(h, VEGAS_ERR_CUDA, e);
     }
     return VEGAS_OK;
 }
@@ -1142,6 +1191,8 @@ void do_step(vegas_gpu* h, void* obs_row, void* scratch_row) {
     const bool rec = obs_row != nullptr;
     if (h->family == FAM_HEIS_BASIS && bpipe_plan(h)) {
         bpipe_step(h, (double*)(rec ? obs_row : scratch_row), rec);
+    } else if (h->family == FAM_HEIS_BASIS && bwave_plan(h)) {
+        bwave_step(h, (double*)(rec ? obs_row : scratch_row), rec);   // a failed launch surfaces through cudaGetLastError / h->err
     } else if (h->family == FAM_HEIS_BASIS) {
         for (int b = 0; b < h->n_colours; ++b) basis_pass_any(h, rec ? 1 : 0, b, (double*)(rec ? obs_row : scratch_row));
     } else if (h->family == FAM_HEIS_STENCIL && pipe_plan(h)) {
@@ -1253,11 +1304,29 @@ __global__ void pipe_halo_wait_kernel(const unsigned long long* flags, unsigned 
     __threadfence_system();
 }
 
+// The same for a slab that steps with the wave-ordered bcc / fcc kernel: words [a] / [4 + c] count the steps whose plane 0 /
+// top plane of colour a / c the upper / lower neighbour has stored into my halos.
+__global__ void bwave_halo_wait_kernel(const unsigned long long* flags, unsigned long long target, uint32_t nb) {
+    if (threadIdx.x < 8 && (threadIdx.x & 3u) < nb) {
+        unsigned long long v;
+        for (uint32_t spins = 0; spins < (1u << 22); ++spins) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory");
+            if (v >= target) break;
+            __nanosleep(256);
+        }
+    }
+    __threadfence_system();
+}
+
 int measure_now(vegas_gpu* h, Canon& out) {
     unsigned long long* row = h->obs + (OBS_CAP + 1) * OBS_W;
     CU(cudaMemsetAsync(row, 0, OBS_W * 8, h->stream));
     if (h->slab && h->pipe && h->pipe_slab_steps > 0) {
         pipe_halo_wait_kernel<<<1, 32, 0, h->stream>>>(h->flags + PIPE_FLAG_WORD, h->pipe_slab_steps * (unsigned long long)heis_pipe_tiles(h->pipe));
+        h->launches++;
+    }
+    if (h->slab && h->bwave && basis_wave_steps_done(h->bwave) > 0) {
+        bwave_halo_wait_kernel<<<1, 32, 0, h->stream>>>(h->flags + BWAVE_FLAG_WORD, basis_wave_steps_done(h->bwave), (uint32_t)h->n_colours);
         h->launches++;
     }
     if (h->family == FAM_ISING_MSC || h->family == FAM_HEIS_STENCIL) stencil_colour_pass(h, 2, 1, row);
@@ -1532,6 +1601,7 @@ void vegas_gpu_destroy(vegas_gpu_t h) {
     cudaFree(h->wave_done); cudaFree(h->wave_error);
     heis_pipe_destroy(h->pipe);
     basis_pipe_destroy(h->bpipe);
+    basis_wave_destroy(h->bwave);
     if (h->stream_b) { cudaStreamSynchronize(h->stream_b); cudaStreamDestroy(h->stream_b); }
     if (h->ev_main) cudaEventDestroy(h->ev_main);
     if (h->ev_bnd) cudaEventDestroy(h->ev_bnd);
@@ -2172,6 +2242,8 @@ int vegas_gpu_slab_connect(vegas_gpu_t h, const void* lower, const void* upper) 
     h->connected = true;
     h->pipe_slab_steps = 0;
     if (h->pipe_planned) { heis_pipe_destroy(h->pipe); h->pipe = nullptr; h->pipe_planned = false; }
+    if (h->bwave_planned) { basis_wave_destroy(h->bwave); h->bwave = nullptr; h->bwave_planned = false; }
+    CU(cudaMemset(h->flags + BWAVE_FLAG_WORD, 0, 8 * sizeof(unsigned long long)));   // the wave step counts from the connection on
     preload_slab_kernels(h);
     return push_boundaries(h);
 }
@@ -2199,6 +2271,8 @@ int vegas_gpu_slab_connect_local(vegas_gpu_t h, vegas_gpu_t lower, vegas_gpu_t u
     h->connected = true;
     h->pipe_slab_steps = 0;
     if (h->pipe_planned) { heis_pipe_destroy(h->pipe); h->pipe = nullptr; h->pipe_planned = false; }
+    if (h->bwave_planned) { basis_wave_destroy(h->bwave); h->bwave = nullptr; h->bwave_planned = false; }
+    CU(cudaMemset(h->flags + BWAVE_FLAG_WORD, 0, 8 * sizeof(unsigned long long)));   // the wave step counts from the connection on
     preload_slab_kernels(h);
     return push_boundaries(h);
 }
@@ -2211,6 +2285,19 @@ int vegas_gpu_check_basis_tables(void) {
 int vegas_gpu_wave_schedule(uint32_t n_chunks, uint32_t lag, uint32_t steps, uint32_t* units, uint64_t capacity, uint64_t* count) {
     if (n_chunks == 0 || n_chunks >= (1u << 24) || steps == 0 || steps > (uint32_t)WAVE_MAX_STEPS || !count) return VEGAS_ERR_INVALID;
     const std::vector<uint32_t> u = wave_units_for(n_chunks, std::max<uint32_t>(3, lag), steps);
+    *count = u.size();
+    if (units) {
+        if (capacity < u.size()) return VEGAS_ERR_INVALID;
+        std::memcpy(units, u.data(), u.size() * sizeof(uint32_t));
+    }
+    return VEGAS_OK;
+}
+
+int vegas_gpu_basis_wave_schedule(int unitcell, uint32_t nz, uint32_t lag, uint32_t* units, uint64_t capacity, uint64_t* count, uint32_t need[4]) {
+    if ((unitcell != VEGAS_BCC && unitcell != VEGAS_FCC) || nz == 0 || nz >= (1u << 24) || lag == 0 || !count || !need) return VEGAS_ERR_INVALID;
+    uint32_t nd[4];
+    const std::vector<uint32_t> u = basis_wave_units(unitcell == VEGAS_BCC ? 1 : 2, nz, lag, nd);
+    for (int b = 0; b < 4; ++b) need[b] = nd[b];
     *count = u.size();
     if (units) {
         if (capacity < u.size()) return VEGAS_ERR_INVALID;
@@ -2242,6 +2329,10 @@ int vegas_gpu_set_tuning(vegas_gpu_t h, const char* key, long value) {
     else if (k == "basis_pipe_lead") h->bpipe_lead = (uint32_t)value;
     else if (k == "basis_pipe_pub") h->bpipe_pub = (uint32_t)value;
     else if (k == "basis_pipe_tiles") h->bpipe_tiles = (uint32_t)value;
+    else if (k == "basis_wave") h->bwave_enable = (int)value;
+    else if (k == "basis_wave_lag") h->bwave_lag = (uint32_t)value;
+    else if (k == "basis_wave_ipt") h->bwave_ipt = (uint32_t)value;
+    else if (k == "basis_wave_grid") h->bwave_grid = (uint32_t)value;
     else if (k == "basis_vec") h->basis_vec = (int)value;
     else if (k == "resident_max") { h->resident_max = (uint32_t)value; h->resident_cols = -2; }
     else return fail(h, VEGAS_ERR_INVALID, "unknown tuning key: " + k);
@@ -2249,6 +2340,8 @@ int vegas_gpu_set_tuning(vegas_gpu_t h, const char* key, long value) {
     h->wave_ready = false;
     if (h->pipe_planned) { cudaStreamSynchronize(h->stream); heis_pipe_destroy(h->pipe); h->pipe = nullptr; h->pipe_planned = false; }
     if (h->bpipe_planned) { cudaStreamSynchronize(h->stream); basis_pipe_destroy(h->bpipe); h->bpipe = nullptr; h->bpipe_planned = false; }
+    // a connected slab keeps its wave state: the neighbours' flag words count its steps
+    if (h->bwave_planned && !(h->slab && h->bwave)) { cudaStreamSynchronize(h->stream); basis_wave_destroy(h->bwave); h->bwave = nullptr; h->bwave_planned = false; }
     return VEGAS_OK;
 }
 
@@ -2256,6 +2349,7 @@ const char* vegas_gpu_step_kernel(vegas_gpu_t h) {
     if (!h) return "";
     if (h->family == FAM_HEIS_STENCIL && cudaSetDevice(h->device) == cudaSuccess && pipe_plan(h)) return "heis_pipe";
     if (h->family == FAM_HEIS_BASIS && cudaSetDevice(h->device) == cudaSuccess && bpipe_plan(h)) return "basis_pipe";
+    if (h->family == FAM_HEIS_BASIS && cudaSetDevice(h->device) == cudaSuccess && bwave_plan(h)) return "basis_wave";
     if (h->family == FAM_HEIS_STENCIL && cudaSetDevice(h->device) == cudaSuccess && wave_plan(h)) return "heis_wave";
     if (h->family == FAM_HEIS_STENCIL && cudaSetDevice(h->device) == cudaSuccess && fused_plan(h)) return "heis_fused";
     if (resident_plan(h)) return h->family == FAM_ISING_GEN ? "ising_resident" : "heis_resident";
