@@ -109,6 +109,7 @@ def lib() -> C.CDLL:
     L.vo_hysteresis_points.argtypes = [f64, f64, vp, u64]; L.vo_hysteresis_points.restype = u64
     L.vo_stat_line.argtypes = [C.POINTER(StatRow), C.c_char_p, C.c_size_t]
     L.vo_philox4x32_10.argtypes = [vp, vp, vp]
+    L.vo_philox4x32.argtypes = [vp, vp, C.c_int, vp]
     L.vo_replay_ising_msc.argtypes = [C.POINTER(HamS), C.POINTER(ThermoS), C.c_int, u64, u64, u64, u64, u64, vp]
     L.vo_replay_ising_msc.restype = u64
     L.vo_replay_ising_sites.argtypes = [C.POINTER(HamS), C.POINTER(ThermoS), C.c_int, u64, u64, u64, vp, C.c_int, vp]
@@ -349,7 +350,13 @@ def hysteresis_points(max_field, field_step):
     return out
 
 
-def philox(ctr, key):
+PHILOX_ROUNDS = 7   # VO_PHILOX_ROUNDS (oracle/vegas_oracle.h) = PHILOX_ROUNDS of the GPU kernels (csrc/common.cuh)
+
+
+def philox(ctr, key, rounds=10):
     c = np.asarray(ctr, np.uint32); k = np.asarray(key, np.uint32); o = np.zeros(4, np.uint32)
-    lib().vo_philox4x32_10(_ptr(c), _ptr(k), _ptr(o))
+    if rounds == 10:
+        lib().vo_philox4x32_10(_ptr(c), _ptr(k), _ptr(o))
+    else:
+        lib().vo_philox4x32(_ptr(c), _ptr(k), int(rounds), _ptr(o))
     return o

@@ -583,12 +583,12 @@ int vo_stat_line(const vo_stat_row* r, char* buf, size_t cap) {
                     r->mean_m, r->chi, r->binder);
 }
 
-/* ======================================================================== Philox4x32-10 */
-/* Random123 Philox4x32-10; constants as in curand_philox4x32_x.h:88-91.  Used only by the
+/* ======================================================================== Philox4x32-R */
+/* Random123 Philox4x32 with R rounds; constants as in curand_philox4x32_x.h:88-91.  Used only by the
  * replay checker (oracle/vegas_replay.c) to re-derive the GPU's random numbers on the CPU. */
-void vo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+void vo_philox4x32(const uint32_t ctr[4], const uint32_t key[2], int rounds, uint32_t out[4]) {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < rounds; ++r) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
         uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
@@ -597,3 +597,4 @@ void vo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
+void vo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { vo_philox4x32(ctr, key, 10, out); }

@@ -164,7 +164,9 @@ uint64_t vo_hysteresis_points(double max_field, double field_step, double* out, 
 /* StatSensor line, "{:.16} x7" (instrument.rs:113-123). Returns chars written. */
 int vo_stat_line(const vo_stat_row* row, char* buf, size_t cap);
 
-/* ---------------------------------------------------------------- Philox4x32-10 (Random123 KAT-checked) */
+/* ---------------------------------------------------------------- Philox4x32-R (Random123 KAT-checked for R = 7 and 10) */
+#define VO_PHILOX_ROUNDS 7   /* rounds the GPU kernels draw with (PHILOX_ROUNDS, vegas_rs_b200/csrc/common.cuh): the replay uses the same */
+void vo_philox4x32(const uint32_t ctr[4], const uint32_t key[2], int rounds, uint32_t out[4]);
 void vo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 
 /* ---------------------------------------------------------------- replay of one GPU-ordered sweep (vegas_replay.c) */

@@ -21,7 +21,7 @@ static void philox_at(uint64_t index, uint64_t sweep, uint32_t call, uint64_t se
     uint32_t ctr[4] = {(uint32_t)index, (uint32_t)(index >> 32), (uint32_t)sweep,
                        ((uint32_t)(sweep >> 32) & 0x00FFFFFFu) | (call << 24)};
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
-    vo_philox4x32_10(ctr, key, out);
+    vo_philox4x32(ctr, key, VO_PHILOX_ROUNDS, out);
 }
 
 /* accept iff U < floor(exp(-delta/T) * 2^64); delta < 0 or p >= 1 always accepts (u < 1). */

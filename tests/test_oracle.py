@@ -42,9 +42,20 @@ def test_reference_state_unit_tests():
 
 
 def test_philox_known_answers():
+    """Random123's kat_vectors lines for philox4x32 with 10 rounds (the library default) and with 7 (the Crush-resistant
+    minimum the kernels and the replay draw with: PHILOX_ROUNDS / VO_PHILOX_ROUNDS)."""
     for k in GOLD["derived"]["philox4x32_10_kat"]:
         out = ob.philox(k["ctr"], k["key"])
         assert [f"{int(x):08x}" for x in out] == k["out"]
+    for k in GOLD["derived"]["philox4x32_7_kat"]:
+        out = ob.philox(k["ctr"], k["key"], rounds=7)
+        assert [f"{int(x):08x}" for x in out] == k["out"]
+    # the constant is the same on both sides of the parity tests
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "vegas_rs_b200", "csrc", "common.cuh")).read()
+    hdr = open(os.path.join(root, "oracle", "vegas_oracle.h")).read()
+    import re
+    assert int(re.search(r"#define VEGAS_PHILOX_ROUNDS (\d+)", src).group(1)) == int(re.search(r"#define VO_PHILOX_ROUNDS (\d+)", hdr).group(1)) == ob.PHILOX_ROUNDS
 
 
 def test_program_schedules():

@@ -6,31 +6,40 @@
 namespace vg {
 
 // ---------------------------------------------------------------------------------------
-// Philox4x32-10 (Random123), counter-based, all state in registers.  The key is the run
+// Philox4x32-7 (Random123), counter-based, all state in registers.  The key is the run
 // seed; the counter is (site-or-word index, sweep, call) so that any decomposition of the
 // lattice over GPUs reproduces the same random numbers per site.
 // Round keys are thread-invariant, so the compiler keeps them on the uniform datapath.
+// Rounds: 7 is the fewest for which Philox4x32 passes BigCrush (Salmon et al., SC'11, table 2: the
+// "Crush-resistant" minimum; the library default of 10 is that plus a safety margin).  The generator is a
+// third of the Ising kernel's instructions: 7 rounds measured +14 % on 1024^3, +9 % on 8192^2, +2.5 % on
+// the Heisenberg kernels (profiles/r02/README.md).  The oracle replays with the same constant
+// (VO_PHILOX_ROUNDS, oracle/vegas_oracle.h); both are pinned by Random123's 7- and 10-round known answers.
 // ---------------------------------------------------------------------------------------
 // Round keys are precomputed on the host (PhiloxKey, passed by value = constant bank) so that no
 // per-thread integer adds are spent on the key schedule.
+#ifndef VEGAS_PHILOX_ROUNDS
+#define VEGAS_PHILOX_ROUNDS 7
+#endif
+constexpr int PHILOX_ROUNDS = VEGAS_PHILOX_ROUNDS;
 struct PhiloxKey {
-    uint32_t k[10][2];
+    uint32_t k[PHILOX_ROUNDS][2];
 };
 
 inline PhiloxKey make_philox_key(uint64_t seed) {
     PhiloxKey pk;
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < PHILOX_ROUNDS; ++r) {
         pk.k[r][0] = k0; pk.k[r][1] = k1;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     return pk;
 }
 
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKey& pk,
+__device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKey& pk,
                                               uint32_t (&out)[4]) {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < PHILOX_ROUNDS; ++r) {
         const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
         const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
         const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ pk.k[r][0];
@@ -47,7 +56,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 // colour for word-keyed streams), c2 = sweep low, c3 = sweep bits 32..55 | call << 24.
 __device__ __forceinline__ void philox_at(uint64_t index, uint64_t sweep, uint32_t call, const PhiloxKey& pk,
                                           uint32_t (&out)[4]) {
-    philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), (uint32_t)sweep,
+    philox4x32((uint32_t)index, (uint32_t)(index >> 32), (uint32_t)sweep,
                   ((uint32_t)(sweep >> 32) & 0x00FFFFFFu) | (call << 24), pk, out);
 }
 

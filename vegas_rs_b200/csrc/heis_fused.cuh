@@ -144,7 +144,7 @@ heis_fused_kernel(FusedPtrs<real> P, FusedGeom g, HeisParams<real> p, uint64_t s
 #pragma unroll
             for (int e = 0; e < N; e += 2) {
                 uint32_t w[4];
-                philox4x32_10(s_lo + 2u * e, s_hi, c2, c3, pk, w);
+                philox4x32(s_lo + 2u * e, s_hi, c2, c3, pk, w);
 #pragma unroll
                 for (int h2 = 0; h2 < 2; ++h2) {
                     HeisRand<real> rnd;
