@@ -199,6 +199,8 @@ int vegas_gpu_slab_connect_local(vegas_gpu_t self, vegas_gpu_t lower, vegas_gpu_
  *                       "basis_wave_ipt" (16-byte work items per thread and tile, 0 = auto), "basis_wave_grid" (cap on the
  *                       number of CTAs, 0 = as many as are co-resident).  Opt-in: a third less DRAM traffic, but slower than
  *                       the colour launches so far (per-item synchronisation, no L1 reuse between rows)
+ *     "msc_full"      : 1 (default) the Ising colour pass without per-row bounds and predicates whenever the launch grid covers
+ *                       the lattice exactly (uniform J > 0, no field, not a slab boundary plane), 0 always the generic variant
  *     "basis_vec"     : 1 (default) 16-byte accesses in the bcc / fcc colour pass when nx % 4 == 0 (fp64: % 2), 0 scalar
  *     "resident_max"  : largest site count of a general-family lattice that runs batches of steps in ONE launch with
  *                       the State in shared memory (default 8192; 0 = always one launch per colour)

@@ -64,7 +64,10 @@ __host__ __device__ constexpr int msc_rows(int ndim) { return ndim == 2 ? MSC_RO
 // HALO:  planes z-1 / z+1 outside the local range come from oth_lo / oth_hi and boundary words are also stored into the
 //        neighbours' halos (connected slab); otherwise the periodic wrap of `oth` itself is used and those four
 //        pointers are never touched (fewer uniform registers: the Philox round keys and threshold bits stay resident).
-template <int NDIM, bool FIELD, int NSLOT, bool RANDPROP, int MODE, bool FERRO = false, bool HALO = true>
+// FULL:  the grid covers the lattice exactly (Wx % blockDim.x == 0, Ly % (blockDim.y * K) == 0; never with HALO): no thread or
+//        row is ever inactive and every address is one base offset plus compile-time multiples of the row pitch -- the
+//        generic prologue (per-row bounds, wraps and predicates) was ~50 of the ~275 instructions per word.
+template <int NDIM, bool FIELD, int NSLOT, bool RANDPROP, int MODE, bool FERRO = false, bool HALO = true, bool FULL = false>
 __global__ void __launch_bounds__(256, MSC_MINB)
 ising_msc_kernel(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth, const uint32_t* __restrict__ oth_lo,
                  const uint32_t* __restrict__ oth_hi, uint32_t* __restrict__ peer_lo, uint32_t* __restrict__ peer_hi,
@@ -75,8 +78,9 @@ ising_msc_kernel(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth, c
     __shared__ int s_acc[3];
     __shared__ unsigned int s_cnt;
     // straggler records of the warp-compacted tail (NSLOT <= 3): one per word that still holds an undecided spin after
-    // 8 bit-planes: {eq, pm0, pm1, pm2, widx lo, widx hi, n0, n1, n2, word offset, cand}; at most K * 32 per warp
-    constexpr int REC_W = 11;
+    // 8 bit-planes: {eq, n0, n1, n2, word offset, cand, pm0, pm1, pm2}; at most K * 32 per warp.  FERRO: the slot masks
+    // follow from the counts and are not stored; the word index (RNG key) always follows from the word offset.
+    constexpr int REC_W = FERRO ? (RANDPROP ? 6 : 5) : 9;
     __shared__ uint32_t s_rec[NSLOT <= 3 ? 8 : 1][NSLOT <= 3 ? K * 32 : 1][NSLOT <= 3 ? REC_W : 1];
     uint32_t n_rec = 0;  // warp-uniform
     if (threadIdx.x == 0 && threadIdx.y == 0) { s_acc[0] = 0; s_acc[1] = 0; s_acc[2] = 0; s_cnt = 0; }
@@ -88,7 +92,8 @@ ising_msc_kernel(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth, c
     const uint32_t zl = z_begin + blockIdx.z * z_step;   // z_step > 1: the two boundary planes of a slab in one launch
     const uint32_t Wx = g.Wx, Ly = g.Ly;
     const uint32_t plane = Ly * Wx;            // 32-bit word offsets: a colour array has < 2^32 words
-    const bool active = w < Wx && y0 < Ly;
+    static_assert(!(FULL && HALO), "FULL is an interior / single-handle variant");
+    const bool active = FULL || (w < Wx && y0 < Ly);
     int acc[3] = {0, 0, 0};
     const uint32_t lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31u, warp = (threadIdx.y * blockDim.x + threadIdx.x) >> 5;
 
@@ -101,6 +106,22 @@ ising_msc_kernel(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth, c
     // Inactive lanes (ragged grids) load nothing and carry zero masks through the warp-collective code below.
     uint32_t rows[K + 2];
     uint32_t sv[K], cwv[K], Cv[K], Dv[K];
+    if constexpr (FULL) {
+        // 32-bit word offsets relative to (zl, y0, w); the additions wrap modulo 2^32 and land inside the array
+        const uint32_t row0 = base + y0 * Wx;
+        rows[0] = oth[base + (y0 == 0 ? Ly - 1 : y0 - 1) * Wx];
+        rows[K + 1] = oth[base + (y0 + K == Ly ? 0u : y0 + K) * Wx];
+        const uint32_t dw[2] = {(rp0 ? wr : wl) - w, (rp0 ? wl : wr) - w};
+        const uint32_t dzm = zl == 0 ? (g.Lz - 1) * plane : 0u - plane, dzp = zl + 1 == g.Lz ? 0u - zl * plane : plane;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const uint32_t o = row0 + k * Wx;
+            rows[k + 1] = oth[o];
+            sv[k] = own[o];
+            cwv[k] = oth[o + dw[k & 1]];
+            if (NDIM == 3) { Cv[k] = oth[o + dzm]; Dv[k] = oth[o + dzp]; } else { Cv[k] = 0; Dv[k] = 0; }
+        }
+    } else {
 #pragma unroll
     for (int k = -1; k <= K; ++k) {
         uint32_t y = y0 + k;
@@ -129,10 +150,11 @@ ising_msc_kernel(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth, c
             }
         }
     }
+    }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const uint32_t y = y0 + k;
-        const bool in = active && y < Ly;
+        const bool in = FULL || (active && y < Ly);
         const uint32_t rp = (rp0 + k) & 1u;
         const uint32_t s = sv[k], N0 = rows[k + 1];
         // x-neighbour 2 sits one compact index to the left (row parity 0) or right (1): shift with carry
@@ -199,8 +221,32 @@ ising_msc_kernel(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth, c
                 philox_at(widx, sweep, ch, pk, r);
                 planes(ch, r, pm, eq, lt);
             };
-            chunk(0);  // 8 planes are needed by practically every word: no loop control, two calls in flight
-            chunk(1);
+            if constexpr (NSLOT <= 3) {
+                // 8 planes are needed by practically every word: both calls unconditionally, and the compare as ONE
+                // borrow chain from the least significant of the 8 planes up: l <- (t & ~u) | (~(t ^ u) & l) leaves the
+                // verdict of the MOST significant plane where U and the threshold differ, ea the spins where none does
+                // (2 logic operations per plane instead of the 3 of the MSB-first form; same decisions).
+                uint32_t r0[4], r1[4], t0[4] = {0u, 0u, 0u, 0u}, t1[4] = {0u, 0u, 0u, 0u};
+                philox_at(widx, sweep, 0u, pk, r0);
+                philox_at(widx, sweep, 1u, pk, r1);
+#pragma unroll
+                for (int q = 0; q < NSLOT; ++q) {
+#pragma unroll
+                    for (int pl = 0; pl < 4; ++pl) { t0[pl] += pm[q] * thr.bit[q][pl]; t1[pl] += pm[q] * thr.bit[q][4 + pl]; }
+                }
+                uint32_t l8 = 0u, ea = 0xFFFFFFFFu;
+#pragma unroll
+                for (int pl = 7; pl >= 0; --pl) {
+                    const uint32_t t = pl < 4 ? t0[pl] : t1[pl - 4], u = pl < 4 ? r0[pl] : r1[pl - 4];
+                    l8 = (t & ~u) | (~(t ^ u) & l8);
+                    ea &= ~(t ^ u);
+                }
+                lt = eq & l8;
+                eq &= ea;
+            } else {
+                chunk(0);
+                chunk(1);
+            }
             if constexpr (NSLOT <= 3) {
                 // Tail.  After 8 planes about 6 % of the words still hold an undecided spin.  Running every lane through
                 // more chunks would cost the whole warp a Philox call per word; instead the word is finished
@@ -210,11 +256,12 @@ ising_msc_kernel(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth, c
                 const uint32_t need = __ballot_sync(0xffffffffu, eq != 0u);
                 if (eq != 0u) {
                     uint32_t* q = s_rec[warp][n_rec + __popc(need & ((1u << lane) - 1u))];
-                    q[0] = eq;
+                    q[0] = eq; q[1] = n0; q[2] = n1; q[3] = n2; q[4] = base + y * Wx;
+                    if (!FERRO || RANDPROP) q[5] = cand;
+                    if (!FERRO) {
 #pragma unroll
-                    for (int i = 0; i < NSLOT; ++i) q[1 + i] = pm[i];
-                    q[4] = (uint32_t)widx; q[5] = (uint32_t)(widx >> 32);
-                    q[6] = n0; q[7] = n1; q[8] = n2; q[9] = base + y * Wx; q[10] = cand;
+                        for (int i = 0; i < NSLOT; ++i) q[6 + i] = pm[i];
+                    }
                 }
                 n_rec += __popc(need);
             } else {
@@ -249,9 +296,15 @@ ising_msc_kernel(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth, c
                 if (idx < n_rec) {
                     const uint32_t* q = s_rec[warp][idx];
                     uint32_t e = q[0], l = 0u, m[NSLOT];
+                    const uint32_t r0 = q[1], r1 = q[2], r2 = q[3], off = q[4];
 #pragma unroll
-                    for (int i = 0; i < NSLOT; ++i) m[i] = q[1 + i];
-                    const uint64_t wi = (uint64_t)q[4] | ((uint64_t)q[5] << 32);
+                    for (int i = 0; i < NSLOT; ++i) {
+                        if (FERRO) m[i] = i >= Z / 2 ? 0u : ((i & 1 ? r0 : ~r0) & (i & 2 ? r1 : ~r1) & ~r2);
+                        else m[i] = q[6 + i];
+                    }
+                    const uint32_t rcand = (!FERRO || RANDPROP) ? q[5] : 0xFFFFFFFFu;
+                    // word offset -> global word index of the colour array (the key the main loop drew with)
+                    const uint64_t wi = ((uint64_t)off + (uint64_t)g.z_offset * plane) | ((uint64_t)colour << 62);
                     for (uint32_t ch = 2; e != 0u && ch < 16u; ++ch) {
                         uint32_t r[4], tb[4] = {0u, 0u, 0u, 0u};
                         philox_at(wi, sweep, ch, pk, r);
@@ -267,9 +320,8 @@ ising_msc_kernel(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth, c
                             e ^= tt;
                         }
                     }
-                    const uint32_t f = l & q[10];  // spins accepted after all: flip them on top of the provisional word
+                    const uint32_t f = l & rcand;  // spins accepted after all: flip them on top of the provisional word
                     if (f != 0u) {
-                        const uint32_t off = q[9];
                         const uint32_t prov = own[off], fin = prov ^ f;
                         own[off] = fin;
                         if (NDIM == 3 && HALO) {
@@ -280,7 +332,7 @@ ising_msc_kernel(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth, c
                         acc[2] += __popc(f);
                         if (MODE != 0) {
                             // a flipped spin with antiparallel count c ends with Z - c: the sum of final counts moves by Z - 2c
-                            const int dc = Z * __popc(f) - 2 * (__popc(q[6] & f) + 2 * __popc(q[7] & f) + 4 * __popc(q[8] & f));
+                            const int dc = Z * __popc(f) - 2 * (__popc(r0 & f) + 2 * __popc(r1 & f) + 4 * __popc(r2 & f));
                             acc[0] -= 2 * dc;
                             acc[1] += 2 * (__popc(f & ~prov) - __popc(f & prov));
                         }

@@ -129,6 +129,7 @@ struct vegas_gpu {
     std::vector<uint64_t> h_row_ptr; std::vector<uint32_t> h_col; std::vector<double> h_val;  // csr input copy
     std::vector<uint8_t> h_colour;
     // --- shared-memory-resident batches of steps for small general-family lattices (resident.cuh)
+    int msc_full = 1;                     // tuning key "msc_full": the exact-cover variant of the Ising colour pass when the grid allows
     int basis_vec = 1;                    // tuning key "basis_vec": 16-byte accesses in the bcc / fcc colour pass when nx allows
     uint32_t resident_max = 8192;         // tuning key "resident_max": largest site count that takes this path (0: never)
     int resident_cols = -2;               // cached resident_columns(): -2 not planned yet, -1 no, 0 direct, > 0 table columns
@@ -334,7 +335,7 @@ MscSlots<NSLOT> slots_prefix(const MscSlots<MSC_MAX_SLOT>& a) {
     return r;
 }
 
-template <int NDIM, bool FIELD, int NSLOT, bool RP, bool FERRO, bool HALO>
+template <int NDIM, bool FIELD, int NSLOT, bool RP, bool FERRO, bool HALO, bool FULL = false>
 void launch_msc_mode(vegas_gpu* h, int mode, dim3 grid, dim3 block, uint32_t* own, const uint32_t* oth, const uint32_t* lo,
                      const uint32_t* hi, uint32_t* plo, uint32_t* phi, int colour, uint32_t zb, uint32_t zstep,
                      unsigned long long* obs, cudaStream_t st) {
@@ -343,10 +344,10 @@ void launch_msc_mode(vegas_gpu* h, int mode, dim3 grid, dim3 block, uint32_t* ow
     const MscSlots<NSLOT> sl = slots_prefix<NSLOT>(h->msc_slots);
     const MscThr<NSLOT> th = thr_prefix<NSLOT>(h->msc_thr);
     if (mode == 0)
-        ising_msc_kernel<NDIM, FIELD, NSLOT, RP, 0, FERRO, HALO><<<grid, block, 0, st>>>(own, oth, lo, hi, plo, phi, g, colour, zb, zstep,
+        ising_msc_kernel<NDIM, FIELD, NSLOT, RP, 0, FERRO, HALO, FULL><<<grid, block, 0, st>>>(own, oth, lo, hi, plo, phi, g, colour, zb, zstep,
                                                                                       sl, th, h->sweeps, pk, obs);
     else
-        ising_msc_kernel<NDIM, FIELD, NSLOT, RP, 1, FERRO, HALO><<<grid, block, 0, st>>>(own, oth, lo, hi, plo, phi, g, colour, zb, zstep,
+        ising_msc_kernel<NDIM, FIELD, NSLOT, RP, 1, FERRO, HALO, FULL><<<grid, block, 0, st>>>(own, oth, lo, hi, plo, phi, g, colour, zb, zstep,
                                                                                       sl, th, h->sweeps, pk, obs);
 }
 
@@ -365,6 +366,7 @@ void launch_msc(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, ui
     // halo pointers matter only for launches that touch local plane 0 or Lz-1 of a connected slab; everything else
     // (single handle: periodic wrap of `oth` itself; interior planes of a slab) takes the leaner variant
     const bool halo = h->slab && h->connected && (zb == 0 || zb + (zc - 1) * zstep + 1 >= g.Lz);
+    const bool full = h->msc_full != 0 && g.Wx % block.x == 0 && g.Ly % (block.y * msc_rows(NDIM)) == 0;
     h->launches++;
     if (mode == 2) {
         ising_msc_kernel<NDIM, false, 3, false, 2><<<grid, block, 0, st>>>(own, oth, lo, hi, plo, phi, g, colour, zb, zstep,
@@ -376,7 +378,10 @@ void launch_msc(vegas_gpu* h, int mode, int colour, uint32_t zb, uint32_t zc, ui
         if (rp) ML(true, 14, true, false, true); else ML(true, 14, false, false, true);
     } else if (h->msc_ferro) {
         if (halo) { if (rp) ML(false, 3, true, true, true); else ML(false, 3, false, true, true); }
-        else { if (rp) ML(false, 3, true, true, false); else ML(false, 3, false, true, false); }
+        else if (full) {   // the grid covers the lattice exactly: the variant without per-row bounds and predicates
+            if (rp) launch_msc_mode<NDIM, false, 3, true, true, false, true>(h, mode, grid, block, own, oth, lo, hi, plo, phi, colour, zb, zstep, obs, st);
+            else launch_msc_mode<NDIM, false, 3, false, true, false, true>(h, mode, grid, block, own, oth, lo, hi, plo, phi, colour, zb, zstep, obs, st);
+        } else { if (rp) ML(false, 3, true, true, false); else ML(false, 3, false, true, false); }
     } else {
         if (rp) ML(false, 3, true, false, true); else ML(false, 3, false, false, true);
     }
@@ -2334,6 +2339,7 @@ int vegas_gpu_set_tuning(vegas_gpu_t h, const char* key, long value) {
     else if (k == "basis_wave_ipt") h->bwave_ipt = (uint32_t)value;
     else if (k == "basis_wave_grid") h->bwave_grid = (uint32_t)value;
     else if (k == "basis_vec") h->basis_vec = (int)value;
+    else if (k == "msc_full") h->msc_full = (int)value;
     else if (k == "resident_max") { h->resident_max = (uint32_t)value; h->resident_cols = -2; }
     else return fail(h, VEGAS_ERR_INVALID, "unknown tuning key: " + k);
     h->fused_ready = false;  // re-plan at the next step
