@@ -50,6 +50,13 @@ __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { r
 #endif               // 1024^3 / 8192^2 (profiles/r02o*): 2 -> 2.319e12 / 1.888e12, 3 -> 2.337e12 / 1.852e12, 4 -> 2.423e12 / 1.867e12
 // rows (words along y) per thread: amortises addressing, shares the y-neighbour loads.  2-D lattices are small
 // (8192^2 = 1 Mi words per colour): 1, 2, 4 rows per thread measured 1.42e12, 1.76e12, 1.91e12 attempts/s there.
+// of the 8 threshold bit-planes of the main compare, how many are built with logic operations instead of multiply-adds.
+// ncu of the all-IMAD kernel: FMA-heavy pipe 67 % busy (IMAD 2, IMAD.WIDE 4 cycles per warp instruction), ALU pipe 53 % --
+// yet moving planes to the ALU pipe loses: 0 / 2 / 4 / 8 planes measured 3.06e12 / 3.04e12 / 2.99e12 / 2.86e12 attempts/s
+// on 1024^3 (profiles/r02/i5.sh): the and-or form needs the negated bits and one more operation per plane
+#ifndef MSC_LOP_PLANES
+#define MSC_LOP_PLANES 0
+#endif
 #ifndef MSC_ROWS_2D
 #define MSC_ROWS_2D 4
 #endif
@@ -229,10 +236,17 @@ ising_msc_kernel(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth, c
                 uint32_t r0[4], r1[4], t0[4] = {0u, 0u, 0u, 0u}, t1[4] = {0u, 0u, 0u, 0u};
                 philox_at(widx, sweep, 0u, pk, r0);
                 philox_at(widx, sweep, 1u, pk, r1);
+                // threshold bit-planes: sum_q pm[q] * bit (IMAD, FMA-heavy pipe) for the first 8 - MSC_LOP_PLANES planes,
+                // or_q pm[q] & -bit (LOP3, ALU pipe) for the rest: the split balances the two pipes
 #pragma unroll
-                for (int q = 0; q < NSLOT; ++q) {
+                for (int pl = 0; pl < 8; ++pl) {
+                    uint32_t t = 0u;
 #pragma unroll
-                    for (int pl = 0; pl < 4; ++pl) { t0[pl] += pm[q] * thr.bit[q][pl]; t1[pl] += pm[q] * thr.bit[q][4 + pl]; }
+                    for (int q = 0; q < NSLOT; ++q) {
+                        if (pl < 8 - MSC_LOP_PLANES) t += pm[q] * thr.bit[q][pl];
+                        else t |= pm[q] & (0u - thr.bit[q][pl]);
+                    }
+                    if (pl < 4) t0[pl] = t; else t1[pl - 4] = t;
                 }
                 uint32_t l8 = 0u, ea = 0xFFFFFFFFu;
 #pragma unroll
