@@ -45,12 +45,13 @@ WORKLOADS = {
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from the committed `ncu --set full`
 # captures (cold cache): (bytes, source)
 NCU_TRAFFIC = {
-    "ising3d_1024": {"ising_msc": (134.37e6 + 30.83e6, "profiles/r01o_ising_msc.metrics.txt (one colour pass)")},
-    "heis3d_512": {"heis_pipe": (1.674e9 + 1.555e9, "profiles/r02_heis_pipe.metrics.txt (one step = both colours, one launch)"),
+    "ising3d_1024": {"ising_msc": (134.37e6 + 30.64e6, "profiles/r02_ising_msc.metrics.txt (one colour pass)")},
+    "heis3d_512": {"heis_pipe": (2.379e9 + 1.557e9, "profiles/r02_heis_pipe.metrics.txt (one step = both colours, one launch)"),
                    "heis_wave": (2.887e9 + 1.562e9, "profiles/r01u_heis_wave.metrics.txt (one step = both colours)"),
                    "heis_stencil": (2.42e9, "profiles/r01o_heis_stencil.metrics.txt (one colour pass)")},
     "heis_fcc_384": {"heis_basis": (2.829e9 + 0.686e9, "profiles/r01z_heis_basis_vec.metrics.txt (one colour pass)"),
-                     "basis_pipe": (2.981e9 + 2.667e9, "profiles/r02_basis_pipe.metrics.txt (one step = four colours, one launch)")},
+                     "basis_pipe": (7.813e9 + 2.714e9, "profiles/r02_basis_pipe.metrics.txt (one step = four colours, one launch)"),
+                     "basis_wave": (6.068e9 + 3.168e9, "profiles/r02_basis_wave.metrics.txt (one step = four colours, one launch)")},
 }
 # step kernels that do every colour of a step in ONE launch
 ONE_LAUNCH_KERNELS = ("heis_pipe", "basis_pipe", "basis_wave", "heis_wave", "heis_fused")
