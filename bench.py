@@ -302,9 +302,11 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, world: int, devi
             t = torch.tensor([dt], device=f"cuda:{device}")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        nbytes = arr.nbytes
+        nbytes = int(g.state_transfer_bytes)   # what crosses PCIe: the host State itself, or its sign bitmap (host-packed Ising path)
         e2e = {"value": n_local * world * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": nbytes,
-               "d2h_bytes_per_step": nbytes + 32, "steps": e2e_steps,
+               "d2h_bytes_per_step": nbytes + 32, "steps": e2e_steps, "host_state_bytes": arr.nbytes,
+               "transfer": ("sign bitmap, packed / unpacked by the host threads of the C ABI chunk by chunk, copies overlapped"
+                            if nbytes != arr.nbytes else "the reference's host layout as it is"),
                "api": "vegas_gpu_step_host_* (host State in, host State out, E and M back)" if not slab else
                       "vegas_gpu_upload_* + vegas_gpu_step + vegas_gpu_download_* per slab"}
     # ---- the same steps through the host layer: Machine::measure_for with StatSensor + ObservableSensor fed from the

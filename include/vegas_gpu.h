@@ -201,6 +201,10 @@ int vegas_gpu_slab_connect_local(vegas_gpu_t self, vegas_gpu_t lower, vegas_gpu_
  *                       the colour launches so far (per-item synchronisation, no L1 reuse between rows)
  *     "msc_full"      : 1 (default) the Ising colour pass without per-row bounds and predicates whenever the launch grid covers
  *                       the lattice exactly (uniform J > 0, no field, not a slab boundary plane), 0 always the generic variant
+ *     "host_pack_min" : fewest spins of an ising_msc lattice for which upload / download / step_host move a sign BITMAP over
+ *                       PCIe (host threads convert the int8 State chunk by chunk, copies overlap; VEGAS_HOST_THREADS, default
+ *                       min(16, cores)) instead of one byte per spin; default 2^22, 0 = always, -1 = never;
+ *                       "host_pack_chunk" = spins per pipelined chunk (default 2^26)
  *     "basis_vec"     : 1 (default) 16-byte accesses in the bcc / fcc colour pass when nx % 4 == 0 (fp64: % 2), 0 scalar
  *     "resident_max"  : largest site count of a general-family lattice that runs batches of steps in ONE launch with
  *                       the State in shared memory (default 8192; 0 = always one launch per colour)
@@ -214,6 +218,13 @@ int vegas_gpu_wave_schedule(uint32_t n_chunks, uint32_t lag, uint32_t steps, uin
  * between consecutive colours: units[i] = colour << 24 | plane, n_basis * nz entries (count = 0: too few planes for the
  * scheme); need[b] bit 2a + r = colour b on plane z waits for colour a on plane (z + r) % nz.  unitcell: VEGAS_BCC / VEGAS_FCC. */
 int vegas_gpu_basis_wave_schedule(int unitcell, uint32_t nz, uint32_t lag, uint32_t* units, uint64_t capacity, uint64_t* count, uint32_t need[4]);
+/* bytes one upload (or download) of this handle's State moves over PCIe: 24 n (Heisenberg, f64 AoS), n (Ising, one byte per
+ * spin) or n / 8 (Ising on the host-packed path, see "host_pack_min") */
+uint64_t vegas_gpu_state_transfer_bytes(vegas_gpu_t);
+/* host-only: the State <-> sign-bitmap conversion of the host-packed transfer (words[i] bit b = s[32 i + b] > 0), run on
+ * `threads` workers in chunks of `chunk_words`, exposed so that it is tested without a GPU */
+int vegas_gpu_host_pack(const int8_t* s, uint32_t* words, uint64_t n_words, int threads, uint64_t chunk_words);
+int vegas_gpu_host_unpack(const uint32_t* words, int8_t* s, uint64_t n_words, int threads, uint64_t chunk_words);
 /* name of the kernel the NEXT step will launch: "heis_fused", "heis_stencil", "ising_msc", ... */
 const char* vegas_gpu_step_kernel(vegas_gpu_t);
 

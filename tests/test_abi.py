@@ -176,6 +176,28 @@ def test_basis_wave_schedule_dependencies_precede_their_users(built, uc, nb, nz,
     assert lib.vegas_gpu_basis_wave_schedule(uc, 3, 3, None, 0, C.byref(count), need.ctypes.data_as(C.c_void_p)) == 0 and count.value == 0
 
 
+@pytest.mark.parametrize("n_words,threads,chunk", [(1, 1, 1), (37, 1, 8), (1000, 3, 64), (4096, 4, 1 << 20), (513, 5, 100)])
+def test_host_pack_round_trip(built, n_words, threads, chunk):
+    """The host side of the bitmap State transfer (csrc/host_pack.cpp): words[i] bit b = (s[32 i + b] > 0) for the reference's
+    +1 / -1 bytes (src/state.rs:60-63), chunked over worker threads; unpack restores the State byte for byte."""
+    from vegas_rs_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(n_words)
+    s = (2 * rng.integers(0, 2, 32 * n_words) - 1).astype(np.int8)
+    words = np.zeros(n_words, np.uint32)
+    assert lib.vegas_gpu_host_pack(s.ctypes.data, words.ctypes.data, n_words, threads, chunk) == 0
+    want = np.packbits((s > 0).reshape(n_words, 32), axis=1, bitorder="little").view(np.uint32).ravel()
+    assert np.array_equal(words, want)
+    back = np.zeros_like(s)
+    assert lib.vegas_gpu_host_unpack(words.ctypes.data, back.ctypes.data, n_words, threads, chunk) == 0
+    assert np.array_equal(back, s)
+    # an unaligned State buffer (numpy slices) takes the unaligned store path
+    buf = np.zeros(32 * n_words + 1, np.int8)
+    assert lib.vegas_gpu_host_unpack(words.ctypes.data, buf[1:].ctypes.data, n_words, threads, chunk) == 0
+    assert np.array_equal(buf[1:], s)
+    assert lib.vegas_gpu_host_pack(None, words.ctypes.data, n_words, threads, chunk) != 0
+
+
 def test_rust_shim_struct_layout_matches_header():
     """bindings/rust/gpu.rs cannot be compiled here; at least its #[repr(C)] structs must list the fields of
     include/vegas_gpu.h in the same order, and every extern function it declares must exist in the headers."""

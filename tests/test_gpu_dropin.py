@@ -94,6 +94,33 @@ def _onsager(T):
     return u, m
 
 
+@pytest.mark.parametrize("size,chunk", [((128, 16, 16), 4096), ((64, 6, 4), 1 << 26), ((256, 32, 8), 2048)])
+def test_host_packed_state_transfer(built, size, chunk):
+    """Big ising_msc lattices move their State over PCIe as a sign bitmap packed by host threads (host_pack.cpp) and split into
+    the colour arrays by a kernel; forced here on small lattices (host_pack_min = 0), with many pipelined chunks.  Upload,
+    download and the literal Integrator::step entry point must be indistinguishable from the byte-per-spin path."""
+    n = size[0] * size[1] * size[2]
+    s = random_state(ob.ISING, n, 5)
+    ref = vg.GpuMetropolis(vg.ISING, unitcell=vg.SC, size=size, seed=77)
+    ref.set_tuning("host_pack_min", -1)
+    assert ref.state_transfer_bytes == n
+    g = vg.GpuMetropolis(vg.ISING, unitcell=vg.SC, size=size, seed=77)
+    g.set_tuning("host_pack_min", 0); g.set_tuning("host_pack_chunk", chunk)
+    assert g.kernel_family == "ising_msc" and g.state_transfer_bytes == n // 8
+    ref.upload(s); g.upload(s)
+    assert np.array_equal(g.download(), s) and np.array_equal(ref.download(), s)
+    for h in (ref, g):
+        h.set_thermostat(4.0, (0, 0, 1.0), 0.25)
+    a, b = s.copy(), s.copy()
+    for _ in range(3):
+        _, ea, ma = ref.step_host(a)
+        _, eb, mb = g.step_host(b)
+        assert ea == eb and np.array_equal(ma, mb) and np.array_equal(a, b)
+    assert not np.array_equal(a, s)
+    # the bitmap path accepts any byte > 0 as Up and anything else as Down, like the byte path's pack kernel
+    ref.close(); g.close()
+
+
 def test_full_size_ising_2d_8192_matches_onsager(built):
     """BASELINE config[1] at its full size (67 M spins, multi-spin-coded kernel): the energy per site and |m| per site
     of the equilibrated lattice equal Onsager's exact infinite-lattice values within 1e-3 at T = 2.0 (ordered) and T = 2.6

@@ -25,6 +25,7 @@ _DEPS = {
     "basis_pipe.cu": ["basis_pipe.hpp", "pipe_ptx.cuh", "heis_basis.cuh", "heis.cuh", "common.cuh"],
     "basis_wave.cu": ["basis_wave.hpp", "pipe_ptx.cuh", "heis_basis.cuh", "heis.cuh", "common.cuh"],
     "vegas_host.cpp": ["vegas_host.hpp"],
+    "host_pack.cpp": ["host_pack.hpp"],
 }
 
 

@@ -423,6 +423,53 @@ ising_msc_unpack_kernel(int8_t* __restrict__ dst, const uint32_t* __restrict__ c
     }
 }
 
+// The same conversions from / to a sign BITMAP in natural site order (bit x & 31 of word x >> 5 of a row of Lx spins: 1 = Up),
+// what the host packs for big lattices (host_pack.cpp): 1/8 of the PCIe bytes.  One thread owns 64 consecutive x.
+__device__ __forceinline__ uint32_t compress_even_bits(uint64_t v) {   // bits 0, 2, 4, ... of v -> bits 0, 1, 2, ...
+    v &= 0x5555555555555555ull;
+    v = (v | (v >> 1)) & 0x3333333333333333ull;
+    v = (v | (v >> 2)) & 0x0f0f0f0f0f0f0f0full;
+    v = (v | (v >> 4)) & 0x00ff00ff00ff00ffull;
+    v = (v | (v >> 8)) & 0x0000ffff0000ffffull;
+    v = (v | (v >> 16)) & 0x00000000ffffffffull;
+    return (uint32_t)v;
+}
+__device__ __forceinline__ uint64_t spread_to_even_bits(uint32_t w) {  // bits 0, 1, 2, ... of w -> bits 0, 2, 4, ...
+    uint64_t v = w;
+    v = (v | (v << 16)) & 0x0000ffff0000ffffull;
+    v = (v | (v << 8)) & 0x00ff00ff00ff00ffull;
+    v = (v | (v << 4)) & 0x0f0f0f0f0f0f0f0full;
+    v = (v | (v << 2)) & 0x3333333333333333ull;
+    v = (v | (v << 1)) & 0x5555555555555555ull;
+    return v;
+}
+__global__ void __launch_bounds__(256)
+ising_msc_from_bitmap_kernel(const uint2* __restrict__ bitmap, uint32_t* __restrict__ c0, uint32_t* __restrict__ c1,
+                             uint32_t Wx, uint32_t Ly, uint32_t Lz, uint32_t z_offset) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)Wx * Ly * Lz;
+    if (t >= total) return;
+    const uint32_t y = (uint32_t)((t / Wx) % Ly), z = (uint32_t)(t / ((size_t)Wx * Ly));
+    const uint32_t par = (y + z + z_offset) & 1u;  // colour of x = 0 in this row
+    const uint2 q = bitmap[t];
+    const uint64_t v = (uint64_t)q.x | ((uint64_t)q.y << 32);
+    const uint32_t even = compress_even_bits(v), odd = compress_even_bits(v >> 1);
+    c0[t] = par ? odd : even;
+    c1[t] = par ? even : odd;
+}
+__global__ void __launch_bounds__(256)
+ising_msc_to_bitmap_kernel(uint2* __restrict__ bitmap, const uint32_t* __restrict__ c0, const uint32_t* __restrict__ c1,
+                           uint32_t Wx, uint32_t Ly, uint32_t Lz, uint32_t z_offset) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)Wx * Ly * Lz;
+    if (t >= total) return;
+    const uint32_t y = (uint32_t)((t / Wx) % Ly), z = (uint32_t)(t / ((size_t)Wx * Ly));
+    const uint32_t par = (y + z + z_offset) & 1u;
+    const uint32_t even = par ? c1[t] : c0[t], odd = par ? c0[t] : c1[t];
+    const uint64_t v = spread_to_even_bits(even) | (spread_to_even_bits(odd) << 1);
+    bitmap[t] = make_uint2((uint32_t)v, (uint32_t)(v >> 32));
+}
+
 // State::rand_with_size on device (src/state.rs:260-262): one fair bit per spin.
 __global__ void __launch_bounds__(256)
 ising_msc_randomize_kernel(uint32_t* __restrict__ c0, uint32_t* __restrict__ c1, size_t words_local, uint64_t word_offset,

@@ -20,6 +20,7 @@
 #include "heis_pipe.hpp"
 #include "basis_pipe.hpp"
 #include "basis_wave.hpp"
+#include "host_pack.hpp"
 #include "ising_msc.cuh"
 #include "lattice.hpp"
 #include "resident.cuh"
@@ -129,6 +130,12 @@ struct vegas_gpu {
     std::vector<uint64_t> h_row_ptr; std::vector<uint32_t> h_col; std::vector<double> h_val;  // csr input copy
     std::vector<uint8_t> h_colour;
     // --- shared-memory-resident batches of steps for small general-family lattices (resident.cuh)
+    // --- host-packed State transfer of big ising_msc lattices (host_pack.cpp): sign bitmap over PCIe instead of one byte per spin
+    long host_pack_min = 1l << 22;        // tuning key "host_pack_min": fewest spins that take it (0 = always, -1 = never)
+    uint64_t host_pack_chunk = 1ull << 26; // tuning key "host_pack_chunk": spins per pipelined chunk
+    uint32_t* hp_host = nullptr;          // pinned staging bitmap (n / 8 bytes)
+    uint32_t* hp_dev = nullptr;           // device bitmap
+    std::vector<cudaEvent_t> hp_events;
     int msc_full = 1;                     // tuning key "msc_full": the exact-cover variant of the Ising colour pass when the grid allows
     int basis_vec = 1;                    // tuning key "basis_vec": 16-byte accesses in the bcc / fcc colour pass when nx allows
     uint32_t resident_max = 8192;         // tuning key "resident_max": largest site count that takes this path (0: never)
@@ -1606,6 +1613,9 @@ void vegas_gpu_destroy(vegas_gpu_t h) {
     cudaFree(h->wave_done); cudaFree(h->wave_error);
     heis_pipe_destroy(h->pipe);
     basis_pipe_destroy(h->bpipe);
+    if (h->hp_host) cudaFreeHost(h->hp_host);
+    cudaFree(h->hp_dev);
+    for (cudaEvent_t ev : h->hp_events) cudaEventDestroy(ev);
     basis_wave_destroy(h->bwave);
     if (h->stream_b) { cudaStreamSynchronize(h->stream_b); cudaStreamDestroy(h->stream_b); }
     if (h->ev_main) cudaEventDestroy(h->ev_main);
@@ -1693,12 +1703,41 @@ int vegas_gpu_colours(vegas_gpu_t h, uint8_t* colour_of_site) {
 }
 
 // ---- state I/O --------------------------------------------------------------------------
+namespace {
+// staging buffers of the host-packed transfer, allocated at first use; false: this handle takes the byte-per-spin path
+bool host_pack_ready(vegas_gpu* h) {
+    if (h->family != FAM_ISING_MSC || h->host_pack_min < 0 || (long)std::min<uint64_t>(h->n, 1ull << 62) < h->host_pack_min || h->n % 64) return false;
+    if (h->hp_host && h->hp_dev) return true;
+    const size_t bytes = (size_t)(h->n / 8);
+    if (!h->hp_host && cudaHostAlloc((void**)&h->hp_host, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); h->hp_host = nullptr; return false; }
+    if (!h->hp_dev && cudaMalloc((void**)&h->hp_dev, bytes) != cudaSuccess) { cudaGetLastError(); h->hp_dev = nullptr; return false; }
+    return true;
+}
+}  // namespace
+
 int vegas_gpu_upload_ising(vegas_gpu_t h, const int8_t* s, uint64_t n) {
     if (!h || !s) return VEGAS_ERR_INVALID;
     if (h->md.model != VEGAS_ISING || n != h->n) return fail(h, VEGAS_ERR_INVALID, "upload_ising: wrong model or size");
     CU(cudaSetDevice(h->device));
     if (h->family == FAM_ISING_GEN) {
         CU(cudaMemcpyAsync(h->g_s8, s, n, cudaMemcpyHostToDevice, h->stream));
+    } else if (host_pack_ready(h)) {
+        // big lattice: the host threads turn the State into a sign bitmap chunk by chunk (1/8 of the PCIe bytes); the copy of
+        // a finished chunk overlaps the packing of the next ones; one kernel splits the bitmap into the colour arrays
+        const size_t words = (size_t)(n / 32);
+        int err = 0;
+        host_chunked(words, (size_t)(h->host_pack_chunk / 32), host_pack_threads(),
+                     [&](size_t first, size_t nw) { host_pack_signs(s + 32 * first, h->hp_host + first, nw); },
+                     [&](size_t, size_t first, size_t nw) {
+                         if (cudaMemcpyAsync(h->hp_dev + first, h->hp_host + first, nw * 4, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) err = 1;
+                     },
+                     nullptr);
+        if (err) CU(cudaGetLastError());
+        const uint32_t Wx = (uint32_t)(h->ld.nx / 64);
+        const size_t total = (size_t)Wx * h->ld.ny * h->ld.nz;
+        ising_msc_from_bitmap_kernel<<<cdiv(total, 256), 256, 0, h->stream>>>((const uint2*)h->hp_dev, h->msc[0], h->msc[1], Wx,
+                                                                             (uint32_t)h->ld.ny, (uint32_t)h->ld.nz, (uint32_t)h->z_offset);
+        h->launches++;
     } else {
         int8_t* tmp = nullptr;
         CU(cudaMallocAsync(&tmp, n, h->stream));
@@ -1721,6 +1760,31 @@ int vegas_gpu_download_ising(vegas_gpu_t h, int8_t* s, uint64_t n) {
     CU(cudaSetDevice(h->device));
     if (h->family == FAM_ISING_GEN) {
         CU(cudaMemcpyAsync(s, h->g_s8, n, cudaMemcpyDeviceToHost, h->stream));
+    } else if (host_pack_ready(h)) {
+        // the reverse: colour arrays -> bitmap on the device, chunked copies, the host threads write the int8 State of a chunk
+        // as soon as its copy has landed (one event per chunk)
+        const uint32_t Wx = (uint32_t)(h->ld.nx / 64);
+        const size_t total = (size_t)Wx * h->ld.ny * h->ld.nz;
+        ising_msc_to_bitmap_kernel<<<cdiv(total, 256), 256, 0, h->stream>>>((uint2*)h->hp_dev, h->msc[0], h->msc[1], Wx,
+                                                                           (uint32_t)h->ld.ny, (uint32_t)h->ld.nz, (uint32_t)h->z_offset);
+        h->launches++;
+        const size_t words = (size_t)(n / 32), cw = (size_t)(h->host_pack_chunk / 32), n_chunks = (words + cw - 1) / cw;
+        while (h->hp_events.size() < n_chunks) {
+            cudaEvent_t ev;
+            CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            h->hp_events.push_back(ev);
+        }
+        for (size_t c = 0; c < n_chunks; ++c) {
+            const size_t first = c * cw, nw = std::min(cw, words - first);
+            CU(cudaMemcpyAsync(h->hp_host + first, h->hp_dev + first, nw * 4, cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaEventRecord(h->hp_events[c], h->stream));
+        }
+        int err = 0;
+        host_chunked(words, cw, host_pack_threads(),
+                     [&](size_t first, size_t nw) { host_unpack_signs(h->hp_host + first, s + 32 * first, nw); },
+                     nullptr,
+                     [&](size_t c) { if (cudaEventSynchronize(h->hp_events[c]) != cudaSuccess) err = 1; });
+        if (err) CU(cudaGetLastError());
     } else {
         int8_t* tmp = nullptr;
         CU(cudaMallocAsync(&tmp, n, h->stream));
@@ -2311,6 +2375,26 @@ int vegas_gpu_basis_wave_schedule(int unitcell, uint32_t nz, uint32_t lag, uint3
     return VEGAS_OK;
 }
 
+uint64_t vegas_gpu_state_transfer_bytes(vegas_gpu_t h) {
+    if (!h) return 0;
+    if (h->md.model == VEGAS_HEISENBERG) return h->n * 24;
+    if (cudaSetDevice(h->device) == cudaSuccess && host_pack_ready(h)) return h->n / 8;
+    return h->n;
+}
+
+int vegas_gpu_host_pack(const int8_t* s, uint32_t* words, uint64_t n_words, int threads, uint64_t chunk_words) {
+    if (!s || !words || threads < 1) return VEGAS_ERR_INVALID;
+    host_chunked((size_t)n_words, (size_t)std::max<uint64_t>(1, chunk_words), (unsigned)threads,
+                 [&](size_t first, size_t nw) { host_pack_signs(s + 32 * first, words + first, nw); }, nullptr, nullptr);
+    return VEGAS_OK;
+}
+int vegas_gpu_host_unpack(const uint32_t* words, int8_t* s, uint64_t n_words, int threads, uint64_t chunk_words) {
+    if (!s || !words || threads < 1) return VEGAS_ERR_INVALID;
+    host_chunked((size_t)n_words, (size_t)std::max<uint64_t>(1, chunk_words), (unsigned)threads,
+                 [&](size_t first, size_t nw) { host_unpack_signs(words + first, s + 32 * first, nw); }, nullptr, nullptr);
+    return VEGAS_OK;
+}
+
 // ---- tuning knobs ---------------------------------------------------------------------------
 int vegas_gpu_set_tuning(vegas_gpu_t h, const char* key, long value) {
     if (!h || !key) return VEGAS_ERR_INVALID;
@@ -2340,6 +2424,8 @@ int vegas_gpu_set_tuning(vegas_gpu_t h, const char* key, long value) {
     else if (k == "basis_wave_grid") h->bwave_grid = (uint32_t)value;
     else if (k == "basis_vec") h->basis_vec = (int)value;
     else if (k == "msc_full") h->msc_full = (int)value;
+    else if (k == "host_pack_min") h->host_pack_min = value;
+    else if (k == "host_pack_chunk") h->host_pack_chunk = (uint64_t)std::max<long>(64, value) / 64 * 64;
     else if (k == "resident_max") { h->resident_max = (uint32_t)value; h->resident_cols = -2; }
     else return fail(h, VEGAS_ERR_INVALID, "unknown tuning key: " + k);
     h->fused_ready = false;  // re-plan at the next step

@@ -128,6 +128,10 @@ class GpuMetropolis:
     def launches(self) -> int: return self._lib.vegas_gpu_launch_count(self._h)
     @property
     def stream(self) -> int: return self._lib.vegas_gpu_stream(self._h) or 0
+    @property
+    def state_transfer_bytes(self) -> int:
+        """bytes one upload / download of the State moves over PCIe (n / 8 on the host-packed Ising path)"""
+        return self._lib.vegas_gpu_state_transfer_bytes(self._h)
 
     def adjacency(self):
         n, nnz = C.c_uint64(), C.c_uint64()
