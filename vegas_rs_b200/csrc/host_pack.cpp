@@ -78,7 +78,11 @@ unsigned host_pack_threads() {
         const long v = std::strtol(e, nullptr, 10);
         if (v >= 1 && v <= 256) return (unsigned)v;
     }
-    const unsigned hc = std::thread::hardware_concurrency();
+    unsigned hc = std::thread::hardware_concurrency();
+    if (const char* e = std::getenv("LOCAL_WORLD_SIZE")) {   // one process per GPU (torchrun): the ranks share the host's cores
+        const long r = std::strtol(e, nullptr, 10);
+        if (r > 1 && r <= 64) hc = std::max(1u, hc / (unsigned)r);
+    }
     return std::max(1u, std::min(16u, hc ? hc : 1u));
 }
 

@@ -15,7 +15,7 @@ void host_pack_signs(const int8_t* s, uint32_t* words, size_t n_words);
 // s[32 i + b] = bit ? +1 : -1
 void host_unpack_signs(const uint32_t* words, int8_t* s, size_t n_words);
 
-unsigned host_pack_threads();   // VEGAS_HOST_THREADS, else min(16, hardware_concurrency)
+unsigned host_pack_threads();   // VEGAS_HOST_THREADS, else min(16, hardware_concurrency / LOCAL_WORLD_SIZE)
 
 // Runs `work(chunk, first_word, n_words)` for every chunk in order on `threads` workers (each worker takes an equal share of
 // every chunk) and calls `done(chunk)` on the CALLING thread as soon as all workers have finished that chunk; before a
