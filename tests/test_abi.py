@@ -176,7 +176,7 @@ def test_basis_wave_schedule_dependencies_precede_their_users(built, uc, nb, nz,
     assert lib.vegas_gpu_basis_wave_schedule(uc, 3, 3, None, 0, C.byref(count), need.ctypes.data_as(C.c_void_p)) == 0 and count.value == 0
 
 
-@pytest.mark.parametrize("n_words,threads,chunk", [(1, 1, 1), (37, 1, 8), (1000, 3, 64), (4096, 4, 1 << 20), (513, 5, 100)])
+@pytest.mark.parametrize("n_words,threads,chunk", [(1, 1, 1), (37, 1, 8), (1000, 3, 64), (4096, 4, 1 << 20), (8192, 3, 1000), (20000, 5, 700)])
 def test_host_pack_round_trip(built, n_words, threads, chunk):
     """The host side of the bitmap State transfer (csrc/host_pack.cpp): words[i] bit b = (s[32 i + b] > 0) for the reference's
     +1 / -1 bytes (src/state.rs:60-63), chunked over worker threads; unpack restores the State byte for byte."""

@@ -94,7 +94,7 @@ def _onsager(T):
     return u, m
 
 
-@pytest.mark.parametrize("size,chunk", [((128, 16, 16), 4096), ((64, 6, 4), 1 << 26), ((256, 32, 8), 2048)])
+@pytest.mark.parametrize("size,chunk", [((128, 16, 16), 4096), ((64, 6, 4), 1 << 26), ((512, 32, 16), 16384)])
 def test_host_packed_state_transfer(built, size, chunk):
     """Big ising_msc lattices move their State over PCIe as a sign bitmap packed by host threads (host_pack.cpp) and split into
     the colour arrays by a kernel; forced here on small lattices (host_pack_min = 0), with many pipelined chunks.  Upload,

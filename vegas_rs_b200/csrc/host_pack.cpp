@@ -102,13 +102,29 @@ void host_chunked(size_t total_words, size_t chunk_words, unsigned threads,
         }
         return;
     }
+    // a lattice of a few chunks' worth of words does not pay for thread start-up
+    if (total_words < 4096) threads = 1;
+    if (threads == 1) { host_chunked(total_words, chunk_words, 1, work, done, wait_ready); return; }
     std::vector<std::atomic<unsigned>> finished(n_chunks);
     std::vector<std::atomic<unsigned>> ready(n_chunks);
     for (size_t c = 0; c < n_chunks; ++c) { finished[c].store(0); ready[c].store(wait_ready ? 0u : 1u); }
     std::vector<std::thread> pool;
     pool.reserve(threads);
+    std::atomic<int> go(0);   // 1: all workers exist, start; 2: a worker could not be created, leave
+    auto single = [&]() {
+        for (size_t c = 0; c < n_chunks; ++c) {
+            const size_t first = c * chunk_words, nw = std::min(chunk_words, total_words - first);
+            if (wait_ready) wait_ready(c);
+            work(first, nw);
+            if (done) done(c, first, nw);
+        }
+    };
+    try {
     for (unsigned t = 0; t < threads; ++t)
         pool.emplace_back([&, t]() {
+            int g;
+            while ((g = go.load(std::memory_order_acquire)) == 0) std::this_thread::yield();
+            if (g == 2) return;
             for (size_t c = 0; c < n_chunks; ++c) {
                 while (ready[c].load(std::memory_order_acquire) == 0u) std::this_thread::yield();
                 const size_t first = c * chunk_words, nw = std::min(chunk_words, total_words - first);
@@ -117,6 +133,13 @@ void host_chunked(size_t total_words, size_t chunk_words, unsigned threads,
                 finished[c].fetch_add(1u, std::memory_order_release);
             }
         });
+    } catch (...) {   // out of threads: the workers that exist leave, the caller does the work itself
+        go.store(2, std::memory_order_release);
+        for (auto& th : pool) th.join();
+        single();
+        return;
+    }
+    go.store(1, std::memory_order_release);
     // the calling thread owns the CUDA side: it opens chunks (wait_ready) and hands finished ones on (done), in order
     size_t opened = 0;
     for (size_t c = 0; c < n_chunks; ++c) {

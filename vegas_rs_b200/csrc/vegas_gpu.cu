@@ -1726,12 +1726,16 @@ int vegas_gpu_upload_ising(vegas_gpu_t h, const int8_t* s, uint64_t n) {
         // a finished chunk overlaps the packing of the next ones; one kernel splits the bitmap into the colour arrays
         const size_t words = (size_t)(n / 32);
         int err = 0;
-        host_chunked(words, (size_t)(h->host_pack_chunk / 32), host_pack_threads(),
-                     [&](size_t first, size_t nw) { host_pack_signs(s + 32 * first, h->hp_host + first, nw); },
-                     [&](size_t, size_t first, size_t nw) {
-                         if (cudaMemcpyAsync(h->hp_dev + first, h->hp_host + first, nw * 4, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) err = 1;
-                     },
-                     nullptr);
+        try {
+            host_chunked(words, (size_t)(h->host_pack_chunk / 32), host_pack_threads(),
+                         [&](size_t first, size_t nw) { host_pack_signs(s + 32 * first, h->hp_host + first, nw); },
+                         [&](size_t, size_t first, size_t nw) {
+                             if (cudaMemcpyAsync(h->hp_dev + first, h->hp_host + first, nw * 4, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) err = 1;
+                         },
+                         nullptr);
+        } catch (const std::exception& e) {   // worker threads could not be started: nothing crosses the C ABI as an exception
+            return fail(h, VEGAS_ERR_ALLOC, std::string("upload_ising: host packing failed: ") + e.what());
+        }
         if (err) CU(cudaGetLastError());
         const uint32_t Wx = (uint32_t)(h->ld.nx / 64);
         const size_t total = (size_t)Wx * h->ld.ny * h->ld.nz;
@@ -1780,10 +1784,15 @@ int vegas_gpu_download_ising(vegas_gpu_t h, int8_t* s, uint64_t n) {
             CU(cudaEventRecord(h->hp_events[c], h->stream));
         }
         int err = 0;
-        host_chunked(words, cw, host_pack_threads(),
-                     [&](size_t first, size_t nw) { host_unpack_signs(h->hp_host + first, s + 32 * first, nw); },
-                     nullptr,
-                     [&](size_t c) { if (cudaEventSynchronize(h->hp_events[c]) != cudaSuccess) err = 1; });
+        try {
+            host_chunked(words, cw, host_pack_threads(),
+                         [&](size_t first, size_t nw) { host_unpack_signs(h->hp_host + first, s + 32 * first, nw); },
+                         nullptr,
+                         [&](size_t c) { if (cudaEventSynchronize(h->hp_events[c]) != cudaSuccess) err = 1; });
+        } catch (const std::exception& e) {
+            cudaStreamSynchronize(h->stream);
+            return fail(h, VEGAS_ERR_ALLOC, std::string("download_ising: host unpacking failed: ") + e.what());
+        }
         if (err) CU(cudaGetLastError());
     } else {
         int8_t* tmp = nullptr;
