@@ -178,7 +178,8 @@ int vegas_gpu_slab_connect_local(vegas_gpu_t self, vegas_gpu_t lower, vegas_gpu_
  *                       "heis_pipe_tiles" (bands of rows per colour, 0 = auto: half the SM count), "heis_pipe_vec" (sites per
  *                       consumer thread: a whole or half 16-byte vector, 0 = auto), "heis_pipe_lead" (planes the first
  *                       colour may run ahead of the second, 0 = auto; bounds the working set kept in L2), "heis_pipe_pub"
- *                       (planes per published progress update = per gpu-scope release, 0 = auto)
+ *                       (planes per published progress update = per gpu-scope release, 0 = auto), "heis_pipe_backoff" /
+ *                       "heis_pipe_backoff_helper" (ns a consumer / helper warp sleeps between failed mbarrier polls)
  *     "heis_wave"     : -1 auto (default: lattices with >= 32 planes), 0 never, 1 always -- both colour passes of a
  *                       Heisenberg step as ONE persistent launch in wave order (second pass finds the first in L2);
  *                       "heis_wave_planes" (planes per chunk, default 4), "heis_wave_lag" (positions a colour pass

@@ -51,6 +51,7 @@ struct PipeArgs {
     const CUtensorMap* maps;
     HeisGeom g;
     uint32_t tiles, rows, tiles_long, S, SO, n_cw, lead, pub_every;
+    uint32_t backoff_consumer, backoff_helper;   // ns slept between failed barrier polls (0: re-poll at once)
     unsigned long long* prog;            // [2][tiles] planes finished (published), monotone over the launches
     unsigned long long base;             // value of every progress counter when this launch starts
     const unsigned long long* flags;     // HALO: [lower, upper][colour] boundary-plane CTAs that have stored into my halos
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(MAXT, 1) heis_pipe_kernel(const __grid_constan
             if (is_halo) { array = 2u + oc * 2u + (pl < 0 ? 0u : 1u); zc = 0u; }
             uint32_t good = 1u, fenced = 0u;
             if (lane == 0) {
-                if (q >= S && !wait_bar(empty_o + slot, parity ^ 1u, abort_flag, A.error, PIPE_ERR_EMPTY)) good = 0u;
+                if (q >= S && !wait_bar(empty_o + slot, parity ^ 1u, abort_flag, A.error, PIPE_ERR_EMPTY, A.backoff_helper)) good = 0u;
                 if (good && is_halo) {
                     // a neighbour's boundary plane: wait until all its CTAs have stored it.  Other colour = phase - 1's
                     // output of THIS step for colour 1, the previous step's colour 1 for colour 0.
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(MAXT, 1) heis_pipe_kernel(const __grid_constan
             if (lane == 0) {
                 if (phase == 0 && i >= A.lead && seen_tail < A.base + (unsigned long long)(i - A.lead) + 1ull &&
                     !wait_counter<false>(tail, A.base + (unsigned long long)(i - A.lead) + 1ull, seen_tail, abort_flag, A.error, PIPE_ERR_GATE)) good = 0u;
-                if (good && i >= SO && !wait_bar(empty_w + slot, parity ^ 1u, abort_flag, A.error, PIPE_ERR_EMPTY)) good = 0u;
+                if (good && i >= SO && !wait_bar(empty_w + slot, parity ^ 1u, abort_flag, A.error, PIPE_ERR_EMPTY, A.backoff_helper)) good = 0u;
                 if (good) mbar_expect_tx(full_w + slot, bytes_w);
             }
             good = __shfl_sync(0xffffffffu, good, 0);
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(MAXT, 1) heis_pipe_kernel(const __grid_constan
                 }
             };
             for (uint32_t i = 0; i < Lz; ++i) {
-                if (!wait_bar(done + pd.slot, pd.parity, abort_flag, A.error, PIPE_ERR_FULL)) break;
+                if (!wait_bar(done + pd.slot, pd.parity, abort_flag, A.error, PIPE_ERR_FULL, A.backoff_helper)) break;
                 pd.advance(PIPE_DONE_SLOTS);
                 // plane i sits updated in its own-ring slot: store it; then retire plane i - 1 (slot readable again once the
                 // store has read it, progress published once its writes are complete)
@@ -351,10 +352,10 @@ __global__ void __launch_bounds__(MAXT, 1) heis_pipe_kernel(const __grid_constan
         for (uint32_t i = 0; i < Lz; ++i) {
             const uint32_t qb = mz.qbase(i);
             for (; q_waited <= qb + 2u; ++q_waited) {
-                ok = ok && wait_bar(full_o + p_wait.slot, p_wait.parity, abort_flag, A.error, PIPE_ERR_FULL);
+                ok = ok && wait_bar(full_o + p_wait.slot, p_wait.parity, abort_flag, A.error, PIPE_ERR_FULL, A.backoff_consumer);
                 p_wait.advance(S);
             }
-            ok = ok && wait_bar(full_w + p_own.slot, p_own.parity, abort_flag, A.error, PIPE_ERR_FULL);
+            ok = ok && wait_bar(full_w + p_own.slot, p_own.parity, abort_flag, A.error, PIPE_ERR_FULL, A.backoff_consumer);
             if (!__all_sync(0xffffffffu, ok)) break;
             const uint32_t z = mz.z_of(i);
             const uint32_t slot_lo = p_lo.slot, slot_n0 = slot_lo + 1 == S ? 0u : slot_lo + 1, slot_hi = slot_n0 + 1 == S ? 0u : slot_n0 + 1;
@@ -701,6 +702,7 @@ int heis_pipe_step(HeisPipeState* st, const HeisParams<real>& p, bool flip, bool
     // neighbours); leads below 2 pub + 8 can deadlock (publication lags the update by the store's completion and the
     // releaser's turn-around)
     A.pub_every = std::max(1u, d.pub_every ? d.pub_every : 8u);
+    A.backoff_consumer = d.backoff_consumer; A.backoff_helper = d.backoff_helper;
     A.lead = std::max(2u * A.pub_every + 8u, d.lead ? d.lead : 8u * A.pub_every);
     A.prog = st->d_prog;
     A.base = st->launches * (unsigned long long)d.Lz;

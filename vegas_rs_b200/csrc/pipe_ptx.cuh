@@ -74,11 +74,16 @@ constexpr unsigned long long PIPE_TIMEOUT_NS = 4000000000ull;   // a wait that l
 enum PipeError : unsigned int { PIPE_ERR_FULL = 1, PIPE_ERR_EMPTY = 2, PIPE_ERR_GATE = 3, PIPE_ERR_PEER = 4 };
 
 // Waits for phase `parity` of an mbarrier.  False when the launch is being abandoned (abort flag) or on time-out.
-__device__ __forceinline__ bool wait_bar(uint64_t* b, uint32_t parity, volatile uint32_t* abort_flag, unsigned int* gerr, unsigned int code) {
+// backoff_ns: the hardware suspend of try_wait is ended by EVERY mbarrier event of the CTA, so a waiting warp re-polls about
+// every 50 ns and the polls of a phase-pipelined kernel add up to a quarter of its issued instructions
+// (profiles/r02/README.md section 8); an unconditional sleep between polls trades wake-up latency for issue slots.
+__device__ __forceinline__ bool wait_bar(uint64_t* b, uint32_t parity, volatile uint32_t* abort_flag, unsigned int* gerr, unsigned int code,
+                                         uint32_t backoff_ns = 0u) {
     if (mbar_try_wait(b, parity)) return true;
     const unsigned long long t0 = global_timer();
     uint32_t n = 0;
     while (!mbar_try_wait(b, parity)) {
+        if (backoff_ns) __nanosleep(backoff_ns);
         if ((++n & 63u) == 0) {
             if (*abort_flag) return false;
             if (global_timer() - t0 > PIPE_TIMEOUT_NS) { *abort_flag = 1u; atomicExch(gerr, code); return false; }
