@@ -696,14 +696,14 @@ int heis_pipe_step(HeisPipeState* st, const HeisParams<real>& p, bool flip, bool
     A.g.Hx = st->Hx; A.g.Gx = st->Hx / st->V; A.g.Ly = d.Ly; A.g.Lz = d.Lz; A.g.z_offset = d.z_offset; A.g.Lx = d.Lx;
     A.tiles = st->tiles; A.rows = st->rows; A.tiles_long = st->tiles_long; A.S = st->S; A.SO = st->SO; A.n_cw = st->n_cw;
     // Defaults measured on 512^3 fp32 (profiles/r02/README.md): publishing every plane makes the fronts wait on each other's
-    // release latency (pub 1 / lead 32: 0.95 ms per step), every 4th with a lead of 32 planes 0.85 ms; with the 7-round
-    // generator the consumers are faster and pub 8 / lead 64 wins by 3 % (0.825 against 0.851 ms, profiles/r02/h2.sh, h3.sh;
-    // 100 MB between the fronts still live in L2 because a band's tiles are only ever read by its own SM and two
-    // neighbours); leads below 2 pub + 8 can deadlock (publication lags the update by the store's completion and the
-    // releaser's turn-around)
-    A.pub_every = std::max(1u, d.pub_every ? d.pub_every : 8u);
+    // release latency (pub 1 / lead 32: 0.95 ms per step), every 4th with a lead of 32 planes 0.85 ms.  With the 7-round
+    // generator the consumers are faster and want a longer lead: pub 4 / lead 48 0.826 ms and 4.03 GB of DRAM traffic per
+    // 512^3 step, pub 8 / lead 64 0.829 ms and 4.33 GB, pub 4 / lead 32 0.861 ms (profiles/r02/h7.sh; the lead is a cap, the
+    // second colour normally follows pub + 2..4 planes behind the first).  Leads below 2 pub + 8 can deadlock (publication
+    // lags the update by the store's completion and the releaser's turn-around)
+    A.pub_every = std::max(1u, d.pub_every ? d.pub_every : 4u);
+    A.lead = std::max(2u * A.pub_every + 8u, d.lead ? d.lead : 12u * A.pub_every);
     A.backoff_consumer = d.backoff_consumer; A.backoff_helper = d.backoff_helper;
-    A.lead = std::max(2u * A.pub_every + 8u, d.lead ? d.lead : 8u * A.pub_every);
     A.prog = st->d_prog;
     A.base = st->launches * (unsigned long long)d.Lz;
     A.flags = d.flags;
