@@ -179,7 +179,9 @@ int vegas_gpu_slab_connect_local(vegas_gpu_t self, vegas_gpu_t lower, vegas_gpu_
  *                       consumer thread: a whole or half 16-byte vector, 0 = auto), "heis_pipe_lead" (planes the first
  *                       colour may run ahead of the second, 0 = auto; bounds the working set kept in L2), "heis_pipe_pub"
  *                       (planes per published progress update = per gpu-scope release, 0 = auto), "heis_pipe_backoff" /
- *                       "heis_pipe_backoff_helper" (ns a consumer / helper warp sleeps between failed mbarrier polls)
+ *                       "heis_pipe_backoff_helper" (ns a consumer / helper warp sleeps between failed mbarrier polls),
+ *                       "heis_pipe_l2" (1, default: L2 eviction-priority hints on the TMA loads / stores -- what the next colour is about
+ *                       to read is kept, what was used for the last time in this step goes first; 0: none)
  *     "heis_wave"     : -1 auto (default: lattices with >= 32 planes), 0 never, 1 always -- both colour passes of a
  *                       Heisenberg step as ONE persistent launch in wave order (second pass finds the first in L2);
  *                       "heis_wave_planes" (planes per chunk, default 4), "heis_wave_lag" (positions a colour pass

@@ -52,6 +52,7 @@ struct PipeArgs {
     HeisGeom g;
     uint32_t tiles, rows, tiles_long, S, SO, n_cw, lead, pub_every;
     uint32_t backoff_consumer, backoff_helper;   // ns slept between failed barrier polls (0: re-poll at once)
+    uint32_t l2_hints;                           // != 0: TMA loads / stores carry L2 eviction-priority hints
     unsigned long long* prog;            // [2][tiles] planes finished (published), monotone over the launches
     unsigned long long base;             // value of every progress counter when this launch starts
     const unsigned long long* flags;     // HALO: [lower, upper][colour] boundary-plane CTAs that have stored into my halos
@@ -169,6 +170,9 @@ __global__ void __launch_bounds__(MAXT, 1) heis_pipe_kernel(const __grid_constan
         const uint32_t my_row = my_part == 0 ? 0u : (my_part == 1 ? 1u : 1u + nr);
         const uint32_t my_kind = my_part == 1 ? kind : 2u;
         bool ok = true;
+        // L2 hints: the first phase's `other` planes are the last phase's own planes a few planes later (keep them); every other
+        // phase reads its `other` planes (the previous phase's output) for the last time in this step
+        const uint64_t pol_other = phase + 1 < n_phases ? l2_policy_evict_last() : l2_policy_evict_first();
         RingPos po;              // next `other` slot to fill; parity = of the fill being made
         unsigned long long seen[3] = {0, 0, 0};   // lane 0: last progress values read (monotone counters)
         uint32_t q_next = 0, z_next = (phase + Lz - 1) % Lz;     // non-slab: plane of entry q_next (advances with wrap)
@@ -212,7 +216,8 @@ __global__ void __launch_bounds__(MAXT, 1) heis_pipe_kernel(const __grid_constan
             if (lane < 9) {
                 if (both & 2u) fence_proxy_async();   // data written through the generic proxy by other SMs, read by TMA
                 real* dst = ring_o + (size_t)slot * stage_o + (my_c * orow + my_row) * Hx;
-                tma_load_3d(dst, A.maps + (size_t)array * 9 + my_c * 3 + my_kind, full_o + slot, 0u, my_y, zc);
+                if (A.l2_hints) tma_load_3d_hint(dst, A.maps + (size_t)array * 9 + my_c * 3 + my_kind, full_o + slot, 0u, my_y, zc, pol_other);
+                else tma_load_3d(dst, A.maps + (size_t)array * 9 + my_c * 3 + my_kind, full_o + slot, 0u, my_y, zc);
             }
         };
         // sequence entries in the order the consumers need them: q <= qbase(i) + 2 before step i
@@ -260,6 +265,7 @@ __global__ void __launch_bounds__(MAXT, 1) heis_pipe_kernel(const __grid_constan
         // the first phase may lead the last one by at most `lead` planes: everything in between stays in L2
         const unsigned long long* const tail = A.prog + (size_t)(n_phases - 1) * A.tiles + tile;
         unsigned long long seen_tail = 0;
+        const uint64_t pol_own = l2_policy_evict_first();
         RingPos pw;
         for (uint32_t i = 0; i < Lz; ++i) {
             const uint32_t slot = pw.slot, parity = pw.parity;
@@ -275,7 +281,9 @@ __global__ void __launch_bounds__(MAXT, 1) heis_pipe_kernel(const __grid_constan
             if (!good) break;
             if (lane < 3) {
                 real* dst = ring_w + (size_t)slot * stage_w + (lane * rows) * Hx;
-                tma_load_3d(dst, A.maps + (size_t)colour * 9 + lane * 3 + kind, full_w + slot, 0u, y0, mz.z_of(i));
+                // own planes are read once per step: never worth keeping
+                if (A.l2_hints) tma_load_3d_hint(dst, A.maps + (size_t)colour * 9 + lane * 3 + kind, full_w + slot, 0u, y0, mz.z_of(i), pol_own);
+                else tma_load_3d(dst, A.maps + (size_t)colour * 9 + lane * 3 + kind, full_w + slot, 0u, y0, mz.z_of(i));
             }
         }
     } else if (warp == n_cw + 1) {
@@ -284,6 +292,7 @@ __global__ void __launch_bounds__(MAXT, 1) heis_pipe_kernel(const __grid_constan
         // their arrive on the `done` barrier)
         if (lane == 0 && has_publisher) {
             RingPos pd, pown;
+            const uint64_t pol_store = phase + 1 < n_phases ? l2_policy_evict_last() : l2_policy_evict_first();
             uint32_t since_pub = 0;
             const uint32_t kind = nr == rows ? 0u : 1u;
             uint32_t n_bnd = 0;
@@ -305,7 +314,12 @@ __global__ void __launch_bounds__(MAXT, 1) heis_pipe_kernel(const __grid_constan
                 const CUtensorMap* m = A.maps + (size_t)colour * 9;
                 const uint32_t z = mz.z_of(i);
 #pragma unroll
-                for (uint32_t c = 0; c < 3; ++c) tma_store_3d(m + c * 3 + kind, src + (c * rows) * Hx, 0u, y0, z);
+                for (uint32_t c = 0; c < 3; ++c) {
+                    // the updated tile is the next phase's `other` plane within a few planes (keep it); the last phase's output
+                    // is not read again before the next step
+                    if (A.l2_hints) tma_store_3d_hint(m + c * 3 + kind, src + (c * rows) * Hx, 0u, y0, z, pol_store);
+                    else tma_store_3d(m + c * 3 + kind, src + (c * rows) * Hx, 0u, y0, z);
+                }
                 tma_store_commit();
                 tma_store_wait_read<0>();               // the store has read the slot: the producer may refill it
                 mbar_arrive(empty_w + pown.slot);
@@ -703,7 +717,7 @@ int heis_pipe_step(HeisPipeState* st, const HeisParams<real>& p, bool flip, bool
     // lags the update by the store's completion and the releaser's turn-around)
     A.pub_every = std::max(1u, d.pub_every ? d.pub_every : 4u);
     A.lead = std::max(2u * A.pub_every + 8u, d.lead ? d.lead : 12u * A.pub_every);
-    A.backoff_consumer = d.backoff_consumer; A.backoff_helper = d.backoff_helper;
+    A.backoff_consumer = d.backoff_consumer; A.backoff_helper = d.backoff_helper; A.l2_hints = d.l2_hints;
     A.prog = st->d_prog;
     A.base = st->launches * (unsigned long long)d.Lz;
     A.flags = d.flags;

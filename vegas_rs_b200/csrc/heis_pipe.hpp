@@ -26,6 +26,7 @@ struct HeisPipeDesc {
     uint32_t stages_other = 0, stages_own = 0, tiles = 0, vec = 0;   // vec: sites per consumer thread
     uint32_t lead = 0;      // planes the first colour may run ahead of the last (>= 2 pub_every + 2; bounds the L2 working set)
     uint32_t pub_every = 0; // planes per published progress update (one gpu-scope release fence each)
+    uint32_t l2_hints = 1;  // 1: L2 eviction-priority hints on the TMA loads / stores (keep what the next phase reads, drop the rest first)
     uint32_t backoff_consumer = 0, backoff_helper = 0;   // ns slept between failed mbarrier polls of the consumer / helper warps
 };
 

@@ -91,7 +91,7 @@ struct vegas_gpu {
     int wave_grid = 0;
     // --- phase-pipelined TMA kernel (heis_pipe.cu): the default step of big 3-D sc Heisenberg lattices
     int pipe_enable = -1;                 // tuning key heis_pipe: -1 auto (>= 32 planes), 0 never, 1 whenever the lattice fits
-    uint32_t pipe_stages_other = 0, pipe_stages_own = 0, pipe_tiles = 0, pipe_vec = 0, pipe_lead = 0, pipe_pub = 0, pipe_backoff_c = 0, pipe_backoff_h = 0;   // tuning keys heis_pipe_stages / _own / _tiles / _vec (0 = auto)
+    uint32_t pipe_stages_other = 0, pipe_stages_own = 0, pipe_tiles = 0, pipe_vec = 0, pipe_lead = 0, pipe_pub = 0, pipe_backoff_c = 0, pipe_backoff_h = 0, pipe_l2 = 1;   // tuning keys heis_pipe_stages / _own / _tiles / _vec (0 = auto)
     bool pipe_planned = false;
     uint64_t pipe_slab_steps = 0;         // pipelined steps since the slab was connected (the neighbours' boundary counters are relative to it)
     HeisPipeState* pipe = nullptr;
@@ -989,7 +989,7 @@ bool pipe_plan(vegas_gpu* h) {
         d.flags = h->flags + PIPE_FLAG_WORD;
         d.peer_flags[0] = h->peer_flags[0] + PIPE_FLAG_WORD; d.peer_flags[1] = h->peer_flags[1] + PIPE_FLAG_WORD;
     }
-    d.stages_other = h->pipe_stages_other; d.stages_own = h->pipe_stages_own; d.tiles = h->pipe_tiles; d.vec = h->pipe_vec; d.lead = h->pipe_lead; d.pub_every = h->pipe_pub; d.backoff_consumer = h->pipe_backoff_c; d.backoff_helper = h->pipe_backoff_h;
+    d.stages_other = h->pipe_stages_other; d.stages_own = h->pipe_stages_own; d.tiles = h->pipe_tiles; d.vec = h->pipe_vec; d.lead = h->pipe_lead; d.pub_every = h->pipe_pub; d.backoff_consumer = h->pipe_backoff_c; d.backoff_helper = h->pipe_backoff_h; d.l2_hints = h->pipe_l2;
     h->pipe = heis_pipe_create(d, h->pipe_why);
     return h->pipe != nullptr;
 }
@@ -2423,6 +2423,7 @@ int vegas_gpu_set_tuning(vegas_gpu_t h, const char* key, long value) {
     else if (k == "heis_pipe_vec") h->pipe_vec = (uint32_t)value;
     else if (k == "heis_pipe_lead") h->pipe_lead = (uint32_t)value;
     else if (k == "heis_pipe_pub") h->pipe_pub = (uint32_t)value;
+    else if (k == "heis_pipe_l2") h->pipe_l2 = (uint32_t)value;
     else if (k == "heis_pipe_backoff") h->pipe_backoff_c = (uint32_t)value;
     else if (k == "heis_pipe_backoff_helper") h->pipe_backoff_h = (uint32_t)value;
     else if (k == "basis_pipe") h->bpipe_enable = (int)value;
