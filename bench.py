@@ -46,7 +46,7 @@ WORKLOADS = {
 # captures (cold cache): (bytes, source)
 NCU_TRAFFIC = {
     "ising3d_1024": {"ising_msc": (134.37e6 + 30.64e6, "profiles/r02_ising_msc.metrics.txt (one colour pass)")},
-    "heis3d_512": {"heis_pipe": (2.379e9 + 1.557e9, "profiles/r02_heis_pipe.metrics.txt (one step = both colours, one launch)"),
+    "heis3d_512": {"heis_pipe": (1.914e9 + 1.534e9, "profiles/r02_heis_pipe.metrics.txt (one step = both colours, one launch)"),
                    "heis_wave": (2.887e9 + 1.562e9, "profiles/r01u_heis_wave.metrics.txt (one step = both colours)"),
                    "heis_stencil": (2.42e9, "profiles/r01o_heis_stencil.metrics.txt (one colour pass)")},
     "heis_fcc_384": {"heis_basis": (2.829e9 + 0.686e9, "profiles/r01z_heis_basis_vec.metrics.txt (one colour pass)"),
