@@ -140,7 +140,7 @@ BASIS_CASES = [
 def test_basis_pipe_identical_to_colour_passes(built, uc, size, precision, tiles, lead, pub, proposal):
     kw = dict(unitcell=uc, size=size, precision=precision, seed=31, anisotropy=((0.6, 0, 0.8), 0.15), proposal=proposal)
     ref = vg.GpuMetropolis(vg.HEISENBERG, **kw)
-    ref.set_tuning("basis_pipe", 0); ref.set_tuning("basis_wave", 0)
+    ref.set_tuning("basis_pipe", 0); ref.set_tuning("basis_wave", 0); ref.set_tuning("basis_pair", 0)
     assert ref.step_kernel == "heis_basis"
     ref.randomize(); ref.set_thermostat(1.4, (0, 0, 1.0), 0.4)
     e0, m0 = ref.step(3)
@@ -215,7 +215,7 @@ WAVE_CASES = [
 def test_basis_wave_identical_to_colour_passes(built, uc, size, precision, lag, ipt, grid, proposal):
     kw = dict(unitcell=uc, size=size, precision=precision, seed=33, anisotropy=((0.6, 0, 0.8), 0.15), proposal=proposal)
     ref = vg.GpuMetropolis(vg.HEISENBERG, **kw)
-    ref.set_tuning("basis_wave", 0)
+    ref.set_tuning("basis_wave", 0); ref.set_tuning("basis_pair", 0)
     assert ref.step_kernel == "heis_basis"
     ref.randomize(); ref.set_thermostat(1.4, (0, 0, 1.0), 0.4)
     e0, m0 = ref.step(3)
@@ -280,4 +280,79 @@ def test_basis_wave_is_opt_in(built):
     g = vg.GpuMetropolis(vg.HEISENBERG, unitcell=vg.FCC, size=(64, 32, 4), seed=5)     # too few planes for the wave order
     g.set_tuning("basis_wave", 1)
     assert g.step_kernel == "heis_basis"
+    g.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K4f: the fcc step as two PAIR launches (heis_basis_pair_kernel in vegas_rs_b200/csrc/heis_basis.cuh), arrays S -> D
+# ---------------------------------------------------------------------------------------------------------------------
+# (size, precision, rows per CTA): one tile per plane (the recomputed row is the tile's own first row), ragged last tile,
+# one-row tiles, tiles larger than the plane, config[4] rows
+PAIR_CASES = [
+    ((16, 6, 5), vg.F32, 0),
+    ((16, 6, 5), vg.F32, 4),
+    ((8, 9, 3), vg.F64, 2),
+    ((4, 2, 2), vg.F32, 1),
+    ((24, 7, 1), vg.F32, 3),
+    ((12, 5, 4), vg.F64, 64),
+    ((384, 40, 3), vg.F32, 0),
+]
+
+
+@pytest.mark.parametrize("size,precision,rows", PAIR_CASES)
+@pytest.mark.parametrize("proposal", [vg.PROPOSE_RANDOM, vg.PROPOSE_FLIP], ids=["random", "flip"])
+def test_basis_pair_identical_to_colour_passes(built, size, precision, rows, proposal):
+    kw = dict(unitcell=vg.FCC, size=size, precision=precision, seed=35, anisotropy=((0.6, 0, 0.8), 0.15), proposal=proposal)
+    ref = vg.GpuMetropolis(vg.HEISENBERG, **kw)
+    ref.set_tuning("basis_pair", 0)
+    assert ref.step_kernel == "heis_basis"
+    g = vg.GpuMetropolis(vg.HEISENBERG, **kw)
+    g.set_tuning("basis_pair", 1)
+    if rows:
+        g.set_tuning("basis_pair_rows", rows); g.set_tuning("basis_pair_chunk", 1 + rows % 3)
+    assert g.step_kernel == "basis_pair"
+    n = g.n_sites
+    s0 = random_state(ob.HEISENBERG, n, 9)
+    tol = 1e-12 if precision == vg.F64 else 1e-6
+    for h in (ref, g):
+        h.upload(s0); h.set_thermostat(1.4, (0, 0, 1.0), 0.4)
+    # odd and even numbers of steps (the two array sets swap after every step), recorded and not, measure-only entry points
+    for k, observe in ((1, True), (2, False), (3, True), (1, False)):
+        ra = ref.step(k, observe=observe); ga = g.step(k, observe=observe)
+        assert np.array_equal(g.download(), ref.download())
+        if observe:
+            assert np.allclose(ga[0], ra[0], rtol=tol, atol=tol * n) and np.allclose(ga[1], ra[1], rtol=10 * tol, atol=10 * tol * n)
+        assert abs(g.total_energy() - ref.total_energy()) <= tol * n * 10
+        assert np.allclose(g.magnetization(), ref.magnetization(), rtol=10 * tol, atol=10 * tol * n)
+    assert g.attempt_count() == ref.attempt_count()
+    # a new State after an odd number of steps lands in the current set
+    s1 = random_state(ob.HEISENBERG, n, 10)
+    for h in (ref, g):
+        h.upload(s1)
+    ref.step(2, observe=False); g.step(2, observe=False)
+    assert np.array_equal(g.download(), ref.download())
+    ref.close(); g.close()
+
+
+def test_basis_pair_replays_the_reference_rule(built):
+    """fcc, fp64: every decision of the pair launches against the oracle replay (Hamiltonian::energy of src/energy.rs, accept
+    rule of src/integrator.rs:82-88); the fused E and M equal total_energy / magnetization of the replayed state."""
+    lat = dict(unitcell=vg.FCC, size=(8, 6, 4))
+    kw = dict(exchange=1.0, zeeman=True, anisotropy=((0.6, 0.0, 0.8), 0.25))
+    g = vg.GpuMetropolis(vg.HEISENBERG, precision=vg.F64, seed=12, **kw, **lat)
+    g.set_tuning("basis_pair", 1); g.set_tuning("basis_pair_rows", 4)
+    assert g.step_kernel == "basis_pair"
+    H, _ = oracle_model(ob.HEISENBERG, **kw, **lat)
+    n = g.n_sites
+    g.upload(random_state(ob.HEISENBERG, n, 3))
+    cpu = g.download(); col = g.colours()
+    g.set_thermostat(1.5, (0, 0, 1.0), 0.7)
+    th = H.thermostat(1.5, (0, 0, 1.0), 0.7)
+    for _ in range(3):
+        sweep = g.sweeps
+        e, m = g.step(1)
+        H.replay_heisenberg(th, ob.PROPOSE_RANDOM, False, 12, sweep, col, g.n_colours, cpu)
+        assert np.max(np.abs(g.download() - cpu)) < 1e-12
+        assert abs(e[0] - H.total_energy(th, cpu)) < 1e-12 * n * 10
+        assert np.max(np.abs(m[0] - cpu.sum(axis=0))) < 1e-12 * n
     g.close()

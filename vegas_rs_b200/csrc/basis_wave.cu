@@ -92,7 +92,7 @@ __device__ __forceinline__ void wave_tile(const BasisWaveArgs<real>& A, uint32_t
     for (uint32_t it = 0; it < A.ipt; ++it) {
         const uint32_t w = w0 + it * blockDim.x;
         if (w >= items) break;
-        basis_vec_item<real, UC, B, FLIP, RECORD ? 1 : 0, SLAB>(A.P, A.peers, A.g, z, zs, w, VX, A.p, A.sweep, A.pk, fs, accepted);
+        basis_vec_item<real, UC, B, FLIP, RECORD ? 1 : 0, SLAB>(A.P, A.P, A.peers, A.g, z, zs, w, VX, A.p, A.sweep, A.pk, fs, accepted);
     }
 }
 

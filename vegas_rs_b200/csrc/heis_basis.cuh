@@ -168,10 +168,12 @@ heis_basis_kernel(BasisPtrs<real> P, BasisPeers<real> peers, BasisGeom g, uint32
 // One work item of K4v: the N cells x0 .. x0+N-1 of row iy of plane iz (w = iy * VX + x0 / N).  Shared by the per-colour
 // launches (heis_basis_vec_kernel) and the wave-ordered persistent step (basis_wave.cu): same loads, same summation
 // order, same random numbers.
+// W: where the updated spins go (the pair kernel below writes a second set of arrays; everywhere else W is P).  counted = false:
+// a redundantly computed row -- same update, but it enters neither the observables nor the accepted count.
 template <typename real, int UC, int B, bool FLIP, int MODE, bool SLAB>
-__device__ __forceinline__ void basis_vec_item(const BasisPtrs<real>& P, const BasisPeers<real>& peers, const BasisGeom& g, uint32_t iz,
-                                               const int (&zs)[3], uint32_t w, uint32_t VX, const HeisParams<real>& p, uint64_t sweep,
-                                               const PhiloxKey& pk, real (&fs)[5], int& accepted) {
+__device__ __forceinline__ void basis_vec_item(const BasisPtrs<real>& P, const BasisPtrs<real>& W, const BasisPeers<real>& peers, const BasisGeom& g,
+                                               uint32_t iz, const int (&zs)[3], uint32_t w, uint32_t VX, const HeisParams<real>& p, uint64_t sweep,
+                                               const PhiloxKey& pk, real (&fs)[5], int& accepted, bool counted = true) {
     constexpr int NB = BasisCell<UC>::NB, Z = BasisCell<UC>::Z, N = VecOf<real>::N;
     const uint32_t iy = w / VX, x0 = (w - iy * VX) * N;
     const uint32_t ys[3] = {iy == 0 ? g.ny - 1 : iy - 1, iy, iy + 1 == g.ny ? 0u : iy + 1};
@@ -221,9 +223,9 @@ __device__ __forceinline__ void basis_vec_item(const BasisPtrs<real>& P, const B
             heis_rand((gcell + e) * NB + B, sweep, pk, rnd);
             const bool ok = heis_attempt<real, FLIP>(sx[e], sy[e], sz[e], heis_field(p.J, n[0][e], p.h[0]), heis_field(p.J, n[1][e], p.h[1]),
                                                      heis_field(p.J, n[2][e], p.h[2]), p, rnd);
-            accepted += ok ? 1 : 0;
+            accepted += (ok && counted) ? 1 : 0;
         }
-        vec_store(P.s[B][0] + cell, sx); vec_store(P.s[B][1] + cell, sy); vec_store(P.s[B][2] + cell, sz);
+        vec_store(W.s[B][0] + cell, sx); vec_store(W.s[B][1] + cell, sy); vec_store(W.s[B][2] + cell, sz);
         if (SLAB) {  // boundary planes also go straight into the neighbours' halo planes (peer memory over NVLink)
             const size_t in_plane = (size_t)iy * g.nx + x0, pl = (size_t)g.ny * g.nx;
             if (iz == 0 && peers.lo != nullptr) {
@@ -236,7 +238,7 @@ __device__ __forceinline__ void basis_vec_item(const BasisPtrs<real>& P, const B
             }
         }
     }
-    if (MODE != 0) {
+    if (MODE != 0 && counted) {
 #pragma unroll
         for (int e = 0; e < N; ++e) {
             fs[0] += sx[e] * l[0][e] + sy[e] * l[1][e] + sz[e] * l[2][e];
@@ -263,7 +265,76 @@ heis_basis_vec_kernel(BasisPtrs<real> P, BasisPeers<real> peers, BasisGeom g, ui
     for (uint32_t it = 0; it < items_per_thread; ++it) {
         const uint32_t w = w0 + it * blockDim.x;
         if (w >= items) break;
-        basis_vec_item<real, UC, B, FLIP, MODE, SLAB>(P, peers, g, iz, zs, w, VX, p, sweep, pk, fs, accepted);
+        basis_vec_item<real, UC, B, FLIP, MODE, SLAB>(P, P, peers, g, iz, zs, w, VX, p, sweep, pk, fs, accepted);
+    }
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    if (MODE != 0) {
+        acc[0] = 2.0 * (double)p.J * (double)fs[0];
+#pragma unroll
+        for (int i = 1; i < 5; ++i) acc[i] = (double)fs[i];
+    }
+    acc[5] = (double)accepted;
+    if (MODE == 0) {
+        double a1[1] = {acc[5]};
+        block_atomic_add<double, 1>(a1, s_red, obs + 5);
+    } else {
+        block_atomic_add<double, 6>(acc, s_red, obs);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K4f: TWO consecutive colours (B0, B0 + 1) of a periodic fcc step in one launch, without any inter-CTA synchronisation.
+// As four launches every colour pass reads all four sublattices and writes one (5 array sweeps per pass, 62 B/attempt measured
+// against 24 algorithmic); a pair launch reads four and writes two (36 B/attempt for the step).  What makes it possible:
+//   * in the fcc unit-cell table the bonds between colours 2k and 2k + 1 have dz = 0 and, seen from the second colour,
+//     dy in {0, +1} (checked on the host before this kernel is chosen): the second colour on rows [r0, r1) of a plane needs
+//     the first colour's NEW spins on rows [r0, r1] of the same plane only;
+//   * a CTA owns rows [r0, r1) of one plane.  It updates the first colour on rows [r0, r1] -- row r1 belongs to the next
+//     CTA, which computes the identical update (same inputs, site-keyed random numbers), so it is computed twice and
+//     counted once -- then, after a CTA barrier, the second colour on its own rows;
+//   * the step goes from one set of arrays to another (S = before, D = after; swapped by the host after every step), so
+//     that a redundantly updated row never sees a neighbour that another CTA has already moved on: every read of an "old"
+//     spin comes from S, which no launch of this step writes, every read of a "new" spin of a LOWER colour from D.
+// Same work item as the colour launches (basis_vec_item): bit-identical trajectories.
+// ---------------------------------------------------------------------------------------
+template <typename real, int UC, int B0, bool FLIP, int MODE>
+__global__ void __launch_bounds__(128, BASIS_VEC_MINB)
+heis_basis_pair_kernel(BasisPtrs<real> S, BasisPtrs<real> D, BasisGeom g, uint32_t rows_per_cta, uint32_t chunk_rows, HeisParams<real> p,
+                       uint64_t sweep, PhiloxKey pk, double* __restrict__ obs) {
+    constexpr int N = VecOf<real>::N, NB = BasisCell<UC>::NB;
+    static_assert(B0 + 1 < NB, "a pair is (B0, B0 + 1)");
+    __shared__ double s_red[6 * 32];
+    const uint32_t iz = blockIdx.z, VX = g.nx / N;
+    const uint32_t r0 = blockIdx.x * rows_per_cta, r1 = min(r0 + rows_per_cta, g.ny);
+    const int zs[3] = {(int)(iz == 0 ? g.nz - 1 : iz - 1), (int)iz, (int)(iz + 1 == g.nz ? 0u : iz + 1)};
+    const BasisPeers<real> no_peers{nullptr, nullptr};
+    // what colour B reads: lower colours are final (D), itself and higher colours are still the old state (S)
+    BasisPtrs<real> R0, R1;
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { R0.s[b][c] = b < B0 ? D.s[b][c] : S.s[b][c]; R1.s[b][c] = b <= B0 ? D.s[b][c] : S.s[b][c]; }
+    real fs[5] = {0, 0, 0, 0, 0};
+    int accepted = 0;
+    // The two colours alternate in chunks of `chunk_rows` rows so that the second colour finds the partner rows the first one
+    // has just read in L1 / L2 (a whole tile per colour puts 520 MB between the two uses: measured 14.6 GB per step, as much
+    // as four launches).  First colour: row r0, then per chunk the rows (ra, rb] -- rb may be r1, the row after my tile
+    // (periodic in y), recomputed here and counted by its owner.
+    auto first = [&](uint32_t ra, uint32_t rb) {   // rows [ra, rb) in tile coordinates that may run one past r1
+        const uint32_t n = (rb - ra) * VX;
+        for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) {
+            const uint32_t dr = t / VX, y = ra + dr, row = y == g.ny ? 0u : y;
+            basis_vec_item<real, UC, B0, FLIP, MODE, false>(R0, D, no_peers, g, iz, zs, row * VX + (t - dr * VX), VX, p, sweep, pk, fs, accepted, y < r1);
+        }
+    };
+    first(r0, r0 + 1u);
+    for (uint32_t ra = r0; ra < r1; ra += chunk_rows) {
+        const uint32_t rb = min(ra + chunk_rows, r1);
+        first(ra + 1u, rb + 1u);
+        __syncthreads();   // the first colour's new spins on rows [ra, rb] were stored by threads of this CTA
+        const uint32_t n2 = (rb - ra) * VX;
+        for (uint32_t t = threadIdx.x; t < n2; t += blockDim.x)
+            basis_vec_item<real, UC, B0 + 1, FLIP, MODE, false>(R1, D, no_peers, g, iz, zs, ra * VX + t, VX, p, sweep, pk, fs, accepted);
     }
     double acc[6] = {0, 0, 0, 0, 0, 0};
     if (MODE != 0) {

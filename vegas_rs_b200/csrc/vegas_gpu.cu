@@ -101,6 +101,12 @@ struct vegas_gpu {
     uint32_t bpipe_lead = 0, bpipe_pub = 0, bpipe_tiles = 0;
     bool bpipe_planned = false;
     BasisPipeState* bpipe = nullptr;
+    // --- pair launches of the fcc step (heis_basis_pair_kernel): colours (0,1) and (2,3) in one launch each, S -> D arrays
+    int bpair_enable = -1;                // tuning key basis_pair: 1 whenever possible (single-handle fcc); -1 / 0: colour launches
+    uint32_t bpair_rows = 0;              // tuning key basis_pair_rows: rows of a plane per CTA (0 = auto: 16)
+    uint32_t bpair_chunk = 0;             // tuning key basis_pair_chunk: rows the two colours alternate in (0 = auto: 4)
+    void* hb2[4][3] = {};                 // the second set of arrays (allocated at first use); hb / hb2 swap after every pair step
+    int bpair_ok = -1;                    // cached: the unit-cell table has the structure the pair kernel needs
     // --- wave-ordered bcc / fcc step (basis_wave.cu): the colour passes of a step as one persistent launch, L2-friendly order
     int bwave_enable = -1;                // tuning key basis_wave: 1 whenever possible; -1 / 0: colour launches
     uint32_t bwave_lag = 0, bwave_ipt = 0, bwave_grid = 0;   // tuning keys basis_wave_lag / _ipt / _grid (0 = auto)
@@ -1010,6 +1016,73 @@ bool bpipe_plan(vegas_gpu* h) {
     return h->bpipe != nullptr;
 }
 
+// ---- fcc pair launches (heis_basis_pair_kernel) -----------------------------------------------------
+// bonds between colours b0 and b0 + 1, seen from b0 + 1: dz must be 0 and dy in {0, +1}
+template <int UC>
+bool pair_structure_ok() {
+    constexpr int NB = BasisCell<UC>::NB;
+    if (NB % 2) return false;
+    for (int e = 0; e < BasisCell<UC>::NE; ++e) {
+        int s = 0, t = 0, dx = 0, dy = 0, dz = 0;
+        BasisCell<UC>::edge(e, s, t, dx, dy, dz);
+        int lo = s, hi = t, ddy = dy, ddz = dz;              // neighbour of `lo` at +d is `hi`
+        if (lo > hi) { std::swap(lo, hi); ddy = -dy; ddz = -dz; }
+        if (hi != lo + 1 || (lo & 1)) continue;              // not a bond inside a pair
+        // seen from hi, the neighbour lo sits at -d
+        if (ddz != 0 || !(-ddy == 0 || -ddy == 1)) return false;
+    }
+    return true;
+}
+
+bool bpair_plan(vegas_gpu* h) {
+    // opt-in (tuning key basis_pair=1): bit-identical and synchronisation-free, but the 1184 co-resident CTAs put 65-520 MB
+    // between a CTA's two uses of its partner rows, so the second colour re-reads them from DRAM: 12.4-15.6 GB and
+    // 2.55-2.87 ms per fcc 384^3 step against 14 GB and 2.45 ms for four colour launches (profiles/r02/README.md section 11)
+    if (h->family != FAM_HEIS_BASIS || h->slab || h->bpair_enable != 1 || h->basis_vec == 0) return false;
+    if (h->ld.unitcell != VEGAS_FCC) return false;
+    const uint32_t NV = h->md.precision == VEGAS_F64 ? 2u : 4u;
+    if (h->ld.nx % NV) return false;
+    if (h->bpair_ok < 0) h->bpair_ok = pair_structure_ok<2>() ? 1 : 0;
+    if (!h->bpair_ok) return false;
+    if (!h->hb2[0][0]) {   // second set of arrays, once
+        const size_t bytes = (size_t)(h->n / h->n_colours) * real_bytes(h);
+        for (int b = 0; b < h->n_colours; ++b)
+            for (int k = 0; k < 3; ++k)
+                if (cudaMalloc(&h->hb2[b][k], bytes) != cudaSuccess) {
+                    cudaGetLastError();
+                    for (int bb = 0; bb < 4; ++bb) for (int kk = 0; kk < 3; ++kk) { cudaFree(h->hb2[bb][kk]); h->hb2[bb][kk] = nullptr; }
+                    h->bpair_enable = 0;   // not enough memory for the second set: colour launches
+                    return false;
+                }
+    }
+    return true;
+}
+
+template <typename real>
+void bpair_step_t(vegas_gpu* h, double* obs_row, bool record) {
+    const BasisGeom g = basis_geom(h);
+    const HeisParams<real> p = heis_params<real>(h);
+    const PhiloxKey pk = make_philox_key(h->md.seed);
+    const bool flip = h->md.proposal == VEGAS_PROPOSE_FLIP;
+    BasisPtrs<real> S = basis_ptrs<real>(h), D{};
+    for (int b = 0; b < 4; ++b) for (int c = 0; c < 3; ++c) D.s[b][c] = (real*)h->hb2[b][c];
+    const uint32_t rows = std::max<uint32_t>(1, std::min<uint32_t>(h->bpair_rows ? h->bpair_rows : 16u, g.ny));
+    const uint32_t chunk = std::max<uint32_t>(1, h->bpair_chunk ? h->bpair_chunk : 4u);
+    const dim3 grid(cdiv(g.ny, rows), 1, g.nz);
+#define BP(B0)                                                                                                                  \
+    do {                                                                                                                        \
+        if (record) { if (flip) heis_basis_pair_kernel<real, 2, B0, true, 1><<<grid, 128, 0, h->stream>>>(S, D, g, rows, chunk, p, h->sweeps, pk, obs_row); \
+                      else heis_basis_pair_kernel<real, 2, B0, false, 1><<<grid, 128, 0, h->stream>>>(S, D, g, rows, chunk, p, h->sweeps, pk, obs_row); }   \
+        else { if (flip) heis_basis_pair_kernel<real, 2, B0, true, 0><<<grid, 128, 0, h->stream>>>(S, D, g, rows, chunk, p, h->sweeps, pk, obs_row);      \
+               else heis_basis_pair_kernel<real, 2, B0, false, 0><<<grid, 128, 0, h->stream>>>(S, D, g, rows, chunk, p, h->sweeps, pk, obs_row); }          \
+        h->launches++;                                                                                                          \
+    } while (0)
+    BP(0);
+    BP(2);
+#undef BP
+    for (int b = 0; b < 4; ++b) for (int c = 0; c < 3; ++c) std::swap(h->hb[b][c], h->hb2[b][c]);   // D is the State now
+}
+
 bool bwave_plan(vegas_gpu* h) {
     if (h->bwave_planned) return basis_wave_usable(h->bwave);
     // opt-in (tuning key basis_wave=1): 9.2 GB of DRAM traffic per fcc 384^3 step against 14 GB for four colour launches, but
@@ -1205,6 +1278,9 @@ void do_step(vegas_gpu* h, void* obs_row, void* scratch_row) {
         bpipe_step(h, (double*)(rec ? obs_row : scratch_row), rec);
     } else if (h->family == FAM_HEIS_BASIS && bwave_plan(h)) {
         bwave_step(h, (double*)(rec ? obs_row : scratch_row), rec);   // a failed launch surfaces through cudaGetLastError / h->err
+    } else if (h->family == FAM_HEIS_BASIS && bpair_plan(h)) {
+        if (h->md.precision == VEGAS_F64) bpair_step_t<double>(h, (double*)(rec ? obs_row : scratch_row), rec);
+        else bpair_step_t<float>(h, (double*)(rec ? obs_row : scratch_row), rec);
     } else if (h->family == FAM_HEIS_BASIS) {
         for (int b = 0; b < h->n_colours; ++b) basis_pass_any(h, rec ? 1 : 0, b, (double*)(rec ? obs_row : scratch_row));
     } else if (h->family == FAM_HEIS_STENCIL && pipe_plan(h)) {
@@ -1617,6 +1693,7 @@ void vegas_gpu_destroy(vegas_gpu_t h) {
     cudaFree(h->hp_dev);
     for (cudaEvent_t ev : h->hp_events) cudaEventDestroy(ev);
     basis_wave_destroy(h->bwave);
+    for (int b = 0; b < 4; ++b) for (int k = 0; k < 3; ++k) cudaFree(h->hb2[b][k]);
     if (h->stream_b) { cudaStreamSynchronize(h->stream_b); cudaStreamDestroy(h->stream_b); }
     if (h->ev_main) cudaEventDestroy(h->ev_main);
     if (h->ev_bnd) cudaEventDestroy(h->ev_bnd);
@@ -2430,6 +2507,9 @@ int vegas_gpu_set_tuning(vegas_gpu_t h, const char* key, long value) {
     else if (k == "basis_pipe_lead") h->bpipe_lead = (uint32_t)value;
     else if (k == "basis_pipe_pub") h->bpipe_pub = (uint32_t)value;
     else if (k == "basis_pipe_tiles") h->bpipe_tiles = (uint32_t)value;
+    else if (k == "basis_pair") h->bpair_enable = (int)value;
+    else if (k == "basis_pair_rows") h->bpair_rows = (uint32_t)value;
+    else if (k == "basis_pair_chunk") h->bpair_chunk = (uint32_t)value;
     else if (k == "basis_wave") h->bwave_enable = (int)value;
     else if (k == "basis_wave_lag") h->bwave_lag = (uint32_t)value;
     else if (k == "basis_wave_ipt") h->bwave_ipt = (uint32_t)value;
@@ -2454,6 +2534,7 @@ const char* vegas_gpu_step_kernel(vegas_gpu_t h) {
     if (h->family == FAM_HEIS_STENCIL && cudaSetDevice(h->device) == cudaSuccess && pipe_plan(h)) return "heis_pipe";
     if (h->family == FAM_HEIS_BASIS && cudaSetDevice(h->device) == cudaSuccess && bpipe_plan(h)) return "basis_pipe";
     if (h->family == FAM_HEIS_BASIS && cudaSetDevice(h->device) == cudaSuccess && bwave_plan(h)) return "basis_wave";
+    if (h->family == FAM_HEIS_BASIS && cudaSetDevice(h->device) == cudaSuccess && bpair_plan(h)) return "basis_pair";
     if (h->family == FAM_HEIS_STENCIL && cudaSetDevice(h->device) == cudaSuccess && wave_plan(h)) return "heis_wave";
     if (h->family == FAM_HEIS_STENCIL && cudaSetDevice(h->device) == cudaSuccess && fused_plan(h)) return "heis_fused";
     if (resident_plan(h)) return h->family == FAM_ISING_GEN ? "ising_resident" : "heis_resident";
