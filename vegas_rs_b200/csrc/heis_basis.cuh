@@ -297,8 +297,11 @@ heis_basis_vec_kernel(BasisPtrs<real> P, BasisPeers<real> peers, BasisGeom g, ui
 //     spin comes from S, which no launch of this step writes, every read of a "new" spin of a LOWER colour from D.
 // Same work item as the colour launches (basis_vec_item): bit-identical trajectories.
 // ---------------------------------------------------------------------------------------
+#ifndef BASIS_PAIR_MINB
+#define BASIS_PAIR_MINB BASIS_VEC_MINB
+#endif
 template <typename real, int UC, int B0, bool FLIP, int MODE>
-__global__ void __launch_bounds__(128, BASIS_VEC_MINB)
+__global__ void __launch_bounds__(128, BASIS_PAIR_MINB)
 heis_basis_pair_kernel(BasisPtrs<real> S, BasisPtrs<real> D, BasisGeom g, uint32_t rows_per_cta, uint32_t chunk_rows, HeisParams<real> p,
                        uint64_t sweep, PhiloxKey pk, double* __restrict__ obs) {
     constexpr int N = VecOf<real>::N, NB = BasisCell<UC>::NB;
