@@ -297,8 +297,11 @@ heis_basis_vec_kernel(BasisPtrs<real> P, BasisPeers<real> peers, BasisGeom g, ui
 //     spin comes from S, which no launch of this step writes, every read of a "new" spin of a LOWER colour from D.
 // Same work item as the colour launches (basis_vec_item): bit-identical trajectories.
 // ---------------------------------------------------------------------------------------
+// resident CTAs per SM the pair kernel is compiled for: fewer, fatter CTAs keep the window between a CTA's two colours inside
+// L2 and more loads in flight per thread.  fcc 384^3, 32 rows per tile, colours alternating every 4 rows: 8 CTAs (64 registers)
+// 2.69 ms, 4 (128) 2.48, 3 (170) 2.22, 2 (221) 2.31 (profiles/r02/p4.sh)
 #ifndef BASIS_PAIR_MINB
-#define BASIS_PAIR_MINB BASIS_VEC_MINB
+#define BASIS_PAIR_MINB 3
 #endif
 template <typename real, int UC, int B0, bool FLIP, int MODE>
 __global__ void __launch_bounds__(128, BASIS_PAIR_MINB)

@@ -103,7 +103,7 @@ struct vegas_gpu {
     BasisPipeState* bpipe = nullptr;
     // --- pair launches of the fcc step (heis_basis_pair_kernel): colours (0,1) and (2,3) in one launch each, S -> D arrays
     int bpair_enable = -1;                // tuning key basis_pair: 1 whenever possible (single-handle fcc); -1 / 0: colour launches
-    uint32_t bpair_rows = 0;              // tuning key basis_pair_rows: rows of a plane per CTA (0 = auto: 16)
+    uint32_t bpair_rows = 0;              // tuning key basis_pair_rows: rows of a plane per CTA (0 = auto: 32)
     uint32_t bpair_chunk = 0;             // tuning key basis_pair_chunk: rows the two colours alternate in (0 = auto: 4)
     void* hb2[4][3] = {};                 // the second set of arrays (allocated at first use); hb / hb2 swap after every pair step
     int bpair_ok = -1;                    // cached: the unit-cell table has the structure the pair kernel needs
@@ -1035,9 +1035,10 @@ bool pair_structure_ok() {
 }
 
 bool bpair_plan(vegas_gpu* h) {
-    // opt-in (tuning key basis_pair=1): bit-identical and synchronisation-free, but the 1184 co-resident CTAs put 65-520 MB
-    // between a CTA's two uses of its partner rows, so the second colour re-reads them from DRAM: 12.4-15.6 GB and
-    // 2.55-2.87 ms per fcc 384^3 step against 14 GB and 2.45 ms for four colour launches (profiles/r02/README.md section 11)
+    // opt-in (tuning key basis_pair=1): bit-identical and synchronisation-free; with 3 fat CTAs per SM the window between a
+    // CTA's two colours fits L2 and the step takes 2.22 ms per fcc 384^3 step against 2.45 for four colour launches -- at twice
+    // the State in HBM and for single handles only (a slab would need the second array set in its IPC allocation), which is
+    // why it is not the default (profiles/r02/README.md section 11)
     if (h->family != FAM_HEIS_BASIS || h->slab || h->bpair_enable != 1 || h->basis_vec == 0) return false;
     if (h->ld.unitcell != VEGAS_FCC) return false;
     const uint32_t NV = h->md.precision == VEGAS_F64 ? 2u : 4u;
@@ -1066,7 +1067,7 @@ void bpair_step_t(vegas_gpu* h, double* obs_row, bool record) {
     const bool flip = h->md.proposal == VEGAS_PROPOSE_FLIP;
     BasisPtrs<real> S = basis_ptrs<real>(h), D{};
     for (int b = 0; b < 4; ++b) for (int c = 0; c < 3; ++c) D.s[b][c] = (real*)h->hb2[b][c];
-    const uint32_t rows = std::max<uint32_t>(1, std::min<uint32_t>(h->bpair_rows ? h->bpair_rows : 16u, g.ny));
+    const uint32_t rows = std::max<uint32_t>(1, std::min<uint32_t>(h->bpair_rows ? h->bpair_rows : 32u, g.ny));
     const uint32_t chunk = std::max<uint32_t>(1, h->bpair_chunk ? h->bpair_chunk : 4u);
     const dim3 grid(cdiv(g.ny, rows), 1, g.nz);
 #define BP(B0)                                                                                                                  \
