@@ -50,6 +50,7 @@ NCU_TRAFFIC = {
                    "heis_wave": (2.887e9 + 1.562e9, "profiles/r01u_heis_wave.metrics.txt (one step = both colours)"),
                    "heis_stencil": (2.42e9, "profiles/r01o_heis_stencil.metrics.txt (one colour pass)")},
     "heis_fcc_384": {"heis_basis": (2.829e9 + 0.686e9, "profiles/r01z_heis_basis_vec.metrics.txt (one colour pass)"),
+                     "basis_pair": (2.989e9 + 1.357e9, "profiles/r02_basis_pair.metrics.txt (one pair launch = two colours)"),
                      "basis_pipe": (7.813e9 + 2.714e9, "profiles/r02_basis_pipe.metrics.txt (one step = four colours, one launch)"),
                      "basis_wave": (6.068e9 + 3.168e9, "profiles/r02_basis_wave.metrics.txt (one step = four colours, one launch)")},
 }

@@ -269,7 +269,7 @@ def test_basis_wave_replays_the_reference_rule(built):
 
 def test_basis_wave_is_opt_in(built):
     g = vg.GpuMetropolis(vg.HEISENBERG, unitcell=vg.FCC, size=(64, 32, 32), seed=5)
-    assert g.step_kernel == "heis_basis"          # measured slower than the colour launches so far: not a default
+    assert g.step_kernel == "heis_basis"          # a State that fits in L2: colour launches; the wave kernel is opt-in
     g.set_tuning("basis_wave", 1)
     assert g.step_kernel == "basis_wave"
     g.randomize(); g.set_thermostat(1.0, (0, 0, 1.0), 0.3)
@@ -355,4 +355,19 @@ def test_basis_pair_replays_the_reference_rule(built):
         assert np.max(np.abs(g.download() - cpu)) < 1e-12
         assert abs(e[0] - H.total_energy(th, cpu)) < 1e-12 * n * 10
         assert np.max(np.abs(m[0] - cpu.sum(axis=0))) < 1e-12 * n
+    g.close()
+
+
+def test_basis_pair_is_the_default_beyond_l2(built):
+    g = vg.GpuMetropolis(vg.HEISENBERG, unitcell=vg.FCC, size=(128, 128, 32), seed=5)     # 2 Mi sites x 12 B = 24 MiB < L2
+    assert g.step_kernel == "heis_basis"
+    g.close()
+    g = vg.GpuMetropolis(vg.HEISENBERG, unitcell=vg.FCC, size=(256, 128, 96), seed=5)     # 12.6 M sites: 151 MB
+    assert g.step_kernel == "basis_pair"
+    g.randomize(); g.set_thermostat(1.0, (0, 0, 1.0), 0.3)
+    e, m = g.step(3)
+    assert abs(g.total_energy() - e[-1]) < 1e-5 * abs(e[-1]) + 1e-5 * g.n_sites
+    assert np.max(np.abs(g.magnetization() - m[-1])) < 1e-5 * g.n_sites
+    g.set_tuning("basis_pair", 0)
+    assert g.step_kernel == "heis_basis"
     g.close()

@@ -102,7 +102,7 @@ struct vegas_gpu {
     bool bpipe_planned = false;
     BasisPipeState* bpipe = nullptr;
     // --- pair launches of the fcc step (heis_basis_pair_kernel): colours (0,1) and (2,3) in one launch each, S -> D arrays
-    int bpair_enable = -1;                // tuning key basis_pair: 1 whenever possible (single-handle fcc); -1 / 0: colour launches
+    int bpair_enable = -1;                // tuning key basis_pair: -1 auto (single-handle fcc lattices larger than L2), 0 never, 1 whenever possible
     uint32_t bpair_rows = 0;              // tuning key basis_pair_rows: rows of a plane per CTA (0 = auto: 32)
     uint32_t bpair_chunk = 0;             // tuning key basis_pair_chunk: rows the two colours alternate in (0 = auto: 4)
     void* hb2[4][3] = {};                 // the second set of arrays (allocated at first use); hb / hb2 swap after every pair step
@@ -1035,11 +1035,12 @@ bool pair_structure_ok() {
 }
 
 bool bpair_plan(vegas_gpu* h) {
-    // opt-in (tuning key basis_pair=1): bit-identical and synchronisation-free; with 3 fat CTAs per SM the window between a
-    // CTA's two colours fits L2 and the step takes 2.22 ms per fcc 384^3 step against 2.45 for four colour launches -- at twice
-    // the State in HBM and for single handles only (a slab would need the second array set in its IPC allocation), which is
-    // why it is not the default (profiles/r02/README.md section 11)
-    if (h->family != FAM_HEIS_BASIS || h->slab || h->bpair_enable != 1 || h->basis_vec == 0) return false;
+    // Bit-identical to the colour launches and synchronisation-free; with 3 fat CTAs per SM the window between a CTA's two
+    // colours fits L2: 2.22 ms per fcc 384^3 step against 2.45 for four colour launches (profiles/r02/README.md section 11).
+    // Default (-1) for single-handle lattices beyond L2 size; it needs the State twice in HBM.  Slabs keep the colour launches
+    // (the second array set would have to live in the slab's IPC allocation with its own halo planes).
+    if (h->family != FAM_HEIS_BASIS || h->slab || h->bpair_enable == 0 || h->basis_vec == 0) return false;
+    if (h->bpair_enable < 0 && h->n * 3 * real_bytes(h) < (96ull << 20)) return false;   // auto: the State does not fit in L2
     if (h->ld.unitcell != VEGAS_FCC) return false;
     const uint32_t NV = h->md.precision == VEGAS_F64 ? 2u : 4u;
     if (h->ld.nx % NV) return false;
