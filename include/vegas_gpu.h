@@ -198,8 +198,8 @@ int vegas_gpu_slab_connect_local(vegas_gpu_t self, vegas_gpu_t lower, vegas_gpu_
  *                       colour), 1 whenever possible -- the fcc step as TWO launches, colours (0, 1) and (2, 3), each CTA updating
  *                       the first colour on its rows plus one (recomputed) row and then the second colour, from one set of arrays
  *                       to a second one (swapped after every step; twice the State in HBM), no inter-CTA synchronisation
- *                       (heis_basis_pair_kernel); "basis_pair_rows" = rows of a plane per CTA (0 = auto: 32), "basis_pair_chunk" =
- *                       rows after which the CTA switches between its two colours (0 = auto: 4).  9 % faster than four launches
+ *                       (heis_basis_pair_kernel); "basis_pair_rows" = rows of a plane per CTA (0 = auto: 48), "basis_pair_chunk" =
+ *                       rows after which the CTA switches between its two colours (0 = auto: the fewest that keep every thread busy).  9 % faster than four launches
  *                       on fcc 384^3 (three fat CTAs per SM keep the window between the two colours inside L2); slabs keep the
  *                       colour launches
  *     "basis_wave"    : 1 whenever the lattice has enough planes; default -1 / 0: one launch per colour -- all 2 / 4 colour

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <numeric>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -103,8 +104,8 @@ struct vegas_gpu {
     BasisPipeState* bpipe = nullptr;
     // --- pair launches of the fcc step (heis_basis_pair_kernel): colours (0,1) and (2,3) in one launch each, S -> D arrays
     int bpair_enable = -1;                // tuning key basis_pair: -1 auto (single-handle fcc lattices larger than L2), 0 never, 1 whenever possible
-    uint32_t bpair_rows = 0;              // tuning key basis_pair_rows: rows of a plane per CTA (0 = auto: 32)
-    uint32_t bpair_chunk = 0;             // tuning key basis_pair_chunk: rows the two colours alternate in (0 = auto: 4)
+    uint32_t bpair_rows = 0;              // tuning key basis_pair_rows: rows of a plane per CTA (0 = auto: 48; 24 / 32 / 48 / 96 rows: 2.18 / 2.21 / 2.15 / 2.27 ms)
+    uint32_t bpair_chunk = 0;             // tuning key basis_pair_chunk: rows the two colours alternate in (0 = auto)
     void* hb2[4][3] = {};                 // the second set of arrays (allocated at first use); hb / hb2 swap after every pair step
     int bpair_ok = -1;                    // cached: the unit-cell table has the structure the pair kernel needs
     // --- wave-ordered bcc / fcc step (basis_wave.cu): the colour passes of a step as one persistent launch, L2-friendly order
@@ -1068,8 +1069,12 @@ void bpair_step_t(vegas_gpu* h, double* obs_row, bool record) {
     const bool flip = h->md.proposal == VEGAS_PROPOSE_FLIP;
     BasisPtrs<real> S = basis_ptrs<real>(h), D{};
     for (int b = 0; b < 4; ++b) for (int c = 0; c < 3; ++c) D.s[b][c] = (real*)h->hb2[b][c];
-    const uint32_t rows = std::max<uint32_t>(1, std::min<uint32_t>(h->bpair_rows ? h->bpair_rows : 32u, g.ny));
-    const uint32_t chunk = std::max<uint32_t>(1, h->bpair_chunk ? h->bpair_chunk : 4u);
+    const uint32_t rows = std::max<uint32_t>(1, std::min<uint32_t>(h->bpair_rows ? h->bpair_rows : 48u, g.ny));
+    // rows after which a CTA switches colours: as few as keep all 128 threads busy (rows * vectors per row a multiple of 128);
+    // fcc 384^3 (96 vectors per row): 4 rows 2.21 ms, 2 / 3 / 5 / 6 rows 2.57 / 2.52 / 2.38 / 2.51, 8 rows 2.58 (window beyond L2)
+    uint32_t auto_chunk = 128u / std::gcd(g.nx / (uint32_t)VecOf<real>::N, 128u);
+    if (auto_chunk > 8u) auto_chunk = 4u;
+    const uint32_t chunk = std::max<uint32_t>(1, h->bpair_chunk ? h->bpair_chunk : auto_chunk);
     const dim3 grid(cdiv(g.ny, rows), 1, g.nz);
 #define BP(B0)                                                                                                                  \
     do {                                                                                                                        \
