@@ -194,14 +194,14 @@ int vegas_gpu_slab_connect_local(vegas_gpu_t self, vegas_gpu_t lower, vegas_gpu_
  *                       from L2; "basis_pipe_lead" (planes the first colour may lead the last, 0 = auto), "basis_pipe_pub"
  *                       (planes per published progress update, 0 = auto: 1), "basis_pipe_tiles" (bands per colour, 0 = auto).
  *                       Opt-in: compulsory DRAM traffic only, but latency bound and slower than the colour launches so far
- *     "basis_pair"    : -1 auto (default: single-handle periodic fcc lattices whose State exceeds L2), 0 never (one launch per
+ *     "basis_pair"    : -1 auto (default: periodic fcc lattices, single handle or connected z-slab, whose State exceeds L2), 0 never (one launch per
  *                       colour), 1 whenever possible -- the fcc step as TWO launches, colours (0, 1) and (2, 3), each CTA updating
  *                       the first colour on its rows plus one (recomputed) row and then the second colour, from one set of arrays
  *                       to a second one (swapped after every step; twice the State in HBM), no inter-CTA synchronisation
  *                       (heis_basis_pair_kernel); "basis_pair_rows" = rows of a plane per CTA (0 = auto: 48), "basis_pair_chunk" =
  *                       rows after which the CTA switches between its two colours (0 = auto: the fewest that keep every thread busy).  9 % faster than four launches
- *                       on fcc 384^3 (three fat CTAs per SM keep the window between the two colours inside L2); slabs keep the
- *                       colour launches
+ *                       on fcc 384^3 (three fat CTAs per SM keep the window between the two colours inside L2); connected fcc
+ *                       z-slabs hold both array sets in their one allocation and swap in lock step
  *     "basis_wave"    : 1 whenever the lattice has enough planes; default -1 / 0: one launch per colour -- all 2 / 4 colour
  *                       passes of a periodic bcc / fcc Heisenberg step as ONE persistent cooperative launch whose work items
  *                       (those of the colour launches) are drawn in wave order, colour b a few planes behind colour b-1, so

@@ -371,3 +371,51 @@ def test_basis_pair_is_the_default_beyond_l2(built):
     g.set_tuning("basis_pair", 0)
     assert g.step_kernel == "heis_basis"
     g.close()
+
+
+@pytest.mark.parametrize("nslab,precision", [(2, vg.F32), (3, vg.F64), (4, vg.F32)])
+def test_basis_pair_on_slabs_bit_identical(built, nslab, precision):
+    """z-slabs stepping with the pair launches (each slab keeps two array sets in its one allocation, all slabs swap in lock step,
+    boundary planes go into the neighbours' halos of the set being written) reproduce the single handle's colour launches."""
+    Lx, Ly, nz = 16, 10, 4
+    Lz = nz * nslab
+    kw = dict(unitcell=vg.FCC, seed=41, precision=precision, anisotropy=((0.6, 0, 0.8), 0.15))
+    whole = vg.GpuMetropolis(vg.HEISENBERG, size=(Lx, Ly, Lz), **kw)
+    whole.set_tuning("basis_pair", 0)
+    s = random_state(ob.HEISENBERG, Lx * Ly * Lz * 4, 17)
+    whole.upload(s)
+    slabs = [vg.GpuMetropolis(vg.HEISENBERG, size=(Lx, Ly, nz), nz_global=Lz, z_offset=r * nz, **kw) for r in range(nslab)]
+    plane = Lx * Ly * 4
+    for r, sl in enumerate(slabs):
+        sl.set_tuning("basis_pair", 1); sl.set_tuning("basis_pair_rows", 4)
+        sl.upload(s[r * nz * plane:(r + 1) * nz * plane])
+    for r, sl in enumerate(slabs):
+        sl.slab_connect_local(slabs[(r - 1) % nslab], slabs[(r + 1) % nslab])
+    assert all(sl.step_kernel == "basis_pair" for sl in slabs)
+    whole.set_thermostat(1.3, (0, 0, 1.0), 0.3)
+    for sl in slabs:
+        sl.set_thermostat(1.3, (0, 0, 1.0), 0.3)
+    tol = 1e-12 if precision == vg.F64 else 1e-6
+    for k in (1, 2, 2):   # odd and even numbers of steps: the sets swap every step (5 in all: the upload below meets set 1)
+        e, m = whole.step(k)
+        for _ in range(k):
+            for sl in slabs:
+                sl.step_async(1, True)
+            parts = [sl.read_observables(1) for sl in slabs]
+        assert np.array_equal(np.concatenate([sl.download() for sl in slabs]), whole.download())
+        e_sum = sum(p[0][0] for p in parts)
+        assert abs(e_sum - e[-1]) <= tol * abs(e[-1]) * 10 + tol
+        assert abs(sum(sl.total_energy() for sl in slabs) - whole.total_energy()) <= tol * abs(e[-1]) * 10 + tol
+    # a new State after an odd number of steps: upload pushes the boundary planes into the neighbours' CURRENT set
+    s2 = random_state(ob.HEISENBERG, Lx * Ly * Lz * 4, 18)
+    whole.upload(s2)
+    for r, sl in enumerate(slabs):
+        sl.upload(s2[r * nz * plane:(r + 1) * nz * plane])
+    whole.step(2, observe=False)
+    for _ in range(2):
+        for sl in slabs:
+            sl.step_async(1, False)
+    assert np.array_equal(np.concatenate([sl.download() for sl in slabs]), whole.download())
+    for sl in slabs:
+        sl.close()
+    whole.close()

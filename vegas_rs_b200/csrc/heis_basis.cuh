@@ -303,17 +303,18 @@ heis_basis_vec_kernel(BasisPtrs<real> P, BasisPeers<real> peers, BasisGeom g, ui
 #ifndef BASIS_PAIR_MINB
 #define BASIS_PAIR_MINB 3
 #endif
-template <typename real, int UC, int B0, bool FLIP, int MODE>
+// SLAB: planes -1 and nz of every array are halo planes the z-neighbours store into; `peers` are the bases of THEIR copy of the
+// array set this launch writes (D), so that my boundary planes land in their halos; planes z_begin, z_begin + z_step, ...
+template <typename real, int UC, int B0, bool FLIP, int MODE, bool SLAB = false>
 __global__ void __launch_bounds__(128, BASIS_PAIR_MINB)
-heis_basis_pair_kernel(BasisPtrs<real> S, BasisPtrs<real> D, BasisGeom g, uint32_t rows_per_cta, uint32_t chunk_rows, HeisParams<real> p,
-                       uint64_t sweep, PhiloxKey pk, double* __restrict__ obs) {
+heis_basis_pair_kernel(BasisPtrs<real> S, BasisPtrs<real> D, BasisPeers<real> peers, BasisGeom g, uint32_t rows_per_cta, uint32_t chunk_rows,
+                       uint32_t z_begin, uint32_t z_step, HeisParams<real> p, uint64_t sweep, PhiloxKey pk, double* __restrict__ obs) {
     constexpr int N = VecOf<real>::N, NB = BasisCell<UC>::NB;
     static_assert(B0 + 1 < NB, "a pair is (B0, B0 + 1)");
     __shared__ double s_red[6 * 32];
-    const uint32_t iz = blockIdx.z, VX = g.nx / N;
+    const uint32_t iz = z_begin + blockIdx.z * z_step, VX = g.nx / N;
     const uint32_t r0 = blockIdx.x * rows_per_cta, r1 = min(r0 + rows_per_cta, g.ny);
-    const int zs[3] = {(int)(iz == 0 ? g.nz - 1 : iz - 1), (int)iz, (int)(iz + 1 == g.nz ? 0u : iz + 1)};
-    const BasisPeers<real> no_peers{nullptr, nullptr};
+    const int zs[3] = {SLAB ? (int)iz - 1 : (int)(iz == 0 ? g.nz - 1 : iz - 1), (int)iz, SLAB ? (int)iz + 1 : (int)(iz + 1 == g.nz ? 0u : iz + 1)};
     // what colour B reads: lower colours are final (D), itself and higher colours are still the old state (S)
     BasisPtrs<real> R0, R1;
 #pragma unroll
@@ -330,7 +331,7 @@ heis_basis_pair_kernel(BasisPtrs<real> S, BasisPtrs<real> D, BasisGeom g, uint32
         const uint32_t n = (rb - ra) * VX;
         for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) {
             const uint32_t dr = t / VX, y = ra + dr, row = y == g.ny ? 0u : y;
-            basis_vec_item<real, UC, B0, FLIP, MODE, false>(R0, D, no_peers, g, iz, zs, row * VX + (t - dr * VX), VX, p, sweep, pk, fs, accepted, y < r1);
+            basis_vec_item<real, UC, B0, FLIP, MODE, SLAB>(R0, D, peers, g, iz, zs, row * VX + (t - dr * VX), VX, p, sweep, pk, fs, accepted, y < r1);
         }
     };
     first(r0, r0 + 1u);
@@ -340,7 +341,7 @@ heis_basis_pair_kernel(BasisPtrs<real> S, BasisPtrs<real> D, BasisGeom g, uint32
         __syncthreads();   // the first colour's new spins on rows [ra, rb] were stored by threads of this CTA
         const uint32_t n2 = (rb - ra) * VX;
         for (uint32_t t = threadIdx.x; t < n2; t += blockDim.x)
-            basis_vec_item<real, UC, B0 + 1, FLIP, MODE, false>(R1, D, no_peers, g, iz, zs, ra * VX + t, VX, p, sweep, pk, fs, accepted);
+            basis_vec_item<real, UC, B0 + 1, FLIP, MODE, SLAB>(R1, D, peers, g, iz, zs, ra * VX + t, VX, p, sweep, pk, fs, accepted);
     }
     double acc[6] = {0, 0, 0, 0, 0, 0};
     if (MODE != 0) {

@@ -108,6 +108,8 @@ struct vegas_gpu {
     uint32_t bpair_chunk = 0;             // tuning key basis_pair_chunk: rows the two colours alternate in (0 = auto)
     void* hb2[4][3] = {};                 // the second set of arrays (allocated at first use); hb / hb2 swap after every pair step
     int bpair_ok = -1;                    // cached: the unit-cell table has the structure the pair kernel needs
+    size_t pair_set_bytes = 0;            // fcc slab: its ONE allocation holds two array sets this many bytes apart (0: one set)
+    int cur_set = 0;                      // which of the two sets hb points at (all ranks of a slab group swap in lock step)
     // --- wave-ordered bcc / fcc step (basis_wave.cu): the colour passes of a step as one persistent launch, L2-friendly order
     int bwave_enable = -1;                // tuning key basis_wave: 1 whenever possible; -1 / 0: colour launches
     uint32_t bwave_lag = 0, bwave_ipt = 0, bwave_grid = 0;   // tuning keys basis_wave_lag / _ipt / _grid (0 = auto)
@@ -530,7 +532,15 @@ void preload_basis_one() {
     preload(heis_basis_vec_kernel<real, UC, B, false, 2, true>);
 }
 template <typename real>
+void preload_pair_slab() {
+    preload(heis_basis_pair_kernel<real, 2, 0, false, 0, true>); preload(heis_basis_pair_kernel<real, 2, 0, false, 1, true>);
+    preload(heis_basis_pair_kernel<real, 2, 0, true, 0, true>); preload(heis_basis_pair_kernel<real, 2, 0, true, 1, true>);
+    preload(heis_basis_pair_kernel<real, 2, 2, false, 0, true>); preload(heis_basis_pair_kernel<real, 2, 2, false, 1, true>);
+    preload(heis_basis_pair_kernel<real, 2, 2, true, 0, true>); preload(heis_basis_pair_kernel<real, 2, 2, true, 1, true>);
+}
+template <typename real>
 void preload_basis_slab() {
+    preload_pair_slab<real>();
     preload_basis_one<real, 1, 0>(); preload_basis_one<real, 1, 1>();
     preload_basis_one<real, 2, 0>(); preload_basis_one<real, 2, 1>(); preload_basis_one<real, 2, 2>(); preload_basis_one<real, 2, 3>();
 }
@@ -702,6 +712,9 @@ BasisGeom basis_geom(const vegas_gpu* h) {
     return g;
 }
 
+// base of array set `set` in the lower (0) / upper (1) neighbour's slab allocation
+char* peer_set(const vegas_gpu* h, int which, int set) { return (char*)h->peer_halo[which] + (size_t)set * h->pair_set_bytes; }
+
 template <typename real, int UC, int B>
 void basis_launch(vegas_gpu* h, int mode, double* obs, uint32_t zb, uint32_t zc, uint32_t zstep, cudaStream_t st) {
     const BasisGeom g = basis_geom(h);
@@ -715,7 +728,7 @@ void basis_launch(vegas_gpu* h, int mode, double* obs, uint32_t zb, uint32_t zc,
     const bool flip = h->md.proposal == VEGAS_PROPOSE_FLIP;
     const bool slab = h->slab && h->connected;
     BasisPeers<real> peers{};
-    if (slab && mode != 2) { peers.lo = (real*)h->peer_halo[0]; peers.hi = (real*)h->peer_halo[1]; }
+    if (slab && mode != 2) { peers.lo = (real*)peer_set(h, 0, h->cur_set); peers.hi = (real*)peer_set(h, 1, h->cur_set); }
     h->launches++;
     constexpr uint32_t NV = (uint32_t)VecOf<real>::N;
     if (h->basis_vec != 0 && g.nx % NV == 0) {
@@ -1040,14 +1053,17 @@ bool bpair_plan(vegas_gpu* h) {
     // colours fits L2: 2.22 ms per fcc 384^3 step against 2.45 for four colour launches (profiles/r02/README.md section 11).
     // Default (-1) for single-handle lattices beyond L2 size; it needs the State twice in HBM.  Slabs keep the colour launches
     // (the second array set would have to live in the slab's IPC allocation with its own halo planes).
-    if (h->family != FAM_HEIS_BASIS || h->slab || h->bpair_enable == 0 || h->basis_vec == 0) return false;
+    if (h->family != FAM_HEIS_BASIS || h->bpair_enable == 0 || h->basis_vec == 0) return false;
+    // a slab steps from one array set of its allocation into the other, in lock step with its neighbours; it needs the
+    // connection, three planes, and no wave state (which captured the set it was created on)
+    if (h->slab && !(h->pair_set_bytes && h->connected && h->ld.nz >= 3 && !h->bwave)) return false;
     if (h->bpair_enable < 0 && h->n * 3 * real_bytes(h) < (96ull << 20)) return false;   // auto: the State does not fit in L2
     if (h->ld.unitcell != VEGAS_FCC) return false;
     const uint32_t NV = h->md.precision == VEGAS_F64 ? 2u : 4u;
     if (h->ld.nx % NV) return false;
     if (h->bpair_ok < 0) h->bpair_ok = pair_structure_ok<2>() ? 1 : 0;
     if (!h->bpair_ok) return false;
-    if (!h->hb2[0][0]) {   // second set of arrays, once
+    if (!h->hb2[0][0]) {   // second set of arrays, once (a slab's second set lives in its one allocation)
         const size_t bytes = (size_t)(h->n / h->n_colours) * real_bytes(h);
         for (int b = 0; b < h->n_colours; ++b)
             for (int k = 0; k < 3; ++k)
@@ -1075,19 +1091,51 @@ void bpair_step_t(vegas_gpu* h, double* obs_row, bool record) {
     uint32_t auto_chunk = 128u / std::gcd(g.nx / (uint32_t)VecOf<real>::N, 128u);
     if (auto_chunk > 8u) auto_chunk = 4u;
     const uint32_t chunk = std::max<uint32_t>(1, h->bpair_chunk ? h->bpair_chunk : auto_chunk);
-    const dim3 grid(cdiv(g.ny, rows), 1, g.nz);
-#define BP(B0)                                                                                                                  \
-    do {                                                                                                                        \
-        if (record) { if (flip) heis_basis_pair_kernel<real, 2, B0, true, 1><<<grid, 128, 0, h->stream>>>(S, D, g, rows, chunk, p, h->sweeps, pk, obs_row); \
-                      else heis_basis_pair_kernel<real, 2, B0, false, 1><<<grid, 128, 0, h->stream>>>(S, D, g, rows, chunk, p, h->sweeps, pk, obs_row); }   \
-        else { if (flip) heis_basis_pair_kernel<real, 2, B0, true, 0><<<grid, 128, 0, h->stream>>>(S, D, g, rows, chunk, p, h->sweeps, pk, obs_row);      \
-               else heis_basis_pair_kernel<real, 2, B0, false, 0><<<grid, 128, 0, h->stream>>>(S, D, g, rows, chunk, p, h->sweeps, pk, obs_row); }          \
-        h->launches++;                                                                                                          \
+    const bool slab = h->slab;
+    BasisPeers<real> peers{nullptr, nullptr};
+    if (slab) { peers.lo = (real*)peer_set(h, 0, h->cur_set ^ 1); peers.hi = (real*)peer_set(h, 1, h->cur_set ^ 1); }   // the neighbours' D sets
+    const uint32_t nz = g.nz;
+    // planes zb, zb + zstep, ... (zc of them) of pair B0 on stream st
+    auto launch = [&](int B0, uint32_t zb, uint32_t zc, uint32_t zstep, cudaStream_t st) {
+        if (zc == 0) return;
+        const dim3 grid(cdiv(g.ny, rows), 1, zc);
+#define BPK(B0v, F, M, SL) heis_basis_pair_kernel<real, 2, B0v, F, M, SL><<<grid, 128, 0, st>>>(S, D, peers, g, rows, chunk, zb, zstep, p, h->sweeps, pk, obs_row)
+#define BPM(B0v, SL)                                                                              \
+    do {                                                                                          \
+        if (record) { if (flip) BPK(B0v, true, 1, SL); else BPK(B0v, false, 1, SL); }             \
+        else { if (flip) BPK(B0v, true, 0, SL); else BPK(B0v, false, 0, SL); }                    \
     } while (0)
-    BP(0);
-    BP(2);
-#undef BP
+        if (B0 == 0) { if (slab) BPM(0, true); else BPM(0, false); }
+        else { if (slab) BPM(2, true); else BPM(2, false); }
+#undef BPM
+#undef BPK
+        h->launches++;
+    };
+    for (int B0 = 0; B0 < 4; B0 += 2) {
+        if (!slab) { launch(B0, 0, nz, 1, h->stream); continue; }
+        // connected slab: the same flag protocol and stream structure as the colour launches (basis_pass_any), one exchange
+        // per PAIR launch: the boundary planes wait for the neighbours' previous launch, store into their halos, signal
+        h->pass_counter++;
+        if (!h->peer_is_ipc) {   // all slabs in one process: one stream
+            if (h->pass_counter > 1) { wait_kernel<<<1, 32, 0, h->stream>>>(h->flags, h->pass_counter - 1, h->slab_error); h->launches++; }
+            launch(B0, 0, 2, nz - 1, h->stream);
+            signal_kernel<<<1, 32, 0, h->stream>>>(h->peer_flags[0], h->peer_flags[1], h->pass_counter);
+            h->launches++;
+            launch(B0, 1, nz - 2, 1, h->stream);
+            continue;
+        }
+        cudaEventRecord(h->ev_main, h->stream);
+        cudaStreamWaitEvent(h->stream_b, h->ev_main, 0);
+        cudaStreamWaitEvent(h->stream, h->ev_bnd, 0);
+        if (h->pass_counter > 1) { wait_kernel<<<1, 32, 0, h->stream_b>>>(h->flags, h->pass_counter - 1, h->slab_error); h->launches++; }
+        launch(B0, 0, 2, nz - 1, h->stream_b);
+        signal_kernel<<<1, 32, 0, h->stream_b>>>(h->peer_flags[0], h->peer_flags[1], h->pass_counter);
+        h->launches++;
+        cudaEventRecord(h->ev_bnd, h->stream_b);
+        launch(B0, 1, nz - 2, 1, h->stream);
+    }
     for (int b = 0; b < 4; ++b) for (int c = 0; c < 3; ++c) std::swap(h->hb[b][c], h->hb2[b][c]);   // D is the State now
+    h->cur_set ^= 1;
 }
 
 bool bwave_plan(vegas_gpu* h) {
@@ -1109,7 +1157,7 @@ bool bwave_plan(vegas_gpu* h) {
     d.lag = h->bwave_lag; d.ipt = h->bwave_ipt; d.grid = h->bwave_grid;
     if (h->slab) {
         d.slab = true;
-        d.peer_lo = h->peer_halo[0]; d.peer_hi = h->peer_halo[1];
+        d.peer_lo = peer_set(h, 0, h->cur_set); d.peer_hi = peer_set(h, 1, h->cur_set);
         d.flags = h->flags + BWAVE_FLAG_WORD;
         d.peer_flags[0] = h->peer_flags[0] + BWAVE_FLAG_WORD; d.peer_flags[1] = h->peer_flags[1] + BWAVE_FLAG_WORD;
     }
@@ -1598,13 +1646,20 @@ int vegas_gpu_create_lattice(const vegas_model_desc* md, const vegas_lattice_des
         } else {
             // ONE 2 MiB-granular allocation (its CUDA IPC handle maps exactly this range in the neighbour): the arrays
             // [basis][component], each with a halo plane below and above its nz local planes, then the flags
+            // fcc: TWO such array sets, for the pair launches that step from one set into the other (heis_basis_pair_kernel)
             const size_t ext = cells + 2 * pl;
             h->halo_plane_bytes = pl * real_bytes(h);
-            h->halo_bytes = ((size_t)h->n_colours * 3 * ext * real_bytes(h) + 255) / 256 * 256;
+            const size_t set_bytes = ((size_t)h->n_colours * 3 * ext * real_bytes(h) + 255) / 256 * 256;
+            const int n_sets = ldesc->unitcell == VEGAS_FCC ? 2 : 1;
+            h->pair_set_bytes = n_sets == 2 ? set_bytes : 0;
+            h->halo_bytes = set_bytes * n_sets;
             h->slab_bytes = (h->halo_bytes + 256 + (2u << 20) - 1) / (2u << 20) * (2u << 20);
             if (cudaMalloc(&h->halo, h->slab_bytes) != cudaSuccess) return bail(fail(h, VEGAS_ERR_ALLOC, "cudaMalloc (spins + halos) failed"));
             for (int b = 0; b < h->n_colours; ++b)
-                for (int k = 0; k < 3; ++k) h->hb[b][k] = (char*)h->halo + ((size_t)(b * 3 + k) * ext + pl) * real_bytes(h);
+                for (int k = 0; k < 3; ++k) {
+                    h->hb[b][k] = (char*)h->halo + ((size_t)(b * 3 + k) * ext + pl) * real_bytes(h);
+                    if (n_sets == 2) h->hb2[b][k] = (char*)h->hb[b][k] + set_bytes;
+                }
             h->flags = (unsigned long long*)((char*)h->halo + h->halo_bytes);
             cudaMemsetAsync(h->halo, 0, h->slab_bytes, h->stream);
             const unsigned long long magic = 0x76656761735f6770ull ^ h->z_offset;  // checked by the peer after mapping
@@ -1700,7 +1755,7 @@ void vegas_gpu_destroy(vegas_gpu_t h) {
     cudaFree(h->hp_dev);
     for (cudaEvent_t ev : h->hp_events) cudaEventDestroy(ev);
     basis_wave_destroy(h->bwave);
-    for (int b = 0; b < 4; ++b) for (int k = 0; k < 3; ++k) cudaFree(h->hb2[b][k]);
+    if (!h->slab) for (int b = 0; b < 4; ++b) for (int k = 0; k < 3; ++k) cudaFree(h->hb2[b][k]);
     if (h->stream_b) { cudaStreamSynchronize(h->stream_b); cudaStreamDestroy(h->stream_b); }
     if (h->ev_main) cudaEventDestroy(h->ev_main);
     if (h->ev_bnd) cudaEventDestroy(h->ev_bnd);
@@ -1977,8 +2032,8 @@ int push_boundaries(vegas_gpu* h) {
         const size_t ext = (size_t)(h->n / h->n_colours) + 2 * pl;
         for (int a = 0; a < h->n_colours * 3; ++a) {
             const char* mine = (const char*)h->hb[a / 3][a % 3];
-            char* lo_dst = (char*)h->peer_halo[0] + ((size_t)a * ext + (size_t)(h->ld.nz + 1) * pl) * rb;
-            char* hi_dst = (char*)h->peer_halo[1] + ((size_t)a * ext) * rb;
+            char* lo_dst = peer_set(h, 0, h->cur_set) + ((size_t)a * ext + (size_t)(h->ld.nz + 1) * pl) * rb;
+            char* hi_dst = peer_set(h, 1, h->cur_set) + ((size_t)a * ext) * rb;
             copy_plane_kernel<<<cdiv(n4, 256), 256, 0, h->stream>>>((uint32_t*)lo_dst, (const uint32_t*)mine, n4);
             copy_plane_kernel<<<cdiv(n4, 256), 256, 0, h->stream>>>((uint32_t*)hi_dst, (const uint32_t*)(mine + (size_t)(h->ld.nz - 1) * pl * rb), n4);
             h->launches += 2;
