@@ -4,7 +4,8 @@ N=${1:-8}
 out=gpurun_out/r02t8; mkdir -p $out
 T="timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"
 nproc > $out/nproc.txt
-for k in ising fcc; do $T tests/mp_slab_check.py $k 2>&1 | grep -E "mp_slab_check|Error|error" | head -2 | tee -a $out/checks.txt; done
+for k in ising; do $T tests/mp_slab_check.py $k 2>&1 | grep -E "mp_slab_check|Error|error" | head -2 | tee -a $out/checks.txt; done
+VEGAS_TUNE=basis_pair=1 $T tests/mp_slab_check.py fcc 2>&1 | grep -E "mp_slab_check|Error|error" | head -2 | tee -a $out/checks.txt
 VEGAS_TUNE=heis_pipe=1 $T tests/mp_slab_check.py heisenberg 2>&1 | grep -E "mp_slab_check|Error|error" | head -2 | tee -a $out/checks.txt
 $T tests/mp_machine_check.py ising 2>&1 | grep -E "mp_machine_check|Error|error" | head -2 | tee -a $out/checks.txt
 $T bench.py --gpus $N --steps 20 --warmup 3 --no-cpu > $out/bench_n$N.json 2> $out/bench_n$N.err; tail -2 $out/bench_n$N.err
