@@ -886,6 +886,17 @@ int fused_step_t(vegas_gpu* h, double* obs_row, bool record) {
 }
 
 // ---- persistent wave step (heis_wave_kernel) ------------------------------------------------------
+template <typename real>
+const void* wave_kernel_ptr_t(bool flip, bool rec, bool multi) {
+#define WK(F, R) (multi ? (const void*)heis_wave_kernel<real, F, R, true> : (const void*)heis_wave_kernel<real, F, R, false>)
+    if (flip) return rec ? WK(true, true) : WK(true, false);
+    return rec ? WK(false, true) : WK(false, false);
+#undef WK
+}
+const void* wave_kernel_ptr(bool f64, bool flip, bool rec, bool multi) {
+    return f64 ? wave_kernel_ptr_t<double>(flip, rec, multi) : wave_kernel_ptr_t<float>(flip, rec, multi);
+}
+
 // Unit order of a launch of `k` steps (2k phases) over n chunks: phase p visits chunk (p + pos) % n at time slot
 // pos + p * lag; slots ascending, phases ascending inside a slot (see heis.cuh, K3w).
 std::vector<uint32_t> wave_units_for(uint32_t n, uint32_t lag, uint32_t k) {
@@ -932,11 +943,17 @@ bool wave_plan(vegas_gpu* h) {
     h->wave_sched = ws;
     h->wave_kmax = kmax;
     // every CTA of the grid must be resident at once (static round-robin over the items)
-    int per_sm = 0, sms = 0;
+    // (the grid must fit EVERY instantiation that can be launched, and the launch is cooperative so that
+    // co-residency is guaranteed by the driver or the launch fails -- never a silent dependency time-out)
+    int per_sm = 1 << 30, sms = 0, coop = 0;
     const bool f64 = h->md.precision == VEGAS_F64;
-    cudaError_t e = f64 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, heis_wave_kernel<double, false, true, true>, 128, 0)
-                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, heis_wave_kernel<float, false, true, true>, 128, 0);
-    if (e != cudaSuccess || per_sm < 1 || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) != cudaSuccess) return false;
+    for (int v = 0; v < 8; ++v) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, wave_kernel_ptr(f64, v & 1, v & 2, v & 4), 128, 0) != cudaSuccess || n < 1) { cudaGetLastError(); return false; }
+        per_sm = std::min(per_sm, n);
+    }
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device) != cudaSuccess || !coop) { cudaGetLastError(); return false; }
     h->wave_grid = per_sm * sms;
     h->wave_ready = true;
     return true;
@@ -969,16 +986,18 @@ void wave_steps_t(vegas_gpu* h, uint32_t k, double* obs_row, bool record) {
     const PhiloxKey pk = make_philox_key(h->md.seed);
     const bool flip = h->md.proposal == VEGAS_PROPOSE_FLIP;
     const int grid = (int)std::min<uint64_t>((uint64_t)h->wave_grid, (uint64_t)ws.n_units * ws.tiles);
-    const int stride = record ? OBS_W : 0;
+    int stride = record ? OBS_W : 0;
+    uint64_t sweep = h->sweeps;
+    PhiloxKey key = pk;
+    HeisGeom geom = g;
+    HeisParams<real> par = p;
     h->launches++;
-#define WL(FLIP, REC)                                                                                                         \
-    do {                                                                                                                      \
-        if (k > 1) heis_wave_kernel<real, FLIP, REC, true><<<grid, 128, 0, h->stream>>>(P0, P1, g, ws, p, h->sweeps, pk, obs_row, stride); \
-        else heis_wave_kernel<real, FLIP, REC, false><<<grid, 128, 0, h->stream>>>(P0, P1, g, ws, p, h->sweeps, pk, obs_row, stride);      \
-    } while (0)
-    if (record) { if (flip) WL(true, true); else WL(false, true); }
-    else { if (flip) WL(true, false); else WL(false, false); }
-#undef WL
+    void* args[] = {&P0, &P1, &geom, &ws, &par, &sweep, &key, &obs_row, &stride};
+    const cudaError_t e = cudaLaunchCooperativeKernel(wave_kernel_ptr_t<real>(flip, record, k > 1), dim3(grid), dim3(128), args, 0, h->stream);
+    if (e != cudaSuccess) {   // co-residency refused: the caller's cudaGetLastError check reports it; two-pass kernels from now on
+        h->err = std::string("heis_wave_kernel cooperative launch failed: ") + cudaGetErrorString(e);
+        h->wave_ready = false; h->wave_enable = 0;
+    }
 }
 
 // ---- phase-pipelined TMA step (heis_pipe.cu) ---------------------------------------------------------
