@@ -225,6 +225,9 @@ int vegas_gpu_set_tuning(vegas_gpu_t, const char* key, long value);
  * (units[i] = phase << 24 | chunk, phase = 2 * step + colour; 2 * steps * n_chunks entries).  Exposed so that the
  * schedule's invariant -- every unit comes after the three units it waits for -- is tested without a GPU. */
 int vegas_gpu_wave_schedule(uint32_t n_chunks, uint32_t lag, uint32_t steps, uint32_t* units, uint64_t capacity, uint64_t* count);
+/* host-only: 1 when the unit-cell bond table has the structure the pair launches (heis_basis_pair_kernel) rely on -- every bond
+ * between colours 2k and 2k + 1 has dz = 0 and, seen from 2k + 1, dy in {0, +1} -- else 0 (fcc: 1, bcc: 0) */
+int vegas_gpu_basis_pair_structure(int unitcell);
 /* host-only: the unit order of one wave-ordered bcc / fcc step (basis_wave.cu) over `nz` cell planes with `lag` time slots
  * between consecutive colours: units[i] = colour << 24 | plane, n_basis * nz entries (count = 0: too few planes for the
  * scheme); need[b] bit 2a + r = colour b on plane z waits for colour a on plane (z + r) % nz.  unitcell: VEGAS_BCC / VEGAS_FCC. */

@@ -198,6 +198,35 @@ def test_host_pack_round_trip(built, n_words, threads, chunk):
     assert lib.vegas_gpu_host_pack(None, words.ctypes.data, n_words, threads, chunk) != 0
 
 
+def test_basis_pair_structure_matches_the_adjacency(built):
+    """heis_basis_pair_kernel updates colours 2k and 2k + 1 in one launch without inter-CTA synchronisation; that is only right if
+    every neighbour of a colour-(2k + 1) site inside colour 2k lies in the SAME cell plane and in row y or y + 1.  Checked here
+    against the adjacency the lattice generator exports (vegas_gpu_lattice_adjacency), independently of the kernel's tables."""
+    from vegas_rs_b200 import _lib
+    lib = _lib.load()
+    for uc, nb, want in ((2, 4, 1), (1, 2, 0)):
+        d = _lib.LatticeDesc(uc, 5, 6, 7, 1, 1, 1, 0, 0, 0)
+        n, nnz = C.c_uint64(), C.c_uint64()
+        assert lib.vegas_gpu_lattice_adjacency(C.byref(d), 1.0, C.byref(n), C.byref(nnz), None, None, None) == 0
+        rp = np.zeros(n.value + 1, np.uint64); col = np.zeros(nnz.value, np.uint32)
+        assert lib.vegas_gpu_lattice_adjacency(C.byref(d), 1.0, C.byref(n), C.byref(nnz), rp.ctypes.data_as(C.c_void_p), col.ctypes.data_as(C.c_void_p), None) == 0
+        ok = True
+        for i in range(n.value):
+            b, cell = i % nb, i // nb
+            if b % 2 == 0:
+                continue
+            yi, zi = (cell // 5) % 6, cell // 30
+            for j in col[int(rp[i]):int(rp[i + 1])]:
+                a, cj = int(j) % nb, int(j) // nb
+                if a != b - 1:
+                    continue
+                yj, zj = (cj // 5) % 6, cj // 30
+                dy, dz = (yj - yi + 3) % 6 - 3, (zj - zi + 3) % 7 - 3
+                ok = ok and dz == 0 and dy in (0, 1)
+        assert int(ok) == want == lib.vegas_gpu_basis_pair_structure(uc), (uc, ok)
+    assert lib.vegas_gpu_basis_pair_structure(0) == 0
+
+
 def test_rust_shim_struct_layout_matches_header():
     """bindings/rust/gpu.rs cannot be compiled here; at least its #[repr(C)] structs must list the fields of
     include/vegas_gpu.h in the same order, and every extern function it declares must exist in the headers."""

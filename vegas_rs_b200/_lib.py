@@ -48,6 +48,7 @@ SYMBOLS = [
     ("vegas_gpu_state_transfer_bytes", _u64, [_vp]),
     ("vegas_gpu_host_pack", _int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_uint64]),
     ("vegas_gpu_host_unpack", _int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_uint64]),
+    ("vegas_gpu_basis_pair_structure", _int, [C.c_int]),
     ("vegas_gpu_basis_wave_schedule", _int, [C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p]),
     ("vegas_gpu_upload_ising", _int, [_vp, _vp, _u64]),
     ("vegas_gpu_upload_heisenberg", _int, [_vp, _vp, _u64]),

@@ -2529,6 +2529,12 @@ int vegas_gpu_wave_schedule(uint32_t n_chunks, uint32_t lag, uint32_t steps, uin
     return VEGAS_OK;
 }
 
+int vegas_gpu_basis_pair_structure(int unitcell) {
+    if (unitcell == VEGAS_FCC) return pair_structure_ok<2>() ? 1 : 0;
+    if (unitcell == VEGAS_BCC) return pair_structure_ok<1>() ? 1 : 0;
+    return 0;
+}
+
 int vegas_gpu_basis_wave_schedule(int unitcell, uint32_t nz, uint32_t lag, uint32_t* units, uint64_t capacity, uint64_t* count, uint32_t need[4]) {
     if ((unitcell != VEGAS_BCC && unitcell != VEGAS_FCC) || nz == 0 || nz >= (1u << 24) || lag == 0 || !count || !need) return VEGAS_ERR_INVALID;
     uint32_t nd[4];
