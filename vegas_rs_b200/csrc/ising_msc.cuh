@@ -47,7 +47,8 @@ __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { r
 
 #ifndef MSC_MINB
 #define MSC_MINB 4   // resident CTAs of 256 threads per SM the sweep kernel is compiled for (register cap 64).  Measured on
-#endif               // 1024^3 / 8192^2 (profiles/r02o*): 2 -> 2.319e12 / 1.888e12, 3 -> 2.337e12 / 1.852e12, 4 -> 2.423e12 / 1.867e12
+#endif               // 1024^3 / 8192^2 (profiles/r02o*): 2 -> 2.319e12 / 1.888e12, 3 -> 2.337e12 / 1.852e12, 4 -> 2.423e12 / 1.867e12;
+                     // final kernel (profiles/r02/i6.sh): 4 -> 3.065e12 / 2.43e12, 5 (48 registers, 16-40 B spilled) -> 2.995e12 / 2.32e12
 // rows (words along y) per thread: amortises addressing, shares the y-neighbour loads.  2-D lattices are small
 // (8192^2 = 1 Mi words per colour): 1, 2, 4 rows per thread measured 1.42e12, 1.76e12, 1.91e12 attempts/s there.
 // of the 8 threshold bit-planes of the main compare, how many are built with logic operations instead of multiply-adds.
